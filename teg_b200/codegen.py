@@ -1,0 +1,277 @@
+"""CUDA emitter: Schedule -> one sm_100a translation unit (the new ``CUDA`` target).
+
+Counterpart of the reference's text emitter (teg/ir/passes/to_c.py:260-651 + c_math.py +
+data/templates/rectangular_rule.template.c), but what comes out is a *batched kernel*, not a header
+of scalar ``__device__`` functions (which is all ``--target CUDA_C`` gives, teg/__main__.py:100-109):
+
+  <name>_uniform   1 thread: evaluates every launch-invariant value once and writes the table that
+                   the runtime copies into ``tegU`` (``__constant__``), so per-instance code reads
+                   them as constant-bank operands: no registers, no loads.
+  <name>_main      thread per instance: coalesced SoA loads of the per-instance arguments, the
+                   scheduled guards / fused midpoint loops, coalesced SoA stores of the outputs.
+
+Arithmetic is emitted one IEEE operation per reference operation, in the reference's order, and the
+unit is compiled with ``--fmad=false``: sample placement ``lb + step * (i + 0.5)``, every comparison
+operand and every left-fold ``out = out + f * step`` round exactly as in the C backend, so
+discontinuity classification -- and therefore every result -- is reproducible bit for bit on the
+same inputs (libm transcendentals excepted).
+
+The two instance bodies are emitted as ``TEGB_FN`` functions; the runtime header makes that
+``__device__ __forceinline__``.  (tests/ re-define it to compile the very same text for the host and
+compare it with the oracle on machines without a GPU -- a checker, never a product path.)
+"""
+from __future__ import annotations
+
+import hashlib
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+from .dag import Dag
+from .schedule import Block, Eval, IfGroup, LoopGroup, Schedule, Scheduler
+
+_MATH = {
+    'float': {'sqrt': 'sqrtf', 'sin': 'sinf', 'cos': 'cosf', 'asin': 'asinf', 'atan2': 'atan2f'},
+    'double': {'sqrt': 'sqrt', 'sin': 'sin', 'cos': 'cos', 'asin': 'asin', 'atan2': 'atan2'},
+}
+
+
+def literal(text: str, ctype: str) -> str:
+    """Decimal constant in working precision, the way to_c.py:231-247 prints it (``1.0f`` / ``1``)."""
+    t = text.strip()
+    if not any(ch in t for ch in '.eEn'):      # integer spelling ('n' covers inf/nan)
+        t += '.0'
+    if 'inf' in t or 'nan' in t:
+        raise ValueError('non-finite literal')
+    return f'{t}f' if ctype == 'float' else t
+
+
+@dataclass
+class KernelSource:
+    name: str
+    ctype: str
+    num_samples: int
+    source: str
+    uniform_kernel: str
+    main_kernel: str
+    n_uniform: int
+    scalar_args: List[int]          # argument indices passed (by value) to the uniform kernel, in order
+    array_args: List[int]           # argument indices passed (as pointers) to the main kernel, in order
+    n_outputs: int
+    block_size: int
+    stats: Dict[str, float]
+
+    @property
+    def key(self) -> str:
+        return hashlib.sha256(self.source.encode()).hexdigest()[:24]
+
+
+class Emitter:
+    def __init__(self, sch: Schedule, ctype: str, num_samples: int, name: str,
+                 block_size: int = 128, unroll_inner: int = 32, unroll_outer: int = 1):
+        assert ctype in ('float', 'double')
+        self.sch = sch
+        self.dag: Dag = sch.dag
+        self.nodes = sch.dag.nodes
+        self.ctype = ctype
+        self.N = int(num_samples)
+        self.name = name
+        self.block_size = block_size
+        self.unroll_inner = unroll_inner
+        self.unroll_outer = unroll_outer
+        self.helper = Scheduler(sch.dag, sch.array_args)      # for resolve / bool_value
+        self.lines: List[str] = []
+        self.loop_counter = 0
+        # static op statistics (per execution of each block, weighted later by trip counts)
+        self.stats = {'ops_instance': 0, 'ops_guarded': 0, 'ops_sample_static': 0}
+
+    # --------------------------------------------------------------- references
+    def ref(self, i: int, known: Dict[int, bool]) -> str:
+        i = self.helper.resolve(i, known)
+        n = self.nodes[i]
+        if n.is_bool:
+            v = self.helper.bool_value(i, known)
+            if v is not None:
+                return 'true' if v else 'false'
+        if n.op == 'const':
+            return literal(n.attr, self.ctype)
+        if i in self.sch.uniform_slots and self.in_main:
+            slot = self.sch.uniform_slots[i]
+            return f'(tegU[{slot}] != 0)' if n.is_bool else f'tegU[{slot}]'
+        if n.op == 'bvar':
+            return f'x{i}'
+        return f'v{i}'
+
+    def expr(self, i: int, known: Dict[int, bool]) -> str:
+        n = self.nodes[i]
+        r = lambda a: self.ref(a, known)     # noqa: E731
+        op = n.op
+        m = _MATH[self.ctype]
+        if op == 'add':
+            return f'{r(n.args[0])} + {r(n.args[1])}'
+        if op == 'mul':
+            return f'{r(n.args[0])} * {r(n.args[1])}'
+        if op == 'div':
+            return f'{r(n.args[0])} / {r(n.args[1])}'
+        if op == 'lt':
+            return f'{r(n.args[0])} < {r(n.args[1])}'
+        if op == 'and':
+            return f'{r(n.args[0])} && {r(n.args[1])}'
+        if op == 'or':
+            return f'{r(n.args[0])} || {r(n.args[1])}'
+        if op == 'sel':
+            return f'{r(n.args[0])} ? {r(n.args[1])} : {r(n.args[2])}'
+        if op in ('sqrt', 'sin', 'cos', 'asin'):
+            return f'{m[op]}({r(n.args[0])})'
+        if op == 'atan2':
+            return f'{m[op]}({r(n.args[0])}, {r(n.args[1])})'
+        if op == 'in':
+            return f'a{n.attr}'
+        raise NotImplementedError(f'CUDA backend does not support instruction class "{op}"')
+
+    def decl(self, i: int) -> str:
+        return 'bool' if self.nodes[i].is_bool else 'T'
+
+    # ------------------------------------------------------------------- blocks
+    def emit(self, line: str, ind: int):
+        self.lines.append('    ' * ind + line)
+
+    def block(self, b: Block, ind: int, depth: int):
+        known = b.known
+        for st in b.stmts:
+            if isinstance(st, Eval):
+                i = st.node
+                self.emit(f'const {self.decl(i)} v{i} = {self.expr(i, known)};', ind)
+            elif isinstance(st, IfGroup):
+                for s in st.sels:
+                    self.emit(f'T v{s};', ind)
+                self.emit(f'if ({self.ref(st.cond, known)}) {{', ind)
+                self.block(st.then_block, ind + 1, depth)
+                for s in st.sels:
+                    self.emit(f'v{s} = {self.ref(self.nodes[s].args[1], st.then_block.known)};', ind + 1)
+                self.emit('} else {', ind)
+                self.block(st.else_block, ind + 1, depth)
+                for s in st.sels:
+                    self.emit(f'v{s} = {self.ref(self.nodes[s].args[2], st.else_block.known)};', ind + 1)
+                self.emit('}', ind)
+            elif isinstance(st, LoopGroup):
+                self.loop(st, known, ind, depth)
+            else:  # pragma: no cover
+                raise TypeError(st)
+
+    def loop(self, st: LoopGroup, known: Dict[int, bool], ind: int, depth: int):
+        """data/templates/rectangular_rule.template.c:1-11, several accumulators per pass."""
+        k = self.loop_counter
+        self.loop_counter += 1
+        N = self.N
+        innermost = not any(isinstance(s, LoopGroup) for s in st.body.walk())
+        for q in st.quads:
+            self.emit(f'T v{q} = {literal("0", self.ctype)};', ind)
+        self.emit('{', ind)
+        self.emit(f'const T lo{k} = {self.ref(st.lo, known)};', ind + 1)
+        self.emit(f'const T step{k} = ((T)({self.ref(st.hi, known)} - lo{k})) / (T){N};', ind + 1)
+        if innermost:
+            unroll = N if N <= self.unroll_inner else 4
+        else:
+            unroll = self.unroll_outer
+        self.emit(f'#pragma unroll {unroll}', ind + 1)
+        self.emit(f'for (unsigned int s{k} = 0; s{k} < {N}u; ++s{k}) {{', ind + 1)
+        self.emit(f'const T x{st.bvar} = lo{k} + step{k} * ((T)s{k} + {literal("0.5", self.ctype)});', ind + 2)
+        self.block(st.body, ind + 2, depth + 1)
+        for q in st.quads:
+            body = self.ref(self.nodes[q].args[2], st.body.known)
+            self.emit(f'v{q} = v{q} + {body} * step{k};', ind + 2)
+        self.emit('}', ind + 1)
+        self.emit('}', ind)
+
+    # ------------------------------------------------------------------- kernels
+    def uniform_body(self) -> List[str]:
+        self.in_main = False
+        self.lines = []
+        for i in self.sch.uniform_nodes:
+            n = self.nodes[i]
+            self.emit(f'const {self.decl(i)} v{i} = {self.expr(i, {})};', 1)
+        for i, slot in sorted(self.sch.uniform_slots.items(), key=lambda kv: kv[1]):
+            n = self.nodes[i]
+            val = f'(v{i} ? {literal("1", self.ctype)} : {literal("0", self.ctype)})' if n.is_bool else f'v{i}'
+            self.emit(f'U[{slot}] = {val};', 1)
+        return self.lines
+
+    def main_body(self) -> List[str]:
+        self.in_main = True
+        self.lines = []
+        self.block(self.sch.main, 1, 0)
+        for k, o in enumerate(self.sch.outputs):
+            self.emit(f'out{k}[i] = {self.ref(o, self.sch.main.known)};', 1)
+        return self.lines
+
+    def generate(self) -> KernelSource:
+        sch = self.sch
+        T = self.ctype
+        name = self.name
+        nu = max(1, len(sch.uniform_slots))
+        scal = list(sch.scalar_args)
+        arrs = list(sch.array_args)
+        # only scalar arguments the uniform prologue actually reads
+        used_in = {self.nodes[i].attr for i in sch.uniform_nodes if self.nodes[i].op == 'in'}
+        uni = self.uniform_body()
+        main = self.main_body()
+        used_arr = set()
+        for ln in main:
+            pass
+        live = set(self.dag.reachable(sch.outputs))
+        used_arr = {self.nodes[i].attr for i in live if self.nodes[i].op == 'in' and self.nodes[i].attr in set(arrs)}
+
+        uparams = ', '.join([f'const T a{a}' for a in scal] + ['T* __restrict__ U'])
+        mparams = ', '.join([f'const T* __restrict__ in{a}' for a in arrs] +
+                            [f'T* __restrict__ out{k}' for k in range(len(sch.outputs))] + ['const long long n'])
+        margs = ', '.join([f'in{a}' for a in arrs] + [f'out{k}' for k in range(len(sch.outputs))])
+        loads = [f'    const T a{a} = in{a}[i];' for a in arrs if a in used_arr]
+        src: List[str] = []
+        src.append(f'// generated by teg_b200.codegen for program "{self.dag.name}"  (precision {T}, {self.N} samples)')
+        src.append('#include "teg_b200_runtime.cuh"')
+        src.append(f'typedef {T} T;')
+        src.append(f'#define TEGB_NUM_UNIFORM {nu}')
+        src.append('TEGB_UNIFORM_TABLE(T, tegU, TEGB_NUM_UNIFORM);')
+        src.append('')
+        src.append(f'TEGB_FN void {name}_uniform_body({uparams}) {{')
+        for a in scal:
+            if a not in used_in:
+                src.append(f'    (void)a{a};')
+        src += uni
+        src.append('}')
+        src.append('')
+        src.append(f'TEGB_FN void {name}_instance(const long long i, {mparams}) {{')
+        src.append('    (void)n;')
+        src += loads
+        src += main
+        src.append('}')
+        src.append('')
+        src.append('#ifdef __CUDACC__')
+        src.append(f'extern "C" __global__ void {name}_uniform({uparams}) {{')
+        src.append(f'    if (blockIdx.x == 0 && threadIdx.x == 0) {name}_uniform_body('
+                   + ', '.join([f'a{a}' for a in scal] + ['U']) + ');')
+        src.append('}')
+        src.append('')
+        src.append(f'extern "C" __global__ void __launch_bounds__({self.block_size}) {name}_main({mparams}) {{')
+        src.append('    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;')
+        src.append(f'    if (i < n) {name}_instance(i, {margs}, n);')
+        src.append('}')
+        src.append('#endif')
+        text = '\n'.join(src) + '\n'
+        return KernelSource(name=name, ctype=T, num_samples=self.N, source=text,
+                            uniform_kernel=f'{name}_uniform', main_kernel=f'{name}_main',
+                            n_uniform=nu, scalar_args=scal, array_args=arrs,
+                            n_outputs=len(sch.outputs), block_size=self.block_size, stats=dict(self.stats))
+
+
+def generate(sch: Schedule, ctype: str = 'float', num_samples: int = 50, name: Optional[str] = None,
+             **opts) -> KernelSource:
+    name = name or _c_ident(sch.dag.name)
+    return Emitter(sch, ctype, num_samples, name, **opts).generate()
+
+
+def _c_ident(s: str) -> str:
+    out = ''.join(ch if (ch.isalnum() or ch == '_') else '_' for ch in s)
+    if not out or out[0].isdigit():
+        out = 'p_' + out
+    return out
