@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- integral evaluations / s for the BASELINE.json headline workload.
+
+    python bench.py --gpus N --steps K --warmup W          # our arm (CUDA, sm_100a)
+    python bench.py --impl reference ...                    # the reference's C backend on the host cores
+
+Workload (config.workload = "tri_raster_4096"): the per-pixel triangle rasterization integral plus its
+reverse derivative w.r.t. the six vertex coordinates (oracle/scenes.py: tri_primal + tri_grad, the
+program of SURVEY.md §8(d) config 2) on a 4096 x 4096 pixel grid per GPU, 16 midpoint samples per
+integral (256 samples per pixel for the value, 16 per active delta term for the gradient).
+One *step* = one pass over the whole batch: value image, per-pixel gradients, and the per-parameter
+gradient sum (+ one NCCL all-reduce of the 6-vector when N > 1).  One *integral evaluation* = one
+pixel instance (value + its reverse derivative).  Multi-GPU is weak scaling: the image grows to
+(4096 N) x 4096 pixels over the same domain and rank r owns rows [4096 r, 4096 (r+1)).
+
+Nothing here reads /root/reference: programs come from tests/golden/programs/*.tegp, the CPU
+baseline from oracle/_ref/*.so (the reference's own generated C, built where the reference exists)
+or, failing that, from the oracle port.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+PROGRAM_DIR = os.path.join(ROOT, 'tests', 'golden', 'programs')
+NUM_SAMPLES = 16
+WORKLOAD = 'tri_raster_4096'
+
+
+def load_text(scene: str) -> str:
+    with open(os.path.join(PROGRAM_DIR, f'{scene}.tegp')) as f:
+        return f.read()
+
+
+# ------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-lms', '100',
+                 '-i', str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------------- reference (CPU) arm
+def cpu_runner(threads: int):
+    """Returns (kind, run(scene, inputs) -> ndarray).  'reference' = oracle/_ref (the reference's own C)."""
+    from oracle import Oracle, RefLib, ref_lib_path
+    if all(os.path.exists(ref_lib_path(s, np.float32, NUM_SAMPLES)) for s in ('tri_primal', 'tri_grad')):
+        libs = {s: RefLib(s, np.float32, NUM_SAMPLES) for s in ('tri_primal', 'tri_grad')}
+        return 'reference', lambda scene, inputs: libs[scene].eval(inputs, threads=threads)
+    libs = {s: Oracle(load_text(s)) for s in ('tri_primal', 'tri_grad')}
+    return 'port', lambda scene, inputs: libs[scene].eval(inputs, NUM_SAMPLES, np.float32, threads=threads)
+
+
+def cpu_sample_inputs(res: int, n_rows: int):
+    """Bounded sample of the workload: n_rows pixel rows spread evenly over the res x res grid."""
+    from teg_b200.tegp import Program
+    from teg_b200.workloads import TRIANGLE, bind, pixel_boxes
+    prog = Program.loads(load_text('tri_primal'))
+    stride = max(1, res // n_rows)
+    rows = np.arange(0, res, stride)[:n_rows]
+    parts = [pixel_boxes((res, res), rows=(int(r), int(r) + 1)) for r in rows]
+    box = [np.concatenate([p[k] for p in parts]) for k in range(4)]
+    vals = dict(zip(('x_lb', 'x_ub', 'y_lb', 'y_ub'), box), **TRIANGLE)
+    return bind(prog.args, vals), len(rows) * res
+
+
+def time_cpu(run, inputs, reps: int = 3) -> float:
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        run('tri_primal', inputs)
+        run('tri_grad', inputs)
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def run_reference_arm(args) -> int:
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    kind, run = cpu_runner(threads)
+    inputs, n_inst = cpu_sample_inputs(args.res, args.cpu_rows)
+    for _ in range(max(args.warmup, 1)):
+        run('tri_primal', inputs)
+        run('tri_grad', inputs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run('tri_primal', inputs)
+        run('tri_grad', inputs)
+    dt = time.perf_counter() - t0
+    value = n_inst * args.steps / dt
+    sample = f'{args.cpu_rows} evenly spaced pixel rows of the {args.res}x{args.res} grid ({n_inst} instances) per step'
+    line = {
+        'impl': 'reference', 'metric': 'integral_evals_per_s', 'value': value, 'unit': 'integral evals/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'res': args.res, 'num_samples': NUM_SAMPLES,
+                   'programs': ['tri_primal', 'tri_grad']},
+        'cpu_baseline': {'value': value, 'unit': 'integral evals/s', 'cores': threads, 'kind': kind,
+                         'sample': sample},
+        'e2e': {'value': value, 'unit': 'integral evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--res', type=int, default=4096)
+    ap.add_argument('--cpu-rows', type=int, default=256, help='pixel rows in the bounded CPU sample')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from teg_b200 import CUDA_EvalMode, runtime
+    from teg_b200.opcount import count as op_count
+    from teg_b200.schedule import make_schedule
+    from teg_b200.tegp import Program
+    from teg_b200.workloads import TRIANGLE
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    assert world == args.gpus or world == 1, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the CUDA backend has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    res = args.res
+    res_x_total = res * world                  # weak scaling: rank r owns rows [res*r, res*(r+1))
+    rows = (res * rank, res * (rank + 1))
+    n_local = res * res
+    primal = Program.loads(load_text('tri_primal'))
+    grad = Program.loads(load_text('tri_grad'))
+    m_primal = CUDA_EvalMode(primal, num_samples=NUM_SAMPLES, device=local_rank)
+    m_grad = CUDA_EvalMode(grad, num_samples=NUM_SAMPLES, device=local_rank)
+    box = primal.args[:4]
+    params = {lab: TRIANGLE[lab.rsplit('_', 1)[0]] for lab in primal.args[4:]}
+    gparams = {lab: TRIANGLE[lab.rsplit('_', 1)[0]] for lab in grad.args[4:]}
+    bounds = ((0.0, 1.0), (0.0, 1.0))
+
+    stream = torch.cuda.current_stream(dev)
+    sptr = stream.cuda_stream
+    img = torch.empty((1, res, res), dtype=torch.float32, device=dev)
+    gimg = torch.empty((6, res, res), dtype=torch.float32, device=dev)
+    gsum = torch.zeros(6, dtype=torch.float32, device=dev)
+    ws_bytes = runtime.reduce_workspace_bytes(6, n_local, 4)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    gcols = [gimg[k].data_ptr() for k in range(6)]
+
+    ev = {k: [] for k in ('primal', 'grad', 'reduce')}
+
+    def step(record: bool):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
+        if record:
+            e[0].record(stream)
+        m_primal.render(box, (res_x_total, res), bounds, params, rows=rows, out=img, stream=sptr)
+        if record:
+            e[1].record(stream)
+        m_grad.render(box, (res_x_total, res), bounds, gparams, rows=rows, out=gimg, stream=sptr)
+        if record:
+            e[2].record(stream)
+        runtime.reduce_sum(gcols, n_local, 4, gsum.data_ptr(), ws.data_ptr(), ws_bytes, stream=sptr)
+        if record:
+            e[3].record(stream)
+        if world > 1:
+            dist.all_reduce(gsum)
+        if record:
+            ev['primal'].append((e[0], e[1]))
+            ev['grad'].append((e[1], e[2]))
+            ev['reduce'].append((e[2], e[3]))
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    launches0 = runtime.launch_count()
+    for _ in range(args.warmup):
+        step(False)
+    sync_all()
+    launches_warm = runtime.launch_count()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    sync_all()
+    t_begin.record(stream)
+    for _ in range(args.steps):
+        step(True)
+    t_end.record(stream)
+    sync_all()
+    total_ms = t_begin.elapsed_time(t_end)
+    clocks = sampler.stop() if rank == 0 else None
+    launches_timed = runtime.launch_count() - launches_warm
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = n_local * world * args.steps / (total_ms * 1e-3)
+
+    phase_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in ev.items()}
+
+    # sanity: the summed image is the triangle area, the summed gradient its analytic derivative
+    area = float(img.double().sum().item())
+    gvec = gsum.cpu().numpy().astype(np.float64)
+
+    # ---------------------------------------------------------------- e2e: host buffers, copies inside
+    e2e = None
+    if not args.no_e2e:
+        h_img = torch.empty((res, res), dtype=torch.float32).pin_memory()
+        h_g = torch.empty(6, dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            # inputs of the step: the 6 vertex coordinates, passed by value as kernel parameters of the
+            # uniform prologue (twice: value and gradient program); the pixel grid is index arithmetic
+            step(False)
+            h_img.copy_(img[0], non_blocking=True)
+            h_g.copy_(gsum, non_blocking=True)
+            stream.synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        k_e2e = max(3, min(args.steps, 10))
+        for _ in range(k_e2e):
+            e2e_step()
+        sync_all()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {'value': n_local * world * k_e2e / float(te.item()), 'unit': 'integral evals/s',
+               'h2d_bytes_per_step': 2 * 6 * 4,
+               'd2h_bytes_per_step': int(h_img.numel() * 4 + h_g.numel() * 4),
+               'api': 'CUDA_EvalMode.render (pixel boxes generated on device) + tegb_reduce_sum; image and '
+                      'gradient vector copied to pinned host memory every step', 'steps': k_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ------------------------------------------------------------------------------------- roofline
+    sch = make_schedule(m_primal.dag, [0, 1, 2, 3])
+    oc = op_count(sch, NUM_SAMPLES)
+    flops_per_launch = oc.unguarded * n_local           # primal has no guards: exact
+    peak_tflops, clk_mhz = runtime.fma_peak(4, local_rank)
+    nominal = 2 * 128 * 148 * 1965e6 / 1e12
+    achieved = flops_per_launch / (phase_ms['primal'] * 1e-3) / 1e12
+    roofline = {'bound': 'fp32_fma', 'kernel': 'tri_primal_main', 'achieved': achieved, 'peak': peak_tflops,
+                'unit': 'TFLOP/s', 'frac': achieved / peak_tflops, 'traffic': None,
+                'peak_source': 'FFMA micro-benchmark (tegb_fma_peak) measured in this run; MEASURED_PEAKS.json '
+                               'has no fp32 figure', 'peak_nominal': nominal,
+                'algorithmic_ops_per_instance': oc.unguarded, 'ops_per_inner_sample': oc.per_sample_inner,
+                'kernel_ms': phase_ms['primal'],
+                'hbm_GBps_out': (n_local * 4 * 7) / (ms_per_step * 1e-3) / 1e9}
+
+    # ----------------------------------------------------------------------------------- cpu baseline
+    cpu = None
+    if not args.no_cpu and world == 1:
+        threads = os.cpu_count() or 1
+        kind, run = cpu_runner(threads)
+        inputs, n_inst = cpu_sample_inputs(res, args.cpu_rows)
+        run('tri_primal', inputs)
+        best = time_cpu(run, inputs, reps=3)
+        kind1, run1 = cpu_runner(1)
+        inputs1, n1 = cpu_sample_inputs(res, max(8, args.cpu_rows // 16))
+        best1 = time_cpu(run1, inputs1, reps=2)
+        cpu = {'value': n_inst / best, 'unit': 'integral evals/s', 'cores': threads, 'kind': kind,
+               'sample': f'{args.cpu_rows} evenly spaced pixel rows of the {res}x{res} grid ({n_inst} instances), '
+                         f'best of 3', 'value_1core': n1 / best1}
+
+    line = {
+        'metric': 'integral_evals_per_s', 'value': value, 'unit': 'integral evals/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'res_per_gpu': [res, res], 'num_samples': NUM_SAMPLES,
+                   'programs': ['tri_primal', 'tri_grad'], 'outputs': 'value image + 6 per-pixel gradient '
+                   'images + [6] gradient sum', 'l2': f'no flush: each step writes {n_local * 4 * 7 / 1e6:.0f} MB '
+                   'of outputs (> 126 MB L2); inputs are generated from the pixel index',
+                   'parallelism': f'rows sharded over {world} GPU(s), one NCCL all-reduce of the [6] gradient'},
+        'phase_ms': phase_ms, 'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e,
+        'gpu_launches': int(launches_timed), 'clocks': clocks,
+        'check': {'sum_value': area, 'expected_area_per_rank': 0.2325 if world == 1 else None,
+                  'grad_sum': gvec.tolist()},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,129 @@
+/*
+ * tegb200.h -- C ABI of libtegb200.so, the thin runtime behind Teg's CUDA evaluation backend.
+ *
+ * This is the drop-in boundary for the hot path "evaluate a reduced Teg program over a batch of
+ * independent instances".  Plain C types only (pointers, sizes, doubles); no torch / C++ types.
+ * Every entry point returns 0 on success and a non-zero tegb_status otherwise; the message is then
+ * available from tegb_last_error() (thread-local).  Nothing here ever abort()s.
+ *
+ * What each entry point replaces in the reference (/root/reference):
+ *
+ *   tegb_compile            C_EvalMode._preprocess + _compile: write tegout_N.h / main_N.cc and shell out
+ *                           to `g++ -O3 -std=c++11 -fPIC` (teg/eval/c_eval.py:100-127).  Here: NVRTC,
+ *                           sm_100a, --fmad=false, in process, result is a cubin.
+ *   tegb_program_create     the `main()` the reference generates around the entry function
+ *                           (teg/eval/c_eval.py:58-98): binds the entry points and argument layout.
+ *   tegb_program_launch /   C_EvalMode.eval (teg/eval/c_eval.py:129-157): one Popen of the compiled exe
+ *   tegb_program_eval_host  per instance with argv marshalling and stdout parsing.  Here: ONE launch for
+ *                           n instances, structure-of-arrays inputs/outputs.
+ *   tegb_render_launch      the per-pixel Python double loop of tests/plot.py:8-29 (render_image):
+ *                           pixel boxes are generated on the device from the instance index.
+ *   tegb_reduce_sum         (new) per-parameter sum of reverse-mode gradients over instances.
+ *   tegb_allreduce_sum      (new) the one collective of the multi-GPU path (NCCL sum of the [P] vector).
+ *   tegb_last_error         replaces `assert err is None` (c_eval.py:125,147), which can never fire.
+ *
+ * Layout: argument a of instance i is in_ptrs[j][i] (j = position of a among the array arguments);
+ * output component k of instance i is out_ptrs[k][i].  Element type is float or double per program.
+ */
+#ifndef TEGB200_H
+#define TEGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    TEGB_OK = 0,
+    TEGB_ERR_INVALID = 1,      /* bad argument */
+    TEGB_ERR_COMPILE = 2,      /* NVRTC rejected the source; tegb_last_error() holds the log */
+    TEGB_ERR_CUDA = 3,         /* driver / runtime error */
+    TEGB_ERR_NO_DEVICE = 4,    /* no usable CUDA device or driver */
+    TEGB_ERR_NCCL = 5
+} tegb_status;
+
+typedef struct tegb_module tegb_module;     /* one compiled translation unit (cubin) */
+typedef struct tegb_program tegb_program;   /* uniform + main kernel of one Teg program, loaded on a device */
+
+/* how the runtime obtains an argument that is not a per-instance array */
+typedef struct {
+    const char *uniform_kernel;   /* <name>_uniform */
+    const char *main_kernel;      /* <name>_main */
+    const char *uniform_symbol;   /* name of the __constant__ table ("tegU") */
+    int elem_size;                /* 4 = float, 8 = double */
+    int n_uniform;                /* entries of the uniform table */
+    int n_scalar_args;            /* by-value arguments of the uniform kernel */
+    int n_array_args;             /* pointer arguments of the main kernel */
+    int n_grid_args;              /* arguments generated from the pixel index (0 unless a render program) */
+    int n_outputs;                /* output streams of the main kernel */
+    int block_size;               /* threads per block the main kernel was generated for */
+} tegb_program_desc;
+
+/* pixel grid of tests/plot.py:11-16: np.linspace(lo, hi, res+1) per axis, instance = nx * res_y + ny */
+typedef struct {
+    double x_lo, x_hi, y_lo, y_hi;
+    int32_t res_x, res_y;
+    int32_t row_begin, row_end;   /* rows nx in [row_begin, row_end) are evaluated (multi-GPU sharding) */
+} tegb_grid;
+
+const char *tegb_last_error(void);
+int tegb_version(void);
+
+/* number of CUDA devices visible (0 without a driver); never fails */
+int tegb_device_count(void);
+
+/* --- JIT ---------------------------------------------------------------------------------- */
+/* CUDA text -> cubin for `arch` ("sm_100a").  Needs no GPU.  `opts`: extra NVRTC options separated by
+ * spaces (may be NULL).  The runtime header teg_b200_runtime.cuh is supplied by the library. */
+int tegb_compile(const char *cuda_src, const char *arch, const char *opts, tegb_module **out);
+int tegb_module_from_cubin(const void *cubin, size_t nbytes, tegb_module **out);
+int tegb_module_cubin(const tegb_module *m, const void **cubin, size_t *nbytes);
+const char *tegb_module_log(const tegb_module *m);
+void tegb_module_destroy(tegb_module *m);
+
+/* --- programs ----------------------------------------------------------------------------- */
+int tegb_program_create(tegb_module *m, const tegb_program_desc *desc, int device, tegb_program **out);
+void tegb_program_destroy(tegb_program *p);
+
+/* Device buffers.  scalars[n_scalar_args] are converted to the program's element type.
+ * in_ptrs[n_array_args], out_ptrs[n_outputs]: device pointers to n elements each.  Asynchronous on
+ * `stream` (a cudaStream_t; NULL = default stream). */
+int tegb_program_launch(tegb_program *p, const double *scalars, const void *const *in_ptrs,
+                        void *const *out_ptrs, int64_t n, void *stream);
+
+/* Host buffers: copies inputs H2D, launches, copies outputs D2H, synchronises.  Device staging buffers
+ * are owned by the program and grow on demand. */
+int tegb_program_eval_host(tegb_program *p, const double *scalars, const void *const *host_in,
+                           void *const *host_out, int64_t n);
+
+/* Render: the program's grid arguments (pixel box bounds) are generated in-kernel from the instance
+ * index; out_ptrs[k] receive (row_end-row_begin)*res_y elements. */
+int tegb_render_launch(tegb_program *p, const double *scalars, const tegb_grid *grid,
+                       void *const *out_ptrs, void *stream);
+
+/* kernels launched by this library since load (for accounting) */
+int64_t tegb_launch_count(void);
+
+/* --- reductions / collectives ------------------------------------------------------------- */
+/* out[k] = sum_i in_ptrs[k][i], k < n_cols: deterministic (fixed order for a given n), two launches.
+ * `out` is a device pointer to n_cols elements.  workspace: device, >= tegb_reduce_workspace_bytes. */
+size_t tegb_reduce_workspace_bytes(int n_cols, int64_t n, int elem_size);
+int tegb_reduce_sum(const void *const *in_ptrs, int n_cols, int64_t n, int elem_size, void *out,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* NCCL: 128-byte unique id for bootstrap, communicator creation, in-place sum all-reduce. */
+int tegb_nccl_unique_id(void *id128);
+int tegb_nccl_comm_create(const void *id128, int world_size, int rank, int device, void **comm);
+int tegb_nccl_comm_destroy(void *comm);
+int tegb_allreduce_sum(void *buf, int64_t count, int elem_size, void *comm, void *stream);
+
+/* --- measurement -------------------------------------------------------------------------- */
+/* dependent-chain FMA micro-benchmark: achieved TFLOP/s (2 flops per FMA) on `device` */
+int tegb_fma_peak(int elem_size, int device, double *tflops, double *sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEGB200_H */

@@ -139,13 +139,20 @@ def main(argv=None) -> int:
     for scene, builder in SCENES.items():
         if only and scene not in only:
             continue
+        path = os.path.join(PROG_DIR, f'{scene}.tegp')
+        if not args.force and not args.programs_only and os.path.exists(path):
+            # fast path: every variant was already built from exactly this committed TEGP text
+            cur = hashlib.sha256(open(path).read().encode()).hexdigest()
+            keys = [f'{scene}_{prec}_N{ns}' for prec, ns in VARIANTS.get(scene, [])]
+            if all(manifest.get(k, {}).get('tegp_sha256') == cur and
+                   os.path.exists(os.path.join(REF_DIR, k + '.so')) for k in keys):
+                continue
         t0 = time.time()
         Var.global_uid = 1000          # reproducible labels, clear of the module-level constants
         program, arglist = builder()
         prog = from_teg(program, arglist, name=scene)
         text = prog.dumps()
         sha = hashlib.sha256(text.encode()).hexdigest()
-        path = os.path.join(PROG_DIR, f'{scene}.tegp')
         old = open(path).read() if os.path.exists(path) else None
         if old != text:
             with open(path, 'w') as f:

@@ -56,6 +56,7 @@ class KernelSource:
     n_uniform: int
     scalar_args: List[int]          # argument indices passed (by value) to the uniform kernel, in order
     array_args: List[int]           # argument indices passed (as pointers) to the main kernel, in order
+    grid_args: List[int]            # (x_lb, x_ub, y_lb, y_ub) argument indices generated from the pixel index
     n_outputs: int
     block_size: int
     stats: Dict[str, float]
@@ -204,28 +205,28 @@ class Emitter:
             self.emit(f'out{k}[i] = {self.ref(o, self.sch.main.known)};', 1)
         return self.lines
 
-    def generate(self) -> KernelSource:
+    def generate(self, grid_args: Sequence[int] = ()) -> KernelSource:
+        """grid_args: argument indices of (x_lb, x_ub, y_lb, y_ub) when they are generated from the pixel
+        index (render programs, tests/plot.py:8-29) instead of being streamed from per-instance arrays."""
         sch = self.sch
         T = self.ctype
         name = self.name
         nu = max(1, len(sch.uniform_slots))
         scal = list(sch.scalar_args)
-        arrs = list(sch.array_args)
-        # only scalar arguments the uniform prologue actually reads
+        grid = list(grid_args)
+        assert all(g in sch.array_args for g in grid), 'grid arguments must be scheduled as per-instance'
+        assert not grid or len(grid) == 4, 'a render program takes exactly x_lb, x_ub, y_lb, y_ub on the grid'
+        arrs = [a for a in sch.array_args if a not in grid]
+        assert not (grid and arrs), 'render programs cannot also stream per-instance arrays'
         used_in = {self.nodes[i].attr for i in sch.uniform_nodes if self.nodes[i].op == 'in'}
         uni = self.uniform_body()
         main = self.main_body()
-        used_arr = set()
-        for ln in main:
-            pass
-        live = set(self.dag.reachable(sch.outputs))
-        used_arr = {self.nodes[i].attr for i in live if self.nodes[i].op == 'in' and self.nodes[i].attr in set(arrs)}
+        varying = list(sch.array_args)       # instance-function value parameters (arrays and grid alike)
 
         uparams = ', '.join([f'const T a{a}' for a in scal] + ['T* __restrict__ U'])
-        mparams = ', '.join([f'const T* __restrict__ in{a}' for a in arrs] +
-                            [f'T* __restrict__ out{k}' for k in range(len(sch.outputs))] + ['const long long n'])
-        margs = ', '.join([f'in{a}' for a in arrs] + [f'out{k}' for k in range(len(sch.outputs))])
-        loads = [f'    const T a{a} = in{a}[i];' for a in arrs if a in used_arr]
+        outs_decl = [f'T* __restrict__ out{k}' for k in range(len(sch.outputs))]
+        outs_use = [f'out{k}' for k in range(len(sch.outputs))]
+        iparams = ', '.join(['const long long i'] + [f'const T a{a}' for a in varying] + outs_decl)
         src: List[str] = []
         src.append(f'// generated by teg_b200.codegen for program "{self.dag.name}"  (precision {T}, {self.N} samples)')
         src.append('#include "teg_b200_runtime.cuh"')
@@ -240,9 +241,9 @@ class Emitter:
         src += uni
         src.append('}')
         src.append('')
-        src.append(f'TEGB_FN void {name}_instance(const long long i, {mparams}) {{')
-        src.append('    (void)n;')
-        src += loads
+        src.append(f'TEGB_FN void {name}_instance({iparams}) {{')
+        for a in varying:
+            src.append(f'    (void)a{a};')
         src += main
         src.append('}')
         src.append('')
@@ -252,22 +253,39 @@ class Emitter:
                    + ', '.join([f'a{a}' for a in scal] + ['U']) + ');')
         src.append('}')
         src.append('')
-        src.append(f'extern "C" __global__ void __launch_bounds__({self.block_size}) {name}_main({mparams}) {{')
-        src.append('    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;')
-        src.append(f'    if (i < n) {name}_instance(i, {margs}, n);')
-        src.append('}')
+        if grid:
+            # pixel (nx, ny) -> instance nx * res_y + ny; box bounds from the two np.linspace edge tables
+            mparams = ', '.join(['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
+                                 'const int row0'] + outs_decl)
+            src.append(f'extern "C" __global__ void __launch_bounds__({self.block_size}) {name}_main({mparams}) {{')
+            src.append('    const int ny = blockIdx.x * blockDim.x + threadIdx.x;')
+            src.append('    if (ny >= res_y) return;')
+            src.append('    const int nx = row0 + blockIdx.y;')
+            src.append('    const long long i = (long long)blockIdx.y * res_y + ny;')
+            loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye[ny]', grid[3]: 'ye[ny + 1]'}
+            call = ', '.join(['i'] + [loads[a] for a in varying] + outs_use)
+            src.append(f'    {name}_instance({call});')
+            src.append('}')
+        else:
+            mparams = ', '.join([f'const T* __restrict__ in{a}' for a in arrs] + outs_decl + ['const long long n'])
+            src.append(f'extern "C" __global__ void __launch_bounds__({self.block_size}) {name}_main({mparams}) {{')
+            src.append('    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;')
+            src.append('    if (i >= n) return;')
+            call = ', '.join(['i'] + [f'in{a}[i]' for a in varying] + outs_use)
+            src.append(f'    {name}_instance({call});')
+            src.append('}')
         src.append('#endif')
         text = '\n'.join(src) + '\n'
         return KernelSource(name=name, ctype=T, num_samples=self.N, source=text,
                             uniform_kernel=f'{name}_uniform', main_kernel=f'{name}_main',
-                            n_uniform=nu, scalar_args=scal, array_args=arrs,
+                            n_uniform=nu, scalar_args=scal, array_args=arrs, grid_args=grid,
                             n_outputs=len(sch.outputs), block_size=self.block_size, stats=dict(self.stats))
 
 
 def generate(sch: Schedule, ctype: str = 'float', num_samples: int = 50, name: Optional[str] = None,
-             **opts) -> KernelSource:
+             grid_args: Sequence[int] = (), **opts) -> KernelSource:
     name = name or _c_ident(sch.dag.name)
-    return Emitter(sch, ctype, num_samples, name, **opts).generate()
+    return Emitter(sch, ctype, num_samples, name, **opts).generate(grid_args=grid_args)
 
 
 def _c_ident(s: str) -> str:

@@ -1,0 +1,612 @@
+// tegb200.cu -- libtegb200.so: the C-ABI runtime of the Teg CUDA (sm_100a) evaluation backend.
+//
+// See include/tegb200.h for the contract and for which reference code each entry point replaces.
+// Contents:
+//   * NVRTC JIT of generated translation units (teg_b200/codegen.py) to sm_100a cubins;
+//   * module loading / kernel launch through the CUDA driver API (resolved lazily with dlopen so the
+//     library loads -- and compiles programs -- on machines without a GPU);
+//   * static kernels: deterministic column sums (gradient reduction), FMA-peak micro-benchmark;
+//   * NCCL all-reduce of the parameter-gradient vector (libnccl resolved lazily).
+//
+// Build (see __graft_entry__.build):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --fmad=false -shared
+//        -Xcompiler -fPIC tegb200.cu -o libtegb200.so -lnvrtc -ldl
+
+#include "tegb200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "tegb200_runtime_header.inc"   // const char TEGB_RUNTIME_HEADER[] = contents of teg_b200_runtime.cuh
+
+// ---------------------------------------------------------------------------------------------- errors
+static thread_local char g_err[8192];
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char *tegb_last_error(void) { return g_err; }
+extern "C" int tegb_version(void) { return 100; }
+extern "C" int64_t tegb_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------- driver API shim
+namespace drv {
+typedef CUresult (*cuInit_t)(unsigned int);
+typedef CUresult (*cuGetErrorString_t)(CUresult, const char **);
+typedef CUresult (*cuModuleLoadData_t)(CUmodule *, const void *);
+typedef CUresult (*cuModuleUnload_t)(CUmodule);
+typedef CUresult (*cuModuleGetFunction_t)(CUfunction *, CUmodule, const char *);
+typedef CUresult (*cuModuleGetGlobal_t)(CUdeviceptr *, size_t *, CUmodule, const char *);
+typedef CUresult (*cuLaunchKernel_t)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                                     unsigned, CUstream, void **, void **);
+typedef CUresult (*cuMemcpyDtoDAsync_t)(CUdeviceptr, CUdeviceptr, size_t, CUstream);
+
+static void *lib = nullptr;
+static cuInit_t Init;
+static cuGetErrorString_t GetErrorString;
+static cuModuleLoadData_t ModuleLoadData;
+static cuModuleUnload_t ModuleUnload;
+static cuModuleGetFunction_t ModuleGetFunction;
+static cuModuleGetGlobal_t ModuleGetGlobal;
+static cuLaunchKernel_t LaunchKernel;
+static cuMemcpyDtoDAsync_t MemcpyDtoDAsync;
+static std::once_flag once;
+static bool ok = false;
+static std::string why;
+
+static void load() {
+    lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { why = std::string("cannot load libcuda.so.1: ") + dlerror(); return; }
+#define SYM(var, name)                                                   \
+    var = (decltype(var))dlsym(lib, name);                               \
+    if (!var) { why = std::string("libcuda.so.1 lacks ") + name; return; }
+    SYM(Init, "cuInit");
+    SYM(GetErrorString, "cuGetErrorString");
+    SYM(ModuleLoadData, "cuModuleLoadData");
+    SYM(ModuleUnload, "cuModuleUnload");
+    SYM(ModuleGetFunction, "cuModuleGetFunction");
+    SYM(ModuleGetGlobal, "cuModuleGetGlobal_v2");
+    SYM(LaunchKernel, "cuLaunchKernel");
+    SYM(MemcpyDtoDAsync, "cuMemcpyDtoDAsync_v2");
+#undef SYM
+    CUresult r = Init(0);
+    if (r != CUDA_SUCCESS) { why = "cuInit failed (no usable CUDA driver/device)"; return; }
+    ok = true;
+}
+
+static bool ready() {
+    std::call_once(once, load);
+    return ok;
+}
+
+static const char *errstr(CUresult r) {
+    const char *s = nullptr;
+    if (GetErrorString && GetErrorString(r, &s) == CUDA_SUCCESS && s) return s;
+    return "unknown CUDA driver error";
+}
+}  // namespace drv
+
+#define CU_CHECK(call)                                                                      \
+    do {                                                                                    \
+        CUresult _r = (call);                                                               \
+        if (_r != CUDA_SUCCESS) return fail(TEGB_ERR_CUDA, "%s failed: %s", #call, drv::errstr(_r)); \
+    } while (0)
+
+#define RT_CHECK(call)                                                                           \
+    do {                                                                                         \
+        cudaError_t _e = (call);                                                                 \
+        if (_e != cudaSuccess) return fail(TEGB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+extern "C" int tegb_device_count(void) {
+    if (!drv::ready()) return 0;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------ JIT
+struct tegb_module {
+    std::vector<char> cubin;
+    std::string log;
+};
+
+extern "C" int tegb_compile(const char *cuda_src, const char *arch, const char *opts, tegb_module **out) {
+    if (!cuda_src || !out) return fail(TEGB_ERR_INVALID, "tegb_compile: null argument");
+    *out = nullptr;
+    const char *header_names[] = {"teg_b200_runtime.cuh"};
+    const char *header_srcs[] = {TEGB_RUNTIME_HEADER};
+    nvrtcProgram prog;
+    nvrtcResult r = nvrtcCreateProgram(&prog, cuda_src, "teg_program.cu", 1, header_srcs, header_names);
+    if (r != NVRTC_SUCCESS) return fail(TEGB_ERR_COMPILE, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
+
+    std::vector<std::string> o;
+    o.push_back(std::string("--gpu-architecture=") + (arch && *arch ? arch : "sm_100a"));
+    o.push_back("--fmad=false");       // one IEEE operation per reference operation (parity contract)
+    o.push_back("--std=c++17");
+    o.push_back("-lineinfo");
+    if (opts) {
+        std::string s(opts), tok;
+        for (size_t i = 0; i <= s.size(); i++) {
+            if (i == s.size() || s[i] == ' ') { if (!tok.empty()) o.push_back(tok); tok.clear(); }
+            else tok.push_back(s[i]);
+        }
+    }
+    std::vector<const char *> oc;
+    for (auto &s : o) oc.push_back(s.c_str());
+    r = nvrtcCompileProgram(prog, (int)oc.size(), oc.data());
+    size_t logsz = 0;
+    nvrtcGetProgramLogSize(prog, &logsz);
+    std::string log(logsz > 0 ? logsz : 1, '\0');
+    if (logsz > 1) nvrtcGetProgramLog(prog, &log[0]);
+    if (r != NVRTC_SUCCESS) {
+        int rc = fail(TEGB_ERR_COMPILE, "NVRTC: %s\n%s", nvrtcGetErrorString(r), log.c_str());
+        nvrtcDestroyProgram(&prog);
+        return rc;
+    }
+    size_t sz = 0;
+    r = nvrtcGetCUBINSize(prog, &sz);
+    if (r != NVRTC_SUCCESS || sz == 0) {
+        nvrtcDestroyProgram(&prog);
+        return fail(TEGB_ERR_COMPILE, "nvrtcGetCUBINSize: %s (arch must be a real sm_XX)", nvrtcGetErrorString(r));
+    }
+    tegb_module *m = new tegb_module();
+    m->cubin.resize(sz);
+    nvrtcGetCUBIN(prog, m->cubin.data());
+    m->log = log.c_str();
+    nvrtcDestroyProgram(&prog);
+    *out = m;
+    return TEGB_OK;
+}
+
+extern "C" int tegb_module_from_cubin(const void *cubin, size_t nbytes, tegb_module **out) {
+    if (!cubin || !nbytes || !out) return fail(TEGB_ERR_INVALID, "tegb_module_from_cubin: null argument");
+    tegb_module *m = new tegb_module();
+    m->cubin.assign((const char *)cubin, (const char *)cubin + nbytes);
+    *out = m;
+    return TEGB_OK;
+}
+
+extern "C" int tegb_module_cubin(const tegb_module *m, const void **cubin, size_t *nbytes) {
+    if (!m || !cubin || !nbytes) return fail(TEGB_ERR_INVALID, "tegb_module_cubin: null argument");
+    *cubin = m->cubin.data();
+    *nbytes = m->cubin.size();
+    return TEGB_OK;
+}
+
+extern "C" const char *tegb_module_log(const tegb_module *m) { return m ? m->log.c_str() : ""; }
+extern "C" void tegb_module_destroy(tegb_module *m) { delete m; }
+
+// ------------------------------------------------------------------------------------------- programs
+struct tegb_program {
+    tegb_program_desc d;
+    int device = 0;
+    CUmodule mod = nullptr;
+    CUfunction f_uniform = nullptr, f_main = nullptr;
+    CUdeviceptr u_const = 0;      // __constant__ table inside the module
+    size_t u_const_bytes = 0;
+    void *u_stage = nullptr;      // device buffer the uniform kernel writes
+    // staging for tegb_program_eval_host
+    std::vector<void *> d_in, d_out;
+    int64_t cap = 0;
+    // pixel-edge tables for tegb_render_launch
+    void *d_xe = nullptr, *d_ye = nullptr;
+    std::vector<char> h_xe, h_ye;
+    tegb_grid grid_cached{};
+    bool grid_valid = false;
+};
+
+extern "C" int tegb_program_create(tegb_module *m, const tegb_program_desc *desc, int device, tegb_program **out) {
+    if (!m || !desc || !out) return fail(TEGB_ERR_INVALID, "tegb_program_create: null argument");
+    *out = nullptr;
+    if (desc->elem_size != 4 && desc->elem_size != 8) return fail(TEGB_ERR_INVALID, "elem_size must be 4 or 8");
+    if (desc->n_outputs < 1 || desc->block_size < 32 || desc->block_size > 1024)
+        return fail(TEGB_ERR_INVALID, "bad program description");
+    if (!drv::ready()) return fail(TEGB_ERR_NO_DEVICE, "CUDA driver unavailable: %s", drv::why.c_str());
+    RT_CHECK(cudaSetDevice(device));
+    RT_CHECK(cudaFree(0));      // make the primary context current for the driver calls below
+    tegb_program *p = new tegb_program();
+    p->d = *desc;
+    p->device = device;
+    CUresult r = drv::ModuleLoadData(&p->mod, m->cubin.data());
+    if (r != CUDA_SUCCESS) { delete p; return fail(TEGB_ERR_CUDA, "cuModuleLoadData: %s", drv::errstr(r)); }
+    auto bail = [&](int rc) { drv::ModuleUnload(p->mod); if (p->u_stage) cudaFree(p->u_stage); delete p; return rc; };
+    r = drv::ModuleGetFunction(&p->f_uniform, p->mod, desc->uniform_kernel);
+    if (r != CUDA_SUCCESS) return bail(fail(TEGB_ERR_CUDA, "kernel %s: %s", desc->uniform_kernel, drv::errstr(r)));
+    r = drv::ModuleGetFunction(&p->f_main, p->mod, desc->main_kernel);
+    if (r != CUDA_SUCCESS) return bail(fail(TEGB_ERR_CUDA, "kernel %s: %s", desc->main_kernel, drv::errstr(r)));
+    r = drv::ModuleGetGlobal(&p->u_const, &p->u_const_bytes, p->mod, desc->uniform_symbol);
+    if (r != CUDA_SUCCESS) return bail(fail(TEGB_ERR_CUDA, "symbol %s: %s", desc->uniform_symbol, drv::errstr(r)));
+    size_t want = (size_t)(desc->n_uniform > 0 ? desc->n_uniform : 1) * desc->elem_size;
+    if (p->u_const_bytes < want) return bail(fail(TEGB_ERR_INVALID, "uniform table smaller than described"));
+    if (cudaMalloc(&p->u_stage, want) != cudaSuccess) return bail(fail(TEGB_ERR_CUDA, "cudaMalloc(uniform stage) failed"));
+    *out = p;
+    return TEGB_OK;
+}
+
+extern "C" void tegb_program_destroy(tegb_program *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    for (void *q : p->d_in) if (q) cudaFree(q);
+    for (void *q : p->d_out) if (q) cudaFree(q);
+    if (p->u_stage) cudaFree(p->u_stage);
+    if (p->d_xe) cudaFree(p->d_xe);
+    if (p->d_ye) cudaFree(p->d_ye);
+    if (p->mod) drv::ModuleUnload(p->mod);
+    delete p;
+}
+
+// uniform prologue: 1 thread evaluates the launch-invariant values, then they are published to __constant__
+static int run_uniform(tegb_program *p, const double *scalars, CUstream st) {
+    const int ns = p->d.n_scalar_args;
+    std::vector<float> sf(ns > 0 ? ns : 1);
+    std::vector<double> sd(ns > 0 ? ns : 1);
+    std::vector<void *> args;
+    for (int i = 0; i < ns; i++) {
+        if (!scalars) return fail(TEGB_ERR_INVALID, "scalars is NULL but the program has scalar arguments");
+        if (p->d.elem_size == 4) { sf[i] = (float)scalars[i]; args.push_back(&sf[i]); }
+        else { sd[i] = scalars[i]; args.push_back(&sd[i]); }
+    }
+    args.push_back(&p->u_stage);
+    CU_CHECK(drv::LaunchKernel(p->f_uniform, 1, 1, 1, 1, 1, 1, 0, st, args.data(), nullptr));
+    g_launches++;
+    CU_CHECK(drv::MemcpyDtoDAsync(p->u_const, (CUdeviceptr)p->u_stage,
+                                  (size_t)(p->d.n_uniform > 0 ? p->d.n_uniform : 1) * p->d.elem_size, st));
+    return TEGB_OK;
+}
+
+extern "C" int tegb_program_launch(tegb_program *p, const double *scalars, const void *const *in_ptrs,
+                                   void *const *out_ptrs, int64_t n, void *stream) {
+    if (!p || !out_ptrs || n < 0) return fail(TEGB_ERR_INVALID, "tegb_program_launch: bad argument");
+    if (p->d.n_grid_args != 0) return fail(TEGB_ERR_INVALID, "render program: use tegb_render_launch");
+    if (p->d.n_array_args > 0 && !in_ptrs) return fail(TEGB_ERR_INVALID, "in_ptrs is NULL");
+    if (n == 0) return TEGB_OK;
+    RT_CHECK(cudaSetDevice(p->device));
+    CUstream st = (CUstream)stream;
+    int rc = run_uniform(p, scalars, st);
+    if (rc) return rc;
+    std::vector<const void *> ins(p->d.n_array_args > 0 ? p->d.n_array_args : 1);
+    std::vector<void *> outs(p->d.n_outputs);
+    std::vector<void *> args;
+    for (int i = 0; i < p->d.n_array_args; i++) { ins[i] = in_ptrs[i]; args.push_back(&ins[i]); }
+    for (int k = 0; k < p->d.n_outputs; k++) { outs[k] = out_ptrs[k]; args.push_back(&outs[k]); }
+    long long nn = n;
+    args.push_back(&nn);
+    const unsigned bs = (unsigned)p->d.block_size;
+    const long long blocks = (n + bs - 1) / bs;
+    if (blocks > 2147483647LL) return fail(TEGB_ERR_INVALID, "too many instances for one launch");
+    CU_CHECK(drv::LaunchKernel(p->f_main, (unsigned)blocks, 1, 1, bs, 1, 1, 0, st, args.data(), nullptr));
+    g_launches++;
+    return TEGB_OK;
+}
+
+static int ensure_staging(tegb_program *p, int64_t n) {
+    if (n <= p->cap && (int)p->d_in.size() == p->d.n_array_args && (int)p->d_out.size() == p->d.n_outputs)
+        return TEGB_OK;
+    for (void *q : p->d_in) if (q) cudaFree(q);
+    for (void *q : p->d_out) if (q) cudaFree(q);
+    p->d_in.assign(p->d.n_array_args, nullptr);
+    p->d_out.assign(p->d.n_outputs, nullptr);
+    p->cap = 0;
+    const size_t bytes = (size_t)n * p->d.elem_size;
+    for (auto &q : p->d_in) RT_CHECK(cudaMalloc(&q, bytes));
+    for (auto &q : p->d_out) RT_CHECK(cudaMalloc(&q, bytes));
+    p->cap = n;
+    return TEGB_OK;
+}
+
+extern "C" int tegb_program_eval_host(tegb_program *p, const double *scalars, const void *const *host_in,
+                                      void *const *host_out, int64_t n) {
+    if (!p || !host_out || n < 0) return fail(TEGB_ERR_INVALID, "tegb_program_eval_host: bad argument");
+    if (p->d.n_array_args > 0 && !host_in) return fail(TEGB_ERR_INVALID, "host_in is NULL");
+    if (n == 0) return TEGB_OK;
+    RT_CHECK(cudaSetDevice(p->device));
+    int rc = ensure_staging(p, n);
+    if (rc) return rc;
+    const size_t bytes = (size_t)n * p->d.elem_size;
+    cudaStream_t st = 0;
+    for (int i = 0; i < p->d.n_array_args; i++)
+        RT_CHECK(cudaMemcpyAsync(p->d_in[i], host_in[i], bytes, cudaMemcpyHostToDevice, st));
+    rc = tegb_program_launch(p, scalars, (const void *const *)p->d_in.data(), p->d_out.data(), n, st);
+    if (rc) return rc;
+    for (int k = 0; k < p->d.n_outputs; k++)
+        RT_CHECK(cudaMemcpyAsync(host_out[k], p->d_out[k], bytes, cudaMemcpyDeviceToHost, st));
+    RT_CHECK(cudaStreamSynchronize(st));
+    return TEGB_OK;
+}
+
+// np.linspace(lo, hi, res + 1) as numpy computes it (float64): step = (hi-lo)/res; y[j] = j*step + lo;
+// y[res] = hi  (numpy/_core/function_base.py; tests/plot.py:11-12 is the caller being reproduced)
+static void linspace_edges(double lo, double hi, int res, int elem_size, std::vector<char> &out) {
+    out.resize((size_t)(res + 1) * elem_size);
+    const double delta = hi - lo;
+    const double step = delta / (double)res;
+    for (int j = 0; j <= res; j++) {
+        double v;
+        if (step == 0.0) { v = ((double)j / (double)res) * delta + lo; }
+        else { volatile double t = (double)j * step; v = t + lo; }
+        if (j == res) v = hi;
+        if (elem_size == 4) ((float *)out.data())[j] = (float)v;
+        else ((double *)out.data())[j] = v;
+    }
+}
+
+extern "C" int tegb_render_launch(tegb_program *p, const double *scalars, const tegb_grid *g,
+                                  void *const *out_ptrs, void *stream) {
+    if (!p || !g || !out_ptrs) return fail(TEGB_ERR_INVALID, "tegb_render_launch: bad argument");
+    if (p->d.n_grid_args != 4 || p->d.n_array_args != 0)
+        return fail(TEGB_ERR_INVALID, "not a render program (needs exactly the 4 pixel-box arguments on the grid)");
+    if (g->res_x < 1 || g->res_y < 1 || g->row_begin < 0 || g->row_end > g->res_x || g->row_begin > g->row_end)
+        return fail(TEGB_ERR_INVALID, "bad grid");
+    if (g->row_end == g->row_begin) return TEGB_OK;
+    RT_CHECK(cudaSetDevice(p->device));
+    CUstream st = (CUstream)stream;
+    const bool same = p->grid_valid && p->grid_cached.x_lo == g->x_lo && p->grid_cached.x_hi == g->x_hi &&
+                      p->grid_cached.y_lo == g->y_lo && p->grid_cached.y_hi == g->y_hi &&
+                      p->grid_cached.res_x == g->res_x && p->grid_cached.res_y == g->res_y;
+    if (!same) {
+        // the previous tables may still be in use by an earlier launch on this stream
+        RT_CHECK(cudaStreamSynchronize((cudaStream_t)st));
+        if (p->d_xe) { cudaFree(p->d_xe); p->d_xe = nullptr; }
+        if (p->d_ye) { cudaFree(p->d_ye); p->d_ye = nullptr; }
+        linspace_edges(g->x_lo, g->x_hi, g->res_x, p->d.elem_size, p->h_xe);
+        linspace_edges(g->y_lo, g->y_hi, g->res_y, p->d.elem_size, p->h_ye);
+        RT_CHECK(cudaMalloc(&p->d_xe, p->h_xe.size()));
+        RT_CHECK(cudaMalloc(&p->d_ye, p->h_ye.size()));
+        RT_CHECK(cudaMemcpyAsync(p->d_xe, p->h_xe.data(), p->h_xe.size(), cudaMemcpyHostToDevice, (cudaStream_t)st));
+        RT_CHECK(cudaMemcpyAsync(p->d_ye, p->h_ye.data(), p->h_ye.size(), cudaMemcpyHostToDevice, (cudaStream_t)st));
+        p->grid_cached = *g;
+        p->grid_valid = true;
+    }
+    int rc = run_uniform(p, scalars, st);
+    if (rc) return rc;
+    std::vector<void *> outs(p->d.n_outputs);
+    std::vector<void *> args;
+    int res_y = g->res_y, row0 = g->row_begin;
+    args.push_back(&p->d_xe);
+    args.push_back(&p->d_ye);
+    args.push_back(&res_y);
+    args.push_back(&row0);
+    for (int k = 0; k < p->d.n_outputs; k++) { outs[k] = out_ptrs[k]; args.push_back(&outs[k]); }
+    const unsigned bs = (unsigned)p->d.block_size;
+    const unsigned gx = (unsigned)((g->res_y + bs - 1) / bs);
+    const unsigned gy = (unsigned)(g->row_end - g->row_begin);
+    if (gy > 65535u) return fail(TEGB_ERR_INVALID, "more than 65535 rows in one render launch");
+    CU_CHECK(drv::LaunchKernel(p->f_main, gx, gy, 1, bs, 1, 1, 0, st, args.data(), nullptr));
+    g_launches++;
+    return TEGB_OK;
+}
+
+// --------------------------------------------------------------------------------- deterministic sums
+// Stage 1: block b sums elements [b*chunk, (b+1)*chunk) of every column: each thread walks its strided
+// subsequence in order, then a fixed shuffle/shared-memory tree combines the 256 partials.  Stage 2: one
+// block combines the per-block partials in the same fixed way.  The result depends only on (n, values).
+static const int RED_THREADS = 256;
+static const int RED_MAX_BLOCKS = 1184;     // 8 blocks per SM x 148 SMs
+
+template <typename T>
+__device__ __forceinline__ T block_sum_fixed(T v, T *smem) {
+    for (int off = 16; off > 0; off >>= 1) v = v + __shfl_down_sync(0xffffffffu, v, off);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    T r = 0;
+    if (warp == 0) {
+        r = lane < (blockDim.x >> 5) ? smem[lane] : (T)0;
+        for (int off = 16; off > 0; off >>= 1) r = r + __shfl_down_sync(0xffffffffu, r, off);
+    }
+    __syncthreads();
+    return r;   // valid in thread 0
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS) colsum_stage1(const T *const *cols, int n_cols, long long n,
+                                                             long long chunk, T *partials) {
+    __shared__ T smem[32];
+    const long long lo = (long long)blockIdx.x * chunk;
+    long long hi = lo + chunk;
+    if (hi > n) hi = n;
+    for (int c = 0; c < n_cols; c++) {
+        const T *col = cols[c];
+        T acc = 0;
+        for (long long i = lo + threadIdx.x; i < hi; i += RED_THREADS) acc = acc + col[i];
+        T s = block_sum_fixed(acc, smem);
+        if (threadIdx.x == 0) partials[(long long)c * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS) colsum_stage2(const T *partials, int n_blocks, T *out) {
+    __shared__ T smem[32];
+    const int c = blockIdx.x;
+    T acc = 0;
+    for (int i = threadIdx.x; i < n_blocks; i += RED_THREADS) acc = acc + partials[(long long)c * n_blocks + i];
+    T s = block_sum_fixed(acc, smem);
+    if (threadIdx.x == 0) out[c] = s;
+}
+
+static int reduce_blocks(int64_t n) {
+    long long b = (n + (long long)RED_THREADS * 8 - 1) / ((long long)RED_THREADS * 8);
+    if (b < 1) b = 1;
+    if (b > RED_MAX_BLOCKS) b = RED_MAX_BLOCKS;
+    return (int)b;
+}
+
+extern "C" size_t tegb_reduce_workspace_bytes(int n_cols, int64_t n, int elem_size) {
+    return (size_t)n_cols * sizeof(void *) + 256 + (size_t)n_cols * reduce_blocks(n) * (size_t)elem_size;
+}
+
+extern "C" int tegb_reduce_sum(const void *const *in_ptrs, int n_cols, int64_t n, int elem_size, void *out,
+                               void *workspace, size_t workspace_bytes, void *stream) {
+    if (!in_ptrs || n_cols < 1 || n < 0 || !out || !workspace) return fail(TEGB_ERR_INVALID, "tegb_reduce_sum: bad argument");
+    if (elem_size != 4 && elem_size != 8) return fail(TEGB_ERR_INVALID, "elem_size must be 4 or 8");
+    if (workspace_bytes < tegb_reduce_workspace_bytes(n_cols, n, elem_size))
+        return fail(TEGB_ERR_INVALID, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = reduce_blocks(n);
+    const long long chunk = (n + blocks - 1) / blocks;
+    // column pointer table lives at the start of the workspace
+    RT_CHECK(cudaMemcpyAsync(workspace, in_ptrs, (size_t)n_cols * sizeof(void *), cudaMemcpyHostToDevice, st));
+    size_t off = ((size_t)n_cols * sizeof(void *) + 255) & ~(size_t)255;
+    char *partials = (char *)workspace + off;
+    if (elem_size == 4) {
+        colsum_stage1<float><<<blocks, RED_THREADS, 0, st>>>((const float *const *)workspace, n_cols, n, chunk, (float *)partials);
+        colsum_stage2<float><<<n_cols, RED_THREADS, 0, st>>>((const float *)partials, blocks, (float *)out);
+    } else {
+        colsum_stage1<double><<<blocks, RED_THREADS, 0, st>>>((const double *const *)workspace, n_cols, n, chunk, (double *)partials);
+        colsum_stage2<double><<<n_cols, RED_THREADS, 0, st>>>((const double *)partials, blocks, (double *)out);
+    }
+    g_launches += 2;
+    RT_CHECK(cudaGetLastError());
+    return TEGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ NCCL
+namespace nccl {
+typedef struct { char internal[128]; } UniqueId;
+typedef int (*GetUniqueId_t)(UniqueId *);
+typedef int (*CommInitRank_t)(void **, int, UniqueId, int);
+typedef int (*CommDestroy_t)(void *);
+typedef int (*AllReduce_t)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef const char *(*GetErrorString_t)(int);
+static void *lib = nullptr;
+static GetUniqueId_t GetUniqueId;
+static CommInitRank_t CommInitRank;
+static CommDestroy_t CommDestroy;
+static AllReduce_t AllReduce;
+static GetErrorString_t GetErrorString;
+static std::once_flag once;
+static bool ok = false;
+static std::string why;
+static void load() {
+    // RTLD_NOLOAD first: reuse the libnccl the process (e.g. torch) already mapped, if any
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW);
+    if (!lib) { why = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+#define SYM(var, name)                                                   \
+    var = (decltype(var))dlsym(lib, name);                               \
+    if (!var) { why = std::string("libnccl lacks ") + name; return; }
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(AllReduce, "ncclAllReduce");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    ok = true;
+}
+static bool ready() { std::call_once(once, load); return ok; }
+}  // namespace nccl
+
+#define NCCL_CHECK(call)                                                                         \
+    do {                                                                                         \
+        int _r = (call);                                                                         \
+        if (_r != 0) return fail(TEGB_ERR_NCCL, "%s failed: %s", #call, nccl::GetErrorString(_r)); \
+    } while (0)
+
+extern "C" int tegb_nccl_unique_id(void *id128) {
+    if (!id128) return fail(TEGB_ERR_INVALID, "null id");
+    if (!nccl::ready()) return fail(TEGB_ERR_NCCL, "%s", nccl::why.c_str());
+    NCCL_CHECK(nccl::GetUniqueId((nccl::UniqueId *)id128));
+    return TEGB_OK;
+}
+
+extern "C" int tegb_nccl_comm_create(const void *id128, int world_size, int rank, int device, void **comm) {
+    if (!id128 || !comm) return fail(TEGB_ERR_INVALID, "null argument");
+    if (!nccl::ready()) return fail(TEGB_ERR_NCCL, "%s", nccl::why.c_str());
+    RT_CHECK(cudaSetDevice(device));
+    nccl::UniqueId id;
+    memcpy(&id, id128, sizeof id);
+    NCCL_CHECK(nccl::CommInitRank(comm, world_size, id, rank));
+    return TEGB_OK;
+}
+
+extern "C" int tegb_nccl_comm_destroy(void *comm) {
+    if (!comm) return TEGB_OK;
+    if (!nccl::ready()) return fail(TEGB_ERR_NCCL, "%s", nccl::why.c_str());
+    NCCL_CHECK(nccl::CommDestroy(comm));
+    return TEGB_OK;
+}
+
+extern "C" int tegb_allreduce_sum(void *buf, int64_t count, int elem_size, void *comm, void *stream) {
+    if (!buf || count < 0 || !comm) return fail(TEGB_ERR_INVALID, "tegb_allreduce_sum: bad argument");
+    if (elem_size != 4 && elem_size != 8) return fail(TEGB_ERR_INVALID, "elem_size must be 4 or 8");
+    if (!nccl::ready()) return fail(TEGB_ERR_NCCL, "%s", nccl::why.c_str());
+    const int dtype = elem_size == 4 ? 7 /* ncclFloat32 */ : 8 /* ncclFloat64 */;
+    NCCL_CHECK(nccl::AllReduce(buf, buf, (size_t)count, dtype, 0 /* ncclSum */, comm, (cudaStream_t)stream));
+    return TEGB_OK;
+}
+
+// ------------------------------------------------------------------------------------ FMA peak (roofline)
+// 8 independent dependent-FMA chains per thread; enough warps to saturate the 4 SMSP issue ports.
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T *sink, int iters, T a, T b) {
+    T x0 = a + (T)threadIdx.x, x1 = x0 + (T)1, x2 = x0 + (T)2, x3 = x0 + (T)3;
+    T x4 = x0 + (T)4, x5 = x0 + (T)5, x6 = x0 + (T)6, x7 = x0 + (T)7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    T s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == (T)123456789) sink[0] = s;     // never true; keeps the chains alive
+}
+
+extern "C" int tegb_fma_peak(int elem_size, int device, double *tflops, double *sm_clock_mhz) {
+    if (!tflops) return fail(TEGB_ERR_INVALID, "null argument");
+    if (elem_size != 4 && elem_size != 8) return fail(TEGB_ERR_INVALID, "elem_size must be 4 or 8");
+    if (!drv::ready()) return fail(TEGB_ERR_NO_DEVICE, "CUDA driver unavailable: %s", drv::why.c_str());
+    RT_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RT_CHECK(cudaGetDeviceProperties(&prop, device));
+    void *sink = nullptr;
+    RT_CHECK(cudaMalloc(&sink, 64));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    const int iters = elem_size == 4 ? 4096 : 1024;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        if (elem_size == 4) fma_peak_kernel<float><<<blocks, threads>>>((float *)sink, iters, 0.999f, 0.001f);
+        else fma_peak_kernel<double><<<blocks, threads>>>((double *)sink, iters, 0.999, 0.001);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        g_launches++;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    RT_CHECK(cudaGetLastError());
+    const double fmas = (double)blocks * threads * (double)iters * 16.0 * 8.0;
+    *tflops = 2.0 * fmas / (best * 1e-3) / 1e12;
+    if (sm_clock_mhz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+        *sm_clock_mhz = khz / 1000.0;
+    }
+    return TEGB_OK;
+}

@@ -1,0 +1,248 @@
+"""``CUDA`` evaluation backend behind Teg's plugin interface.
+
+Mirrors, for this path only:
+  EvalMode                      /root/reference/teg/eval/eval_mode.py:1-7
+  C_EvalMode(expr, num_samples) /root/reference/teg/eval/c_eval.py:22-157   (ctor options, eval(bindings))
+  BACKENDS / evaluate           /root/reference/teg/eval/backend.py:6-41    (registry + per-expression mode cache)
+  render_image                  /root/reference/tests/plot.py:8-29          (per-pixel driver)
+
+Same argument convention: ``bindings`` is keyed by ``Var`` objects and resolved through the labels
+``f'{name}_{uid}'`` (c_eval.py:135); unbound arguments fall back to ``Var.value`` (c_eval.py:136); any
+argument still ``None`` is an ``AssertionError`` (c_eval.py:139-140).  A scalar-only call returns a
+Python ``float`` (or ``list`` of floats for ``Tup`` programs), like c_eval.py:149-157.
+
+Extension (the point of the backend): a binding may be a length-n array / torch tensor.  All array
+bindings must have the same length; scalars broadcast; the result is then ``ndarray[n]`` (or
+``[k, n]`` for Tup programs) -- torch CUDA tensors in, torch CUDA tensors out, without host copies.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import runtime
+from .codegen import KernelSource, generate
+from .dag import Dag, build_dag
+from .schedule import make_schedule
+from .tegp import Program, from_teg, label_of
+
+
+class EvalMode:
+    """reference teg/eval/eval_mode.py:1-7"""
+
+    def __init__(self, name=None):
+        self.name = name
+
+    def eval(self, bindings, **kwargs):
+        raise NotImplementedError('This backend does not support evaluation')
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.split('.')[0] == 'torch'
+
+
+def _np_dtype(float_width: str):
+    return np.float32 if float_width == 'float' else np.float64
+
+
+class CUDA_EvalMode(EvalMode):
+    """Batched sm_100a evaluation of one reduced Teg program.
+
+    expr: a base-language expression (reference ``teg`` objects or ``teg_b200.lang``), a
+          FwdDeriv/RevDeriv wrapper (unwrapped like compile.py:182-183), or a ``tegp.Program``.
+    num_samples: midpoint samples per integral (reference default 50, c_eval.py:26).
+    float_width: 'float' (what C_EvalMode hard-wires, c_eval.py:32) or 'double'
+                 (the CLI's ``-f double``, teg/__main__.py:49-52).
+    """
+
+    def __init__(self, expr, num_samples: int = 50, float_width: str = 'float', device: int = 0,
+                 arglist: Sequence = (), name: str = 'teg_method', use_cache: bool = True,
+                 block_size: int = 128, **codegen_opts):
+        super().__init__(name='CUDA')
+        if float_width in ('single', 'f32', np.float32):
+            float_width = 'float'
+        if float_width in ('f64', np.float64):
+            float_width = 'double'
+        assert float_width in ('float', 'double'), f'Invalid precision setting {float_width}'
+        self.program: Program = expr if isinstance(expr, Program) else from_teg(expr, arglist, name=name)
+        self.dag: Dag = build_dag(self.program)
+        self.num_samples = int(num_samples)
+        self.float_width = float_width
+        self.device = device
+        self.use_cache = use_cache
+        self.block_size = block_size
+        self.codegen_opts = codegen_opts
+        self.arglist: List[Tuple[str, Optional[float]]] = [
+            (lab, self.program.defaults.get(lab)) for lab in self.program.args]
+        self.out_size = len(self.dag.outputs)
+        self.out_is_tuple = self.dag.out_is_tuple
+        self._variants: Dict[tuple, Tuple[KernelSource, runtime.Program]] = {}
+
+    # ------------------------------------------------------------------ compile
+    def kernel_source(self, array_args: Sequence[int], grid_args: Sequence[int] = ()) -> KernelSource:
+        varying = sorted(set(array_args) | set(grid_args))
+        sch = make_schedule(self.dag, varying)
+        return generate(sch, self.float_width, self.num_samples, grid_args=list(grid_args),
+                        block_size=self.block_size, **self.codegen_opts)
+
+    def compiled(self, array_args: Sequence[int], grid_args: Sequence[int] = ()):
+        key = (tuple(sorted(array_args)), tuple(grid_args))
+        hit = self._variants.get(key)
+        if hit is None:
+            ks = self.kernel_source(array_args, grid_args)
+            mod = runtime.Module(ks.source, use_cache=self.use_cache)
+            prog = runtime.Program(mod, ks, device=self.device)
+            hit = (ks, prog)
+            self._variants[key] = hit
+        return hit
+
+    # --------------------------------------------------------------------- eval
+    def _resolve(self, bindings) -> List:
+        by_label = {}
+        for k, v in (bindings or {}).items():
+            by_label[k if isinstance(k, str) else label_of(k)] = v
+        args = [by_label[lab] if lab in by_label else default for lab, default in self.arglist]
+        assert all(a is not None for a in args), \
+            f'No bindings found for {[self.arglist[i][0] for i, a in enumerate(args) if a is None]}'
+        return args
+
+    def eval(self, bindings={}, **kwargs):
+        args = self._resolve(bindings)
+        dt = _np_dtype(self.float_width)
+        is_arr = []
+        n = None
+        any_torch = False
+        for a in args:
+            if _is_torch(a) and a.dim() > 0:
+                is_arr.append(True)
+                any_torch = True
+                ln = a.numel()
+            elif not _is_torch(a) and np.ndim(a) > 0:
+                is_arr.append(True)
+                ln = int(np.size(a))
+            else:
+                is_arr.append(False)
+                continue
+            assert n is None or n == ln, 'all array bindings must have the same length'
+            n = ln
+        array_args = [i for i, f in enumerate(is_arr) if f]
+        ks, prog = self.compiled(array_args)
+        scalars = [float(args[a]) for a in ks.scalar_args]
+        if any_torch:
+            return self._eval_torch(ks, prog, args, scalars, n)
+        batched = n is not None
+        n = 1 if n is None else n
+        ins = [np.ascontiguousarray(np.asarray(args[a], dtype=dt).reshape(-1)) for a in ks.array_args]
+        out = np.empty((ks.n_outputs, n), dtype=dt)
+        prog.eval_host(scalars, [a.ctypes.data for a in ins],
+                       [out[k].ctypes.data for k in range(ks.n_outputs)], n)
+        if not batched:
+            vals = [float(v) for v in out[:, 0]]
+            return vals if self.out_is_tuple and len(vals) > 1 else vals[0]
+        return out if self.out_is_tuple and ks.n_outputs > 1 else out[0]
+
+    def _eval_torch(self, ks, prog, args, scalars, n):
+        import torch
+        tdt = torch.float32 if self.float_width == 'float' else torch.float64
+        dev = torch.device('cuda', self.device)
+        ins = []
+        for a in ks.array_args:
+            t = args[a]
+            if not _is_torch(t):
+                t = torch.as_tensor(np.asarray(t), device=dev)
+            t = t.to(device=dev, dtype=tdt).contiguous().view(-1)
+            ins.append(t)
+        out = torch.empty((ks.n_outputs, n), dtype=tdt, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        prog.launch(scalars, [t.data_ptr() for t in ins], [out[k].data_ptr() for k in range(ks.n_outputs)],
+                    n, stream=stream)
+        return out if self.out_is_tuple and ks.n_outputs > 1 else out[0]
+
+    # ------------------------------------------------------------------- render
+    def render(self, box_vars, res: Tuple[int, int], bounds=((0, 1), (0, 1)), bindings=None,
+               rows: Optional[Tuple[int, int]] = None, out=None, stream: int = 0):
+        """Evaluate over the pixel grid of tests/plot.py:8-29 with on-device pixel boxes.
+
+        box_vars: (x_lb, x_ub, y_lb, y_ub) Vars or labels.  Returns a torch CUDA tensor
+        [k, rows, res_y] (k = program outputs); asynchronous on ``stream``."""
+        import torch
+        labels = [v if isinstance(v, str) else label_of(v) for v in box_vars]
+        pos = {lab: i for i, (lab, _) in enumerate(self.arglist)}
+        grid_args = [pos[lab] for lab in labels]
+        by_label = {}
+        for k, v in (bindings or {}).items():
+            by_label[k if isinstance(k, str) else label_of(k)] = v
+        ks, prog = self.compiled(grid_args, grid_args)
+        scalars = []
+        for a in ks.scalar_args:
+            lab, default = self.arglist[a]
+            v = by_label.get(lab, default)
+            assert v is not None, f'No bindings found for {[lab]}'
+            scalars.append(float(v))
+        r0, r1 = (0, res[0]) if rows is None else rows
+        tdt = torch.float32 if self.float_width == 'float' else torch.float64
+        dev = torch.device('cuda', self.device)
+        if out is None:
+            out = torch.empty((ks.n_outputs, r1 - r0, res[1]), dtype=tdt, device=dev)
+        grid = runtime.Grid(float(bounds[0][0]), float(bounds[0][1]), float(bounds[1][0]), float(bounds[1][1]),
+                            int(res[0]), int(res[1]), int(r0), int(r1))
+        prog.render(scalars, grid, [out[k].data_ptr() for k in range(ks.n_outputs)], stream=stream)
+        return out
+
+
+BACKENDS = {'CUDA': (CUDA_EvalMode, {})}
+
+
+def evaluate(expr, bindings=None, backend=None, **kwargs):
+    """reference teg/eval/backend.py:13-41, with 'CUDA' as the default backend of this package."""
+    if not hasattr(expr, 'mode_cache'):
+        setattr(expr, 'mode_cache', {})
+        setattr(expr, 'mode_options', kwargs)
+    bindings = {} if bindings is None else bindings
+    backend = 'CUDA' if backend is None else backend
+    if backend != 'CUDA':
+        try:
+            from teg.eval.backend import evaluate as ref_evaluate
+        except ImportError as e:
+            raise KeyError(backend) from e
+        return ref_evaluate(expr, bindings, backend=backend, **kwargs)
+    if backend not in expr.mode_cache.keys() or \
+            not all([(key, value) in expr.mode_options.items() for key, value in kwargs.items()]):
+        backend_cls, backend_kwargs = BACKENDS[backend]
+        mode = backend_cls(expr, **kwargs, **backend_kwargs)
+        expr.mode_cache[backend] = mode
+        expr.mode_options = kwargs
+    return expr.mode_cache[backend].eval(bindings=bindings)
+
+
+def register() -> bool:
+    """Add 'CUDA' to the reference's registry (teg/eval/backend.py:6-10) when ``teg`` is importable."""
+    try:
+        import teg.eval.backend as ref_backend
+    except Exception:
+        return False
+    ref_backend.BACKENDS.setdefault('CUDA', (CUDA_EvalMode, {}))
+    return True
+
+
+def render_image(expr, variables=(), res=(64, 64), bounds=((0, 1), (0, 1)), bindings={}, num_samples=20,
+                 float_width='float', device=0):
+    """tests/plot.py:8-29 in one launch.  ``variables`` = ((x_lb, x_ub), (y_lb, y_ub)).
+
+    Returns ``image[nx, ny]`` (numpy), or ``[k, nx, ny]`` for Tup-valued programs."""
+    assert len(variables) == 2, 'Exactly two variable-pairs required'
+    import torch
+    if not hasattr(expr, 'mode_cache'):
+        setattr(expr, 'mode_cache', {})
+    key = ('CUDA_render', num_samples, float_width, device)
+    mode = expr.mode_cache.get(key)
+    if mode is None:
+        mode = CUDA_EvalMode(expr, num_samples=num_samples, float_width=float_width, device=device)
+        expr.mode_cache[key] = mode
+    box = (variables[0][0], variables[0][1], variables[1][0], variables[1][1])
+    out = mode.render(box, res, bounds, bindings)
+    torch.cuda.synchronize(device)
+    img = out.cpu().numpy()
+    return img if (mode.out_is_tuple and img.shape[0] > 1) else img[0]
