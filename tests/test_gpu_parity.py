@@ -119,3 +119,33 @@ def test_reduce_sum_is_deterministic_and_accurate(cuda_device):
         assert np.array_equal(outs[0], outs[1])
         want = np.array([c.double().sum().item() for c in cols])
         assert np.allclose(outs[0], want, rtol=1e-5, atol=1e-3 * np.sqrt(n) * 1e-3 + 1e-6)
+
+
+# ---- against the committed outputs of the reference C backend itself (tests/golden/vectors) --------
+import glob as _glob
+import os as _os
+
+from conftest import ROOT as _ROOT
+
+_VECTORS = sorted(_glob.glob(_os.path.join(_ROOT, 'tests', 'golden', 'vectors', '*.npz')))
+
+
+@pytest.mark.parametrize('path', _VECTORS, ids=[_os.path.basename(p)[:-4] for p in _VECTORS])
+def test_cuda_reproduces_reference_vectors(cuda_device, path):
+    from teg_b200 import CUDA_EvalMode
+    z = np.load(path)
+    name = _os.path.basename(path)[:-4]
+    scene, prec, ns = name.rsplit('_', 2)
+    dtype = np.float32 if prec == 'f32' else np.float64
+    prog = load_program(scene)
+    mode = CUDA_EvalMode(prog, num_samples=int(z['num_samples']), float_width='float' if prec == 'f32' else 'double')
+    inputs = list(z['inputs'])
+    got = np.asarray(mode.eval(dict(zip(prog.args, inputs)))).reshape(z['outputs'].shape)
+    want = z['outputs']
+    assert got.dtype == dtype
+    if scene.startswith('circle'):
+        tol = 1e-5 if prec == 'f32' else 1e-12
+        bad = np.abs(got - want) > tol * np.maximum(np.abs(want), 2.0 / 24)
+        assert bad.mean() < 5e-3
+    else:
+        assert np.array_equal(got, want, equal_nan=True), f'{name}: {np.count_nonzero(got != want)} values differ'

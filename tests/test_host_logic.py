@@ -1,0 +1,122 @@
+"""CPU tests of the backend's host logic: exchange format, DAG, scheduling, code generation, NVRTC.
+
+None of these run a kernel.  The lowering is checked for *value* parity by compiling the generated
+instance functions for the host (tests/host_harness.py, a checker) and comparing with the oracle.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_program, program_text
+
+from host_harness import run_on_host
+from teg_b200.codegen import generate
+from teg_b200.dag import build_dag
+from teg_b200.schedule import make_schedule
+from teg_b200.tegp import Program, from_teg
+from teg_b200.workloads import SCENE_SAMPLES, bind, scene_values
+
+
+def test_tegp_round_trip_and_sharing():
+    for scene in SCENE_SAMPLES:
+        text = program_text(scene)
+        prog = Program.loads(text)
+        assert prog.dumps() == text
+    grad = load_program('tri_grad')
+    assert grad.tree_size() > 20000 and len(grad.nodes) < 1200        # 22.5k-node tree, < 1k unique
+
+
+def test_lang_mirror_builds_the_readme_program():
+    from teg_b200.lang import IfElse, Teg, TegVar, Var
+    x, t = TegVar('x'), Var('t', 0.5)
+    prog = from_teg(Teg(0, 1, IfElse(x < t, 1, 0), x), [t])
+    assert [n.op for n in prog.nodes].count('T') == 1
+    assert prog.args == [f't_{t.uid}'] and prog.defaults[prog.args[0]] == 0.5
+    with pytest.raises(ValueError):
+        from_teg(object())
+
+
+def test_schedule_structure_of_the_triangle_gradient():
+    """12 delta integrals in the reference -> 3 fused loops (one per edge) under 6 guards."""
+    dag = build_dag(load_program('tri_grad'))
+    assert len(dag.outputs) == 6 and dag.out_is_tuple
+    assert dag.stats()['live_nodes'] < 500
+    sch = make_schedule(dag, [0, 1, 2, 3])
+    loops = sch.loops()
+    assert len(loops) == 3 and sorted(len(lp.quads) for lp in loops) == [4, 4, 4]
+    assert len(sch.uniform_slots) > 30          # per-edge normalisation etc. leaves the per-pixel code
+    # with every argument per-instance nothing is uniform
+    sch_all = make_schedule(dag, list(range(10)))
+    assert len(sch_all.uniform_slots) == 0
+
+
+@pytest.mark.parametrize('scene', list(SCENE_SAMPLES))
+def test_generated_code_matches_oracle_on_host(scene):
+    from oracle import Oracle
+    prog = load_program(scene)
+    ns = SCENE_SAMPLES[scene]
+    inputs = bind(prog.args, scene_values(scene, res=(20, 20), n=300))
+    n = max(np.size(v) for v in inputs)
+    arr = [i for i, v in enumerate(inputs) if np.ndim(v) > 0]
+    sch = make_schedule(build_dag(prog), arr)
+    for dtype, ctype in ((np.float32, 'float'), (np.float64, 'double')):
+        ks = generate(sch, ctype, ns)
+        got = run_on_host(ks, inputs, n, dtype)
+        want = Oracle(program_text(scene)).eval(inputs, ns, dtype)
+        assert np.array_equal(got, want, equal_nan=True), f'{scene}/{ctype}'
+
+
+def test_all_arguments_per_instance_and_all_scalar_variants():
+    """The uniform / per-instance split must not change values: every argument streamed, and none."""
+    from oracle import Oracle
+    prog = load_program('tri_grad')
+    inputs = bind(prog.args, scene_values('tri_grad', res=(16, 16)))
+    n = 256
+    dag = build_dag(prog)
+    want = Oracle(program_text('tri_grad')).eval(inputs, 16, np.float32)
+    ks = generate(make_schedule(dag, list(range(len(prog.args)))), 'float', 16)
+    assert np.array_equal(run_on_host(ks, inputs, n, np.float32), want)
+    one = [float(np.ravel(v)[137]) if np.ndim(v) else v for v in inputs]
+    ks = generate(make_schedule(dag, []), 'float', 16)
+    assert np.array_equal(run_on_host(ks, one, 1, np.float32)[:, 0], want[:, 137])
+
+
+@pytest.mark.parametrize('scene', ['tri_primal', 'tri_grad', 'shaded_grad', 'nested3d_grad', 'circle_dt'])
+def test_nvrtc_compiles_generated_kernels_for_sm100a(scene, tmp_path, monkeypatch):
+    """NVRTC needs no GPU: every generated unit must compile for sm_100a (cubin comes back)."""
+    from teg_b200 import runtime
+    monkeypatch.setenv('TEGB200_CACHE_DIR', str(tmp_path))
+    prog = load_program(scene)
+    sch = make_schedule(build_dag(prog), [0, 1, 2, 3])
+    ks = generate(sch, 'float', SCENE_SAMPLES[scene])
+    mod = runtime.Module(ks.source)
+    assert not mod.from_cache and len(mod.cubin()) > 1000
+    again = runtime.Module(ks.source)
+    assert again.from_cache and again.cubin() == mod.cubin()
+    if scene.startswith('tri'):
+        ksr = generate(sch, 'float', 16, grid_args=[0, 1, 2, 3])
+        assert 'xe[nx + 1]' in ksr.source
+        runtime.Module(ksr.source)
+
+
+def test_nvrtc_error_surfaces_as_exception():
+    from teg_b200 import runtime
+    with pytest.raises(runtime.TegbError) as e:
+        runtime.Module('this is not CUDA', use_cache=False)
+    assert 'NVRTC' in str(e.value)
+
+
+def test_opcount_rule_on_the_triangle():
+    from teg_b200.opcount import count
+    sch = make_schedule(build_dag(load_program('tri_primal')), [0, 1, 2, 3])
+    oc = count(sch, 16)
+    # per inner sample: 3 edges x (add, mul, add) + 3 compares + 1 select + 4 template = 17
+    assert oc.per_sample_inner == 17 and oc.samples_unguarded == 256
+    assert oc.unguarded == oc.all_true == 16 * (16 * 17 + 9 + 4)
+    g = count(make_schedule(build_dag(load_program('tri_grad')), [0, 1, 2, 3]), 16)
+    assert g.all_true > g.unguarded and len(g.guards) >= 3
+
+
+def test_exp_is_rejected_like_the_reference():
+    text = 'TEGP 1\nname e\nnodes 2\nC 1\nF Exp 0\nroot 1\nargs 0\n'
+    with pytest.raises(AssertionError):
+        build_dag(Program.loads(text))
