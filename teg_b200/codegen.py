@@ -68,7 +68,7 @@ class KernelSource:
 
 class Emitter:
     def __init__(self, sch: Schedule, ctype: str, num_samples: int, name: str,
-                 block_size: int = 128, unroll_inner: int = 32, unroll_outer: int = 1):
+                 block_size: int = 128, unroll_inner: int = 32, unroll_outer: int = 1, pred_accum: bool = True, use_asm: bool = True):
         assert ctype in ('float', 'double')
         self.sch = sch
         self.dag: Dag = sch.dag
@@ -79,6 +79,8 @@ class Emitter:
         self.block_size = block_size
         self.unroll_inner = unroll_inner
         self.unroll_outer = unroll_outer
+        self.pred_accum = pred_accum
+        self.use_asm = use_asm
         self.helper = Scheduler(sch.dag, sch.array_args)      # for resolve / bool_value
         self.lines: List[str] = []
         self.loop_counter = 0
@@ -178,11 +180,136 @@ class Emitter:
         self.emit(f'for (unsigned int s{k} = 0; s{k} < {N}u; ++s{k}) {{', ind + 1)
         self.emit(f'const T x{st.bvar} = lo{k} + step{k} * ((T)s{k} + {literal("0.5", self.ctype)});', ind + 2)
         self.block(st.body, ind + 2, depth + 1)
+        fixups = []
         for q in st.quads:
-            body = self.ref(self.nodes[q].args[2], st.body.known)
-            self.emit(f'v{q} = v{q} + {body} * step{k};', ind + 2)
+            pf = self._pred_form(self.nodes[q].args[2], st.body) if self.pred_accum else None
+            if pf is not None and pf[0]:
+                conds, val = pf
+                term = f'step{k}' if val is None else f'{val} * step{k}'
+                self._emit_pred_add(f'v{q}', conds, term, st.body.known, ind + 2)
+                fixups.append(q)
+            else:
+                body = self.ref(self.nodes[q].args[2], st.body.known)
+                self.emit(f'v{q} = v{q} + {body} * step{k};', ind + 2)
         self.emit('}', ind + 1)
+        for q in fixups:
+            # skipped terms were `0 * step`: identical for every finite step; keeps NaN/inf steps poisonous
+            self.emit(f'v{q} = v{q} + {literal("0", self.ctype)} * step{k};', ind + 1)
         self.emit('}', ind)
+
+    # ------------------------------------------------------- predicated accumulate (ALU-pipe relief)
+    def _fold_compare(self, c: int, known: Dict[int, bool]):
+        """lt node -> (ptx cmp, lhs text, rhs text).  ``0 < a + b`` is emitted as ``a > -b`` (exact in IEEE
+        arithmetic without flush-to-zero: a float sum is positive iff the exact sum is), which drops the add
+        from the per-sample chain; ``-1 * w`` operands are negated by swapping sides instead."""
+        n = self.nodes[c]
+        x = self.helper.resolve(n.args[0], known)
+        y = self.helper.resolve(n.args[1], known)
+
+        def is_zero(i):
+            m = self.nodes[i]
+            return m.op == 'const' and float(m.attr) == 0.0
+
+        def neg_of(i):
+            """text of -(node i) when that is free, else None"""
+            m = self.nodes[i]
+            if m.op == 'mul':
+                for ka, wa in ((m.args[0], m.args[1]), (m.args[1], m.args[0])):
+                    kk = self.nodes[self.helper.resolve(ka, known)]
+                    if kk.op == 'const' and float(kk.attr) == -1.0:
+                        return self.ref(wa, known)
+            return None
+
+        def free_or_avail(i):
+            return True
+
+        for zero, summ, cmp in ((x, y, 'gt'), (y, x, 'lt')):
+            if is_zero(zero) and self.nodes[summ].op == 'add' and summ not in self.sch.uniform_slots:
+                a, b = (self.helper.resolve(t, known) for t in self.nodes[summ].args)
+                nb = neg_of(b)
+                if nb is not None:
+                    return cmp, self.ref(a, known), nb
+                na = neg_of(a)
+                if na is not None:
+                    return cmp, self.ref(b, known), na
+                return cmp, self.ref(a, known), f'(-{self.ref(b, known)})'
+        return 'lt', self.ref(x, known), self.ref(y, known)
+
+    def _emit_pred_add(self, acc: str, conds: List[int], term: str, known: Dict[int, bool], ind: int):
+        """acc = acc + term  iff all conds: one chained FSETP per comparison, then one predicated add."""
+        leaves: List[int] = []
+
+        def flatten(c: int):
+            c_res = c
+            v = self.helper.bool_value(c_res, known)
+            if v is True:
+                return
+            n = self.nodes[c_res]
+            if n.op == 'and' and c_res not in self.sch.uniform_slots:
+                flatten(n.args[0])
+                flatten(n.args[1])
+            else:
+                leaves.append(c_res)
+
+        for c in conds:
+            flatten(c)
+        if not self.use_asm or not leaves or len(leaves) > 12:
+            cond = ' && '.join(self.ref(c, known) for c in conds)
+            self.emit(f'if ({cond}) {acc} = {acc} + {term};', ind)
+            return
+        sfx, cons = ('f32', 'f') if self.ctype == 'float' else ('f64', 'd')
+        ops: List[str] = []
+        lines: List[str] = ['.reg .pred p;']
+        first = True
+        for c in leaves:
+            n = self.nodes[c]
+            if n.op == 'lt' and c not in self.sch.uniform_slots and self.helper.bool_value(c, known) is None:
+                cmp, lhs, rhs = self._fold_compare(c, known)
+                i0 = len(ops) + 2
+                ops += [f'"{cons}"({lhs})', f'"{cons}"({rhs})']
+                lines.append(f'setp.{cmp}{"" if first else ".and"}.{sfx} p, %{i0}, %{i0 + 1}{"" if first else ", p"};')
+            else:
+                i0 = len(ops) + 2
+                ops.append(f'"r"((int)({self.ref(c, known)}))')
+                lines.append(f'setp.ne{"" if first else ".and"}.b32 p, %{i0}, 0{"" if first else ", p"};')
+            first = False
+        lines.append(f'@p add.rn.{sfx} %0, %0, %1;')
+        body = ' '.join(lines)
+        self.emit(f'asm("{{ {body} }}" : "+{cons}"({acc}) : "{cons}"({term}), {", ".join(ops)});', ind)
+
+    def _pred_form(self, i: int, blk: Block):
+        """Integrand of the shape  [K *] (c ? A : 0)  ->  ([conditions], value text | None for 1).
+
+        ``out + ((c ? A : 0) * K) * step`` equals ``out`` when c is false (adding a signed zero to an
+        accumulator that starts at +0 never changes it), so the accumulate can be predicated on c.
+        Only constants K are accepted: their product with zero is exactly zero."""
+        known = blk.known
+        i = self.helper.resolve(i, known)
+        n = self.nodes[i]
+        if n.op == 'sel' and i in blk.spec:
+            z = self.helper.resolve(n.args[2], known)
+            if self.nodes[z].op == 'const' and float(self.nodes[z].attr) == 0.0:
+                cond = n.args[0]
+                a = self.helper.resolve(n.args[1], known)
+                inner = self._pred_form(a, blk)
+                if inner is not None and inner[0]:
+                    return [cond] + inner[0], inner[1]
+                na = self.nodes[a]
+                if na.op == 'const' and float(na.attr) == 1.0:
+                    return [cond], None
+                return [cond], self.ref(a, known)
+            return None
+        if n.op == 'mul':
+            for ka, sa in ((n.args[0], n.args[1]), (n.args[1], n.args[0])):
+                kk = self.helper.resolve(ka, known)
+                if self.nodes[kk].op == 'const':
+                    inner = self._pred_form(sa, blk)
+                    if inner is not None and inner[0]:
+                        kt = self.ref(kk, known)
+                        vt = literal('1', self.ctype) if inner[1] is None else inner[1]
+                        first = ka == n.args[0]
+                        return inner[0], (f'({kt} * {vt})' if first else f'({vt} * {kt})')
+        return None
 
     # ------------------------------------------------------------------- kernels
     def uniform_body(self) -> List[str]:
