@@ -59,6 +59,8 @@ typedef struct {
     int n_grid_args;              /* arguments generated from the pixel index (0 unless a render program) */
     int n_outputs;                /* output streams of the main kernel */
     int block_size;               /* threads per block the main kernel was generated for */
+    int reduce_outputs;           /* 1: the main kernel writes per-block partial sums; launches then deliver the
+                                     n_outputs per-component sums over all instances to out_ptrs[0] (device) */
 } tegb_program_desc;
 
 /* pixel grid of tests/plot.py:11-16: np.linspace(lo, hi, res+1) per axis, instance = nx * res_y + ny */
@@ -89,7 +91,9 @@ void tegb_program_destroy(tegb_program *p);
 
 /* Device buffers.  scalars[n_scalar_args] are converted to the program's element type.
  * in_ptrs[n_array_args], out_ptrs[n_outputs]: device pointers to n elements each.  Asynchronous on
- * `stream` (a cudaStream_t; NULL = default stream). */
+ * `stream` (a cudaStream_t; NULL = default stream).  For reduce_outputs programs only out_ptrs[0] is
+ * used: a device pointer to n_outputs elements that receive the sums over the n instances (fixed
+ * summation order for a given n: deterministic). */
 int tegb_program_launch(tegb_program *p, const double *scalars, const void *const *in_ptrs,
                         void *const *out_ptrs, int64_t n, void *stream);
 

@@ -59,6 +59,7 @@ class KernelSource:
     grid_args: List[int]            # (x_lb, x_ub, y_lb, y_ub) argument indices generated from the pixel index
     n_outputs: int
     block_size: int
+    reduce_outputs: bool            # main kernel writes per-block partial sums instead of per-instance outputs
     stats: Dict[str, float]
 
     @property
@@ -329,15 +330,19 @@ class Emitter:
         self.lines = []
         self.block(self.sch.main, 1, 0)
         for k, o in enumerate(self.sch.outputs):
-            self.emit(f'out{k}[i] = {self.ref(o, self.sch.main.known)};', 1)
+            self.emit(f'res[{k}] = {self.ref(o, self.sch.main.known)};', 1)
         return self.lines
 
-    def generate(self, grid_args: Sequence[int] = ()) -> KernelSource:
+    def generate(self, grid_args: Sequence[int] = (), reduce_outputs: bool = False) -> KernelSource:
         """grid_args: argument indices of (x_lb, x_ub, y_lb, y_ub) when they are generated from the pixel
-        index (render programs, tests/plot.py:8-29) instead of being streamed from per-instance arrays."""
+        index (render programs, tests/plot.py:8-29) instead of being streamed from per-instance arrays.
+        reduce_outputs: instead of one output stream per component, every block sums its instances'
+        results in a fixed order and writes one partial per component (``partials[k * gridsize + block]``);
+        the runtime adds the partials (reverse-mode gradients w.r.t. shared parameters)."""
         sch = self.sch
         T = self.ctype
         name = self.name
+        K = len(sch.outputs)
         nu = max(1, len(sch.uniform_slots))
         scal = list(sch.scalar_args)
         grid = list(grid_args)
@@ -351,9 +356,9 @@ class Emitter:
         varying = list(sch.array_args)       # instance-function value parameters (arrays and grid alike)
 
         uparams = ', '.join([f'const T a{a}' for a in scal] + ['T* __restrict__ U'])
-        outs_decl = [f'T* __restrict__ out{k}' for k in range(len(sch.outputs))]
-        outs_use = [f'out{k}' for k in range(len(sch.outputs))]
-        iparams = ', '.join(['const long long i'] + [f'const T a{a}' for a in varying] + outs_decl)
+        outs_decl = (['T* __restrict__ partials'] if reduce_outputs
+                     else [f'T* __restrict__ out{k}' for k in range(K)])
+        iparams = ', '.join([f'const T a{a}' for a in varying] + [f'T (&res)[{K}]'])
         src: List[str] = []
         src.append(f'// generated by teg_b200.codegen for program "{self.dag.name}"  (precision {T}, {self.N} samples)')
         src.append('#include "teg_b200_runtime.cuh"')
@@ -386,33 +391,42 @@ class Emitter:
                                  'const int row0'] + outs_decl)
             src.append(f'extern "C" __global__ void __launch_bounds__({self.block_size}) {name}_main({mparams}) {{')
             src.append('    const int ny = blockIdx.x * blockDim.x + threadIdx.x;')
-            src.append('    if (ny >= res_y) return;')
+            src.append('    const bool live = ny < res_y;')
             src.append('    const int nx = row0 + blockIdx.y;')
             src.append('    const long long i = (long long)blockIdx.y * res_y + ny;')
             loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye[ny]', grid[3]: 'ye[ny + 1]'}
-            call = ', '.join(['i'] + [loads[a] for a in varying] + outs_use)
-            src.append(f'    {name}_instance({call});')
-            src.append('}')
+            call = ', '.join([loads[a] for a in varying] + ['res'])
         else:
             mparams = ', '.join([f'const T* __restrict__ in{a}' for a in arrs] + outs_decl + ['const long long n'])
             src.append(f'extern "C" __global__ void __launch_bounds__({self.block_size}) {name}_main({mparams}) {{')
             src.append('    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;')
-            src.append('    if (i >= n) return;')
-            call = ', '.join(['i'] + [f'in{a}[i]' for a in varying] + outs_use)
+            src.append('    const bool live = i < n;')
+            call = ', '.join([f'in{a}[i]' for a in varying] + ['res'])
+        src.append(f'    T res[{K}];')
+        if reduce_outputs:
+            src.append(f'    for (int k = 0; k < {K}; k++) res[k] = {literal("0", T)};')
+            src.append(f'    if (live) {name}_instance({call});')
+            src.append(f'    tegb_block_sum_store<T, {K}, {self.block_size}>(res, partials);')
+        else:
+            src.append('    if (!live) return;')
             src.append(f'    {name}_instance({call});')
-            src.append('}')
+            for k in range(K):
+                src.append(f'    out{k}[i] = res[{k}];')
+        src.append('}')
         src.append('#endif')
         text = '\n'.join(src) + '\n'
         return KernelSource(name=name, ctype=T, num_samples=self.N, source=text,
                             uniform_kernel=f'{name}_uniform', main_kernel=f'{name}_main',
                             n_uniform=nu, scalar_args=scal, array_args=arrs, grid_args=grid,
-                            n_outputs=len(sch.outputs), block_size=self.block_size, stats=dict(self.stats))
+                            n_outputs=K, block_size=self.block_size, reduce_outputs=bool(reduce_outputs),
+                            stats=dict(self.stats))
 
 
 def generate(sch: Schedule, ctype: str = 'float', num_samples: int = 50, name: Optional[str] = None,
-             grid_args: Sequence[int] = (), **opts) -> KernelSource:
+             grid_args: Sequence[int] = (), reduce_outputs: bool = False, **opts) -> KernelSource:
     name = name or _c_ident(sch.dag.name)
-    return Emitter(sch, ctype, num_samples, name, **opts).generate(grid_args=grid_args)
+    return Emitter(sch, ctype, num_samples, name, **opts).generate(grid_args=grid_args,
+                                                                   reduce_outputs=reduce_outputs)
 
 
 def _c_ident(s: str) -> str:

@@ -207,6 +207,9 @@ struct tegb_program {
     // staging for tegb_program_eval_host
     std::vector<void *> d_in, d_out;
     int64_t cap = 0;
+    // per-block partial sums of reduce_outputs programs
+    void *d_partials = nullptr;
+    size_t partials_bytes = 0;
     // pixel-edge tables for tegb_render_launch
     void *d_xe = nullptr, *d_ye = nullptr;
     std::vector<char> h_xe, h_ye;
@@ -248,6 +251,7 @@ extern "C" void tegb_program_destroy(tegb_program *p) {
     for (void *q : p->d_in) if (q) cudaFree(q);
     for (void *q : p->d_out) if (q) cudaFree(q);
     if (p->u_stage) cudaFree(p->u_stage);
+    if (p->d_partials) cudaFree(p->d_partials);
     if (p->d_xe) cudaFree(p->d_xe);
     if (p->d_ye) cudaFree(p->d_ye);
     if (p->mod) drv::ModuleUnload(p->mod);
@@ -273,6 +277,56 @@ static int run_uniform(tegb_program *p, const double *scalars, CUstream st) {
     return TEGB_OK;
 }
 
+
+// --------------------------------------------------------------------------------- deterministic sums
+static const int RED_THREADS = 256;
+static const int RED_MAX_BLOCKS = 1184;     // 8 blocks per SM x 148 SMs
+
+template <typename T>
+__device__ __forceinline__ T block_sum_fixed(T v, T *smem) {
+    for (int off = 16; off > 0; off >>= 1) v = v + __shfl_down_sync(0xffffffffu, v, off);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    T r = 0;
+    if (warp == 0) {
+        r = lane < (blockDim.x >> 5) ? smem[lane] : (T)0;
+        for (int off = 16; off > 0; off >>= 1) r = r + __shfl_down_sync(0xffffffffu, r, off);
+    }
+    __syncthreads();
+    return r;   // valid in thread 0
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS) colsum_stage2(const T *partials, long long n_blocks, T *out) {
+    __shared__ T smem[32];
+    const int c = blockIdx.x;
+    T acc = 0;
+    for (long long i = threadIdx.x; i < n_blocks; i += RED_THREADS) acc = acc + partials[(long long)c * n_blocks + i];
+    T s = block_sum_fixed(acc, smem);
+    if (threadIdx.x == 0) out[c] = s;
+}
+
+// partials buffer of a reduce_outputs program: n_outputs x n_blocks elements
+static int ensure_partials(tegb_program *p, unsigned long long n_blocks) {
+    const size_t need = (size_t)p->d.n_outputs * n_blocks * p->d.elem_size;
+    if (need <= p->partials_bytes) return TEGB_OK;
+    if (p->d_partials) { cudaFree(p->d_partials); p->d_partials = nullptr; p->partials_bytes = 0; }
+    RT_CHECK(cudaMalloc(&p->d_partials, need));
+    p->partials_bytes = need;
+    return TEGB_OK;
+}
+
+static int finish_partials(tegb_program *p, unsigned long long n_blocks, void *out, cudaStream_t st) {
+    if (p->d.elem_size == 4)
+        colsum_stage2<float><<<p->d.n_outputs, RED_THREADS, 0, st>>>((const float *)p->d_partials, (long long)n_blocks, (float *)out);
+    else
+        colsum_stage2<double><<<p->d.n_outputs, RED_THREADS, 0, st>>>((const double *)p->d_partials, (long long)n_blocks, (double *)out);
+    g_launches++;
+    RT_CHECK(cudaGetLastError());
+    return TEGB_OK;
+}
+
 extern "C" int tegb_program_launch(tegb_program *p, const double *scalars, const void *const *in_ptrs,
                                    void *const *out_ptrs, int64_t n, void *stream) {
     if (!p || !out_ptrs || n < 0) return fail(TEGB_ERR_INVALID, "tegb_program_launch: bad argument");
@@ -287,14 +341,21 @@ extern "C" int tegb_program_launch(tegb_program *p, const double *scalars, const
     std::vector<void *> outs(p->d.n_outputs);
     std::vector<void *> args;
     for (int i = 0; i < p->d.n_array_args; i++) { ins[i] = in_ptrs[i]; args.push_back(&ins[i]); }
-    for (int k = 0; k < p->d.n_outputs; k++) { outs[k] = out_ptrs[k]; args.push_back(&outs[k]); }
-    long long nn = n;
-    args.push_back(&nn);
     const unsigned bs = (unsigned)p->d.block_size;
     const long long blocks = (n + bs - 1) / bs;
     if (blocks > 2147483647LL) return fail(TEGB_ERR_INVALID, "too many instances for one launch");
+    if (p->d.reduce_outputs) {
+        rc = ensure_partials(p, (unsigned long long)blocks);
+        if (rc) return rc;
+        args.push_back(&p->d_partials);
+    } else {
+        for (int k = 0; k < p->d.n_outputs; k++) { outs[k] = out_ptrs[k]; args.push_back(&outs[k]); }
+    }
+    long long nn = n;
+    args.push_back(&nn);
     CU_CHECK(drv::LaunchKernel(p->f_main, (unsigned)blocks, 1, 1, bs, 1, 1, 0, st, args.data(), nullptr));
     g_launches++;
+    if (p->d.reduce_outputs) return finish_partials(p, (unsigned long long)blocks, out_ptrs[0], (cudaStream_t)st);
     return TEGB_OK;
 }
 
@@ -307,8 +368,10 @@ static int ensure_staging(tegb_program *p, int64_t n) {
     p->d_out.assign(p->d.n_outputs, nullptr);
     p->cap = 0;
     const size_t bytes = (size_t)n * p->d.elem_size;
+    // a reduce_outputs program delivers its n_outputs sums into d_out[0]
+    const size_t out_bytes = (size_t)(n > p->d.n_outputs ? n : p->d.n_outputs) * p->d.elem_size;
     for (auto &q : p->d_in) RT_CHECK(cudaMalloc(&q, bytes));
-    for (auto &q : p->d_out) RT_CHECK(cudaMalloc(&q, bytes));
+    for (auto &q : p->d_out) RT_CHECK(cudaMalloc(&q, out_bytes));
     p->cap = n;
     return TEGB_OK;
 }
@@ -327,8 +390,14 @@ extern "C" int tegb_program_eval_host(tegb_program *p, const double *scalars, co
         RT_CHECK(cudaMemcpyAsync(p->d_in[i], host_in[i], bytes, cudaMemcpyHostToDevice, st));
     rc = tegb_program_launch(p, scalars, (const void *const *)p->d_in.data(), p->d_out.data(), n, st);
     if (rc) return rc;
-    for (int k = 0; k < p->d.n_outputs; k++)
-        RT_CHECK(cudaMemcpyAsync(host_out[k], p->d_out[k], bytes, cudaMemcpyDeviceToHost, st));
+    if (p->d.reduce_outputs) {
+        // the n_outputs sums were written to the start of d_out[0]; host_out[0] receives them
+        RT_CHECK(cudaMemcpyAsync(host_out[0], p->d_out[0], (size_t)p->d.n_outputs * p->d.elem_size,
+                                 cudaMemcpyDeviceToHost, st));
+    } else {
+        for (int k = 0; k < p->d.n_outputs; k++)
+            RT_CHECK(cudaMemcpyAsync(host_out[k], p->d_out[k], bytes, cudaMemcpyDeviceToHost, st));
+    }
     RT_CHECK(cudaStreamSynchronize(st));
     return TEGB_OK;
 }
@@ -385,38 +454,26 @@ extern "C" int tegb_render_launch(tegb_program *p, const double *scalars, const 
     args.push_back(&p->d_ye);
     args.push_back(&res_y);
     args.push_back(&row0);
-    for (int k = 0; k < p->d.n_outputs; k++) { outs[k] = out_ptrs[k]; args.push_back(&outs[k]); }
     const unsigned bs = (unsigned)p->d.block_size;
     const unsigned gx = (unsigned)((g->res_y + bs - 1) / bs);
     const unsigned gy = (unsigned)(g->row_end - g->row_begin);
     if (gy > 65535u) return fail(TEGB_ERR_INVALID, "more than 65535 rows in one render launch");
+    if (p->d.reduce_outputs) {
+        rc = ensure_partials(p, (unsigned long long)gx * gy);
+        if (rc) return rc;
+        args.push_back(&p->d_partials);
+    } else {
+        for (int k = 0; k < p->d.n_outputs; k++) { outs[k] = out_ptrs[k]; args.push_back(&outs[k]); }
+    }
     CU_CHECK(drv::LaunchKernel(p->f_main, gx, gy, 1, bs, 1, 1, 0, st, args.data(), nullptr));
     g_launches++;
+    if (p->d.reduce_outputs) return finish_partials(p, (unsigned long long)gx * gy, out_ptrs[0], (cudaStream_t)st);
     return TEGB_OK;
 }
 
-// --------------------------------------------------------------------------------- deterministic sums
 // Stage 1: block b sums elements [b*chunk, (b+1)*chunk) of every column: each thread walks its strided
 // subsequence in order, then a fixed shuffle/shared-memory tree combines the 256 partials.  Stage 2: one
 // block combines the per-block partials in the same fixed way.  The result depends only on (n, values).
-static const int RED_THREADS = 256;
-static const int RED_MAX_BLOCKS = 1184;     // 8 blocks per SM x 148 SMs
-
-template <typename T>
-__device__ __forceinline__ T block_sum_fixed(T v, T *smem) {
-    for (int off = 16; off > 0; off >>= 1) v = v + __shfl_down_sync(0xffffffffu, v, off);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) smem[warp] = v;
-    __syncthreads();
-    T r = 0;
-    if (warp == 0) {
-        r = lane < (blockDim.x >> 5) ? smem[lane] : (T)0;
-        for (int off = 16; off > 0; off >>= 1) r = r + __shfl_down_sync(0xffffffffu, r, off);
-    }
-    __syncthreads();
-    return r;   // valid in thread 0
-}
-
 template <typename T>
 __global__ void __launch_bounds__(RED_THREADS) colsum_stage1(const T *const *cols, int n_cols, long long n,
                                                              long long chunk, T *partials) {
@@ -431,16 +488,6 @@ __global__ void __launch_bounds__(RED_THREADS) colsum_stage1(const T *const *col
         T s = block_sum_fixed(acc, smem);
         if (threadIdx.x == 0) partials[(long long)c * gridDim.x + blockIdx.x] = s;
     }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(RED_THREADS) colsum_stage2(const T *partials, int n_blocks, T *out) {
-    __shared__ T smem[32];
-    const int c = blockIdx.x;
-    T acc = 0;
-    for (int i = threadIdx.x; i < n_blocks; i += RED_THREADS) acc = acc + partials[(long long)c * n_blocks + i];
-    T s = block_sum_fixed(acc, smem);
-    if (threadIdx.x == 0) out[c] = s;
 }
 
 static int reduce_blocks(int64_t n) {
@@ -469,10 +516,10 @@ extern "C" int tegb_reduce_sum(const void *const *in_ptrs, int n_cols, int64_t n
     char *partials = (char *)workspace + off;
     if (elem_size == 4) {
         colsum_stage1<float><<<blocks, RED_THREADS, 0, st>>>((const float *const *)workspace, n_cols, n, chunk, (float *)partials);
-        colsum_stage2<float><<<n_cols, RED_THREADS, 0, st>>>((const float *)partials, blocks, (float *)out);
+        colsum_stage2<float><<<n_cols, RED_THREADS, 0, st>>>((const float *)partials, (long long)blocks, (float *)out);
     } else {
         colsum_stage1<double><<<blocks, RED_THREADS, 0, st>>>((const double *const *)workspace, n_cols, n, chunk, (double *)partials);
-        colsum_stage2<double><<<n_cols, RED_THREADS, 0, st>>>((const double *)partials, blocks, (double *)out);
+        colsum_stage2<double><<<n_cols, RED_THREADS, 0, st>>>((const double *)partials, (long long)blocks, (double *)out);
     }
     g_launches += 2;
     RT_CHECK(cudaGetLastError());

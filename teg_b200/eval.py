@@ -81,17 +81,18 @@ class CUDA_EvalMode(EvalMode):
         self._variants: Dict[tuple, Tuple[KernelSource, runtime.Program]] = {}
 
     # ------------------------------------------------------------------ compile
-    def kernel_source(self, array_args: Sequence[int], grid_args: Sequence[int] = ()) -> KernelSource:
+    def kernel_source(self, array_args: Sequence[int], grid_args: Sequence[int] = (),
+                      reduce: bool = False) -> KernelSource:
         varying = sorted(set(array_args) | set(grid_args))
         sch = make_schedule(self.dag, varying)
         return generate(sch, self.float_width, self.num_samples, grid_args=list(grid_args),
-                        block_size=self.block_size, **self.codegen_opts)
+                        reduce_outputs=reduce, block_size=self.block_size, **self.codegen_opts)
 
-    def compiled(self, array_args: Sequence[int], grid_args: Sequence[int] = ()):
-        key = (tuple(sorted(array_args)), tuple(grid_args))
+    def compiled(self, array_args: Sequence[int], grid_args: Sequence[int] = (), reduce: bool = False):
+        key = (tuple(sorted(array_args)), tuple(grid_args), bool(reduce))
         hit = self._variants.get(key)
         if hit is None:
-            ks = self.kernel_source(array_args, grid_args)
+            ks = self.kernel_source(array_args, grid_args, reduce)
             mod = runtime.Module(ks.source, use_cache=self.use_cache)
             prog = runtime.Program(mod, ks, device=self.device)
             hit = (ks, prog)
@@ -108,7 +109,9 @@ class CUDA_EvalMode(EvalMode):
             f'No bindings found for {[self.arglist[i][0] for i, a in enumerate(args) if a is None]}'
         return args
 
-    def eval(self, bindings={}, **kwargs):
+    def eval(self, bindings={}, reduce: bool = False, **kwargs):
+        """reduce=True: return the per-component SUM over the instances (reverse-mode gradients w.r.t.
+        shared parameters) instead of per-instance values; the summation happens inside the kernel."""
         args = self._resolve(bindings)
         dt = _np_dtype(self.float_width)
         is_arr = []
@@ -128,13 +131,17 @@ class CUDA_EvalMode(EvalMode):
             assert n is None or n == ln, 'all array bindings must have the same length'
             n = ln
         array_args = [i for i, f in enumerate(is_arr) if f]
-        ks, prog = self.compiled(array_args)
+        ks, prog = self.compiled(array_args, reduce=reduce)
         scalars = [float(args[a]) for a in ks.scalar_args]
         if any_torch:
-            return self._eval_torch(ks, prog, args, scalars, n)
+            return self._eval_torch(ks, prog, args, scalars, n, reduce)
         batched = n is not None
         n = 1 if n is None else n
         ins = [np.ascontiguousarray(np.asarray(args[a], dtype=dt).reshape(-1)) for a in ks.array_args]
+        if reduce:
+            sums = np.empty(ks.n_outputs, dtype=dt)
+            prog.eval_host(scalars, [a.ctypes.data for a in ins], [sums.ctypes.data], n)
+            return sums if self.out_is_tuple and ks.n_outputs > 1 else sums[0]
         out = np.empty((ks.n_outputs, n), dtype=dt)
         prog.eval_host(scalars, [a.ctypes.data for a in ins],
                        [out[k].ctypes.data for k in range(ks.n_outputs)], n)
@@ -143,7 +150,7 @@ class CUDA_EvalMode(EvalMode):
             return vals if self.out_is_tuple and len(vals) > 1 else vals[0]
         return out if self.out_is_tuple and ks.n_outputs > 1 else out[0]
 
-    def _eval_torch(self, ks, prog, args, scalars, n):
+    def _eval_torch(self, ks, prog, args, scalars, n, reduce=False):
         import torch
         tdt = torch.float32 if self.float_width == 'float' else torch.float64
         dev = torch.device('cuda', self.device)
@@ -154,19 +161,24 @@ class CUDA_EvalMode(EvalMode):
                 t = torch.as_tensor(np.asarray(t), device=dev)
             t = t.to(device=dev, dtype=tdt).contiguous().view(-1)
             ins.append(t)
-        out = torch.empty((ks.n_outputs, n), dtype=tdt, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
+        if reduce:
+            sums = torch.empty(ks.n_outputs, dtype=tdt, device=dev)
+            prog.launch(scalars, [t.data_ptr() for t in ins], [sums.data_ptr()], n, stream=stream)
+            return sums if self.out_is_tuple and ks.n_outputs > 1 else sums[0]
+        out = torch.empty((ks.n_outputs, n), dtype=tdt, device=dev)
         prog.launch(scalars, [t.data_ptr() for t in ins], [out[k].data_ptr() for k in range(ks.n_outputs)],
                     n, stream=stream)
         return out if self.out_is_tuple and ks.n_outputs > 1 else out[0]
 
     # ------------------------------------------------------------------- render
     def render(self, box_vars, res: Tuple[int, int], bounds=((0, 1), (0, 1)), bindings=None,
-               rows: Optional[Tuple[int, int]] = None, out=None, stream: int = 0):
+               rows: Optional[Tuple[int, int]] = None, out=None, stream: int = 0, reduce: bool = False):
         """Evaluate over the pixel grid of tests/plot.py:8-29 with on-device pixel boxes.
 
         box_vars: (x_lb, x_ub, y_lb, y_ub) Vars or labels.  Returns a torch CUDA tensor
-        [k, rows, res_y] (k = program outputs); asynchronous on ``stream``."""
+        [k, rows, res_y] (k = program outputs), or [k] sums over the pixels when ``reduce``;
+        asynchronous on ``stream``."""
         import torch
         labels = [v if isinstance(v, str) else label_of(v) for v in box_vars]
         pos = {lab: i for i, (lab, _) in enumerate(self.arglist)}
@@ -174,7 +186,7 @@ class CUDA_EvalMode(EvalMode):
         by_label = {}
         for k, v in (bindings or {}).items():
             by_label[k if isinstance(k, str) else label_of(k)] = v
-        ks, prog = self.compiled(grid_args, grid_args)
+        ks, prog = self.compiled(grid_args, grid_args, reduce=reduce)
         scalars = []
         for a in ks.scalar_args:
             lab, default = self.arglist[a]
@@ -185,10 +197,12 @@ class CUDA_EvalMode(EvalMode):
         tdt = torch.float32 if self.float_width == 'float' else torch.float64
         dev = torch.device('cuda', self.device)
         if out is None:
-            out = torch.empty((ks.n_outputs, r1 - r0, res[1]), dtype=tdt, device=dev)
+            out = (torch.empty(ks.n_outputs, dtype=tdt, device=dev) if reduce
+                   else torch.empty((ks.n_outputs, r1 - r0, res[1]), dtype=tdt, device=dev))
         grid = runtime.Grid(float(bounds[0][0]), float(bounds[0][1]), float(bounds[1][0]), float(bounds[1][1]),
                             int(res[0]), int(res[1]), int(r0), int(r1))
-        prog.render(scalars, grid, [out[k].data_ptr() for k in range(ks.n_outputs)], stream=stream)
+        ptrs = [out.data_ptr()] if reduce else [out[k].data_ptr() for k in range(ks.n_outputs)]
+        prog.render(scalars, grid, ptrs, stream=stream)
         return out
 
 

@@ -20,6 +20,40 @@
 #  ifndef TEGB_UNIFORM_TABLE
 #    define TEGB_UNIFORM_TABLE(T, name, n) __constant__ T name[n]
 #  endif
+
+/* Fixed-order block sum of K per-thread values (reverse-mode gradients w.r.t. shared parameters):
+ * lanes are folded by a shuffle tree, warps by thread k in warp order; the result for component k goes to
+ * partials[k * (number of blocks) + linear block index].  Warps whose lanes are all exactly zero (the
+ * overwhelmingly common case: only instances crossed by a discontinuity have a non-zero gradient) skip
+ * the shuffles -- adding zeros cannot change a sum, so the value is the same, bit for bit.  Deterministic:
+ * depends only on the launch geometry and the values.  Must be reached by every thread of the block. */
+template <typename T, int K, int BLOCK>
+static __device__ __forceinline__ void tegb_block_sum_store(const T (&v)[K], T* __restrict__ partials) {
+    __shared__ T sm[K][BLOCK / 32];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    bool nz = false;
+#pragma unroll
+    for (int k = 0; k < K; k++) nz = nz || (v[k] != (T)0);
+    const bool any = __any_sync(0xffffffffu, nz);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        T s = v[k];
+        if (any) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s = s + __shfl_down_sync(0xffffffffu, s, off);
+        }
+        if (lane == 0) sm[k][warp] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        T t = sm[threadIdx.x][0];
+#pragma unroll
+        for (int w = 1; w < BLOCK / 32; w++) t = t + sm[threadIdx.x][w];
+        const unsigned long long nblk = (unsigned long long)gridDim.x * gridDim.y * gridDim.z;
+        const unsigned long long blk = ((unsigned long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        partials[(unsigned long long)threadIdx.x * nblk + blk] = t;
+    }
+}
 #else
 #  ifndef TEGB_FN
 #    error "teg_b200 kernels are CUDA-only: there is no host evaluation path"

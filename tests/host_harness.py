@@ -24,11 +24,11 @@ def compile_for_host(ks):
            '#define TEGB_UNIFORM_TABLE(T, name, n) static T name[n]\n#define __restrict__\n')
     uargs = ', '.join([f'sc[{j}]' for j in range(len(ks.scalar_args))] + ['tegU'])
     varying = list(ks.array_args) + list(ks.grid_args)
-    margs = ', '.join(['i'] + [f'in[{j}][i]' for j in range(len(sorted(varying)))] +
-                      [f'out[{k}]' for k in range(ks.n_outputs)])
+    margs = ', '.join([f'in[{j}][i]' for j in range(len(sorted(varying)))] + ['res'])
+    stores = ' '.join(f'out[{k}][i] = res[{k}];' for k in range(ks.n_outputs))
     drv = (f'\nextern "C" void run(const {T}* sc, const {T}* const* in, {T}* const* out, long long n) {{\n'
            f'  {ks.name}_uniform_body({uargs});\n'
-           f'  for (long long i = 0; i < n; i++) {ks.name}_instance({margs});\n}}\n')
+           f'  for (long long i = 0; i < n; i++) {{ {T} res[{ks.n_outputs}]; {ks.name}_instance({margs}); {stores} }}\n}}\n')
     text = pre + ks.source + drv
     os.makedirs(_DIR, exist_ok=True)
     key = hashlib.sha256(text.encode()).hexdigest()[:20]

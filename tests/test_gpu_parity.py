@@ -149,3 +149,30 @@ def test_cuda_reproduces_reference_vectors(cuda_device, path):
         assert bad.mean() < 5e-3
     else:
         assert np.array_equal(got, want, equal_nan=True), f'{name}: {np.count_nonzero(got != want)} values differ'
+
+
+def test_in_kernel_gradient_sum_matches_per_pixel_gradients(cuda_device):
+    """reduce=True (tegb_block_sum_store + colsum_stage2): deterministic, and equal to the float64 sum of
+    the per-pixel gradients up to fp32 summation error; array path and render path both."""
+    import torch
+    from teg_b200 import CUDA_EvalMode
+    prog = load_program('tri_grad')
+    res = (200, 136)                     # not a multiple of the block size: exercises the dead lanes
+    vals = scene_values('tri_grad', res=res)
+    inputs = bind(prog.args, vals)
+    mode = CUDA_EvalMode(prog, num_samples=16)
+    b = dict(zip(prog.args, inputs))
+    per_pixel = np.asarray(mode.eval(b))
+    want = per_pixel.astype(np.float64).sum(axis=1)
+    s1 = np.asarray(mode.eval(b, reduce=True))
+    s2 = np.asarray(mode.eval(b, reduce=True))
+    assert s1.shape == (6,) and np.array_equal(s1, s2)
+    assert np.allclose(s1, want, rtol=2e-6, atol=1e-7)
+    scal = {lab: v for lab, v in zip(prog.args, inputs) if np.ndim(v) == 0}
+    r = mode.render(prog.args[:4], res, ((0, 1), (0, 1)), scal, reduce=True)
+    torch.cuda.synchronize()
+    assert np.allclose(r.cpu().numpy(), want, rtol=2e-6, atol=1e-7)
+    # fp64 program, single instance
+    m64 = CUDA_EvalMode(prog, num_samples=16, float_width='double')
+    one = {lab: (float(np.ravel(v)[9000]) if np.ndim(v) else v) for lab, v in b.items()}
+    assert np.allclose(m64.eval(one, reduce=True), np.asarray(m64.eval(one)), rtol=0, atol=0)
