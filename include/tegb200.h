@@ -61,6 +61,8 @@ typedef struct {
     int block_size;               /* threads per block the main kernel was generated for */
     int reduce_outputs;           /* 1: the main kernel writes per-block partial sums; launches then deliver the
                                      n_outputs per-component sums over all instances to out_ptrs[0] (device) */
+    int team;                     /* threads cooperating on one instance (power of two, 1 = thread per instance);
+                                     > 32 means one block of `team` threads per instance (block_size == team) */
 } tegb_program_desc;
 
 /* pixel grid of tests/plot.py:11-16: np.linspace(lo, hi, res+1) per axis, instance = nx * res_y + ny */

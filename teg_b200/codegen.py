@@ -60,6 +60,7 @@ class KernelSource:
     n_outputs: int
     block_size: int
     reduce_outputs: bool            # main kernel writes per-block partial sums instead of per-instance outputs
+    team: int                       # threads cooperating on one instance (1 = thread per instance)
     stats: Dict[str, float]
 
     @property
@@ -69,7 +70,7 @@ class KernelSource:
 
 class Emitter:
     def __init__(self, sch: Schedule, ctype: str, num_samples: int, name: str,
-                 block_size: int = 128, unroll_inner: int = 32, unroll_outer: int = 1, pred_accum: bool = True, use_asm: bool = True):
+                 block_size: int = 128, unroll_inner: int = 32, unroll_outer: int = 1, pred_accum: bool = True, use_asm: bool = True, team: int = 1):
         assert ctype in ('float', 'double')
         self.sch = sch
         self.dag: Dag = sch.dag
@@ -82,6 +83,8 @@ class Emitter:
         self.unroll_outer = unroll_outer
         self.pred_accum = pred_accum
         self.use_asm = use_asm
+        assert team >= 1 and (team & (team - 1)) == 0 and team <= 1024, 'team must be a power of two <= 1024'
+        self.team = team
         self.helper = Scheduler(sch.dag, sch.array_args)      # for resolve / bool_value
         self.lines: List[str] = []
         self.loop_counter = 0
@@ -177,8 +180,15 @@ class Emitter:
             unroll = N if N <= self.unroll_inner else 4
         else:
             unroll = self.unroll_outer
-        self.emit(f'#pragma unroll {unroll}', ind + 1)
-        self.emit(f'for (unsigned int s{k} = 0; s{k} < {N}u; ++s{k}) {{', ind + 1)
+        teamed = self.team > 1 and depth == 0
+        if teamed:
+            # the instance's team splits the outermost sample loop: member r takes samples r, r+TEAM, ...
+            # (each member still folds its own samples left to right; partial sums are combined below)
+            self.emit('#pragma unroll 1', ind + 1)
+            self.emit(f'for (unsigned int s{k} = team_rank; s{k} < {N}u; s{k} += {self.team}u) {{', ind + 1)
+        else:
+            self.emit(f'#pragma unroll {unroll}', ind + 1)
+            self.emit(f'for (unsigned int s{k} = 0; s{k} < {N}u; ++s{k}) {{', ind + 1)
         self.emit(f'const T x{st.bvar} = lo{k} + step{k} * ((T)s{k} + {literal("0.5", self.ctype)});', ind + 2)
         self.block(st.body, ind + 2, depth + 1)
         fixups = []
@@ -193,6 +203,9 @@ class Emitter:
                 body = self.ref(self.nodes[q].args[2], st.body.known)
                 self.emit(f'v{q} = v{q} + {body} * step{k};', ind + 2)
         self.emit('}', ind + 1)
+        if teamed:
+            for q in st.quads:
+                self.emit(f'v{q} = tegb_team_sum<T, {self.team}>(v{q});', ind + 1)
         for q in fixups:
             # skipped terms were `0 * step`: identical for every finite step; keeps NaN/inf steps poisonous
             self.emit(f'v{q} = v{q} + {literal("0", self.ctype)} * step{k};', ind + 1)
@@ -358,7 +371,8 @@ class Emitter:
         uparams = ', '.join([f'const T a{a}' for a in scal] + ['T* __restrict__ U'])
         outs_decl = (['T* __restrict__ partials'] if reduce_outputs
                      else [f'T* __restrict__ out{k}' for k in range(K)])
-        iparams = ', '.join([f'const T a{a}' for a in varying] + [f'T (&res)[{K}]'])
+        iparams = ', '.join(([] if self.team == 1 else ['const unsigned int team_rank']) +
+                            [f'const T a{a}' for a in varying] + [f'T (&res)[{K}]'])
         src: List[str] = []
         src.append(f'// generated by teg_b200.codegen for program "{self.dag.name}"  (precision {T}, {self.N} samples)')
         src.append('#include "teg_b200_runtime.cuh"')
@@ -385,7 +399,9 @@ class Emitter:
                    + ', '.join([f'a{a}' for a in scal] + ['U']) + ');')
         src.append('}')
         src.append('')
+        team = self.team
         if grid:
+            assert team == 1, 'render programs are thread-per-pixel'
             # pixel (nx, ny) -> instance nx * res_y + ny; box bounds from the two np.linspace edge tables
             mparams = ', '.join(['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
                                  'const int row0'] + outs_decl)
@@ -399,26 +415,36 @@ class Emitter:
         else:
             mparams = ', '.join([f'const T* __restrict__ in{a}' for a in arrs] + outs_decl + ['const long long n'])
             src.append(f'extern "C" __global__ void __launch_bounds__({self.block_size}) {name}_main({mparams}) {{')
-            src.append('    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;')
+            if team == 1:
+                src.append('    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;')
+                call = ', '.join([f'in{a}[i]' for a in varying] + ['res'])
+            else:
+                # TEAM threads per instance (a slice of a warp, a warp, or a whole block)
+                src.append('    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;')
+                src.append(f'    const long long i = gtid / {team};')
+                src.append(f'    const unsigned int team_rank = (unsigned int)(gtid % {team});')
+                call = ', '.join(['team_rank'] + [f'in{a}[i]' for a in varying] + ['res'])
             src.append('    const bool live = i < n;')
-            call = ', '.join([f'in{a}[i]' for a in varying] + ['res'])
         src.append(f'    T res[{K}];')
         if reduce_outputs:
             src.append(f'    for (int k = 0; k < {K}; k++) res[k] = {literal("0", T)};')
             src.append(f'    if (live) {name}_instance({call});')
+            if team > 1:
+                src.append(f'    if (team_rank != 0) {{ for (int k = 0; k < {K}; k++) res[k] = {literal("0", T)}; }}')
             src.append(f'    tegb_block_sum_store<T, {K}, {self.block_size}>(res, partials);')
         else:
             src.append('    if (!live) return;')
             src.append(f'    {name}_instance({call});')
+            guard = '' if team == 1 else 'if (team_rank == 0) '
             for k in range(K):
-                src.append(f'    out{k}[i] = res[{k}];')
+                src.append(f'    {guard}out{k}[i] = res[{k}];')
         src.append('}')
         src.append('#endif')
         text = '\n'.join(src) + '\n'
         return KernelSource(name=name, ctype=T, num_samples=self.N, source=text,
                             uniform_kernel=f'{name}_uniform', main_kernel=f'{name}_main',
                             n_uniform=nu, scalar_args=scal, array_args=arrs, grid_args=grid,
-                            n_outputs=K, block_size=self.block_size, reduce_outputs=bool(reduce_outputs),
+                            n_outputs=K, block_size=self.block_size, reduce_outputs=bool(reduce_outputs), team=self.team,
                             stats=dict(self.stats))
 
 

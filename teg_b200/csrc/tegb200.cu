@@ -223,6 +223,10 @@ extern "C" int tegb_program_create(tegb_module *m, const tegb_program_desc *desc
     if (desc->elem_size != 4 && desc->elem_size != 8) return fail(TEGB_ERR_INVALID, "elem_size must be 4 or 8");
     if (desc->n_outputs < 1 || desc->block_size < 32 || desc->block_size > 1024)
         return fail(TEGB_ERR_INVALID, "bad program description");
+    if (desc->team > 1 && ((desc->team & (desc->team - 1)) != 0 || desc->team > 1024 ||
+                           (desc->team > 32 && desc->team != desc->block_size) ||
+                           (desc->team <= 32 && desc->block_size % desc->team != 0)))
+        return fail(TEGB_ERR_INVALID, "bad team size");
     if (!drv::ready()) return fail(TEGB_ERR_NO_DEVICE, "CUDA driver unavailable: %s", drv::why.c_str());
     RT_CHECK(cudaSetDevice(device));
     RT_CHECK(cudaFree(0));      // make the primary context current for the driver calls below
@@ -342,7 +346,8 @@ extern "C" int tegb_program_launch(tegb_program *p, const double *scalars, const
     std::vector<void *> args;
     for (int i = 0; i < p->d.n_array_args; i++) { ins[i] = in_ptrs[i]; args.push_back(&ins[i]); }
     const unsigned bs = (unsigned)p->d.block_size;
-    const long long blocks = (n + bs - 1) / bs;
+    const long long team = p->d.team > 1 ? p->d.team : 1;
+    const long long blocks = (n * team + bs - 1) / bs;
     if (blocks > 2147483647LL) return fail(TEGB_ERR_INVALID, "too many instances for one launch");
     if (p->d.reduce_outputs) {
         rc = ensure_partials(p, (unsigned long long)blocks);

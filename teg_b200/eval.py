@@ -59,7 +59,7 @@ class CUDA_EvalMode(EvalMode):
 
     def __init__(self, expr, num_samples: int = 50, float_width: str = 'float', device: int = 0,
                  arglist: Sequence = (), name: str = 'teg_method', use_cache: bool = True,
-                 block_size: int = 128, **codegen_opts):
+                 block_size: int = 128, team='auto', **codegen_opts):
         super().__init__(name='CUDA')
         if float_width in ('single', 'f32', np.float32):
             float_width = 'float'
@@ -73,26 +73,54 @@ class CUDA_EvalMode(EvalMode):
         self.device = device
         self.use_cache = use_cache
         self.block_size = block_size
+        # team: threads cooperating on one instance.  1 = thread per instance (bit-exact w.r.t. the C backend:
+        # every sum is the reference's left fold).  'auto' keeps 1 unless the batch is too small to fill the
+        # GPU *and* each instance carries >= 4096 samples; then the outermost sample loop is split over a
+        # team and partial sums are combined in a fixed order (within 1e-5 / 1e-12 of the left fold).
+        assert team == 'auto' or (isinstance(team, int) and team >= 1 and team & (team - 1) == 0 and team <= 1024)
+        self.team = team
         self.codegen_opts = codegen_opts
         self.arglist: List[Tuple[str, Optional[float]]] = [
             (lab, self.program.defaults.get(lab)) for lab in self.program.args]
         self.out_size = len(self.dag.outputs)
         self.out_is_tuple = self.dag.out_is_tuple
         self._variants: Dict[tuple, Tuple[KernelSource, runtime.Program]] = {}
+        self._schedules: Dict[tuple, object] = {}
 
     # ------------------------------------------------------------------ compile
-    def kernel_source(self, array_args: Sequence[int], grid_args: Sequence[int] = (),
-                      reduce: bool = False) -> KernelSource:
-        varying = sorted(set(array_args) | set(grid_args))
-        sch = make_schedule(self.dag, varying)
-        return generate(sch, self.float_width, self.num_samples, grid_args=list(grid_args),
-                        reduce_outputs=reduce, block_size=self.block_size, **self.codegen_opts)
+    def schedule(self, array_args: Sequence[int], grid_args: Sequence[int] = ()):
+        key = tuple(sorted(set(array_args) | set(grid_args)))
+        if key not in self._schedules:
+            self._schedules[key] = make_schedule(self.dag, list(key))
+        return self._schedules[key]
 
-    def compiled(self, array_args: Sequence[int], grid_args: Sequence[int] = (), reduce: bool = False):
-        key = (tuple(sorted(array_args)), tuple(grid_args), bool(reduce))
+    def pick_team(self, n: int, array_args: Sequence[int]) -> int:
+        if self.team != 'auto':
+            return int(self.team)
+        depth = self.schedule(array_args).loop_depth()
+        if depth == 0 or n >= 32768 or float(self.num_samples) ** depth < 4096:
+            return 1
+        cap = 1
+        while cap < self.num_samples and cap < 1024:
+            cap *= 2
+        team = 1
+        while team * 2 <= cap and n * team < 148 * 1024:
+            team *= 2
+        return team
+
+    def kernel_source(self, array_args: Sequence[int], grid_args: Sequence[int] = (),
+                      reduce: bool = False, team: int = 1) -> KernelSource:
+        sch = self.schedule(array_args, grid_args)
+        block = team if team > 32 else self.block_size
+        return generate(sch, self.float_width, self.num_samples, grid_args=list(grid_args),
+                        reduce_outputs=reduce, block_size=block, team=team, **self.codegen_opts)
+
+    def compiled(self, array_args: Sequence[int], grid_args: Sequence[int] = (), reduce: bool = False,
+                 team: int = 1):
+        key = (tuple(sorted(array_args)), tuple(grid_args), bool(reduce), int(team))
         hit = self._variants.get(key)
         if hit is None:
-            ks = self.kernel_source(array_args, grid_args, reduce)
+            ks = self.kernel_source(array_args, grid_args, reduce, team)
             mod = runtime.Module(ks.source, use_cache=self.use_cache)
             prog = runtime.Program(mod, ks, device=self.device)
             hit = (ks, prog)
@@ -131,7 +159,8 @@ class CUDA_EvalMode(EvalMode):
             assert n is None or n == ln, 'all array bindings must have the same length'
             n = ln
         array_args = [i for i, f in enumerate(is_arr) if f]
-        ks, prog = self.compiled(array_args, reduce=reduce)
+        team = self.pick_team(1 if n is None else n, array_args)
+        ks, prog = self.compiled(array_args, reduce=reduce, team=team)
         scalars = [float(args[a]) for a in ks.scalar_args]
         if any_torch:
             return self._eval_torch(ks, prog, args, scalars, n, reduce)

@@ -54,6 +54,34 @@ static __device__ __forceinline__ void tegb_block_sum_store(const T (&v)[K], T* 
         partials[(unsigned long long)threadIdx.x * nblk + blk] = t;
     }
 }
+
+/* Sum over the TEAM threads that cooperate on one instance (TEAM consecutive threads, TEAM a power of two).
+ * TEAM <= 32: xor butterfly inside the team's lanes.  Every stage adds the same two numbers on both partners,
+ * so all members end with the same bits, and the combination order is fixed: deterministic.
+ * TEAM  > 32: the team is the whole block; warp butterflies, then every thread adds the per-warp values in
+ * warp order.  Reached by all members together: guards that enclose a team loop depend only on per-instance
+ * values, which are identical across the team. */
+template <typename T, int TEAM>
+static __device__ __forceinline__ T tegb_team_sum(T v) {
+    if (TEAM <= 32) {
+        const unsigned lane = threadIdx.x & 31u;
+        const unsigned mask = (TEAM == 32) ? 0xffffffffu : (((1u << (TEAM & 31)) - 1u) << (lane & ~(unsigned)(TEAM - 1)));
+#pragma unroll
+        for (int off = TEAM / 2; off > 0; off >>= 1) v = v + __shfl_xor_sync(mask, v, off);
+        return v;
+    } else {
+        __shared__ T sm[32];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
+        __syncthreads();                       /* previous use of sm is over */
+        if ((threadIdx.x & 31u) == 0) sm[threadIdx.x >> 5] = v;
+        __syncthreads();
+        T t = sm[0];
+#pragma unroll
+        for (int w = 1; w < TEAM / 32; w++) t = t + sm[w];
+        return t;
+    }
+}
 #else
 #  ifndef TEGB_FN
 #    error "teg_b200 kernels are CUDA-only: there is no host evaluation path"

@@ -22,7 +22,7 @@ class ProgramDesc(ctypes.Structure):
     _fields_ = [('uniform_kernel', ctypes.c_char_p), ('main_kernel', ctypes.c_char_p),
                 ('uniform_symbol', ctypes.c_char_p), ('elem_size', ctypes.c_int), ('n_uniform', ctypes.c_int),
                 ('n_scalar_args', ctypes.c_int), ('n_array_args', ctypes.c_int), ('n_grid_args', ctypes.c_int),
-                ('n_outputs', ctypes.c_int), ('block_size', ctypes.c_int), ('reduce_outputs', ctypes.c_int)]
+                ('n_outputs', ctypes.c_int), ('block_size', ctypes.c_int), ('reduce_outputs', ctypes.c_int), ('team', ctypes.c_int)]
 
 
 class Grid(ctypes.Structure):
@@ -176,7 +176,8 @@ class Program:
         self._names = (ks.uniform_kernel.encode(), ks.main_kernel.encode(), b'tegU')
         desc = ProgramDesc(self._names[0], self._names[1], self._names[2], self.elem_size, ks.n_uniform,
                            len(ks.scalar_args), len(ks.array_args), len(getattr(ks, 'grid_args', ())),
-                           ks.n_outputs, ks.block_size, int(getattr(ks, 'reduce_outputs', False)))
+                           ks.n_outputs, ks.block_size, int(getattr(ks, 'reduce_outputs', False)),
+                           int(getattr(ks, 'team', 1)))
         self.handle = ctypes.c_void_p()
         check(L.tegb_program_create(module.handle, ctypes.byref(desc), device, ctypes.byref(self.handle)))
 

@@ -85,6 +85,18 @@ class Schedule:
     def guards(self) -> List[IfGroup]:
         return [s for s in self.main.walk() if isinstance(s, IfGroup)]
 
+    def loop_depth(self) -> int:
+        """Deepest nesting of sample loops (0 = the program has no integral left)."""
+        def depth(b: Block) -> int:
+            d = 0
+            for st in b.stmts:
+                if isinstance(st, LoopGroup):
+                    d = max(d, 1 + depth(st.body))
+                elif isinstance(st, IfGroup):
+                    d = max(d, depth(st.then_block), depth(st.else_block))
+            return d
+        return depth(self.main)
+
 
 class Scheduler:
     def __init__(self, dag: Dag, array_args: Sequence[int], spec_limit: int = 6,

@@ -19,15 +19,15 @@ EXACT_SCENES = [s for s in SCENE_SAMPLES if not s.startswith('circle')]
 LIBM_SCENES = ['circle', 'circle_dt']
 
 
-def _run_both(scene, dtype, res=(64, 64), n=4096):
+def _run_both(scene, dtype, res=(64, 64), n=4096, team=1, ns=None):
     from oracle import Oracle
     from teg_b200 import CUDA_EvalMode
     prog = load_program(scene)
-    ns = SCENE_SAMPLES[scene]
+    ns = SCENE_SAMPLES[scene] if ns is None else ns
     vals = scene_values(scene, res=res, n=n)
     inputs = bind(prog.args, vals)
     want = Oracle(program_text(scene)).eval(inputs, ns, dtype, threads=8)
-    mode = CUDA_EvalMode(prog, num_samples=ns, float_width='float' if dtype == np.float32 else 'double')
+    mode = CUDA_EvalMode(prog, num_samples=ns, float_width='float' if dtype == np.float32 else 'double', team=team)
     got = mode.eval(dict(zip(prog.args, inputs)))
     got = np.asarray(got).reshape(want.shape)
     return got, want
@@ -176,3 +176,39 @@ def test_in_kernel_gradient_sum_matches_per_pixel_gradients(cuda_device):
     m64 = CUDA_EvalMode(prog, num_samples=16, float_width='double')
     one = {lab: (float(np.ravel(v)[9000]) if np.ndim(v) else v) for lab, v in b.items()}
     assert np.allclose(m64.eval(one, reduce=True), np.asarray(m64.eval(one)), rtol=0, atol=0)
+
+
+# ---- sample-parallel teams: the outermost loop of each instance split over TEAM threads ------------------
+TEAM_CASES = [('tri_primal', 16, 2), ('tri_primal', 16, 16), ('tri_grad', 16, 8), ('nested2d_value', 64, 32),
+              ('nested2d_grad', 64, 32), ('nested3d_value', 16, 16), ('nested3d_grad', 16, 4),
+              ('readme_primal', 50, 64), ('shaded_grad', 16, 128), ('nested2d_value', 64, 1024),
+              ('bilinear_lerp_grad', 20, 32)]
+
+
+@pytest.mark.parametrize('dtype,tol', [(np.float32, 1e-5), (np.float64, 1e-12)], ids=['f32', 'f64'])
+@pytest.mark.parametrize('scene,ns,team', TEAM_CASES)
+def test_team_kernels_within_stated_tolerance(cuda_device, scene, ns, team, dtype, tol):
+    """Teams re-associate the outermost sum only (fixed order): 1e-5 (fp32) / 1e-12 (fp64) relative to
+    max(|ref|, instance scale) -- the north-star tolerance; sample classification stays bit-identical."""
+    n = 96 if team >= 128 else 1024
+    got, want = _run_both(scene, dtype, res=(32, 32), n=n, team=team, ns=ns)
+    scale = np.maximum(np.abs(want), np.max(np.abs(want), axis=1, keepdims=True) * 1e-2 + 1e-30)
+    err = np.abs(got - want) / scale
+    assert np.nanmax(err) <= tol, f'{scene} team={team}: max scaled error {np.nanmax(err):.3g}'
+    # determinism
+    got2, _ = _run_both(scene, dtype, res=(32, 32), n=n, team=team, ns=ns)
+    assert np.array_equal(got, got2, equal_nan=True)
+
+
+def test_auto_team_policy_and_single_instance_big_integral(cuda_device):
+    """One instance, 2-D integral at 2000 samples per axis (4e6 samples): 'auto' picks a block team; the
+    value matches the oracle's left fold to the stated tolerance."""
+    from oracle import Oracle
+    from teg_b200 import CUDA_EvalMode
+    prog = load_program('nested2d_value')
+    vals = dict(zip(prog.args, [0.0, 1.0, 0.0, 1.0, 0.3, -0.7, 0.2, -0.5, 0.4, 0.1]))
+    mode = CUDA_EvalMode(prog, num_samples=2000)
+    assert mode.pick_team(1, []) == 1024 and mode.pick_team(1 << 20, [0]) == 1
+    got = mode.eval(vals)
+    want = float(Oracle(program_text('nested2d_value')).eval(list(vals.values()), 2000, np.float32)[0, 0])
+    assert isinstance(got, float) and abs(got - want) <= 1e-5 * abs(want)
