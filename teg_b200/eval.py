@@ -59,7 +59,7 @@ class CUDA_EvalMode(EvalMode):
 
     def __init__(self, expr, num_samples: int = 50, float_width: str = 'float', device: int = 0,
                  arglist: Sequence = (), name: str = 'teg_method', use_cache: bool = True,
-                 block_size: int = 128, team='auto', **codegen_opts):
+                 block_size: int = 128, team=1, **codegen_opts):
         super().__init__(name='CUDA')
         if float_width in ('single', 'f32', np.float32):
             float_width = 'float'
@@ -73,10 +73,12 @@ class CUDA_EvalMode(EvalMode):
         self.device = device
         self.use_cache = use_cache
         self.block_size = block_size
-        # team: threads cooperating on one instance.  1 = thread per instance (bit-exact w.r.t. the C backend:
-        # every sum is the reference's left fold).  'auto' keeps 1 unless the batch is too small to fill the
-        # GPU *and* each instance carries >= 4096 samples; then the outermost sample loop is split over a
-        # team and partial sums are combined in a fixed order (within 1e-5 / 1e-12 of the left fold).
+        # team: threads cooperating on one instance.  1 (default) = thread per instance: every sum is the
+        # reference's left fold, results are bit-exact w.r.t. the C backend.  'auto' keeps 1 unless the batch
+        # is too small to fill the GPU *and* each instance carries >= 4096 samples; then the outermost sample
+        # loop is split over a team (slice of a warp / warp / block) and the partial sums are combined in a
+        # fixed order.  That re-associates one sum: deterministic, but only as close to the C backend as the
+        # C backend's own left fold is accurate (~N*eps/2 relative in the working precision).
         assert team == 'auto' or (isinstance(team, int) and team >= 1 and team & (team - 1) == 0 and team <= 1024)
         self.team = team
         self.codegen_opts = codegen_opts

@@ -91,15 +91,21 @@ def test_cuda_replays_reference_suite(cuda_device):
     for k, c in enumerate(CALLS):
         key = (c['program'], c['num_samples'])
         prog = Program.loads(SUITE['programs'][c['program']])
-        if _work(prog, c['num_samples']) > 100 * MAX_WORK:
-            continue            # single-instance 1e8+-sample integrals: covered once the sample-parallel kernel lands
+        heavy = _work(prog, c['num_samples']) > MAX_WORK
+        key = key + (heavy,)
         if c['test'] in UNDEFINED_IN_REFERENCE:
             with pytest.raises(AssertionError):
                 CUDA_EvalMode(prog, num_samples=c['num_samples'])
             continue
         if key not in modes:
-            modes[key] = CUDA_EvalMode(prog, num_samples=c['num_samples'])
+            # light calls: thread per instance = the reference's left fold, compared at the printed 6 digits.
+            # heavy calls (1e8..4e8 samples for ONE instance, the finite-difference helper tests/test.py:74-97):
+            # a block team splits the outermost loop; the reference's own fp32 left fold over 1e4 terms is
+            # itself only good to ~N*eps/2 = 3e-4 relative, which bounds how close any re-association can be
+            # (the reference tests compare these values at places=2).
+            modes[key] = CUDA_EvalMode(prog, num_samples=c['num_samples'], team='auto' if heavy else 1)
         got = modes[key].eval(c['bindings'])
-        if not _close(got, c['result']):
+        ok = _close(got, c['result']) or (heavy and np.allclose(got, c['result'], rtol=3e-4, atol=1e-6))
+        if not ok:
             bad.append((k, c['test'], got, c['result']))
     assert not bad, f'{len(bad)} of {len(CALLS)} calls differ, first: {bad[:3]}'
