@@ -63,6 +63,10 @@ typedef struct {
                                      n_outputs per-component sums over all instances to out_ptrs[0] (device) */
     int team;                     /* threads cooperating on one instance (power of two, 1 = thread per instance);
                                      > 32 means one block of `team` threads per instance (block_size == team) */
+    int grouped;                  /* 1: grouped render program (tegb_render_groups_launch): the scalar arguments are
+                                     per-group arrays, the uniform table has one row per group */
+    int n_pixel_args;             /* grouped programs: arguments read from images indexed by pixel */
+    int accumulate;               /* grouped programs: outputs are added into the images in out_ptrs */
 } tegb_program_desc;
 
 /* pixel grid of tests/plot.py:11-16: np.linspace(lo, hi, res+1) per axis, instance = nx * res_y + ny */
@@ -108,6 +112,19 @@ int tegb_program_eval_host(tegb_program *p, const double *scalars, const void *c
  * index; out_ptrs[k] receive (row_end-row_begin)*res_y elements. */
 int tegb_render_launch(tegb_program *p, const double *scalars, const tegb_grid *grid,
                        void *const *out_ptrs, void *stream);
+
+/* Grouped render: groups [group_begin, group_begin + group_count) (e.g. triangles) are evaluated over their
+ * own pixel windows in ONE launch.  group_ptrs[n_scalar_args]: device arrays with one value per group
+ * (indexed by absolute group number).  windows: device int32 [n_groups][4] = (row_begin, row_end, col_begin,
+ * col_end) in pixels of the full grid; rows are clipped to the grid's [row_begin, row_end) band.
+ * max_rows / max_cols: upper bounds of any window's height / width (launch geometry).  pixel_ptrs
+ * [n_pixel_args]: device images of the band (row-major, (row - grid.row_begin) * res_y + col).
+ * Outputs: images of the band (assigned, or added to when the program accumulates -- then the windows of
+ * one launch must not overlap), or for reduce_outputs programs out_ptrs[0] -> [group_count][n_outputs]
+ * sums over each group's window (row j of the result = group group_begin + j). */
+int tegb_render_groups_launch(tegb_program *p, const void *const *group_ptrs, int group_begin, int group_count,
+                              const tegb_grid *grid, const int32_t *windows, int max_rows, int max_cols,
+                              const void *const *pixel_ptrs, void *const *out_ptrs, void *stream);
 
 /* kernels launched by this library since load (for accounting) */
 int64_t tegb_launch_count(void);

@@ -44,6 +44,8 @@ VARIANTS = {
     'raster_theta': [('f32', 10), ('f64', 10)],
     'shaded_primal': [('f32', 16), ('f64', 16)],
     'shaded_grad': [('f32', 16), ('f64', 16)],
+    'tri_color_primal': [('f32', 16), ('f64', 16)],
+    'tri_color_grad': [('f32', 16), ('f64', 16)],
     'nested2d_value': [('f32', 16), ('f32', 64), ('f64', 16)],
     'nested2d_grad': [('f32', 16), ('f32', 64), ('f64', 16)],
     'nested3d_value': [('f32', 16), ('f64', 16)],

@@ -94,6 +94,36 @@ def shaded_grad():
     return _grad(primal, verts + shader, out=t['Tup'](dL)), [dL] + box + verts + shader
 
 
+def _colored_triangle():
+    """config 5 building block: one flat-coloured triangle, `col` inside, 0 outside (SURVEY §8(d) cfg 5)."""
+    t = _teg()
+    Var, TegVar, Teg, IfElse = t['Var'], t['TegVar'], t['Teg'], t['IfElse']
+    x, y = TegVar('x'), TegVar('y')
+    box = [Var('x_lb'), Var('x_ub'), Var('y_lb'), Var('y_ub')]
+    vs = [(Var(f'px{i}'), Var(f'py{i}')) for i in range(3)]
+    col = Var('col')
+
+    def edge(a, b):
+        return (b[0] - a[0]) * (y - a[1]) - (b[1] - a[1]) * (x - a[0])
+
+    inside = (edge(vs[0], vs[1]) > 0) & (edge(vs[1], vs[2]) > 0) & (edge(vs[2], vs[0]) > 0)
+    primal = Teg(box[0], box[1], Teg(box[2], box[3], IfElse(inside, col, 0), y), x)
+    return primal, box, [v for p in vs for v in p], col
+
+
+def tri_color_primal():
+    primal, box, verts, col = _colored_triangle()
+    return primal, box + verts + [col]
+
+
+def tri_color_grad():
+    """reverse derivative w.r.t. the 6 vertex coordinates and the colour, with an upstream per-pixel dL"""
+    t = _teg()
+    primal, box, verts, col = _colored_triangle()
+    dL = t['Var']('dL')
+    return _grad(primal, verts + [col], out=t['Tup'](dL)), [dL] + box + verts + [col]
+
+
 def raster_theta():
     """tests/rasterize.py:22-40 (corner (0.7,0.7)) with TegVars and pixel-box Vars, FwdDeriv wrt theta."""
     t = _teg()
@@ -270,6 +300,8 @@ SCENES: Dict[str, Callable[[], Tuple[object, List]]] = {
     'raster_theta': raster_theta,
     'shaded_primal': shaded_primal,
     'shaded_grad': shaded_grad,
+    'tri_color_primal': tri_color_primal,
+    'tri_color_grad': tri_color_grad,
     'nested2d_value': nested2d_value,
     'nested2d_grad': nested2d_grad,
     'nested3d_value': nested3d_value,

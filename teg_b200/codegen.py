@@ -61,7 +61,10 @@ class KernelSource:
     block_size: int
     reduce_outputs: bool            # main kernel writes per-block partial sums instead of per-instance outputs
     team: int                       # threads cooperating on one instance (1 = thread per instance)
-    stats: Dict[str, float]
+    grouped: bool = False           # grouped render launch: per-group scalar arguments + pixel windows
+    pixel_args: List[int] = None    # arguments read from pixel-indexed images (grouped launches)
+    accumulate: bool = False        # outputs are added into images
+    stats: Dict[str, float] = None
 
     @property
     def key(self) -> str:
@@ -346,12 +349,18 @@ class Emitter:
             self.emit(f'res[{k}] = {self.ref(o, self.sch.main.known)};', 1)
         return self.lines
 
-    def generate(self, grid_args: Sequence[int] = (), reduce_outputs: bool = False) -> KernelSource:
+    def generate(self, grid_args: Sequence[int] = (), reduce_outputs: bool = False, grouped: bool = False,
+                 pixel_args: Sequence[int] = (), accumulate: bool = False) -> KernelSource:
         """grid_args: argument indices of (x_lb, x_ub, y_lb, y_ub) when they are generated from the pixel
         index (render programs, tests/plot.py:8-29) instead of being streamed from per-instance arrays.
         reduce_outputs: instead of one output stream per component, every block sums its instances'
-        results in a fixed order and writes one partial per component (``partials[k * gridsize + block]``);
-        the runtime adds the partials (reverse-mode gradients w.r.t. shared parameters)."""
+        results in a fixed order and writes one partial per component; the runtime adds the partials
+        (reverse-mode gradients w.r.t. shared parameters).
+        grouped (render programs only): the launch covers G *groups* (e.g. triangles), each with its own
+        values of the scalar arguments and its own window of pixels; launch-invariant values become one
+        table row per group (global memory, staged through shared memory per block) instead of the
+        constant bank.  pixel_args: arguments read from images indexed by pixel (an upstream dL).
+        accumulate: outputs are added into images (groups of one launch must not overlap)."""
         sch = self.sch
         T = self.ctype
         name = self.name
@@ -359,28 +368,37 @@ class Emitter:
         nu = max(1, len(sch.uniform_slots))
         scal = list(sch.scalar_args)
         grid = list(grid_args)
-        assert all(g in sch.array_args for g in grid), 'grid arguments must be scheduled as per-instance'
+        pix = list(pixel_args)
+        assert all(g in sch.array_args for g in grid + pix), 'grid / pixel arguments must be scheduled as per-instance'
         assert not grid or len(grid) == 4, 'a render program takes exactly x_lb, x_ub, y_lb, y_ub on the grid'
-        arrs = [a for a in sch.array_args if a not in grid]
+        assert not grouped or grid, 'grouped launches are render launches'
+        assert not pix or grouped, 'pixel-indexed arguments need a grouped render launch'
+        arrs = [a for a in sch.array_args if a not in grid and a not in pix]
         assert not (grid and arrs), 'render programs cannot also stream per-instance arrays'
         used_in = {self.nodes[i].attr for i in sch.uniform_nodes if self.nodes[i].op == 'in'}
         uni = self.uniform_body()
         main = self.main_body()
-        varying = list(sch.array_args)       # instance-function value parameters (arrays and grid alike)
+        varying = list(sch.array_args)       # instance-function value parameters (arrays, grid, pixel alike)
+        team = self.team
+        bs = self.block_size
 
-        uparams = ', '.join([f'const T a{a}' for a in scal] + ['T* __restrict__ U'])
-        outs_decl = (['T* __restrict__ partials'] if reduce_outputs
-                     else [f'T* __restrict__ out{k}' for k in range(K)])
-        iparams = ', '.join(([] if self.team == 1 else ['const unsigned int team_rank']) +
+        ubody_params = ', '.join([f'const T a{a}' for a in scal] + ['T* __restrict__ U'])
+        if reduce_outputs:
+            outs_decl = ['T* __restrict__ partials']
+        else:
+            outs_decl = [f'T* __restrict__ out{k}' for k in range(K)]
+        iparams = ', '.join((['const T* __restrict__ tegU'] if grouped else []) +
+                            ([] if team == 1 else ['const unsigned int team_rank']) +
                             [f'const T a{a}' for a in varying] + [f'T (&res)[{K}]'])
         src: List[str] = []
         src.append(f'// generated by teg_b200.codegen for program "{self.dag.name}"  (precision {T}, {self.N} samples)')
         src.append('#include "teg_b200_runtime.cuh"')
         src.append(f'typedef {T} T;')
         src.append(f'#define TEGB_NUM_UNIFORM {nu}')
-        src.append('TEGB_UNIFORM_TABLE(T, tegU, TEGB_NUM_UNIFORM);')
+        if not grouped:
+            src.append('TEGB_UNIFORM_TABLE(T, tegU, TEGB_NUM_UNIFORM);')
         src.append('')
-        src.append(f'TEGB_FN void {name}_uniform_body({uparams}) {{')
+        src.append(f'TEGB_FN void {name}_uniform_body({ubody_params}) {{')
         for a in scal:
             if a not in used_in:
                 src.append(f'    (void)a{a};')
@@ -394,65 +412,125 @@ class Emitter:
         src.append('}')
         src.append('')
         src.append('#ifdef __CUDACC__')
-        src.append(f'extern "C" __global__ void {name}_uniform({uparams}) {{')
-        src.append(f'    if (blockIdx.x == 0 && threadIdx.x == 0) {name}_uniform_body('
-                   + ', '.join([f'a{a}' for a in scal] + ['U']) + ');')
-        src.append('}')
-        src.append('')
-        team = self.team
-        if grid:
+        zero = literal('0', T)
+        if grouped:
             assert team == 1, 'render programs are thread-per-pixel'
-            # pixel (nx, ny) -> instance nx * res_y + ny; box bounds from the two np.linspace edge tables
+            uparams = ', '.join([f'const T* __restrict__ g{a}' for a in scal] +
+                                ['const int group_begin', 'const int group_count', 'T* __restrict__ U'])
+            src.append(f'extern "C" __global__ void {name}_uniform({uparams}) {{')
+            src.append('    const int j = blockIdx.x * blockDim.x + threadIdx.x;')
+            src.append('    if (j >= group_count) return;')
+            src.append('    const int g = group_begin + j;')
+            src.append(f'    {name}_uniform_body(' + ', '.join([f'g{a}[g]' for a in scal] +
+                                                             ['U + (size_t)g * TEGB_NUM_UNIFORM']) + ');')
+            src.append('}')
+            src.append('')
             mparams = ', '.join(['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
-                                 'const int row0'] + outs_decl)
-            src.append(f'extern "C" __global__ void __launch_bounds__({self.block_size}) {name}_main({mparams}) {{')
-            src.append('    const int ny = blockIdx.x * blockDim.x + threadIdx.x;')
-            src.append('    const bool live = ny < res_y;')
-            src.append('    const int nx = row0 + blockIdx.y;')
-            src.append('    const long long i = (long long)blockIdx.y * res_y + ny;')
-            loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye[ny]', grid[3]: 'ye[ny + 1]'}
-            call = ', '.join([loads[a] for a in varying] + ['res'])
-        else:
-            mparams = ', '.join([f'const T* __restrict__ in{a}' for a in arrs] + outs_decl + ['const long long n'])
-            src.append(f'extern "C" __global__ void __launch_bounds__({self.block_size}) {name}_main({mparams}) {{')
-            if team == 1:
-                src.append('    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;')
-                call = ', '.join([f'in{a}[i]' for a in varying] + ['res'])
+                                 'const int row0', 'const int row1', 'const int* __restrict__ win',
+                                 'const int group_begin', 'const T* __restrict__ Utab'] +
+                                [f'const T* __restrict__ pix{a}' for a in pix] + outs_decl)
+            src.append(f'extern "C" __global__ void __launch_bounds__({bs}) {name}_main({mparams}) {{')
+            src.append('    // block (bx, by, bz): group group_begin + bz, row by of its window, columns [bx*B, bx*B + B)')
+            src.append('    const int g = group_begin + blockIdx.z;')
+            src.append('    const int w_r0 = max(win[4 * g + 0], row0), w_r1 = min(win[4 * g + 1], row1);')
+            src.append('    const int w_c0 = win[4 * g + 2], w_c1 = win[4 * g + 3];')
+            src.append('    const int nx = w_r0 + blockIdx.y;')
+            src.append('    const int ny = w_c0 + blockIdx.x * blockDim.x + threadIdx.x;')
+            src.append('    const bool block_live = nx < w_r1 && (w_c0 + (int)(blockIdx.x * blockDim.x)) < w_c1;')
+            if reduce_outputs:
+                src.append('    const unsigned long long tiles = (unsigned long long)gridDim.x * gridDim.y;')
+                src.append('    const unsigned long long tile = (unsigned long long)blockIdx.y * gridDim.x + blockIdx.x;')
+                src.append(f'    T* gp = partials + (unsigned long long)blockIdx.z * {K} * tiles;')
+                src.append('    if (!block_live) {')
+                src.append(f'        if (threadIdx.x < {K}) gp[threadIdx.x * tiles + tile] = {zero};')
+                src.append('        return;')
+                src.append('    }')
             else:
-                # TEAM threads per instance (a slice of a warp, a warp, or a whole block)
-                src.append('    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;')
-                src.append(f'    const long long i = gtid / {team};')
-                src.append(f'    const unsigned int team_rank = (unsigned int)(gtid % {team});')
-                call = ', '.join(['team_rank'] + [f'in{a}[i]' for a in varying] + ['res'])
-            src.append('    const bool live = i < n;')
-        src.append(f'    T res[{K}];')
-        if reduce_outputs:
-            src.append(f'    for (int k = 0; k < {K}; k++) res[k] = {literal("0", T)};')
+                src.append('    if (!block_live) return;')
+            src.append('    __shared__ T sU[TEGB_NUM_UNIFORM];')
+            src.append('    for (int j = threadIdx.x; j < TEGB_NUM_UNIFORM; j += blockDim.x) '
+                       'sU[j] = Utab[(size_t)g * TEGB_NUM_UNIFORM + j];')
+            src.append('    __syncthreads();')
+            src.append('    const bool live = ny < w_c1;')
+            src.append('    const long long i = (long long)(nx - row0) * res_y + ny;')
+            loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye[ny]', grid[3]: 'ye[ny + 1]'}
+            for a in pix:
+                loads[a] = f'pix{a}[i]'
+            call = ', '.join(['sU'] + [loads[a] for a in varying] + ['res'])
+            src.append(f'    T res[{K}];')
+            src.append(f'    for (int k = 0; k < {K}; k++) res[k] = {zero};')
             src.append(f'    if (live) {name}_instance({call});')
-            if team > 1:
-                src.append(f'    if (team_rank != 0) {{ for (int k = 0; k < {K}; k++) res[k] = {literal("0", T)}; }}')
-            src.append(f'    tegb_block_sum_store<T, {K}, {self.block_size}>(res, partials);')
+            if reduce_outputs:
+                src.append(f'    tegb_block_sum_store<T, {K}, {bs}>(res, gp, tiles, tile);')
+            elif accumulate:
+                for k in range(K):
+                    src.append(f'    if (live) out{k}[i] = out{k}[i] + res[{k}];')
+            else:
+                for k in range(K):
+                    src.append(f'    if (live) out{k}[i] = res[{k}];')
+            src.append('}')
         else:
-            src.append('    if (!live) return;')
-            src.append(f'    {name}_instance({call});')
-            guard = '' if team == 1 else 'if (team_rank == 0) '
-            for k in range(K):
-                src.append(f'    {guard}out{k}[i] = res[{k}];')
-        src.append('}')
+            src.append(f'extern "C" __global__ void {name}_uniform({ubody_params}) {{')
+            src.append(f'    if (blockIdx.x == 0 && threadIdx.x == 0) {name}_uniform_body('
+                       + ', '.join([f'a{a}' for a in scal] + ['U']) + ');')
+            src.append('}')
+            src.append('')
+            if grid:
+                assert team == 1, 'render programs are thread-per-pixel'
+                # pixel (nx, ny) -> instance nx * res_y + ny; box bounds from the two np.linspace edge tables
+                mparams = ', '.join(['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
+                                     'const int row0'] + outs_decl)
+                src.append(f'extern "C" __global__ void __launch_bounds__({bs}) {name}_main({mparams}) {{')
+                src.append('    const int ny = blockIdx.x * blockDim.x + threadIdx.x;')
+                src.append('    const bool live = ny < res_y;')
+                src.append('    const int nx = row0 + blockIdx.y;')
+                src.append('    const long long i = (long long)blockIdx.y * res_y + ny;')
+                loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye[ny]', grid[3]: 'ye[ny + 1]'}
+                call = ', '.join([loads[a] for a in varying] + ['res'])
+            else:
+                mparams = ', '.join([f'const T* __restrict__ in{a}' for a in arrs] + outs_decl + ['const long long n'])
+                src.append(f'extern "C" __global__ void __launch_bounds__({bs}) {name}_main({mparams}) {{')
+                if team == 1:
+                    src.append('    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;')
+                    call = ', '.join([f'in{a}[i]' for a in varying] + ['res'])
+                else:
+                    # TEAM threads per instance (a slice of a warp, a warp, or a whole block)
+                    src.append('    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;')
+                    src.append(f'    const long long i = gtid / {team};')
+                    src.append(f'    const unsigned int team_rank = (unsigned int)(gtid % {team});')
+                    call = ', '.join(['team_rank'] + [f'in{a}[i]' for a in varying] + ['res'])
+                src.append('    const bool live = i < n;')
+            src.append(f'    T res[{K}];')
+            if reduce_outputs:
+                src.append(f'    for (int k = 0; k < {K}; k++) res[k] = {zero};')
+                src.append(f'    if (live) {name}_instance({call});')
+                if team > 1:
+                    src.append(f'    if (team_rank != 0) {{ for (int k = 0; k < {K}; k++) res[k] = {zero}; }}')
+                src.append(f'    tegb_block_sum_store<T, {K}, {bs}>(res, partials);')
+            else:
+                src.append('    if (!live) return;')
+                src.append(f'    {name}_instance({call});')
+                guard = '' if team == 1 else 'if (team_rank == 0) '
+                for k in range(K):
+                    src.append(f'    {guard}out{k}[i] = res[{k}];')
+            src.append('}')
         src.append('#endif')
         text = '\n'.join(src) + '\n'
         return KernelSource(name=name, ctype=T, num_samples=self.N, source=text,
                             uniform_kernel=f'{name}_uniform', main_kernel=f'{name}_main',
                             n_uniform=nu, scalar_args=scal, array_args=arrs, grid_args=grid,
-                            n_outputs=K, block_size=self.block_size, reduce_outputs=bool(reduce_outputs), team=self.team,
+                            n_outputs=K, block_size=bs, reduce_outputs=bool(reduce_outputs), team=team,
+                            grouped=bool(grouped), pixel_args=pix, accumulate=bool(accumulate),
                             stats=dict(self.stats))
 
 
 def generate(sch: Schedule, ctype: str = 'float', num_samples: int = 50, name: Optional[str] = None,
-             grid_args: Sequence[int] = (), reduce_outputs: bool = False, **opts) -> KernelSource:
+             grid_args: Sequence[int] = (), reduce_outputs: bool = False, grouped: bool = False,
+             pixel_args: Sequence[int] = (), accumulate: bool = False, **opts) -> KernelSource:
     name = name or _c_ident(sch.dag.name)
-    return Emitter(sch, ctype, num_samples, name, **opts).generate(grid_args=grid_args,
-                                                                   reduce_outputs=reduce_outputs)
+    return Emitter(sch, ctype, num_samples, name, **opts).generate(
+        grid_args=grid_args, reduce_outputs=reduce_outputs, grouped=grouped, pixel_args=pixel_args,
+        accumulate=accumulate)
 
 
 def _c_ident(s: str) -> str:

@@ -207,6 +207,13 @@ struct tegb_program {
     // staging for tegb_program_eval_host
     std::vector<void *> d_in, d_out;
     int64_t cap = 0;
+    // grouped programs: one uniform-table row per group
+    void *d_utab = nullptr;
+    size_t utab_bytes = 0;
+    // scalars of the last uniform prologue: identical scalars => the published table is still valid
+    std::vector<double> last_scalars;
+    bool uniform_valid = false;
+    CUstream last_stream = nullptr;
     // per-block partial sums of reduce_outputs programs
     void *d_partials = nullptr;
     size_t partials_bytes = 0;
@@ -240,10 +247,12 @@ extern "C" int tegb_program_create(tegb_module *m, const tegb_program_desc *desc
     if (r != CUDA_SUCCESS) return bail(fail(TEGB_ERR_CUDA, "kernel %s: %s", desc->uniform_kernel, drv::errstr(r)));
     r = drv::ModuleGetFunction(&p->f_main, p->mod, desc->main_kernel);
     if (r != CUDA_SUCCESS) return bail(fail(TEGB_ERR_CUDA, "kernel %s: %s", desc->main_kernel, drv::errstr(r)));
-    r = drv::ModuleGetGlobal(&p->u_const, &p->u_const_bytes, p->mod, desc->uniform_symbol);
-    if (r != CUDA_SUCCESS) return bail(fail(TEGB_ERR_CUDA, "symbol %s: %s", desc->uniform_symbol, drv::errstr(r)));
     size_t want = (size_t)(desc->n_uniform > 0 ? desc->n_uniform : 1) * desc->elem_size;
-    if (p->u_const_bytes < want) return bail(fail(TEGB_ERR_INVALID, "uniform table smaller than described"));
+    if (!desc->grouped) {
+        r = drv::ModuleGetGlobal(&p->u_const, &p->u_const_bytes, p->mod, desc->uniform_symbol);
+        if (r != CUDA_SUCCESS) return bail(fail(TEGB_ERR_CUDA, "symbol %s: %s", desc->uniform_symbol, drv::errstr(r)));
+        if (p->u_const_bytes < want) return bail(fail(TEGB_ERR_INVALID, "uniform table smaller than described"));
+    }
     if (cudaMalloc(&p->u_stage, want) != cudaSuccess) return bail(fail(TEGB_ERR_CUDA, "cudaMalloc(uniform stage) failed"));
     *out = p;
     return TEGB_OK;
@@ -256,6 +265,7 @@ extern "C" void tegb_program_destroy(tegb_program *p) {
     for (void *q : p->d_out) if (q) cudaFree(q);
     if (p->u_stage) cudaFree(p->u_stage);
     if (p->d_partials) cudaFree(p->d_partials);
+    if (p->d_utab) cudaFree(p->d_utab);
     if (p->d_xe) cudaFree(p->d_xe);
     if (p->d_ye) cudaFree(p->d_ye);
     if (p->mod) drv::ModuleUnload(p->mod);
@@ -265,6 +275,10 @@ extern "C" void tegb_program_destroy(tegb_program *p) {
 // uniform prologue: 1 thread evaluates the launch-invariant values, then they are published to __constant__
 static int run_uniform(tegb_program *p, const double *scalars, CUstream st) {
     const int ns = p->d.n_scalar_args;
+    if (ns > 0 && !scalars) return fail(TEGB_ERR_INVALID, "scalars is NULL but the program has scalar arguments");
+    if (p->uniform_valid && p->last_stream == st && (int)p->last_scalars.size() == ns &&
+        (ns == 0 || memcmp(p->last_scalars.data(), scalars, sizeof(double) * ns) == 0))
+        return TEGB_OK;       // same launch-wide arguments as last time: tegU already holds their values
     std::vector<float> sf(ns > 0 ? ns : 1);
     std::vector<double> sd(ns > 0 ? ns : 1);
     std::vector<void *> args;
@@ -278,6 +292,9 @@ static int run_uniform(tegb_program *p, const double *scalars, CUstream st) {
     g_launches++;
     CU_CHECK(drv::MemcpyDtoDAsync(p->u_const, (CUdeviceptr)p->u_stage,
                                   (size_t)(p->d.n_uniform > 0 ? p->d.n_uniform : 1) * p->d.elem_size, st));
+    p->last_scalars.assign(scalars, scalars + ns);
+    p->uniform_valid = true;
+    p->last_stream = st;
     return TEGB_OK;
 }
 
@@ -334,7 +351,7 @@ static int finish_partials(tegb_program *p, unsigned long long n_blocks, void *o
 extern "C" int tegb_program_launch(tegb_program *p, const double *scalars, const void *const *in_ptrs,
                                    void *const *out_ptrs, int64_t n, void *stream) {
     if (!p || !out_ptrs || n < 0) return fail(TEGB_ERR_INVALID, "tegb_program_launch: bad argument");
-    if (p->d.n_grid_args != 0) return fail(TEGB_ERR_INVALID, "render program: use tegb_render_launch");
+    if (p->d.n_grid_args != 0 || p->d.grouped) return fail(TEGB_ERR_INVALID, "render program: use tegb_render_launch");
     if (p->d.n_array_args > 0 && !in_ptrs) return fail(TEGB_ERR_INVALID, "in_ptrs is NULL");
     if (n == 0) return TEGB_OK;
     RT_CHECK(cudaSetDevice(p->device));
@@ -423,34 +440,118 @@ static void linspace_edges(double lo, double hi, int res, int elem_size, std::ve
     }
 }
 
+static int ensure_edges(tegb_program *p, const tegb_grid *g, CUstream st) {
+    const bool same = p->grid_valid && p->grid_cached.x_lo == g->x_lo && p->grid_cached.x_hi == g->x_hi &&
+                      p->grid_cached.y_lo == g->y_lo && p->grid_cached.y_hi == g->y_hi &&
+                      p->grid_cached.res_x == g->res_x && p->grid_cached.res_y == g->res_y;
+    if (same) return TEGB_OK;
+    // the previous tables may still be in use by an earlier launch on this stream
+    RT_CHECK(cudaStreamSynchronize((cudaStream_t)st));
+    if (p->d_xe) { cudaFree(p->d_xe); p->d_xe = nullptr; }
+    if (p->d_ye) { cudaFree(p->d_ye); p->d_ye = nullptr; }
+    linspace_edges(g->x_lo, g->x_hi, g->res_x, p->d.elem_size, p->h_xe);
+    linspace_edges(g->y_lo, g->y_hi, g->res_y, p->d.elem_size, p->h_ye);
+    RT_CHECK(cudaMalloc(&p->d_xe, p->h_xe.size()));
+    RT_CHECK(cudaMalloc(&p->d_ye, p->h_ye.size()));
+    RT_CHECK(cudaMemcpyAsync(p->d_xe, p->h_xe.data(), p->h_xe.size(), cudaMemcpyHostToDevice, (cudaStream_t)st));
+    RT_CHECK(cudaMemcpyAsync(p->d_ye, p->h_ye.data(), p->h_ye.size(), cudaMemcpyHostToDevice, (cudaStream_t)st));
+    p->grid_cached = *g;
+    p->grid_valid = true;
+    return TEGB_OK;
+}
+
+extern "C" int tegb_render_groups_launch(tegb_program *p, const void *const *group_ptrs, int group_begin,
+                                         int group_count, const tegb_grid *g, const int32_t *windows,
+                                         int max_rows, int max_cols, const void *const *pixel_ptrs,
+                                         void *const *out_ptrs, void *stream) {
+    if (!p || !g || !windows || !out_ptrs) return fail(TEGB_ERR_INVALID, "tegb_render_groups_launch: bad argument");
+    if (!p->d.grouped || p->d.n_grid_args != 4) return fail(TEGB_ERR_INVALID, "not a grouped render program");
+    if (p->d.n_scalar_args > 0 && !group_ptrs) return fail(TEGB_ERR_INVALID, "group_ptrs is NULL");
+    if (p->d.n_pixel_args > 0 && !pixel_ptrs) return fail(TEGB_ERR_INVALID, "pixel_ptrs is NULL");
+    if (group_begin < 0 || group_count < 0 || max_rows < 1 || max_cols < 1)
+        return fail(TEGB_ERR_INVALID, "bad group range or window bounds");
+    if (g->res_x < 1 || g->res_y < 1 || g->row_begin < 0 || g->row_end > g->res_x || g->row_begin > g->row_end)
+        return fail(TEGB_ERR_INVALID, "bad grid");
+    if (group_count == 0 || g->row_end == g->row_begin) return TEGB_OK;
+    if (group_count > 65535 || max_rows > 65535) return fail(TEGB_ERR_INVALID, "more than 65535 groups or rows in one launch");
+    RT_CHECK(cudaSetDevice(p->device));
+    CUstream st = (CUstream)stream;
+    int rc = ensure_edges(p, g, st);
+    if (rc) return rc;
+    const int nu = p->d.n_uniform > 0 ? p->d.n_uniform : 1;
+    const size_t need = (size_t)(group_begin + group_count) * nu * p->d.elem_size;
+    if (need > p->utab_bytes) {
+        RT_CHECK(cudaStreamSynchronize((cudaStream_t)st));
+        if (p->d_utab) { cudaFree(p->d_utab); p->d_utab = nullptr; p->utab_bytes = 0; }
+        RT_CHECK(cudaMalloc(&p->d_utab, need));
+        p->utab_bytes = need;
+    }
+    // per-group uniform rows
+    {
+        std::vector<const void *> gp(p->d.n_scalar_args > 0 ? p->d.n_scalar_args : 1);
+        std::vector<void *> args;
+        for (int i = 0; i < p->d.n_scalar_args; i++) { gp[i] = group_ptrs[i]; args.push_back(&gp[i]); }
+        args.push_back(&group_begin);
+        args.push_back(&group_count);
+        args.push_back(&p->d_utab);
+        CU_CHECK(drv::LaunchKernel(p->f_uniform, (unsigned)((group_count + 127) / 128), 1, 1, 128, 1, 1, 0, st,
+                                   args.data(), nullptr));
+        g_launches++;
+    }
+    const unsigned bs = (unsigned)p->d.block_size;
+    const unsigned gx = (unsigned)((max_cols + bs - 1) / bs);
+    int band_rows = g->row_end - g->row_begin;
+    const unsigned gy = (unsigned)(max_rows < band_rows ? max_rows : band_rows);
+    const unsigned gz = (unsigned)group_count;
+    std::vector<const void *> pix(p->d.n_pixel_args > 0 ? p->d.n_pixel_args : 1);
+    std::vector<void *> outs(p->d.n_outputs);
+    std::vector<void *> args;
+    int res_y = g->res_y, row0 = g->row_begin, row1 = g->row_end;
+    args.push_back(&p->d_xe);
+    args.push_back(&p->d_ye);
+    args.push_back(&res_y);
+    args.push_back(&row0);
+    args.push_back(&row1);
+    args.push_back((void *)&windows);
+    args.push_back(&group_begin);
+    args.push_back(&p->d_utab);
+    for (int i = 0; i < p->d.n_pixel_args; i++) { pix[i] = pixel_ptrs[i]; args.push_back(&pix[i]); }
+    const unsigned long long tiles = (unsigned long long)gx * gy;
+    if (p->d.reduce_outputs) {
+        rc = ensure_partials(p, tiles * gz);
+        if (rc) return rc;
+        args.push_back(&p->d_partials);
+    } else {
+        for (int k = 0; k < p->d.n_outputs; k++) { outs[k] = out_ptrs[k]; args.push_back(&outs[k]); }
+    }
+    CU_CHECK(drv::LaunchKernel(p->f_main, gx, gy, gz, bs, 1, 1, 0, st, args.data(), nullptr));
+    g_launches++;
+    if (p->d.reduce_outputs) {
+        // partials: [group][component][tile] -> out[group][component]
+        const int cols = (int)gz * p->d.n_outputs;
+        if (p->d.elem_size == 4)
+            colsum_stage2<float><<<cols, RED_THREADS, 0, (cudaStream_t)st>>>((const float *)p->d_partials, (long long)tiles, (float *)out_ptrs[0]);
+        else
+            colsum_stage2<double><<<cols, RED_THREADS, 0, (cudaStream_t)st>>>((const double *)p->d_partials, (long long)tiles, (double *)out_ptrs[0]);
+        g_launches++;
+        RT_CHECK(cudaGetLastError());
+    }
+    return TEGB_OK;
+}
+
 extern "C" int tegb_render_launch(tegb_program *p, const double *scalars, const tegb_grid *g,
                                   void *const *out_ptrs, void *stream) {
     if (!p || !g || !out_ptrs) return fail(TEGB_ERR_INVALID, "tegb_render_launch: bad argument");
-    if (p->d.n_grid_args != 4 || p->d.n_array_args != 0)
-        return fail(TEGB_ERR_INVALID, "not a render program (needs exactly the 4 pixel-box arguments on the grid)");
+    if (p->d.n_grid_args != 4 || p->d.n_array_args != 0 || p->d.grouped)
+        return fail(TEGB_ERR_INVALID, "not a plain render program (needs exactly the 4 pixel-box arguments on the grid)");
     if (g->res_x < 1 || g->res_y < 1 || g->row_begin < 0 || g->row_end > g->res_x || g->row_begin > g->row_end)
         return fail(TEGB_ERR_INVALID, "bad grid");
     if (g->row_end == g->row_begin) return TEGB_OK;
     RT_CHECK(cudaSetDevice(p->device));
     CUstream st = (CUstream)stream;
-    const bool same = p->grid_valid && p->grid_cached.x_lo == g->x_lo && p->grid_cached.x_hi == g->x_hi &&
-                      p->grid_cached.y_lo == g->y_lo && p->grid_cached.y_hi == g->y_hi &&
-                      p->grid_cached.res_x == g->res_x && p->grid_cached.res_y == g->res_y;
-    if (!same) {
-        // the previous tables may still be in use by an earlier launch on this stream
-        RT_CHECK(cudaStreamSynchronize((cudaStream_t)st));
-        if (p->d_xe) { cudaFree(p->d_xe); p->d_xe = nullptr; }
-        if (p->d_ye) { cudaFree(p->d_ye); p->d_ye = nullptr; }
-        linspace_edges(g->x_lo, g->x_hi, g->res_x, p->d.elem_size, p->h_xe);
-        linspace_edges(g->y_lo, g->y_hi, g->res_y, p->d.elem_size, p->h_ye);
-        RT_CHECK(cudaMalloc(&p->d_xe, p->h_xe.size()));
-        RT_CHECK(cudaMalloc(&p->d_ye, p->h_ye.size()));
-        RT_CHECK(cudaMemcpyAsync(p->d_xe, p->h_xe.data(), p->h_xe.size(), cudaMemcpyHostToDevice, (cudaStream_t)st));
-        RT_CHECK(cudaMemcpyAsync(p->d_ye, p->h_ye.data(), p->h_ye.size(), cudaMemcpyHostToDevice, (cudaStream_t)st));
-        p->grid_cached = *g;
-        p->grid_valid = true;
-    }
-    int rc = run_uniform(p, scalars, st);
+    int rc = ensure_edges(p, g, st);
+    if (rc) return rc;
+    rc = run_uniform(p, scalars, st);
     if (rc) return rc;
     std::vector<void *> outs(p->d.n_outputs);
     std::vector<void *> args;

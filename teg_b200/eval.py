@@ -118,11 +118,18 @@ class CUDA_EvalMode(EvalMode):
                         reduce_outputs=reduce, block_size=block, team=team, **self.codegen_opts)
 
     def compiled(self, array_args: Sequence[int], grid_args: Sequence[int] = (), reduce: bool = False,
-                 team: int = 1):
-        key = (tuple(sorted(array_args)), tuple(grid_args), bool(reduce), int(team))
+                 team: int = 1, grouped: bool = False, pixel_args: Sequence[int] = (), accumulate: bool = False):
+        key = (tuple(sorted(array_args)), tuple(grid_args), bool(reduce), int(team), bool(grouped),
+               tuple(pixel_args), bool(accumulate))
         hit = self._variants.get(key)
         if hit is None:
-            ks = self.kernel_source(array_args, grid_args, reduce, team)
+            if grouped:
+                sch = self.schedule(list(grid_args) + list(pixel_args))
+                ks = generate(sch, self.float_width, self.num_samples, grid_args=list(grid_args),
+                              reduce_outputs=reduce, grouped=True, pixel_args=list(pixel_args),
+                              accumulate=accumulate, block_size=self.block_size, **self.codegen_opts)
+            else:
+                ks = self.kernel_source(array_args, grid_args, reduce, team)
             mod = runtime.Module(ks.source, use_cache=self.use_cache)
             prog = runtime.Program(mod, ks, device=self.device)
             hit = (ks, prog)
@@ -202,6 +209,93 @@ class CUDA_EvalMode(EvalMode):
                     n, stream=stream)
         return out if self.out_is_tuple and ks.n_outputs > 1 else out[0]
 
+    def render_groups(self, box_vars, res: Tuple[int, int], bounds, group_bindings, windows, max_rows: int,
+                      max_cols: int, pixel_bindings=None, rows: Optional[Tuple[int, int]] = None, out=None,
+                      reduce: bool = False, accumulate: bool = False, group_range: Optional[Tuple[int, int]] = None,
+                      stream: int = 0):
+        """One launch over many *groups* (e.g. triangles), each with its own parameter values and its own
+        window of pixels of the tests/plot.py grid.
+
+        group_bindings: {Var | label: torch CUDA tensor [G]} for every non-box, non-pixel argument.
+        windows: int32 CUDA tensor [G, 4] = (row_begin, row_end, col_begin, col_end) per group, in pixels.
+        max_rows / max_cols: upper bounds on the window sizes (launch geometry).
+        pixel_bindings: {Var | label: image tensor [rows, res_y]} read per pixel (an upstream dL).
+        rows: the band of grid rows this device owns (multi-GPU sharding).
+        Output: ``out`` images [k, rows, res_y] (assigned, or added to with ``accumulate`` -- the windows of
+        one launch must then be disjoint), or with ``reduce`` a tensor [G_range, k] of per-group sums."""
+        import torch
+        labels = [v if isinstance(v, str) else label_of(v) for v in box_vars]
+        pos = {lab: i for i, (lab, _) in enumerate(self.arglist)}
+        grid_args = [pos[lab] for lab in labels]
+        pix = {(k if isinstance(k, str) else label_of(k)): v for k, v in (pixel_bindings or {}).items()}
+        grp = {(k if isinstance(k, str) else label_of(k)): v for k, v in (group_bindings or {}).items()}
+        pixel_args = sorted(pos[lab] for lab in pix)
+        ks, prog = self.compiled(grid_args, grid_args, reduce=reduce, grouped=True, pixel_args=pixel_args,
+                                 accumulate=accumulate)
+        tdt = torch.float32 if self.float_width == 'float' else torch.float64
+        dev = torch.device('cuda', self.device)
+        G = int(windows.shape[0])
+        g0, g1 = (0, G) if group_range is None else group_range
+        gptrs, keep = [], []
+        for a in ks.scalar_args:
+            lab, default = self.arglist[a]
+            v = grp.get(lab, default)
+            assert v is not None, f'No bindings found for {[lab]}'
+            if not _is_torch(v) or v.dim() == 0:
+                v = torch.full((G,), float(v), dtype=tdt, device=dev)
+            assert v.is_cuda and v.dtype == tdt and v.numel() == G and v.is_contiguous(), \
+                f'group binding {lab} must be a contiguous CUDA tensor [{G}] of the working precision'
+            keep.append(v)
+            gptrs.append(v.data_ptr())
+        r0, r1 = (0, res[0]) if rows is None else rows
+        pptrs = []
+        for a in ks.pixel_args:
+            img = pix[self.arglist[a][0]]
+            assert img.is_cuda and img.dtype == tdt and img.is_contiguous() and img.numel() == (r1 - r0) * res[1]
+            pptrs.append(img.data_ptr())
+        assert windows.is_cuda and windows.dtype == torch.int32 and windows.is_contiguous() and windows.shape[1] == 4
+        if out is None:
+            out = (torch.empty((g1 - g0, ks.n_outputs), dtype=tdt, device=dev) if reduce
+                   else torch.zeros((ks.n_outputs, r1 - r0, res[1]), dtype=tdt, device=dev))
+        optrs = [out.data_ptr()] if reduce else [out[k].data_ptr() for k in range(ks.n_outputs)]
+        grid = runtime.Grid(float(bounds[0][0]), float(bounds[0][1]), float(bounds[1][0]), float(bounds[1][1]),
+                            int(res[0]), int(res[1]), int(r0), int(r1))
+        prog.render_groups(gptrs, g0, g1 - g0, grid, windows.data_ptr(), int(max_rows), int(max_cols), pptrs,
+                           optrs, stream=stream)
+        self._keepalive = keep
+        return out
+
+    def prepare(self, bindings={}, reduce: bool = False):
+        """Bind once, launch many times: resolves the arguments, moves array bindings to the device, allocates
+        the output and returns a ``PreparedCall`` whose ``run()`` is a single C-ABI call (no per-call Python
+        marshalling).  For optimisation loops and for timing the kernels rather than the interpreter."""
+        import torch
+        args = self._resolve(bindings)
+        tdt = torch.float32 if self.float_width == 'float' else torch.float64
+        dev = torch.device('cuda', self.device)
+        n = None
+        array_args = []
+        for i, a in enumerate(args):
+            ln = a.numel() if (_is_torch(a) and a.dim() > 0) else (int(np.size(a)) if (not _is_torch(a) and np.ndim(a) > 0) else None)
+            if ln is None:
+                continue
+            assert n is None or n == ln, 'all array bindings must have the same length'
+            n = ln
+            array_args.append(i)
+        n_eff = 1 if n is None else n
+        team = self.pick_team(n_eff, array_args)
+        ks, prog = self.compiled(array_args, reduce=reduce, team=team)
+        ins = []
+        for a in ks.array_args:
+            t = args[a]
+            if not _is_torch(t):
+                t = torch.as_tensor(np.asarray(t))
+            ins.append(t.to(device=dev, dtype=tdt).contiguous().view(-1))
+        out = (torch.empty(ks.n_outputs, dtype=tdt, device=dev) if reduce
+               else torch.empty((ks.n_outputs, n_eff), dtype=tdt, device=dev))
+        scalars = [float(args[a]) for a in ks.scalar_args]
+        return PreparedCall(self, ks, prog, scalars, ins, out, n_eff, reduce)
+
     # ------------------------------------------------------------------- render
     def render(self, box_vars, res: Tuple[int, int], bounds=((0, 1), (0, 1)), bindings=None,
                rows: Optional[Tuple[int, int]] = None, out=None, stream: int = 0, reduce: bool = False):
@@ -235,6 +329,33 @@ class CUDA_EvalMode(EvalMode):
         ptrs = [out.data_ptr()] if reduce else [out[k].data_ptr() for k in range(ks.n_outputs)]
         prog.render(scalars, grid, ptrs, stream=stream)
         return out
+
+
+class PreparedCall:
+    """A bound launch (see ``CUDA_EvalMode.prepare``).  ``run()`` re-launches on the current torch stream and
+    returns the (reused) output tensor: [n] / [k, n], or [k] sums for ``reduce``."""
+
+    def __init__(self, mode, ks, prog, scalars, ins, out, n, reduce):
+        self.mode, self.ks, self.prog = mode, ks, prog
+        self.ins, self.out, self.n, self.reduce = ins, out, n, reduce
+        self._scalars = runtime._dbl_array(scalars)
+        self._in = runtime._ptr_array([t.data_ptr() for t in ins])
+        outs = [out.data_ptr()] if reduce else [out[k].data_ptr() for k in range(ks.n_outputs)]
+        self._out = runtime._ptr_array(outs)
+        self._fn = runtime.lib().tegb_program_launch
+        self._h = prog.handle
+
+    def set_scalars(self, values: Sequence[float]) -> None:
+        """New values for the launch-wide (scalar-bound) arguments, in ``ks.scalar_args`` order."""
+        self._scalars = runtime._dbl_array(values)
+
+    def run(self, stream: Optional[int] = None):
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(self.out.device).cuda_stream
+        runtime.check(self._fn(self._h, self._scalars, self._in, self._out, self.n, ctypes.c_void_p(stream)))
+        squeeze = not (self.mode.out_is_tuple and self.ks.n_outputs > 1)
+        return self.out[0] if squeeze else self.out
 
 
 BACKENDS = {'CUDA': (CUDA_EvalMode, {})}

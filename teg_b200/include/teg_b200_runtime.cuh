@@ -28,7 +28,9 @@
  * the shuffles -- adding zeros cannot change a sum, so the value is the same, bit for bit.  Deterministic:
  * depends only on the launch geometry and the values.  Must be reached by every thread of the block. */
 template <typename T, int K, int BLOCK>
-static __device__ __forceinline__ void tegb_block_sum_store(const T (&v)[K], T* __restrict__ partials) {
+static __device__ __forceinline__ void tegb_block_sum_store(const T (&v)[K], T* __restrict__ partials,
+                                                            const unsigned long long nblk,
+                                                            const unsigned long long blk) {
     __shared__ T sm[K][BLOCK / 32];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     bool nz = false;
@@ -49,10 +51,15 @@ static __device__ __forceinline__ void tegb_block_sum_store(const T (&v)[K], T* 
         T t = sm[threadIdx.x][0];
 #pragma unroll
         for (int w = 1; w < BLOCK / 32; w++) t = t + sm[threadIdx.x][w];
-        const unsigned long long nblk = (unsigned long long)gridDim.x * gridDim.y * gridDim.z;
-        const unsigned long long blk = ((unsigned long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
         partials[(unsigned long long)threadIdx.x * nblk + blk] = t;
     }
+}
+
+template <typename T, int K, int BLOCK>
+static __device__ __forceinline__ void tegb_block_sum_store(const T (&v)[K], T* __restrict__ partials) {
+    const unsigned long long nblk = (unsigned long long)gridDim.x * gridDim.y * gridDim.z;
+    const unsigned long long blk = ((unsigned long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    tegb_block_sum_store<T, K, BLOCK>(v, partials, nblk, blk);
 }
 
 /* Sum over the TEAM threads that cooperate on one instance (TEAM consecutive threads, TEAM a power of two).

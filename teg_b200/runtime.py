@@ -22,7 +22,8 @@ class ProgramDesc(ctypes.Structure):
     _fields_ = [('uniform_kernel', ctypes.c_char_p), ('main_kernel', ctypes.c_char_p),
                 ('uniform_symbol', ctypes.c_char_p), ('elem_size', ctypes.c_int), ('n_uniform', ctypes.c_int),
                 ('n_scalar_args', ctypes.c_int), ('n_array_args', ctypes.c_int), ('n_grid_args', ctypes.c_int),
-                ('n_outputs', ctypes.c_int), ('block_size', ctypes.c_int), ('reduce_outputs', ctypes.c_int), ('team', ctypes.c_int)]
+                ('n_outputs', ctypes.c_int), ('block_size', ctypes.c_int), ('reduce_outputs', ctypes.c_int), ('team', ctypes.c_int), ('grouped', ctypes.c_int),
+                ('n_pixel_args', ctypes.c_int), ('accumulate', ctypes.c_int)]
 
 
 class Grid(ctypes.Structure):
@@ -35,6 +36,7 @@ SYMBOLS = [
     'tegb_last_error', 'tegb_version', 'tegb_device_count', 'tegb_compile', 'tegb_module_from_cubin',
     'tegb_module_cubin', 'tegb_module_log', 'tegb_module_destroy', 'tegb_program_create',
     'tegb_program_destroy', 'tegb_program_launch', 'tegb_program_eval_host', 'tegb_render_launch',
+    'tegb_render_groups_launch',
     'tegb_launch_count', 'tegb_reduce_workspace_bytes', 'tegb_reduce_sum', 'tegb_nccl_unique_id',
     'tegb_nccl_comm_create', 'tegb_nccl_comm_destroy', 'tegb_allreduce_sum', 'tegb_fma_peak',
 ]
@@ -73,6 +75,8 @@ def lib():
                                          ctypes.POINTER(vp), i64]
     L.tegb_render_launch.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(Grid),
                                      ctypes.POINTER(vp), vp]
+    L.tegb_render_groups_launch.argtypes = [vp, ctypes.POINTER(vp), i32, i32, ctypes.POINTER(Grid), vp, i32, i32,
+                                            ctypes.POINTER(vp), ctypes.POINTER(vp), vp]
     L.tegb_launch_count.restype = i64
     L.tegb_reduce_workspace_bytes.argtypes = [i32, i64, i32]
     L.tegb_reduce_workspace_bytes.restype = ctypes.c_size_t
@@ -177,7 +181,8 @@ class Program:
         desc = ProgramDesc(self._names[0], self._names[1], self._names[2], self.elem_size, ks.n_uniform,
                            len(ks.scalar_args), len(ks.array_args), len(getattr(ks, 'grid_args', ())),
                            ks.n_outputs, ks.block_size, int(getattr(ks, 'reduce_outputs', False)),
-                           int(getattr(ks, 'team', 1)))
+                           int(getattr(ks, 'team', 1)), int(getattr(ks, 'grouped', False)),
+                           len(getattr(ks, 'pixel_args', None) or ()), int(getattr(ks, 'accumulate', False)))
         self.handle = ctypes.c_void_p()
         check(L.tegb_program_create(module.handle, ctypes.byref(desc), device, ctypes.byref(self.handle)))
 
@@ -193,6 +198,14 @@ class Program:
     def render(self, scalars: Sequence[float], grid: Grid, out_ptrs: Sequence[int], stream: int = 0) -> None:
         check(self._L.tegb_render_launch(self.handle, _dbl_array(scalars), ctypes.byref(grid),
                                          _ptr_array(out_ptrs), ctypes.c_void_p(stream)))
+
+    def render_groups(self, group_ptrs: Sequence[int], group_begin: int, group_count: int, grid: Grid,
+                      windows_ptr: int, max_rows: int, max_cols: int, pixel_ptrs: Sequence[int],
+                      out_ptrs: Sequence[int], stream: int = 0) -> None:
+        check(self._L.tegb_render_groups_launch(self.handle, _ptr_array(group_ptrs), group_begin, group_count,
+                                                ctypes.byref(grid), ctypes.c_void_p(windows_ptr), max_rows,
+                                                max_cols, _ptr_array(pixel_ptrs), _ptr_array(out_ptrs),
+                                                ctypes.c_void_p(stream)))
 
     def __del__(self):
         if getattr(self, 'handle', None) and self.handle.value:

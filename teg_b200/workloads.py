@@ -51,6 +51,11 @@ def scene_values(scene: str, res: Tuple[int, int] = (256, 256), n: int = None, r
     if scene in ('shaded_primal', 'shaded_grad'):
         return {**_boxes(('x_lb', 'x_ub', 'y_lb', 'y_ub'), res, ((0, 1), (0, 1)), rows), **TRIANGLE, **SHADER,
                 'dL': 1.0}
+    if scene in ('tri_color_primal', 'tri_color_grad'):
+        boxes = _boxes(('x_lb', 'x_ub', 'y_lb', 'y_ub'), res, ((0, 1), (0, 1)), rows)
+        m = boxes['x_lb'].size
+        dl = np.random.default_rng(3).uniform(-1, 1, size=m).astype(np.float32).astype(np.float64)
+        return {**boxes, **TRIANGLE, 'col': 0.7, 'dL': dl}
     if scene in ('raster_theta', 'raster_theta_primal'):
         return {**_boxes(('xl', 'xu', 'yl', 'yu'), res, ((0, 1), (0, 1)), rows), 'theta': 0.0, 'dtheta': 1.0}
     if scene.startswith('nested2d') or scene.startswith('nested3d'):
@@ -90,8 +95,73 @@ def bind(prog_args: Sequence[str], values: Dict[str, ArrayOrScalar]) -> List[Arr
 # default number of samples per scene = what oracle/build_ref.py compiled the reference C with
 SCENE_SAMPLES = {
     'readme_primal': 50, 'readme_deriv': 50, 'tri_primal': 16, 'tri_grad': 16,
-    'raster_theta_primal': 10, 'raster_theta': 10, 'shaded_primal': 16, 'shaded_grad': 16,
+    'raster_theta_primal': 10, 'raster_theta': 10, 'shaded_primal': 16, 'shaded_grad': 16, 'tri_color_primal': 16, 'tri_color_grad': 16,
     'nested2d_value': 16, 'nested2d_grad': 16, 'nested3d_value': 16, 'nested3d_grad': 16,
     'simple_line': 20, 'simple_line_grad': 20, 'circle': 20, 'circle_dt': 20,
     'rect_hyperbola': 20, 'rect_hyperbola_grad': 20, 'bilinear_lerp': 20, 'bilinear_lerp_grad': 20,
 }
+
+
+# ----------------------------------------------------------------------------------------- config 5
+def multi_triangle_scene(bands: int = 1, per_band_grid: int = 16, seed: int = 2, res: int = 4096):
+    """K = bands * per_band_grid^2 flat-coloured triangles.
+
+    Domain: x in [0, bands] (one unit square per band / GPU), y in [0, 1]; pixel grid (res * bands) x res.
+    Band b's triangles: centres on a jittered per_band_grid^2 grid of its unit square, circumradius
+    U(0.03, 0.06) * 16 / per_band_grid, random rotation, counter-clockwise, colour U(0, 1),
+    ``default_rng(seed + b)``.  Triangles are ordered by the class (i % 3, j % 3) of their grid cell so
+    that every class occupies a contiguous range whose pixel windows are pairwise disjoint -- the
+    forward pass adds one class per launch (class = ((global grid row) % 3, j % 3)) into the image without atomics, in a fixed order.
+
+    Returns dict(verts [K, 6] float64 (px0, py0, px1, py1, px2, py2), col [K], windows [K, 4] int32
+    (row_begin, row_end, col_begin, col_end), classes [(begin, end)] group ranges, max_rows, max_cols)."""
+    g = per_band_grid
+    scale = 16.0 / g
+    verts, cols, keys = [], [], []
+    for b in range(bands):
+        rng = np.random.default_rng(seed + b)
+        jit = rng.uniform(-0.002, 0.002, size=(g, g, 2)) * scale
+        rad = rng.uniform(0.03, 0.06, size=(g, g)) * scale
+        rot = rng.uniform(0, 2 * np.pi, size=(g, g))
+        col = rng.uniform(0, 1, size=(g, g))
+        for i in range(g):
+            for j in range(g):
+                cx = b + (i + 0.5) / g + jit[i, j, 0]
+                cy = (j + 0.5) / g + jit[i, j, 1]
+                ang = rot[i, j] + np.array([0.0, 2 * np.pi / 3, 4 * np.pi / 3])
+                px = cx + rad[i, j] * np.cos(ang)
+                py = cy + rad[i, j] * np.sin(ang)
+                verts.append([px[0], py[0], px[1], py[1], px[2], py[2]])
+                cols.append(col[i, j])
+                keys.append((((b * g + i) % 3) * 3 + (j % 3), b, i, j))
+    order = sorted(range(len(keys)), key=lambda k: keys[k])
+    verts = np.array(verts)[order]
+    cols = np.array(cols)[order]
+    cls = np.array([keys[k][0] for k in order])
+    # values as the kernels see them (fp32-representable), so host-side windows are consistent
+    verts = verts.astype(np.float32).astype(np.float64)
+    cols = cols.astype(np.float32).astype(np.float64)
+    xs, ys = verts[:, 0::2], verts[:, 1::2]
+    rows_total = res * bands
+    r0 = np.clip(np.floor(xs.min(axis=1) * res).astype(np.int64) - 1, 0, rows_total)
+    r1 = np.clip(np.ceil(xs.max(axis=1) * res).astype(np.int64) + 1, 0, rows_total)
+    c0 = np.clip(np.floor(ys.min(axis=1) * res).astype(np.int64) - 1, 0, res)
+    c1 = np.clip(np.ceil(ys.max(axis=1) * res).astype(np.int64) + 1, 0, res)
+    windows = np.stack([r0, r1, c0, c1], axis=1).astype(np.int32)
+    classes = []
+    for c in range(9):
+        idx = np.nonzero(cls == c)[0]
+        if idx.size:
+            classes.append((int(idx[0]), int(idx[-1]) + 1))
+    return {'verts': verts, 'col': cols, 'windows': windows, 'classes': classes,
+            'max_rows': int((r1 - r0).max()), 'max_cols': int((c1 - c0).max())}
+
+
+def windows_disjoint(windows: np.ndarray) -> bool:
+    """True if no two pixel windows [row_begin, row_end) x [col_begin, col_end) overlap."""
+    w = np.asarray(windows)
+    for a in range(len(w)):
+        for b in range(a + 1, len(w)):
+            if (w[a, 0] < w[b, 1] and w[b, 0] < w[a, 1] and w[a, 2] < w[b, 3] and w[b, 2] < w[a, 3]):
+                return False
+    return True

@@ -213,3 +213,26 @@ def test_auto_team_policy_and_single_instance_big_integral(cuda_device):
     want = float(Oracle(program_text('nested2d_value')).eval(list(vals.values()), 2000, np.float32)[0, 0])
     assert isinstance(got, float) and abs(got - want) <= 2000 * 6e-8 * abs(want)      # N * eps / 2
     assert CUDA_EvalMode(prog, num_samples=2000).pick_team(1, []) == 1                 # default stays exact
+
+
+def test_prepared_call_matches_eval_and_tracks_scalar_updates(cuda_device):
+    import torch
+    from teg_b200 import CUDA_EvalMode
+    prog = load_program('tri_grad')
+    inputs = bind(prog.args, scene_values('tri_grad', res=(48, 48)))
+    b = dict(zip(prog.args, inputs))
+    mode = CUDA_EvalMode(prog, num_samples=16)
+    want = np.asarray(mode.eval(b))
+    call = mode.prepare(b)
+    for _ in range(3):                       # identical scalars: the uniform table is reused, not recomputed
+        got = call.run()
+    torch.cuda.synchronize()
+    assert np.array_equal(got.cpu().numpy(), want)
+    # move a vertex: the cached uniform table must be refreshed
+    b2 = dict(b)
+    b2[prog.args[4]] = 0.2
+    want2 = np.asarray(mode.eval(b2))
+    call.set_scalars([b2[prog.args[a]] for a in call.ks.scalar_args])
+    got2 = call.run()
+    torch.cuda.synchronize()
+    assert np.array_equal(got2.cpu().numpy(), want2) and not np.array_equal(want, want2)
