@@ -19,6 +19,7 @@ def _oracle_scene(scene, res, bands, dL=None):
     img = np.zeros((rows_total, res), dtype=np.float32)
     K = scene['verts'].shape[0]
     g = np.zeros((K, 7))
+    gabs = np.zeros((K, 7))
     xs = np.linspace(0.0, float(bands), rows_total + 1)
     ys = np.linspace(0.0, 1.0, res + 1)
     for g0, g1 in scene['classes']:
@@ -33,7 +34,8 @@ def _oracle_scene(scene, res, bands, dL=None):
             if dL is not None:
                 gk = grad.eval([dL[nx, ny]] + box + par, 16, np.float32, threads=8)
                 g[k] = gk.astype(np.float64).sum(axis=1)
-    return img, g
+                gabs[k] = np.abs(gk.astype(np.float64)).sum(axis=1)
+    return img, g, gabs
 
 
 @pytest.mark.parametrize('bands', [1, 2])
@@ -45,7 +47,7 @@ def test_multi_triangle_forward_backward_match_oracle(cuda_device, bands):
     assert all(windows_disjoint(scene['windows'][a:b]) for a, b in scene['classes'])
     rng = np.random.default_rng(5)
     dL = rng.uniform(-1, 1, size=(res * bands, res)).astype(np.float32)
-    want_img, want_g = _oracle_scene(scene, res, bands, dL)
+    want_img, want_g, want_gabs = _oracle_scene(scene, res, bands, dL)
     imgs, grads = [], []
     for rank in range(bands):
         r = MultiTriangleRasterizer(load_program('tri_color_primal'), load_program('tri_color_grad'), res,
@@ -61,6 +63,6 @@ def test_multi_triangle_forward_backward_match_oracle(cuda_device, bands):
     got_img = np.concatenate(imgs, axis=0)
     assert np.array_equal(got_img, want_img), f'{np.count_nonzero(got_img != want_img)} pixels differ'
     got_g = sum(grads)                       # what the all-reduce computes
-    scale = np.maximum(np.abs(want_g), np.abs(want_g).max(axis=0, keepdims=True) * 1e-3)
-    assert np.max(np.abs(got_g - want_g) / scale) < 2e-5
+    # dL has random signs, so the sums cancel: the fp32 summation error scales with sum |terms|, not |sum|
+    assert np.all(np.abs(got_g - want_g) <= 2e-6 * want_gabs + 1e-12)
     assert np.abs(want_g).max() > 1e-3 and np.count_nonzero(want_img) > 100
