@@ -73,7 +73,7 @@ class KernelSource:
 
 class Emitter:
     def __init__(self, sch: Schedule, ctype: str, num_samples: int, name: str,
-                 block_size: int = 128, unroll_inner: int = 32, unroll_outer: int = 1, pred_accum: bool = True, use_asm: bool = True, team: int = 1):
+                 block_size: int = 128, unroll_inner: int = 32, unroll_outer: int = 1, pred_accum: bool = True, use_asm: bool = True, team: int = 1, coop: bool = True):
         assert ctype in ('float', 'double')
         self.sch = sch
         self.dag: Dag = sch.dag
@@ -89,6 +89,14 @@ class Emitter:
         assert team >= 1 and (team & (team - 1)) == 0 and team <= 1024, 'team must be a power of two <= 1024'
         self.team = team
         self.helper = Scheduler(sch.dag, sch.array_args)      # for resolve / bool_value
+        # warp-cooperative guarded loops (see _coop_if / _coop_loop); needs warp intrinsics, thread per instance
+        self.coop = bool(coop) and team == 1
+        self.guard_ctx: List[str] = []        # per-lane guard conditions enclosing the current (converged) code
+        self.divergent = 0                    # > 0 while emitting inside an ordinary (divergent) if
+        self.coop_map: Dict[int, str] = {}    # node -> name of its warp-broadcast copy inside a coop loop
+        self.ref_log = None                   # dry-run bookkeeping: nodes referenced / defined
+        self.def_log = None
+        self.uses_coop = False
         self.lines: List[str] = []
         self.loop_counter = 0
         # static op statistics (per execution of each block, weighted later by trip counts)
@@ -107,9 +115,17 @@ class Emitter:
         if i in self.sch.uniform_slots and self.in_main:
             slot = self.sch.uniform_slots[i]
             return f'(tegU[{slot}] != 0)' if n.is_bool else f'tegU[{slot}]'
+        if self.ref_log is not None:
+            self.ref_log.add(i)
+        if i in self.coop_map:
+            return self.coop_map[i]
         if n.op == 'bvar':
             return f'x{i}'
         return f'v{i}'
+
+    def _define(self, i: int):
+        if self.def_log is not None:
+            self.def_log.add(i)
 
     def expr(self, i: int, known: Dict[int, bool]) -> str:
         n = self.nodes[i]
@@ -150,11 +166,16 @@ class Emitter:
         for st in b.stmts:
             if isinstance(st, Eval):
                 i = st.node
+                self._define(i)
                 self.emit(f'const {self.decl(i)} v{i} = {self.expr(i, known)};', ind)
+            elif isinstance(st, IfGroup) and self._coop_ok(st, depth):
+                self._coop_if(st, known, ind, depth)
             elif isinstance(st, IfGroup):
                 for s in st.sels:
+                    self._define(s)
                     self.emit(f'T v{s};', ind)
                 self.emit(f'if ({self.ref(st.cond, known)}) {{', ind)
+                self.divergent += 1
                 self.block(st.then_block, ind + 1, depth)
                 for s in st.sels:
                     self.emit(f'v{s} = {self.ref(self.nodes[s].args[1], st.then_block.known)};', ind + 1)
@@ -162,9 +183,13 @@ class Emitter:
                 self.block(st.else_block, ind + 1, depth)
                 for s in st.sels:
                     self.emit(f'v{s} = {self.ref(self.nodes[s].args[2], st.else_block.known)};', ind + 1)
+                self.divergent -= 1
                 self.emit('}', ind)
             elif isinstance(st, LoopGroup):
-                self.loop(st, known, ind, depth)
+                if self.coop and depth == 0 and not self.divergent and self.guard_ctx:
+                    self._coop_loop(st, known, ind)
+                else:
+                    self.loop(st, known, ind, depth)
             else:  # pragma: no cover
                 raise TypeError(st)
 
@@ -175,7 +200,9 @@ class Emitter:
         N = self.N
         innermost = not any(isinstance(s, LoopGroup) for s in st.body.walk())
         for q in st.quads:
+            self._define(q)
             self.emit(f'T v{q} = {literal("0", self.ctype)};', ind)
+        self._define(st.bvar)
         self.emit('{', ind)
         self.emit(f'const T lo{k} = {self.ref(st.lo, known)};', ind + 1)
         self.emit(f'const T step{k} = ((T)({self.ref(st.hi, known)} - lo{k})) / (T){N};', ind + 1)
@@ -213,6 +240,124 @@ class Emitter:
             # skipped terms were `0 * step`: identical for every finite step; keeps NaN/inf steps poisonous
             self.emit(f'v{q} = v{q} + {literal("0", self.ctype)} * step{k};', ind + 1)
         self.emit('}', ind)
+
+    # ------------------------------------------------------ warp-cooperative guarded loops
+    # Reverse-mode programs guard every delta integral with a bound check (teg/passes/delta.py:426-439): a
+    # fraction of a percent of the instances run a loop, scattered along the discontinuities, so a warp that
+    # meets one spends N iterations with one or two useful lanes.  Instead: the whole warp enters the guard when
+    # ANY lane passes it (everything but the loops is evaluated speculatively -- values are pure), and each
+    # pending loop is executed by the warp together: the owner lane's loop inputs are broadcast, lane s
+    # evaluates sample s, and every lane folds the N terms in sample order (the reference's left fold, bit for
+    # bit); the owner keeps the result.
+    @staticmethod
+    def _has_loop(b: Block) -> bool:
+        return any(isinstance(s, LoopGroup) for s in b.walk())
+
+    def _coop_ok(self, st: IfGroup, depth: int) -> bool:
+        if not (self.coop and depth == 0 and not self.divergent and self.in_main):
+            return False
+        if not self._has_loop(st.then_block):
+            return False
+        # the else side must be straight-line code: it is evaluated unconditionally
+        return not any(isinstance(s, (LoopGroup, IfGroup)) for s in st.else_block.walk())
+
+    def _coop_if(self, st: IfGroup, known: Dict[int, bool], ind: int, depth: int):
+        self.uses_coop = True
+        self.block(st.else_block, ind, depth)
+        for s in st.sels:
+            self._define(s)
+            self.emit(f'T v{s} = {self.ref(self.nodes[s].args[2], st.else_block.known)};', ind)
+        cond = self.ref(st.cond, known)
+        ctx = ' && '.join(self.guard_ctx + [f'({cond})'])
+        self.emit(f'if (__any_sync(0xffffffffu, {ctx})) {{', ind)
+        self.guard_ctx.append(f'({cond})')
+        self.block(st.then_block, ind + 1, depth)
+        self.guard_ctx.pop()
+        for s in st.sels:
+            self.emit(f'if ({cond}) v{s} = {self.ref(self.nodes[s].args[1], st.then_block.known)};', ind + 1)
+        self.emit('}', ind)
+
+    def _coop_loop(self, st: LoopGroup, known: Dict[int, bool], ind: int):
+        self.uses_coop = True
+        N = self.N
+        T = self.ctype
+        zero = literal('0', T)
+        # dry run: which per-lane values does the loop (bounds + body + integrands) read from outside?
+        saved = (self.lines, self.loop_counter, self.ref_log, self.def_log)
+        self.lines, self.ref_log, self.def_log = [], set(), set()
+        self._coop_loop_body(st, known, 0, dry=True)
+        inputs = sorted(self.ref_log - self.def_log)
+        self.lines, self.loop_counter, self.ref_log, self.def_log = saved
+        if self.ref_log is not None:
+            self.ref_log.update(inputs)
+        k = self.loop_counter
+        for q in st.quads:
+            self._define(q)
+            self.emit(f'T v{q} = {zero};', ind)
+        self.emit('{', ind)
+        self.emit(f'unsigned int coop_m{k} = __ballot_sync(0xffffffffu, {" && ".join(self.guard_ctx)});', ind + 1)
+        self.emit(f'while (coop_m{k}) {{', ind + 1)
+        self.emit(f'const int coop_src{k} = __ffs(coop_m{k}) - 1;', ind + 2)
+        self.emit(f'coop_m{k} &= coop_m{k} - 1;', ind + 2)
+        old_map = dict(self.coop_map)
+        for i in inputs:
+            n = self.nodes[i]
+            cur = self.ref(i, {})           # current per-lane name (possibly an outer broadcast copy)
+            name = f'c{k}_{i}'
+            if n.is_bool:
+                self.emit(f'const bool {name} = __shfl_sync(0xffffffffu, (int){cur}, coop_src{k}) != 0;', ind + 2)
+            else:
+                self.emit(f'const T {name} = __shfl_sync(0xffffffffu, {cur}, coop_src{k});', ind + 2)
+        for i in inputs:
+            self.coop_map[i] = f'c{k}_{i}'
+        self._coop_loop_body(st, known, ind + 2, dry=False)
+        self.coop_map = old_map
+        for q in st.quads:
+            self.emit(f'if ((int)(threadIdx.x & 31u) == coop_src{k}) v{q} = acc{k}_{q};', ind + 2)
+        self.emit('}', ind + 1)
+        self.emit('}', ind)
+
+    def _coop_loop_body(self, st: LoopGroup, known: Dict[int, bool], ind: int, dry: bool):
+        """One pending loop, executed by the whole warp for the owner lane's (broadcast) inputs."""
+        k = self.loop_counter
+        self.loop_counter += 1
+        N = self.N
+        T = self.ctype
+        zero = literal('0', T)
+        self._define(st.bvar)
+        self.emit(f'const T lo{k} = {self.ref(st.lo, known)};', ind)
+        self.emit(f'const T step{k} = ((T)({self.ref(st.hi, known)} - lo{k})) / (T){N};', ind)
+        for q in st.quads:
+            self.emit(f'T acc{k}_{q} = {zero};', ind)
+        self.emit(f'for (unsigned int base{k} = 0; base{k} < {N}u; base{k} += 32u) {{', ind)
+        self.emit(f'const unsigned int s{k} = base{k} + (threadIdx.x & 31u);', ind + 1)
+        self.emit(f'const T x{st.bvar} = lo{k} + step{k} * ((T)s{k} + {literal("0.5", T)});', ind + 1)
+        saved_div = self.divergent
+        self.divergent += 1                     # nothing inside the per-sample body may use warp collectives
+        self.block(st.body, ind + 1, 1)
+        self.divergent = saved_div
+        fix = []
+        for q in st.quads:
+            pf = self._pred_form(self.nodes[q].args[2], st.body) if self.pred_accum else None
+            if pf is not None and pf[0]:
+                conds, val = pf
+                term = f'step{k}' if val is None else f'{val} * step{k}'
+                cond = ' && '.join([f's{k} < {N}u'] + [f'({self.ref(c, st.body.known)})' for c in conds])
+                self.emit(f'const T t{k}_{q} = ({cond}) ? {term} : {zero};', ind + 1)
+                fix.append(q)
+            else:
+                body = self.ref(self.nodes[q].args[2], st.body.known)
+                self.emit(f'const T t{k}_{q} = (s{k} < {N}u) ? {body} * step{k} : {zero};', ind + 1)
+        # left fold in sample order, computed identically by every lane (adding the +0 of a missing /
+        # skipped sample never changes the accumulator)
+        self.emit(f'const unsigned int cnt{k} = ({N}u - base{k}) < 32u ? ({N}u - base{k}) : 32u;', ind + 1)
+        self.emit(f'for (unsigned int l{k} = 0; l{k} < cnt{k}; ++l{k}) {{', ind + 1)
+        for q in st.quads:
+            self.emit(f'acc{k}_{q} = acc{k}_{q} + __shfl_sync(0xffffffffu, t{k}_{q}, l{k});', ind + 2)
+        self.emit('}', ind + 1)
+        self.emit('}', ind)
+        for q in fix:
+            self.emit(f'acc{k}_{q} = acc{k}_{q} + {zero} * step{k};', ind)
 
     # ------------------------------------------------------- predicated accumulate (ALU-pipe relief)
     def _fold_compare(self, c: int, known: Dict[int, bool]):
@@ -344,6 +489,7 @@ class Emitter:
     def main_body(self) -> List[str]:
         self.in_main = True
         self.lines = []
+        self.guard_ctx = ['live'] if self.coop else []
         self.block(self.sch.main, 1, 0)
         for k, o in enumerate(self.sch.outputs):
             self.emit(f'res[{k}] = {self.ref(o, self.sch.main.known)};', 1)
@@ -387,7 +533,9 @@ class Emitter:
             outs_decl = ['T* __restrict__ partials']
         else:
             outs_decl = [f'T* __restrict__ out{k}' for k in range(K)]
+        coop = self.uses_coop
         iparams = ', '.join((['const T* __restrict__ tegU'] if grouped else []) +
+                            (['const bool live'] if coop else []) +
                             ([] if team == 1 else ['const unsigned int team_rank']) +
                             [f'const T a{a}' for a in varying] + [f'T (&res)[{K}]'])
         src: List[str] = []
@@ -454,12 +602,21 @@ class Emitter:
             src.append('    const bool live = ny < w_c1;')
             src.append('    const long long i = (long long)(nx - row0) * res_y + ny;')
             loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye[ny]', grid[3]: 'ye[ny + 1]'}
+            if coop:
+                # every lane of the warp runs the instance (dead lanes on a clamped pixel, results dropped)
+                src.append('    const int nyc = live ? ny : w_c0 + (int)(blockIdx.x * blockDim.x);')
+                src.append('    const long long ic = (long long)(nx - row0) * res_y + nyc;')
+                loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye[nyc]', grid[3]: 'ye[nyc + 1]'}
             for a in pix:
-                loads[a] = f'pix{a}[i]'
-            call = ', '.join(['sU'] + [loads[a] for a in varying] + ['res'])
+                loads[a] = f'pix{a}[ic]' if coop else f'pix{a}[i]'
+            call = ', '.join(['sU'] + (['live'] if coop else []) + [loads[a] for a in varying] + ['res'])
             src.append(f'    T res[{K}];')
             src.append(f'    for (int k = 0; k < {K}; k++) res[k] = {zero};')
-            src.append(f'    if (live) {name}_instance({call});')
+            if coop:
+                src.append(f'    {name}_instance({call});')
+                src.append(f'    if (!live) {{ for (int k = 0; k < {K}; k++) res[k] = {zero}; }}')
+            else:
+                src.append(f'    if (live) {name}_instance({call});')
             if reduce_outputs:
                 src.append(f'    tegb_block_sum_store<T, {K}, {bs}>(res, gp, tiles, tile);')
             elif accumulate:
@@ -485,14 +642,22 @@ class Emitter:
                 src.append('    const bool live = ny < res_y;')
                 src.append('    const int nx = row0 + blockIdx.y;')
                 src.append('    const long long i = (long long)blockIdx.y * res_y + ny;')
-                loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye[ny]', grid[3]: 'ye[ny + 1]'}
-                call = ', '.join([loads[a] for a in varying] + ['res'])
+                if coop:
+                    src.append('    const int nyc = live ? ny : 0;')
+                    loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye[nyc]', grid[3]: 'ye[nyc + 1]'}
+                else:
+                    loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye[ny]', grid[3]: 'ye[ny + 1]'}
+                call = ', '.join((['live'] if coop else []) + [loads[a] for a in varying] + ['res'])
             else:
                 mparams = ', '.join([f'const T* __restrict__ in{a}' for a in arrs] + outs_decl + ['const long long n'])
                 src.append(f'extern "C" __global__ void __launch_bounds__({bs}) {name}_main({mparams}) {{')
                 if team == 1:
                     src.append('    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;')
-                    call = ', '.join([f'in{a}[i]' for a in varying] + ['res'])
+                    if coop:
+                        src.append('    const long long ic = i < n ? i : 0;')
+                        call = ', '.join(['i < n'] + [f'in{a}[ic]' for a in varying] + ['res'])
+                    else:
+                        call = ', '.join([f'in{a}[i]' for a in varying] + ['res'])
                 else:
                     # TEAM threads per instance (a slice of a warp, a warp, or a whole block)
                     src.append('    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;')
@@ -503,14 +668,22 @@ class Emitter:
             src.append(f'    T res[{K}];')
             if reduce_outputs:
                 src.append(f'    for (int k = 0; k < {K}; k++) res[k] = {zero};')
-                src.append(f'    if (live) {name}_instance({call});')
+                if coop:
+                    src.append(f'    {name}_instance({call});')
+                    src.append(f'    if (!live) {{ for (int k = 0; k < {K}; k++) res[k] = {zero}; }}')
+                else:
+                    src.append(f'    if (live) {name}_instance({call});')
                 if team > 1:
                     src.append(f'    if (team_rank != 0) {{ for (int k = 0; k < {K}; k++) res[k] = {zero}; }}')
                 src.append(f'    tegb_block_sum_store<T, {K}, {bs}>(res, partials);')
             else:
-                src.append('    if (!live) return;')
-                src.append(f'    {name}_instance({call});')
-                guard = '' if team == 1 else 'if (team_rank == 0) '
+                if coop:
+                    src.append(f'    {name}_instance({call});')
+                    guard = 'if (live) '
+                else:
+                    src.append('    if (!live) return;')
+                    src.append(f'    {name}_instance({call});')
+                    guard = '' if team == 1 else 'if (team_rank == 0) '
                 for k in range(K):
                     src.append(f'    {guard}out{k}[i] = res[{k}];')
             src.append('}')

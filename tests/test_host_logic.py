@@ -59,7 +59,7 @@ def test_generated_code_matches_oracle_on_host(scene):
     arr = [i for i, v in enumerate(inputs) if np.ndim(v) > 0]
     sch = make_schedule(build_dag(prog), arr)
     for dtype, ctype in ((np.float32, 'float'), (np.float64, 'double')):
-        ks = generate(sch, ctype, ns, use_asm=False)       # inline PTX cannot be compiled for the host
+        ks = generate(sch, ctype, ns, use_asm=False, coop=False)       # inline PTX cannot be compiled for the host
         got = run_on_host(ks, inputs, n, dtype)
         want = Oracle(program_text(scene)).eval(inputs, ns, dtype)
         assert np.array_equal(got, want, equal_nan=True), f'{scene}/{ctype}'
@@ -73,10 +73,10 @@ def test_all_arguments_per_instance_and_all_scalar_variants():
     n = 256
     dag = build_dag(prog)
     want = Oracle(program_text('tri_grad')).eval(inputs, 16, np.float32)
-    ks = generate(make_schedule(dag, list(range(len(prog.args)))), 'float', 16, use_asm=False)
+    ks = generate(make_schedule(dag, list(range(len(prog.args)))), 'float', 16, use_asm=False, coop=False)
     assert np.array_equal(run_on_host(ks, inputs, n, np.float32), want)
     one = [float(np.ravel(v)[137]) if np.ndim(v) else v for v in inputs]
-    ks = generate(make_schedule(dag, []), 'float', 16, use_asm=False)
+    ks = generate(make_schedule(dag, []), 'float', 16, use_asm=False, coop=False)
     assert np.array_equal(run_on_host(ks, one, 1, np.float32)[:, 0], want[:, 137])
 
 
