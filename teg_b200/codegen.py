@@ -186,7 +186,7 @@ class Emitter:
                 self.divergent -= 1
                 self.emit('}', ind)
             elif isinstance(st, LoopGroup):
-                if self.coop and depth == 0 and not self.divergent and self.guard_ctx:
+                if self.coop and depth == 0 and not self.divergent and len(self.guard_ctx) > 1:
                     self._coop_loop(st, known, ind)
                 else:
                     self.loop(st, known, ind, depth)
