@@ -336,12 +336,26 @@ def main() -> int:
     peak_tflops, clk_mhz = runtime.fma_peak(4, local_rank)
     nominal = 2 * 128 * 148 * 1965e6 / 1e12
     achieved = flops_per_launch / (phase_ms['primal'] * 1e-3) / 1e12
+    traffic = None
+    try:
+        import glob
+        latest = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_traffic.json')))[-1]
+        with open(latest) as f:
+            tj = json.load(f)['tri_primal_main']
+        traffic = tj['dram_bytes_read'] + tj['dram_bytes_write']     # from the committed ncu --set full capture
+    except Exception:
+        pass
     roofline = {'bound': 'fp32_fma', 'kernel': 'tri_primal_main', 'achieved': achieved, 'peak': peak_tflops,
-                'unit': 'TFLOP/s', 'frac': achieved / peak_tflops, 'traffic': None,
+                'unit': 'TFLOP/s', 'frac': achieved / peak_tflops, 'traffic': traffic,
+                'traffic_unit': 'bytes per launch (dram read + write, ncu)', 'algorithmic_bytes': n_local * 4,
                 'peak_source': 'FFMA micro-benchmark (tegb_fma_peak) measured in this run; MEASURED_PEAKS.json '
                                'has no fp32 figure', 'peak_nominal': nominal,
                 'algorithmic_ops_per_instance': oc.unguarded, 'ops_per_inner_sample': oc.per_sample_inner,
                 'kernel_ms': phase_ms['primal'],
+                'note': 'achieved counts the reference program\'s operations (SURVEY 8(d) rule: 17 per inner sample); '
+                        'ptxas tabulates the inner-variable-only terms, so fewer instructions execute and the '
+                        'fraction can exceed 1; the kernel is bound by the ALU pipe (3 FSETP per sample, '
+                        'ncu: alu 84 %, fma 30 %, issue 76 %; profiles/)',
                 'hbm_GBps_out': (n_local * 4) / (ms_per_step * 1e-3) / 1e9}
 
     # ----------------------------------------------------------------------------------- cpu baseline

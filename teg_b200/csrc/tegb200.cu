@@ -302,6 +302,7 @@ static int run_uniform(tegb_program *p, const double *scalars, CUstream st) {
 // --------------------------------------------------------------------------------- deterministic sums
 static const int RED_THREADS = 256;
 static const int RED_MAX_BLOCKS = 1184;     // 8 blocks per SM x 148 SMs
+static const int RED_SLICES = 64;
 
 template <typename T>
 __device__ __forceinline__ T block_sum_fixed(T v, T *smem) {
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(RED_THREADS) colsum_stage2(const T *partials, 
 
 // partials buffer of a reduce_outputs program: n_outputs x n_blocks elements
 static int ensure_partials(tegb_program *p, unsigned long long n_blocks) {
-    const size_t need = (size_t)p->d.n_outputs * n_blocks * p->d.elem_size;
+    const size_t need = (size_t)p->d.n_outputs * (n_blocks + RED_SLICES) * p->d.elem_size;
     if (need <= p->partials_bytes) return TEGB_OK;
     if (p->d_partials) { cudaFree(p->d_partials); p->d_partials = nullptr; p->partials_bytes = 0; }
     RT_CHECK(cudaMalloc(&p->d_partials, need));
@@ -338,12 +339,44 @@ static int ensure_partials(tegb_program *p, unsigned long long n_blocks) {
     return TEGB_OK;
 }
 
+// Sum n_cols columns of n_blocks partials each.  Few long columns would leave the GPU idle (6 blocks for
+// a 6-parameter gradient), so long columns are first cut into RED_SLICES contiguous slices (one block each),
+// then the slice sums are added: still a fixed order for a given n_blocks, i.e. deterministic.
+
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS) colsum_slices(const T *partials, long long n_blocks, long long chunk,
+                                                             T *slices) {
+    __shared__ T smem[32];
+    const int c = blockIdx.y;
+    const long long lo = (long long)blockIdx.x * chunk;
+    long long hi = lo + chunk;
+    if (hi > n_blocks) hi = n_blocks;
+    T acc = 0;
+    for (long long i = lo + threadIdx.x; i < hi; i += RED_THREADS) acc = acc + partials[(long long)c * n_blocks + i];
+    T s = block_sum_fixed(acc, smem);
+    if (threadIdx.x == 0) slices[(long long)c * gridDim.x + blockIdx.x] = s;
+}
+
+template <typename T>
+static void sum_columns(const T *partials, int n_cols, unsigned long long n_blocks, T *out, T *slices, cudaStream_t st) {
+    if (n_blocks >= 16384 && slices) {
+        const long long chunk = (long long)((n_blocks + RED_SLICES - 1) / RED_SLICES);
+        colsum_slices<T><<<dim3(RED_SLICES, n_cols), RED_THREADS, 0, st>>>(partials, (long long)n_blocks, chunk, slices);
+        colsum_stage2<T><<<n_cols, RED_THREADS, 0, st>>>(slices, (long long)RED_SLICES, out);
+        g_launches += 2;
+    } else {
+        colsum_stage2<T><<<n_cols, RED_THREADS, 0, st>>>(partials, (long long)n_blocks, out);
+        g_launches++;
+    }
+}
+
 static int finish_partials(tegb_program *p, unsigned long long n_blocks, void *out, cudaStream_t st) {
+    // slice sums live behind the partials (ensure_partials reserves the room)
+    char *slices = (char *)p->d_partials + (size_t)p->d.n_outputs * n_blocks * p->d.elem_size;
     if (p->d.elem_size == 4)
-        colsum_stage2<float><<<p->d.n_outputs, RED_THREADS, 0, st>>>((const float *)p->d_partials, (long long)n_blocks, (float *)out);
+        sum_columns<float>((const float *)p->d_partials, p->d.n_outputs, n_blocks, (float *)out, (float *)slices, st);
     else
-        colsum_stage2<double><<<p->d.n_outputs, RED_THREADS, 0, st>>>((const double *)p->d_partials, (long long)n_blocks, (double *)out);
-    g_launches++;
+        sum_columns<double>((const double *)p->d_partials, p->d.n_outputs, n_blocks, (double *)out, (double *)slices, st);
     RT_CHECK(cudaGetLastError());
     return TEGB_OK;
 }
