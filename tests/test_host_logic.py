@@ -120,3 +120,29 @@ def test_exp_is_rejected_like_the_reference():
     text = 'TEGP 1\nname e\nnodes 2\nC 1\nF Exp 0\nroot 1\nargs 0\n'
     with pytest.raises(AssertionError):
         build_dag(Program.loads(text))
+
+
+def test_backend_registers_with_reference_registry_when_teg_is_importable():
+    """drop-in: `import teg_b200` adds 'CUDA' to teg.eval.backend.BACKENDS (backend.py:6-10) without editing it"""
+    import os
+    import sys
+    ref = os.environ.get('TEG_REFERENCE_PATH', '/root/reference')
+    if not os.path.isdir(os.path.join(ref, 'teg')):
+        pytest.skip('reference frontend not available on this machine')
+    sys.path.insert(0, ref)
+    sys.dont_write_bytecode = True
+    import teg.eval.backend as ref_backend
+    import teg_b200
+    assert teg_b200.register()
+    assert ref_backend.BACKENDS['CUDA'][0] is teg_b200.CUDA_EvalMode
+    # a live reference expression lowers to the same TEGP text as the committed fixture
+    from teg import IfElse, Teg, TegVar, Var
+    from teg.lang.base import Var as RefVar
+    saved = RefVar.global_uid
+    RefVar.global_uid = 1000
+    try:
+        x, t = TegVar('x'), Var('t', 0.5)
+        prog = from_teg(Teg(0, 1, IfElse(x < t, 1, 0), x), [t], name='readme_primal')
+    finally:
+        RefVar.global_uid = max(saved, RefVar.global_uid)
+    assert prog.dumps() == program_text('readme_primal')
