@@ -42,3 +42,37 @@ def test_exactly_one_mode_and_valid_precision(tmp_path):
     assert _run([], tmp_path).returncode != 0
     assert _run(['-c', '-f', 'half', 'prog.py'], tmp_path).returncode != 0
     assert _run(['-c', '-t', 'OPENCL', 'prog.py'], tmp_path).returncode != 0
+
+
+def test_compact_c_target_is_bit_identical_to_the_oracle(tmp_path):
+    """--target C from the backend's IR: same entry contract as to_c.py, ~60x less code,
+    same bits."""
+    import ctypes
+    import numpy as np
+    from conftest import load_program, program_text
+    from oracle import Oracle
+    from teg_b200.cli import emit_c
+    from teg_b200.workloads import bind, scene_values
+    prog = load_program('tri_grad')
+    code = emit_c(prog, float_type='float', samples=16, method='tri_grad')
+    assert code.count('\n') < 1200                       # the reference emits 33.5 k lines for this program
+    n_args = len(prog.args)
+    params = ', '.join(f'in[{a} * n + i]' for a in range(n_args))
+    code += ('\nextern "C" void run(const float* in, float* out, long n) { for (long i = 0; i < n; i++) { '
+             f'generic_array<float,6> r = tri_grad({params}); for (int j = 0; j < 6; j++) out[j * n + i] = r[j]; }} }}\n')
+    src = tmp_path / 't.cc'
+    src.write_text('template<typename T, int N> struct generic_array { T values[N]; T& operator[](int i) '
+                   '{ return values[i]; } };\n' + code)
+    so = tmp_path / 't.so'
+    subprocess.run(['g++', '-O2', '-std=c++11', '-fPIC', '-shared', '-ffp-contract=off', str(src), '-o', str(so)],
+                   check=True)
+    lib = ctypes.CDLL(str(so))
+    inputs = bind(prog.args, scene_values('tri_grad', res=(24, 24)))
+    n = 576
+    soa = np.empty((n_args, n), dtype=np.float32)
+    for i, v in enumerate(inputs):
+        soa[i] = v
+    out = np.empty((6, n), dtype=np.float32)
+    P = ctypes.POINTER(ctypes.c_float)
+    lib.run(soa.ctypes.data_as(P), out.ctypes.data_as(P), ctypes.c_long(n))
+    assert np.array_equal(out, Oracle(program_text('tri_grad')).eval(inputs, 16, np.float32))
