@@ -73,7 +73,8 @@ class KernelSource:
 
 class Emitter:
     def __init__(self, sch: Schedule, ctype: str, num_samples: int, name: str,
-                 block_size: int = 128, unroll_inner: int = 32, unroll_outer: int = 1, pred_accum: bool = True, use_asm: bool = True, team: int = 1, coop: bool = True):
+                 block_size: int = 128, unroll_inner: int = 32, unroll_outer: int = 1, pred_accum: bool = True, use_asm: bool = True, team: int = 1, coop: bool = True,
+                 pred_mix: float = 0.3125):
         assert ctype in ('float', 'double')
         self.sch = sch
         self.dag: Dag = sch.dag
@@ -86,6 +87,7 @@ class Emitter:
         self.unroll_outer = unroll_outer
         self.pred_accum = pred_accum
         self.use_asm = use_asm
+        self.pred_mix = float(pred_mix)
         assert team >= 1 and (team & (team - 1)) == 0 and team <= 1024, 'team must be a power of two <= 1024'
         self.team = team
         self.helper = Scheduler(sch.dag, sch.array_args)      # for resolve / bool_value
@@ -211,27 +213,49 @@ class Emitter:
         else:
             unroll = self.unroll_outer
         teamed = self.team > 1 and depth == 0
+        # pipe balancing: fully unrolled innermost loops alternate two exact forms of the predicated accumulate
+        # (see _emit_pred_add) so that neither the ALU pipe (compares) nor the issue slots are the lone limit
+        mixed = (innermost and not teamed and self.pred_mix > 0 and self.use_asm and N <= self.unroll_inner
+                 and self.ctype == 'float')
         if teamed:
             # the instance's team splits the outermost sample loop: member r takes samples r, r+TEAM, ...
             # (each member still folds its own samples left to right; partial sums are combined below)
             self.emit('#pragma unroll 1', ind + 1)
             self.emit(f'for (unsigned int s{k} = team_rank; s{k} < {N}u; s{k} += {self.team}u) {{', ind + 1)
+        elif mixed:
+            self.emit('{', ind + 1)         # unrolled by hand below: one scope per sample, in sample order
         else:
             self.emit(f'#pragma unroll {unroll}', ind + 1)
             self.emit(f'for (unsigned int s{k} = 0; s{k} < {N}u; ++s{k}) {{', ind + 1)
-        self.emit(f'const T x{st.bvar} = lo{k} + step{k} * ((T)s{k} + {literal("0.5", self.ctype)});', ind + 2)
-        self.block(st.body, ind + 2, depth + 1)
         fixups = []
-        for q in st.quads:
-            pf = self._pred_form(self.nodes[q].args[2], st.body) if self.pred_accum else None
-            if pf is not None and pf[0]:
-                conds, val = pf
-                term = f'step{k}' if val is None else f'{val} * step{k}'
-                self._emit_pred_add(f'v{q}', conds, term, st.body.known, ind + 2)
-                fixups.append(q)
-            else:
-                body = self.ref(self.nodes[q].args[2], st.body.known)
-                self.emit(f'v{q} = v{q} + {body} * step{k};', ind + 2)
+
+        def sample(sidx: str, form: str, ind2: int):
+            self.emit(f'const T x{st.bvar} = lo{k} + step{k} * ((T){sidx} + {literal("0.5", self.ctype)});', ind2)
+            self.block(st.body, ind2, depth + 1)
+            for q in st.quads:
+                pf = self._pred_form(self.nodes[q].args[2], st.body) if self.pred_accum else None
+                if pf is not None and pf[0]:
+                    conds, val = pf
+                    term = f'step{k}' if val is None else f'{val} * step{k}'
+                    self._emit_pred_add(f'v{q}', conds, term, st.body.known, ind2, form=form)
+                    if q not in fixups:
+                        fixups.append(q)
+                else:
+                    body = self.ref(self.nodes[q].args[2], st.body.known)
+                    self.emit(f'v{q} = v{q} + {body} * step{k};', ind2)
+
+        if mixed:
+            # a fraction pred_mix of the samples (evenly spread) uses the min3 form, the rest the chained form
+            taken = 0
+            for j in range(N):
+                want = int((j + 1) * self.pred_mix + 1e-9)
+                form = 'min3' if want > taken else 'chain'
+                taken = want
+                self.emit('{', ind + 2)
+                sample(f'{j}u', form, ind + 3)
+                self.emit('}', ind + 2)
+        else:
+            sample(f's{k}', 'chain', ind + 2)
         self.emit('}', ind + 1)
         if teamed:
             for q in st.quads:
@@ -397,7 +421,8 @@ class Emitter:
                 return cmp, self.ref(a, known), f'(-{self.ref(b, known)})'
         return 'lt', self.ref(x, known), self.ref(y, known)
 
-    def _emit_pred_add(self, acc: str, conds: List[int], term: str, known: Dict[int, bool], ind: int):
+    def _emit_pred_add(self, acc: str, conds: List[int], term: str, known: Dict[int, bool], ind: int,
+                       form: str = 'chain'):
         """acc = acc + term  iff all conds: one chained FSETP per comparison, then one predicated add."""
         leaves: List[int] = []
 
@@ -420,6 +445,24 @@ class Emitter:
             self.emit(f'if ({cond}) {acc} = {acc} + {term};', ind)
             return
         sfx, cons = ('f32', 'f') if self.ctype == 'float' else ('f64', 'd')
+        all_lt = all(self.nodes[c].op == 'lt' and c not in self.sch.uniform_slots and
+                     self.helper.bool_value(c, known) is None for c in leaves)
+        if form == 'min3' and len(leaves) == 3 and all_lt and self.ctype == 'float':
+            # the same predicate through the FMA pipe: d_k = lhs_k - rhs_k (positive iff lhs_k > rhs_k, exactly),
+            # one 3-input NaN-propagating minimum (FMNMX3, new on sm_100), one compare.  2 ALU-pipe instructions
+            # instead of 3; alternated with the chained form the two pipes are evenly loaded.
+            ops2: List[str] = []
+            subs = []
+            for j, c in enumerate(leaves):
+                cmp, lhs, rhs = self._fold_compare(c, known)
+                a, b = (lhs, rhs) if cmp == 'gt' else (rhs, lhs)
+                i0 = len(ops2) + 2
+                ops2 += [f'"f"({a})', f'"f"({b})']
+                subs.append(f'sub.rn.f32 e{j}, %{i0}, %{i0 + 1};')
+            body = ('.reg .pred p; .reg .f32 e0, e1, e2, m; ' + ' '.join(subs) +
+                    ' min.NaN.f32 m, e0, e1, e2; setp.gt.f32 p, m, 0f00000000; @p add.rn.f32 %0, %0, %1;')
+            self.emit(f'asm("{{ {body} }}" : "+f"({acc}) : "f"({term}), {", ".join(ops2)});', ind)
+            return
         ops: List[str] = []
         lines: List[str] = ['.reg .pred p;']
         first = True
