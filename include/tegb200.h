@@ -78,6 +78,8 @@ typedef struct {
 
 const char *tegb_last_error(void);
 int tegb_version(void);
+/* version of the NVRTC the library loaded, major * 1000 + minor * 10 (e.g. 12090); 0 if none could be loaded */
+int tegb_nvrtc_version(void);
 
 /* number of CUDA devices visible (0 without a driver); never fails */
 int tegb_device_count(void);

@@ -49,7 +49,7 @@ def build_runtime(force: bool = False, verbose: bool = False) -> str:
     _write_header_inc()
     cuda_lib = '/usr/local/cuda/lib64'
     cmd = [_nvcc(), *NVCC_FLAGS, f'-I{ABI_INCLUDE}', f'-I{CSRC}', os.path.join(CSRC, 'tegb200.cu'),
-           '-o', LIB_PATH, f'-L{cuda_lib}', '-lnvrtc', '-ldl', '-Xlinker', f'-rpath={cuda_lib}']
+           '-o', LIB_PATH, '-ldl']
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
     r = subprocess.run(cmd, capture_output=True, text=True)

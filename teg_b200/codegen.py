@@ -461,7 +461,11 @@ class Emitter:
                 subs.append(f'sub.rn.f32 e{j}, %{i0}, %{i0 + 1};')
             body = ('.reg .pred p; .reg .f32 e0, e1, e2, m; ' + ' '.join(subs) +
                     ' min.NaN.f32 m, e0, e1, e2; setp.gt.f32 p, m, 0f00000000; @p add.rn.f32 %0, %0, %1;')
+            self.emit('#ifdef TEGB_HAVE_MIN3', 0)
             self.emit(f'asm("{{ {body} }}" : "+f"({acc}) : "f"({term}), {", ".join(ops2)});', ind)
+            self.emit('#else', 0)
+            self._emit_pred_add(acc, conds, term, known, ind, form='chain')
+            self.emit('#endif', 0)
             return
         ops: List[str] = []
         lines: List[str] = ['.reg .pred p;']

@@ -123,6 +123,63 @@ extern "C" int tegb_device_count(void) {
     return n;
 }
 
+// --------------------------------------------------------------------------------------- NVRTC shim
+// NVRTC is loaded by PATH, not by soname: a process that imported torch already has torch's bundled
+// libnvrtc.so.12 (an older 12.x) mapped, and a soname lookup would silently reuse it.  The toolkit's own
+// NVRTC (>= 12.9: PTX 8.8, 3-input min/max for sm_100) is preferred; TEGB200_NVRTC overrides the path.
+namespace rtc {
+typedef nvrtcResult (*Version_t)(int *, int *);
+typedef nvrtcResult (*CreateProgram_t)(nvrtcProgram *, const char *, const char *, int, const char *const *, const char *const *);
+typedef nvrtcResult (*DestroyProgram_t)(nvrtcProgram *);
+typedef nvrtcResult (*CompileProgram_t)(nvrtcProgram, int, const char *const *);
+typedef nvrtcResult (*GetSize_t)(nvrtcProgram, size_t *);
+typedef nvrtcResult (*GetData_t)(nvrtcProgram, char *);
+typedef const char *(*GetErrorString_t)(nvrtcResult);
+static void *lib = nullptr;
+static Version_t Version;
+static CreateProgram_t CreateProgram;
+static DestroyProgram_t DestroyProgram;
+static CompileProgram_t CompileProgram;
+static GetSize_t GetProgramLogSize, GetCUBINSize;
+static GetData_t GetProgramLog, GetCUBIN;
+static GetErrorString_t GetErrorString;
+static int major = 0, minor = 0;
+static std::once_flag once;
+static bool ok = false;
+static std::string why;
+static void load() {
+    std::vector<std::string> cands;
+    if (const char *e = getenv("TEGB200_NVRTC")) cands.push_back(e);
+    cands.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
+    cands.push_back("/usr/local/cuda/lib64/libnvrtc.so");
+    cands.push_back("libnvrtc.so.12");
+    cands.push_back("libnvrtc.so");
+    for (auto &c : cands) {
+        lib = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (lib) break;
+    }
+    if (!lib) { why = std::string("cannot load NVRTC: ") + dlerror(); return; }
+#define SYM(var, name)                                                   \
+    var = (decltype(var))dlsym(lib, name);                               \
+    if (!var) { why = std::string("NVRTC lacks ") + name; return; }
+    SYM(Version, "nvrtcVersion");
+    SYM(CreateProgram, "nvrtcCreateProgram");
+    SYM(DestroyProgram, "nvrtcDestroyProgram");
+    SYM(CompileProgram, "nvrtcCompileProgram");
+    SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
+    SYM(GetProgramLog, "nvrtcGetProgramLog");
+    SYM(GetCUBINSize, "nvrtcGetCUBINSize");
+    SYM(GetCUBIN, "nvrtcGetCUBIN");
+    SYM(GetErrorString, "nvrtcGetErrorString");
+#undef SYM
+    Version(&major, &minor);
+    ok = true;
+}
+static bool ready() { std::call_once(once, load); return ok; }
+}  // namespace rtc
+
+extern "C" int tegb_nvrtc_version(void) { return rtc::ready() ? rtc::major * 1000 + rtc::minor * 10 : 0; }
+
 // ------------------------------------------------------------------------------------------------ JIT
 struct tegb_module {
     std::vector<char> cubin;
@@ -132,15 +189,18 @@ struct tegb_module {
 extern "C" int tegb_compile(const char *cuda_src, const char *arch, const char *opts, tegb_module **out) {
     if (!cuda_src || !out) return fail(TEGB_ERR_INVALID, "tegb_compile: null argument");
     *out = nullptr;
+    if (!rtc::ready()) return fail(TEGB_ERR_COMPILE, "%s", rtc::why.c_str());
     const char *header_names[] = {"teg_b200_runtime.cuh"};
     const char *header_srcs[] = {TEGB_RUNTIME_HEADER};
     nvrtcProgram prog;
-    nvrtcResult r = nvrtcCreateProgram(&prog, cuda_src, "teg_program.cu", 1, header_srcs, header_names);
-    if (r != NVRTC_SUCCESS) return fail(TEGB_ERR_COMPILE, "nvrtcCreateProgram: %s", nvrtcGetErrorString(r));
+    nvrtcResult r = rtc::CreateProgram(&prog, cuda_src, "teg_program.cu", 1, header_srcs, header_names);
+    if (r != NVRTC_SUCCESS) return fail(TEGB_ERR_COMPILE, "nvrtcCreateProgram: %s", rtc::GetErrorString(r));
 
     std::vector<std::string> o;
     o.push_back(std::string("--gpu-architecture=") + (arch && *arch ? arch : "sm_100a"));
     o.push_back("--fmad=false");       // one IEEE operation per reference operation (parity contract)
+    if (rtc::major > 12 || (rtc::major == 12 && rtc::minor >= 9))
+        o.push_back("-DTEGB_HAVE_MIN3=1");     // PTX 8.8: min.NaN.f32 with three inputs (FMNMX3 on sm_100)
     o.push_back("--std=c++17");
     o.push_back("-lineinfo");
     if (opts) {
@@ -152,27 +212,27 @@ extern "C" int tegb_compile(const char *cuda_src, const char *arch, const char *
     }
     std::vector<const char *> oc;
     for (auto &s : o) oc.push_back(s.c_str());
-    r = nvrtcCompileProgram(prog, (int)oc.size(), oc.data());
+    r = rtc::CompileProgram(prog, (int)oc.size(), oc.data());
     size_t logsz = 0;
-    nvrtcGetProgramLogSize(prog, &logsz);
+    rtc::GetProgramLogSize(prog, &logsz);
     std::string log(logsz > 0 ? logsz : 1, '\0');
-    if (logsz > 1) nvrtcGetProgramLog(prog, &log[0]);
+    if (logsz > 1) rtc::GetProgramLog(prog, &log[0]);
     if (r != NVRTC_SUCCESS) {
-        int rc = fail(TEGB_ERR_COMPILE, "NVRTC: %s\n%s", nvrtcGetErrorString(r), log.c_str());
-        nvrtcDestroyProgram(&prog);
+        int rc = fail(TEGB_ERR_COMPILE, "NVRTC: %s\n%s", rtc::GetErrorString(r), log.c_str());
+        rtc::DestroyProgram(&prog);
         return rc;
     }
     size_t sz = 0;
-    r = nvrtcGetCUBINSize(prog, &sz);
+    r = rtc::GetCUBINSize(prog, &sz);
     if (r != NVRTC_SUCCESS || sz == 0) {
-        nvrtcDestroyProgram(&prog);
-        return fail(TEGB_ERR_COMPILE, "nvrtcGetCUBINSize: %s (arch must be a real sm_XX)", nvrtcGetErrorString(r));
+        rtc::DestroyProgram(&prog);
+        return fail(TEGB_ERR_COMPILE, "nvrtcGetCUBINSize: %s (arch must be a real sm_XX)", rtc::GetErrorString(r));
     }
     tegb_module *m = new tegb_module();
     m->cubin.resize(sz);
-    nvrtcGetCUBIN(prog, m->cubin.data());
+    rtc::GetCUBIN(prog, m->cubin.data());
     m->log = log.c_str();
-    nvrtcDestroyProgram(&prog);
+    rtc::DestroyProgram(&prog);
     *out = m;
     return TEGB_OK;
 }

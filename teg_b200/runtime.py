@@ -33,7 +33,7 @@ class Grid(ctypes.Structure):
 
 
 SYMBOLS = [
-    'tegb_last_error', 'tegb_version', 'tegb_device_count', 'tegb_compile', 'tegb_module_from_cubin',
+    'tegb_last_error', 'tegb_version', 'tegb_nvrtc_version', 'tegb_device_count', 'tegb_compile', 'tegb_module_from_cubin',
     'tegb_module_cubin', 'tegb_module_log', 'tegb_module_destroy', 'tegb_program_create',
     'tegb_program_destroy', 'tegb_program_launch', 'tegb_program_eval_host', 'tegb_render_launch',
     'tegb_render_groups_launch',
@@ -117,7 +117,7 @@ class Module:
         L = lib()
         self._L = L
         self.handle = ctypes.c_void_p()
-        key = hashlib.sha256(f'{L.tegb_version()}|{arch}|{opts}|{source}'.encode()).hexdigest()[:32]
+        key = hashlib.sha256(f'{L.tegb_version()}|{L.tegb_nvrtc_version()}|{arch}|{opts}|{source}'.encode()).hexdigest()[:32]
         path = os.path.join(cache_dir(), f'{key}.cubin')
         self.from_cache = False
         if use_cache and os.path.exists(path):
@@ -148,9 +148,12 @@ class Module:
         return self._L.tegb_module_log(self.handle).decode(errors='replace')
 
     def __del__(self):
-        if getattr(self, 'handle', None) and self.handle.value:
-            self._L.tegb_module_destroy(self.handle)
-            self.handle = ctypes.c_void_p()
+        try:
+            if getattr(self, 'handle', None) and self.handle.value:
+                self._L.tegb_module_destroy(self.handle)
+                self.handle.value = None
+        except Exception:       # interpreter shutdown: module globals may already be gone
+            pass
 
 
 def _ptr_array(ptrs: Sequence[int]):
@@ -208,9 +211,12 @@ class Program:
                                                 ctypes.c_void_p(stream)))
 
     def __del__(self):
-        if getattr(self, 'handle', None) and self.handle.value:
-            self._L.tegb_program_destroy(self.handle)
-            self.handle = ctypes.c_void_p()
+        try:
+            if getattr(self, 'handle', None) and self.handle.value:
+                self._L.tegb_program_destroy(self.handle)
+                self.handle.value = None
+        except Exception:       # interpreter shutdown
+            pass
 
 
 def reduce_workspace_bytes(n_cols: int, n: int, elem_size: int) -> int:
