@@ -74,7 +74,7 @@ class KernelSource:
 class Emitter:
     def __init__(self, sch: Schedule, ctype: str, num_samples: int, name: str,
                  block_size: int = 128, unroll_inner: int = 32, unroll_outer: int = 1, pred_accum: bool = True, use_asm: bool = True, team: int = 1, coop: bool = True,
-                 pred_mix: float = 0.3125):
+                 pred_mix: float = 0.25):
         assert ctype in ('float', 'double')
         self.sch = sch
         self.dag: Dag = sch.dag

@@ -59,7 +59,7 @@ class CUDA_EvalMode(EvalMode):
 
     def __init__(self, expr, num_samples: int = 50, float_width: str = 'float', device: int = 0,
                  arglist: Sequence = (), name: str = 'teg_method', use_cache: bool = True,
-                 block_size: int = 128, team=1, **codegen_opts):
+                 block_size: int = 128, team=1, nvrtc_opts: str = '', **codegen_opts):
         super().__init__(name='CUDA')
         if float_width in ('single', 'f32', np.float32):
             float_width = 'float'
@@ -82,6 +82,7 @@ class CUDA_EvalMode(EvalMode):
         assert team == 'auto' or (isinstance(team, int) and team >= 1 and team & (team - 1) == 0 and team <= 1024)
         self.team = team
         self.codegen_opts = codegen_opts
+        self.nvrtc_opts = nvrtc_opts
         self.arglist: List[Tuple[str, Optional[float]]] = [
             (lab, self.program.defaults.get(lab)) for lab in self.program.args]
         self.out_size = len(self.dag.outputs)
@@ -130,7 +131,7 @@ class CUDA_EvalMode(EvalMode):
                               accumulate=accumulate, block_size=self.block_size, **self.codegen_opts)
             else:
                 ks = self.kernel_source(array_args, grid_args, reduce, team)
-            mod = runtime.Module(ks.source, use_cache=self.use_cache)
+            mod = runtime.Module(ks.source, opts=self.nvrtc_opts, use_cache=self.use_cache)
             prog = runtime.Program(mod, ks, device=self.device)
             hit = (ks, prog)
             self._variants[key] = hit
