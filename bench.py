@@ -172,6 +172,7 @@ def main() -> int:
     ap.add_argument('--cpu-rows', type=int, default=256, help='pixel rows in the bounded CPU sample')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'], help='working precision of the programs')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -203,8 +204,11 @@ def main() -> int:
     n_local = res * res
     primal = Program.loads(load_text('tri_primal'))
     grad = Program.loads(load_text('tri_grad'))
-    m_primal = CUDA_EvalMode(primal, num_samples=NUM_SAMPLES, device=local_rank)
-    m_grad = CUDA_EvalMode(grad, num_samples=NUM_SAMPLES, device=local_rank)
+    fw = 'float' if args.dtype == 'f32' else 'double'
+    tdt = torch.float32 if args.dtype == 'f32' else torch.float64
+    esz = 4 if args.dtype == 'f32' else 8
+    m_primal = CUDA_EvalMode(primal, num_samples=NUM_SAMPLES, device=local_rank, float_width=fw)
+    m_grad = CUDA_EvalMode(grad, num_samples=NUM_SAMPLES, device=local_rank, float_width=fw)
     box = primal.args[:4]
     params = {lab: TRIANGLE[lab.rsplit('_', 1)[0]] for lab in primal.args[4:]}
     gparams = {lab: TRIANGLE[lab.rsplit('_', 1)[0]] for lab in grad.args[4:]}
@@ -212,8 +216,8 @@ def main() -> int:
 
     stream = torch.cuda.current_stream(dev)
     sptr = stream.cuda_stream
-    imgs = [torch.empty((1, res, res), dtype=torch.float32, device=dev) for _ in range(2)]
-    gsums = [torch.zeros(6, dtype=torch.float32, device=dev) for _ in range(2)]
+    imgs = [torch.empty((1, res, res), dtype=tdt, device=dev) for _ in range(2)]
+    gsums = [torch.zeros(6, dtype=tdt, device=dev) for _ in range(2)]
     img, gsum = imgs[0], gsums[0]
 
     ev = {k: [] for k in ('primal', 'grad')}
@@ -291,8 +295,8 @@ def main() -> int:
     # ---------------------------------------------------------------- e2e: host buffers, copies inside
     e2e = None
     if not args.no_e2e:
-        h_imgs = [torch.empty((res, res), dtype=torch.float32).pin_memory() for _ in range(2)]
-        h_gs = [torch.empty(6, dtype=torch.float32).pin_memory() for _ in range(2)]
+        h_imgs = [torch.empty((res, res), dtype=tdt).pin_memory() for _ in range(2)]
+        h_gs = [torch.empty(6, dtype=tdt).pin_memory() for _ in range(2)]
         copy_stream = torch.cuda.Stream(dev)
         done = [torch.cuda.Event() for _ in range(2)]
         copied = [torch.cuda.Event() for _ in range(2)]
@@ -327,8 +331,8 @@ def main() -> int:
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {'value': n_local * world * k_e2e / float(te.item()), 'unit': 'integral evals/s',
-               'h2d_bytes_per_step': 2 * 6 * 4,
-               'd2h_bytes_per_step': int(h_imgs[0].numel() * 4 + h_gs[0].numel() * 4),
+               'h2d_bytes_per_step': 2 * 6 * esz,
+               'd2h_bytes_per_step': int(h_imgs[0].numel() * esz + h_gs[0].numel() * esz),
                'api': 'CUDA_EvalMode.render(...) for the value image and render(..., reduce=True) for the gradient '
                       '(pixel boxes generated on device); image + gradient vector copied to pinned host memory '
                       'every step on a second stream, double-buffered', 'steps': k_e2e,
@@ -343,11 +347,13 @@ def main() -> int:
     sch = make_schedule(m_primal.dag, [0, 1, 2, 3])
     oc = op_count(sch, NUM_SAMPLES)
     flops_per_launch = oc.unguarded * n_local           # primal has no guards: exact
-    peak_tflops, clk_mhz = runtime.fma_peak(4, local_rank)
-    nominal = 2 * 128 * 148 * 1965e6 / 1e12
+    peak_tflops, clk_mhz = runtime.fma_peak(esz, local_rank)
+    nominal = 2 * (128 if esz == 4 else 64) * 148 * 1965e6 / 1e12
     achieved = flops_per_launch / (phase_ms['primal'] * 1e-3) / 1e12
     traffic = None
     try:
+        if esz != 4:
+            raise KeyError('the committed ncu capture is of the fp32 kernel')
         import glob
         latest = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_traffic.json')))[-1]
         with open(latest) as f:
@@ -355,9 +361,9 @@ def main() -> int:
         traffic = tj['dram_bytes_read'] + tj['dram_bytes_write']     # from the committed ncu --set full capture
     except Exception:
         pass
-    roofline = {'bound': 'fp32_fma', 'kernel': 'tri_primal_main', 'achieved': achieved, 'peak': peak_tflops,
+    roofline = {'bound': 'fp32_fma' if esz == 4 else 'fp64_fma', 'kernel': 'tri_primal_main', 'achieved': achieved, 'peak': peak_tflops,
                 'unit': 'TFLOP/s', 'frac': achieved / peak_tflops, 'traffic': traffic,
-                'traffic_unit': 'bytes per launch (dram read + write, ncu)', 'algorithmic_bytes': n_local * 4,
+                'traffic_unit': 'bytes per launch (dram read + write, ncu)', 'algorithmic_bytes': n_local * esz,
                 'peak_source': 'FFMA micro-benchmark (tegb_fma_peak) measured in this run; MEASURED_PEAKS.json '
                                'has no fp32 figure', 'peak_nominal': nominal,
                 'algorithmic_ops_per_instance': oc.unguarded, 'ops_per_inner_sample': oc.per_sample_inner,
@@ -366,7 +372,7 @@ def main() -> int:
                         'ptxas tabulates the inner-variable-only terms, so fewer instructions execute and the '
                         'fraction can exceed 1; the kernel is bound by the ALU pipe (3 FSETP per sample, '
                         'ncu: alu 84 %, fma 30 %, issue 76 %; profiles/)',
-                'hbm_GBps_out': (n_local * 4) / (ms_per_step * 1e-3) / 1e9}
+                'hbm_GBps_out': (n_local * esz) / (ms_per_step * 1e-3) / 1e9}
 
     # ----------------------------------------------------------------------------------- cpu baseline
     cpu = None
@@ -386,7 +392,7 @@ def main() -> int:
     line = {
         'metric': 'integral_evals_per_s', 'value': value, 'unit': 'integral evals/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'res_per_gpu': [res, res], 'num_samples': NUM_SAMPLES,
                    'programs': ['tri_primal', 'tri_grad'], 'outputs': 'value image [4096,4096] + per-parameter '
                    'gradient sum [6] (reduced in-kernel)', 'l2': 'L2 flushed between timed steps by writing a '

@@ -51,8 +51,11 @@ class MultiTriangleRasterizer:
         self.rows = (self.res * self.rank, self.res * (self.rank + 1))
         self.K = 0
 
-    def set_scene(self, verts, col, windows, classes: Sequence[Tuple[int, int]], max_rows: int, max_cols: int):
-        """verts [K, 6], col [K] (host or device), windows int32 [K, 4], classes: disjoint-window group ranges."""
+    def set_scene(self, verts, col, windows, classes: Sequence[Tuple[int, int]], max_rows: int, max_cols: int,
+                  active: Optional[Tuple[int, int]] = None):
+        """verts [K, 6], col [K] (host or device), windows int32 [K, 4], classes: disjoint-window group ranges.
+        active: the contiguous group range whose windows can touch this rank's band (default: all groups);
+        groups outside it are never launched here and get zero gradient rows."""
         torch = self.torch
         verts = torch.as_tensor(np.asarray(verts) if not torch.is_tensor(verts) else verts)
         col = torch.as_tensor(np.asarray(col) if not torch.is_tensor(col) else col)
@@ -63,7 +66,9 @@ class MultiTriangleRasterizer:
         self.params['col'] = col.to(self.dev, self.tdt).contiguous()
         self.windows = torch.as_tensor(np.asarray(windows) if not torch.is_tensor(windows) else windows)
         self.windows = self.windows.to(self.dev, torch.int32).contiguous()
-        self.classes = list(classes)
+        self.active = (0, self.K) if active is None else (int(active[0]), int(active[1]))
+        self.classes = [(max(a, self.active[0]), min(b, self.active[1])) for a, b in classes
+                        if max(a, self.active[0]) < min(b, self.active[1])]
         self.max_rows, self.max_cols = int(max_rows), int(max_cols)
 
     def update_params(self, verts, col):
@@ -94,7 +99,10 @@ class MultiTriangleRasterizer:
             out = torch.empty((self.K, 7), dtype=self.tdt, device=self.dev)
         box = [self.g_lab[b] for b in BOX]
         gb = {self.g_lab[nm]: self.params[nm] for nm in PARAMS}
+        a0, a1 = self.active
+        if (a0, a1) != (0, self.K):
+            out.zero_()
         self.m_grad.render_groups(box, self.grid_res, self.bounds, gb, self.windows, self.max_rows, self.max_cols,
-                                  pixel_bindings={self.g_lab['dL']: dL}, rows=self.rows, out=out, reduce=True,
-                                  stream=stream)
+                                  pixel_bindings={self.g_lab['dL']: dL}, rows=self.rows, out=out[a0:a1], reduce=True,
+                                  group_range=(a0, a1), stream=stream)
         return out

@@ -52,8 +52,10 @@ def test_multi_triangle_forward_backward_match_oracle(cuda_device, bands):
     for rank in range(bands):
         r = MultiTriangleRasterizer(load_program('tri_color_primal'), load_program('tri_color_grad'), res,
                                     bands=bands, rank=rank)
+        br = scene['band_ranges']
+        active = (br[max(rank - 1, 0)][0], br[min(rank + 1, bands - 1)][1]) if bands > 1 else None
         r.set_scene(scene['verts'], scene['col'], scene['windows'], scene['classes'], scene['max_rows'],
-                    scene['max_cols'])
+                    scene['max_cols'], active=active)
         img = r.forward()
         band = torch.as_tensor(dL[res * rank: res * (rank + 1)]).cuda().contiguous()
         g = r.backward(band)

@@ -55,8 +55,10 @@ def main():
     scene = multi_triangle_scene(bands=world, res=res)
     K = scene['verts'].shape[0]
     r = MultiTriangleRasterizer(primal, grad, res, bands=world, rank=rank, device=local)
+    br = scene['band_ranges']
+    active = (br[max(rank - 1, 0)][0], br[min(rank + 1, world - 1)][1])      # own band and its neighbours
     r.set_scene(scene['verts'], scene['col'], scene['windows'], scene['classes'], scene['max_rows'],
-                scene['max_cols'])
+                scene['max_cols'], active=active)
     w = scene['windows'].astype(np.int64)
     r0 = np.clip(w[:, 0], res * rank, res * (rank + 1))
     r1 = np.clip(w[:, 1], res * rank, res * (rank + 1))
