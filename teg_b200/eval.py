@@ -142,7 +142,15 @@ class CUDA_EvalMode(EvalMode):
         by_label = {}
         for k, v in (bindings or {}).items():
             by_label[k if isinstance(k, str) else label_of(k)] = v
-        args = [by_label[lab] if lab in by_label else default for lab, default in self.arglist]
+        live = self.program.live
+        args = []
+        for lab, default in self.arglist:
+            if lab in by_label:
+                args.append(by_label[lab])
+            elif lab in live:                     # c_eval.py:136: the Var's *current* value
+                args.append(live[lab].value)
+            else:
+                args.append(default)
         assert all(a is not None for a in args), \
             f'No bindings found for {[self.arglist[i][0] for i, a in enumerate(args) if a is None]}'
         return args

@@ -88,6 +88,9 @@ class Program:
     root: int = -1
     args: List[str] = field(default_factory=list)            # ordered input labels
     defaults: Dict[str, Optional[float]] = field(default_factory=dict)
+    # label -> live Var object when the program was converted from live expressions (not serialised): the
+    # reference reads ``teg_var.value`` at *eval* time (c_eval.py:136), so later bind_variable() calls count
+    live: Dict[str, object] = field(default_factory=dict, repr=False, compare=False)
 
     # ------------------------------------------------------------------ io
     def dumps(self) -> str:
@@ -270,6 +273,7 @@ def from_teg(expr, arglist: Sequence = (), name: str = 'teg_method') -> Program:
             lab = label_of(e)
             if lab not in prog.defaults or prog.defaults[lab] is None:
                 prog.defaults[lab] = None if e.value is None else float(e.value)
+            prog.live.setdefault(lab, e)
             return intern('V', (), lab)
         if 'FwdDeriv' in names or 'RevDeriv' in names:
             return conv(e.deriv_expr)
@@ -310,6 +314,10 @@ def from_teg(expr, arglist: Sequence = (), name: str = 'teg_method') -> Program:
 
     free = prog.free_labels()
     ordered = [label_of(v) for v in arglist]
+    for v in arglist:
+        prog.live.setdefault(label_of(v), v)
+        if prog.defaults.get(label_of(v)) is None and v.value is not None:
+            prog.defaults[label_of(v)] = float(v.value)
     for lab in ordered:
         if lab not in free:
             # An argument the program does not use is still a (dead) input slot, as in

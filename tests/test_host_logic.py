@@ -146,3 +146,22 @@ def test_backend_registers_with_reference_registry_when_teg_is_importable():
     finally:
         RefVar.global_uid = max(saved, RefVar.global_uid)
     assert prog.dumps() == program_text('readme_primal')
+
+
+def test_unbound_arguments_follow_the_live_var_value_like_c_eval():
+    """c_eval.py:136 reads ``teg_var.value`` at eval time: bind_variable() after the mode was built must count
+    (tests/test.py:74-97 relies on it)."""
+    from teg_b200.eval import CUDA_EvalMode
+    from teg_b200.lang import IfElse, Teg, TegVar, Var
+    x, t = TegVar('x'), Var('t', 0.5)
+    mode = CUDA_EvalMode.__new__(CUDA_EvalMode)          # host-side logic only: no device needed for _resolve
+    prog = from_teg(Teg(0, 1, IfElse(x < t, 1, 0), x))
+    mode.program = prog
+    mode.arglist = [(lab, prog.defaults.get(lab)) for lab in prog.args]
+    assert mode._resolve({}) == [0.5]
+    t.value = 0.75
+    assert mode._resolve({}) == [0.75]
+    assert mode._resolve({t: 0.1}) == [0.1]
+    t.value = None
+    with pytest.raises(AssertionError):
+        mode._resolve({})
