@@ -74,7 +74,7 @@ class KernelSource:
 class Emitter:
     def __init__(self, sch: Schedule, ctype: str, num_samples: int, name: str,
                  block_size: int = 128, unroll_inner: int = 32, unroll_outer: int = 1, pred_accum: bool = True, use_asm: bool = True, team: int = 1, coop: bool = True,
-                 pred_mix: float = 0.25):
+                 pred_mix: float = 0.25, jam: int = 4):
         assert ctype in ('float', 'double')
         self.sch = sch
         self.dag: Dag = sch.dag
@@ -99,6 +99,8 @@ class Emitter:
         self.ref_log = None                   # dry-run bookkeeping: nodes referenced / defined
         self.def_log = None
         self.uses_coop = False
+        self.jam_map: Dict[int, str] = {}     # node -> per-copy name while emitting an unroll-and-jam copy
+        self.jam = int(jam)
         self.lines: List[str] = []
         self.loop_counter = 0
         # static op statistics (per execution of each block, weighted later by trip counts)
@@ -121,6 +123,8 @@ class Emitter:
             self.ref_log.add(i)
         if i in self.coop_map:
             return self.coop_map[i]
+        if i in self.jam_map:
+            return self.jam_map[i]
         if n.op == 'bvar':
             return f'x{i}'
         return f'v{i}'
@@ -197,6 +201,8 @@ class Emitter:
 
     def loop(self, st: LoopGroup, known: Dict[int, bool], ind: int, depth: int):
         """data/templates/rectangular_rule.template.c:1-11, several accumulators per pass."""
+        if self._jam_ok(st, depth):
+            return self._jam_loop(st, known, ind, depth)
         k = self.loop_counter
         self.loop_counter += 1
         N = self.N
@@ -263,6 +269,111 @@ class Emitter:
         for q in fixups:
             # skipped terms were `0 * step`: identical for every finite step; keeps NaN/inf steps poisonous
             self.emit(f'v{q} = v{q} + {literal("0", self.ctype)} * step{k};', ind + 1)
+        self.emit('}', ind)
+
+    # ------------------------------------------------------------ outer-loop blocking (unroll and jam)
+    # Nest  for x { pre(x); for y { body(x, y) }; post }  with a long inner loop: U consecutive x-samples are
+    # carried through ONE pass of the inner loop, so everything that depends on y only (sample placement, the
+    # y-terms of every affine form) is computed once per U samples instead of once per sample.  Each of the U
+    # inner accumulators still receives its own samples in order and the outer accumulator receives the U
+    # inner results in sample order: every sum is the same left fold, bit for bit.  (For short inner loops
+    # the full unroll lets ptxas hoist the same terms by itself.)
+    def _jam_ok(self, st: LoopGroup, depth: int) -> bool:
+        U, N = self.jam, self.N
+        if U < 2 or N <= self.unroll_inner or self.divergent and False:
+            return False
+        teamed = self.team > 1 and depth == 0
+        if N % (U * (self.team if teamed else 1)) != 0:
+            return False
+        inner = [s for s in st.body.stmts if isinstance(s, LoopGroup)]
+        if len(inner) != 1 or any(isinstance(s, IfGroup) for s in st.body.stmts):
+            return False
+        inner = inner[0]
+        if any(not isinstance(s, Eval) for s in inner.body.stmts):
+            return False
+        fv = self.dag.free_bvars
+        if st.bvar in fv(inner.lo) or st.bvar in fv(inner.hi):
+            return False
+        # the inner body must have something to share
+        return any(st.bvar not in fv(s.node) for s in inner.body.stmts)
+
+    def _jam_loop(self, st: LoopGroup, known: Dict[int, bool], ind: int, depth: int):
+        U, N, T = self.jam, self.N, self.ctype
+        zero, half = literal('0', T), literal('0.5', T)
+        k = self.loop_counter
+        self.loop_counter += 1
+        teamed = self.team > 1 and depth == 0
+        inner = [s for s in st.body.stmts if isinstance(s, LoopGroup)][0]
+        pos = st.body.stmts.index(inner)
+        pre, post = st.body.stmts[:pos], st.body.stmts[pos + 1:]
+        fv = self.dag.free_bvars
+        shared = [s for s in inner.body.stmts if st.bvar not in fv(s.node)]
+        percopy = [s for s in inner.body.stmts if st.bvar in fv(s.node)]
+        for q in st.quads:
+            self._define(q)
+            self.emit(f'T v{q} = {zero};', ind)
+        self._define(st.bvar)
+        self.emit('{', ind)
+        self.emit(f'const T lo{k} = {self.ref(st.lo, known)};', ind + 1)
+        self.emit(f'const T step{k} = ((T)({self.ref(st.hi, known)} - lo{k})) / (T){N};', ind + 1)
+        self.emit('#pragma unroll 1', ind + 1)
+        if teamed:
+            self.emit(f'for (unsigned int s{k} = team_rank * {U}u; s{k} < {N}u; s{k} += {self.team * U}u) {{', ind + 1)
+        else:
+            self.emit(f'for (unsigned int s{k} = 0; s{k} < {N}u; s{k} += {U}u) {{', ind + 1)
+        copy_nodes = [st.bvar] + [s.node for s in pre] + list(inner.quads) + [s.node for s in post]
+        maps = [{i: (f'x{i}_{u}' if self.nodes[i].op == 'bvar' else f'v{i}_{u}') for i in copy_nodes} for u in range(U)]
+        saved = dict(self.jam_map)
+        kk = self.loop_counter
+        self.loop_counter += 1
+        # per-copy outer prologue
+        for u in range(U):
+            self.jam_map = {**saved, **maps[u]}
+            self.emit(f'const T x{st.bvar}_{u} = lo{k} + step{k} * ((T)(s{k} + {u}u) + {half});', ind + 2)
+            for s in pre:
+                self._define(s.node)
+                self.emit(f'const {self.decl(s.node)} v{s.node}_{u} = {self.expr(s.node, st.body.known)};', ind + 2)
+            for q in inner.quads:
+                self._define(q)
+                self.emit(f'T v{q}_{u} = {zero};', ind + 2)
+        # the one shared pass over the inner loop
+        self.jam_map = dict(saved)
+        self._define(inner.bvar)
+        self.emit('{', ind + 2)
+        self.emit(f'const T lo{kk} = {self.ref(inner.lo, st.body.known)};', ind + 3)
+        self.emit(f'const T step{kk} = ((T)({self.ref(inner.hi, st.body.known)} - lo{kk})) / (T){N};', ind + 3)
+        self.emit('#pragma unroll 2', ind + 3)
+        self.emit(f'for (unsigned int s{kk} = 0; s{kk} < {N}u; ++s{kk}) {{', ind + 3)
+        self.emit(f'const T x{inner.bvar} = lo{kk} + step{kk} * ((T)s{kk} + {half});', ind + 4)
+        for s in shared:
+            self._define(s.node)
+            self.emit(f'const {self.decl(s.node)} v{s.node} = {self.expr(s.node, inner.body.known)};', ind + 4)
+        for u in range(U):
+            self.jam_map = {**saved, **maps[u]}
+            self.emit('{', ind + 4)
+            for s in percopy:
+                self._define(s.node)
+                self.emit(f'const {self.decl(s.node)} v{s.node} = {self.expr(s.node, inner.body.known)};', ind + 5)
+            for q in inner.quads:
+                body = self.ref(self.nodes[q].args[2], inner.body.known)
+                self.emit(f'v{q}_{u} = v{q}_{u} + {body} * step{kk};', ind + 5)
+            self.emit('}', ind + 4)
+        self.emit('}', ind + 3)
+        self.emit('}', ind + 2)
+        # per-copy epilogue and the outer accumulate, in sample order
+        for u in range(U):
+            self.jam_map = {**saved, **maps[u]}
+            for s in post:
+                self._define(s.node)
+                self.emit(f'const {self.decl(s.node)} v{s.node}_{u} = {self.expr(s.node, st.body.known)};', ind + 2)
+            for q in st.quads:
+                body = self.ref(self.nodes[q].args[2], st.body.known)
+                self.emit(f'v{q} = v{q} + {body} * step{k};', ind + 2)
+        self.jam_map = saved
+        self.emit('}', ind + 1)
+        if teamed:
+            for q in st.quads:
+                self.emit(f'v{q} = tegb_team_sum<T, {self.team}>(v{q});', ind + 1)
         self.emit('}', ind)
 
     # ------------------------------------------------------ warp-cooperative guarded loops

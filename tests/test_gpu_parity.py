@@ -236,3 +236,12 @@ def test_prepared_call_matches_eval_and_tracks_scalar_updates(cuda_device):
     got2 = call.run()
     torch.cuda.synchronize()
     assert np.array_equal(got2.cpu().numpy(), want2) and not np.array_equal(want, want2)
+
+
+@pytest.mark.parametrize('scene,ns', [('nested2d_value', 64), ('nested2d_value', 100), ('nested3d_value', 36),
+                                      ('tri_primal', 40), ('shaded_primal', 48), ('bilinear_lerp', 64)])
+def test_unroll_and_jam_is_bit_exact_on_device(cuda_device, scene, ns):
+    got, want = _run_both(scene, np.float32, res=(24, 24), n=512, ns=ns)
+    assert np.array_equal(got, want, equal_nan=True)
+    got, want = _run_both(scene, np.float64, res=(12, 12), n=128, ns=ns)
+    assert np.array_equal(got, want, equal_nan=True)

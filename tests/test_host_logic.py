@@ -165,3 +165,22 @@ def test_unbound_arguments_follow_the_live_var_value_like_c_eval():
     t.value = None
     with pytest.raises(AssertionError):
         mode._resolve({})
+
+
+@pytest.mark.parametrize('scene', ['nested2d_value', 'nested3d_value', 'tri_primal', 'shaded_primal', 'circle'])
+def test_unroll_and_jam_keeps_every_fold_exact(scene):
+    """Long inner loops (N > 32) carry 4 outer samples through one inner pass; results must stay bit-identical."""
+    from oracle import Oracle
+    prog = load_program(scene)
+    inputs = bind(prog.args, scene_values(scene, res=(6, 6), n=40))
+    n = max(np.size(v) for v in inputs)
+    arr = [i for i, v in enumerate(inputs) if np.ndim(v) > 0]
+    sch = make_schedule(build_dag(prog), arr)
+    for ns in (36, 40):
+        ks = generate(sch, 'float', ns, use_asm=False, coop=False)
+        assert '_3 = ' in ks.source                          # four copies were emitted
+        want = Oracle(program_text(scene)).eval(inputs, ns, np.float32)
+        assert np.array_equal(run_on_host(ks, inputs, n, np.float32), want, equal_nan=True)
+        off = generate(sch, 'float', ns, use_asm=False, coop=False, jam=1)
+        assert '_3 = ' not in off.source
+        assert np.array_equal(run_on_host(off, inputs, n, np.float32), want, equal_nan=True)
