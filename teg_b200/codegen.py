@@ -74,7 +74,7 @@ class KernelSource:
 class Emitter:
     def __init__(self, sch: Schedule, ctype: str, num_samples: int, name: str,
                  block_size: int = 128, unroll_inner: int = 32, unroll_outer: int = 1, pred_accum: bool = True, use_asm: bool = True, team: int = 1, coop: bool = True,
-                 pred_mix: float = 0.25, jam: int = 4):
+                 pred_mix: float = 0.25, jam: int = 4, coop_max_lanes: int = 4):
         assert ctype in ('float', 'double')
         self.sch = sch
         self.dag: Dag = sch.dag
@@ -101,6 +101,7 @@ class Emitter:
         self.uses_coop = False
         self.jam_map: Dict[int, str] = {}     # node -> per-copy name while emitting an unroll-and-jam copy
         self.jam = int(jam)
+        self.coop_max_lanes = int(coop_max_lanes)
         self.lines: List[str] = []
         self.loop_counter = 0
         # static op statistics (per execution of each block, weighted later by trip counts)
@@ -199,17 +200,18 @@ class Emitter:
             else:  # pragma: no cover
                 raise TypeError(st)
 
-    def loop(self, st: LoopGroup, known: Dict[int, bool], ind: int, depth: int):
+    def loop(self, st: LoopGroup, known: Dict[int, bool], ind: int, depth: int, declare: bool = True):
         """data/templates/rectangular_rule.template.c:1-11, several accumulators per pass."""
         if self._jam_ok(st, depth):
-            return self._jam_loop(st, known, ind, depth)
+            return self._jam_loop(st, known, ind, depth, declare)
         k = self.loop_counter
         self.loop_counter += 1
         N = self.N
         innermost = not any(isinstance(s, LoopGroup) for s in st.body.walk())
         for q in st.quads:
             self._define(q)
-            self.emit(f'T v{q} = {literal("0", self.ctype)};', ind)
+            if declare:
+                self.emit(f'T v{q} = {literal("0", self.ctype)};', ind)
         self._define(st.bvar)
         self.emit('{', ind)
         self.emit(f'const T lo{k} = {self.ref(st.lo, known)};', ind + 1)
@@ -297,7 +299,7 @@ class Emitter:
         # the inner body must have something to share
         return any(st.bvar not in fv(s.node) for s in inner.body.stmts)
 
-    def _jam_loop(self, st: LoopGroup, known: Dict[int, bool], ind: int, depth: int):
+    def _jam_loop(self, st: LoopGroup, known: Dict[int, bool], ind: int, depth: int, declare: bool = True):
         U, N, T = self.jam, self.N, self.ctype
         zero, half = literal('0', T), literal('0.5', T)
         k = self.loop_counter
@@ -311,7 +313,8 @@ class Emitter:
         percopy = [s for s in inner.body.stmts if st.bvar in fv(s.node)]
         for q in st.quads:
             self._define(q)
-            self.emit(f'T v{q} = {zero};', ind)
+            if declare:
+                self.emit(f'T v{q} = {zero};', ind)
         self._define(st.bvar)
         self.emit('{', ind)
         self.emit(f'const T lo{k} = {self.ref(st.lo, known)};', ind + 1)
@@ -420,18 +423,30 @@ class Emitter:
         # dry run: which per-lane values does the loop (bounds + body + integrands) read from outside?
         saved = (self.lines, self.loop_counter, self.ref_log, self.def_log)
         self.lines, self.ref_log, self.def_log = [], set(), set()
-        self._coop_loop_body(st, known, 0, dry=True)
+        k = self.loop_counter
+        self.loop_counter += 1
+        self._coop_loop_body(st, known, 0, dry=True, k=k)
         inputs = sorted(self.ref_log - self.def_log)
-        self.lines, self.loop_counter, self.ref_log, self.def_log = saved
+        self.lines, _, self.ref_log, self.def_log = saved
+        self.loop_counter = k + 1
         if self.ref_log is not None:
             self.ref_log.update(inputs)
-        k = self.loop_counter
         for q in st.quads:
             self._define(q)
             self.emit(f'T v{q} = {zero};', ind)
         self.emit('{', ind)
-        self.emit(f'unsigned int coop_m{k} = __ballot_sync(0xffffffffu, {" && ".join(self.guard_ctx)});', ind + 1)
-        self.emit(f'while (coop_m{k}) {{', ind + 1)
+        guard = ' && '.join(self.guard_ctx)
+        self.emit(f'unsigned int coop_m{k} = __ballot_sync(0xffffffffu, {guard});', ind + 1)
+        # Many pending lanes: the ordinary per-lane loop (all of them busy at once) is cheaper than serving
+        # them one by one.  Few (the usual case along a discontinuity): serve each with the whole warp.
+        self.emit(f'if (__popc(coop_m{k}) > {self.coop_max_lanes}) {{', ind + 1)
+        self.emit(f'if ({guard}) {{', ind + 2)
+        saved_div, saved_k = self.divergent, self.loop_counter
+        self.divergent += 1
+        self.loop(st, known, ind + 3, 0, declare=False)
+        self.divergent = saved_div
+        self.emit('}', ind + 2)
+        self.emit(f'}} else while (coop_m{k}) {{', ind + 1)
         self.emit(f'const int coop_src{k} = __ffs(coop_m{k}) - 1;', ind + 2)
         self.emit(f'coop_m{k} &= coop_m{k} - 1;', ind + 2)
         old_map = dict(self.coop_map)
@@ -445,17 +460,15 @@ class Emitter:
                 self.emit(f'const T {name} = __shfl_sync(0xffffffffu, {cur}, coop_src{k});', ind + 2)
         for i in inputs:
             self.coop_map[i] = f'c{k}_{i}'
-        self._coop_loop_body(st, known, ind + 2, dry=False)
+        self._coop_loop_body(st, known, ind + 2, dry=False, k=k)
         self.coop_map = old_map
         for q in st.quads:
             self.emit(f'if ((int)(threadIdx.x & 31u) == coop_src{k}) v{q} = acc{k}_{q};', ind + 2)
         self.emit('}', ind + 1)
         self.emit('}', ind)
 
-    def _coop_loop_body(self, st: LoopGroup, known: Dict[int, bool], ind: int, dry: bool):
+    def _coop_loop_body(self, st: LoopGroup, known: Dict[int, bool], ind: int, dry: bool, k: int):
         """One pending loop, executed by the whole warp for the owner lane's (broadcast) inputs."""
-        k = self.loop_counter
-        self.loop_counter += 1
         N = self.N
         T = self.ctype
         zero = literal('0', T)
