@@ -135,6 +135,8 @@ def run_reference_arm(args) -> int:
         return 0
     threads = os.cpu_count() or 1
     kind, run = cpu_runner(threads)
+    if kind == 'port':          # the interpreter is ~50x slower than compiled C: keep the sample bounded
+        args.cpu_rows = min(args.cpu_rows, 8)
     inputs, n_inst = cpu_sample_inputs(args.res, args.cpu_rows)
     for _ in range(max(args.warmup, 1)):
         run('tri_primal', inputs)
@@ -379,6 +381,8 @@ def main() -> int:
     if not args.no_cpu and world == 1:
         threads = os.cpu_count() or 1
         kind, run = cpu_runner(threads)
+        if kind == 'port':
+            args.cpu_rows = min(args.cpu_rows, 8)
         inputs, n_inst = cpu_sample_inputs(res, args.cpu_rows)
         run('tri_primal', inputs)
         best = time_cpu(run, inputs, reps=3)
