@@ -20,7 +20,6 @@ or, failing that, from the oracle port.
 from __future__ import annotations
 
 import argparse
-import ctypes
 import json
 import os
 import subprocess

@@ -125,7 +125,7 @@ def main(argv=None) -> int:
     import teg
     from teg.lang.base import Var
     from oracle.scenes import SCENES
-    from teg_b200.tegp import from_teg, label_of
+    from teg_b200.tegp import from_teg
 
     os.makedirs(REF_DIR, exist_ok=True)
     os.makedirs(PROG_DIR, exist_ok=True)

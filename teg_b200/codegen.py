@@ -104,8 +104,6 @@ class Emitter:
         self.coop_max_lanes = int(coop_max_lanes)
         self.lines: List[str] = []
         self.loop_counter = 0
-        # static op statistics (per execution of each block, weighted later by trip counts)
-        self.stats = {'ops_instance': 0, 'ops_guarded': 0, 'ops_sample_static': 0}
 
     # --------------------------------------------------------------- references
     def ref(self, i: int, known: Dict[int, bool]) -> str:
@@ -282,7 +280,7 @@ class Emitter:
     # the full unroll lets ptxas hoist the same terms by itself.)
     def _jam_ok(self, st: LoopGroup, depth: int) -> bool:
         U, N = self.jam, self.N
-        if U < 2 or N <= self.unroll_inner or self.divergent and False:
+        if U < 2 or N <= self.unroll_inner:
             return False
         teamed = self.team > 1 and depth == 0
         if N % (U * (self.team if teamed else 1)) != 0:
@@ -529,9 +527,6 @@ class Emitter:
                     if kk.op == 'const' and float(kk.attr) == -1.0:
                         return self.ref(wa, known)
             return None
-
-        def free_or_avail(i):
-            return True
 
         for zero, summ, cmp in ((x, y, 'gt'), (y, x, 'lt')):
             if is_zero(zero) and self.nodes[summ].op == 'add' and summ not in self.sch.uniform_slots:
@@ -865,7 +860,7 @@ class Emitter:
                             n_uniform=nu, scalar_args=scal, array_args=arrs, grid_args=grid,
                             n_outputs=K, block_size=bs, reduce_outputs=bool(reduce_outputs), team=team,
                             grouped=bool(grouped), pixel_args=pix, accumulate=bool(accumulate),
-                            stats=dict(self.stats))
+                            stats={'uses_coop': self.uses_coop, 'loops': self.loop_counter})
 
 
 def generate(sch: Schedule, ctype: str = 'float', num_samples: int = 50, name: Optional[str] = None,

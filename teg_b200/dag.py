@@ -160,10 +160,6 @@ class Dag:
         return {'live_nodes': len(live), **ops}
 
 
-def _bvar_depth_of(dag: Dag, i: int) -> int:
-    return dag.nodes[i].attr
-
-
 def build_dag(prog: Program) -> Dag:
     """TEGP program -> Dag.  Raises the same exception types as the reference lowering for the same
     causes (ValueError for inexpressible nodes / unbound structure, AssertionError for typing violations

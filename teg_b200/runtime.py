@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes
 import hashlib
 import os
-from typing import Optional, Sequence
+from typing import Sequence
 
 from . import build as _build
 
