@@ -78,6 +78,11 @@ def run(config, scene, ns, dtype, res=None, n=None, team=1, check=2048):
             'alg_tflops_lower_bound': oc.unguarded * count / t / 1e12,
             'io_bytes_per_instance': (len(arr) + len(mode.dag.outputs)) * (4 if dtype == np.float32 else 8)}
     line['hbm_GBps'] = line['io_bytes_per_instance'] * count / t / 1e9
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            line['hbm_frac_of_measured_peak'] = line['hbm_GBps'] / json.load(f)['hbm_gbs']
+    except Exception:
+        line['hbm_frac_of_measured_peak'] = line['hbm_GBps'] / 6650.0        # fallback stated in the profiling guide
     path = ref_lib_path(scene, dtype, ns)
     if os.path.exists(path):
         ref = RefLib(scene, dtype, ns)
@@ -103,6 +108,9 @@ def main():
     for scene in ('readme_deriv', 'readme_primal'):
         for dt in (f32, f64):
             run('cfg1_readme_1Mi', scene, 50, dt, n=1 << 20)
+    # config 1 at a size where the HBM streams, not the launch latency, set the time (HBM roofline)
+    for dt in (f32, f64):
+        run('cfg1_readme_64Mi_hbm', 'readme_deriv', 50, dt, n=1 << 26, check=4096)
     # config 2: triangle 256 x 256
     for scene in ('tri_primal', 'tri_grad', 'raster_theta'):
         ns = 10 if scene == 'raster_theta' else 16
