@@ -63,6 +63,8 @@ typedef struct {
                                      n_outputs per-component sums over all instances to out_ptrs[0] (device) */
     int team;                     /* threads cooperating on one instance (power of two, 1 = thread per instance);
                                      > 32 means one block of `team` threads per instance (block_size == team) */
+    int vec;                      /* instances per thread of a streaming program (1 or 4); > 1 requires every
+                                     input / output pointer to be 16-byte aligned */
     int grouped;                  /* 1: grouped render program (tegb_render_groups_launch): the scalar arguments are
                                      per-group arrays, the uniform table has one row per group */
     int n_pixel_args;             /* grouped programs: arguments read from images indexed by pixel */

@@ -64,6 +64,7 @@ class KernelSource:
     grouped: bool = False           # grouped render launch: per-group scalar arguments + pixel windows
     pixel_args: List[int] = None    # arguments read from pixel-indexed images (grouped launches)
     accumulate: bool = False        # outputs are added into images
+    vec: int = 1                    # instances per thread (16-byte vector loads/stores), streaming programs
     stats: Dict[str, float] = None
 
     @property
@@ -662,7 +663,7 @@ class Emitter:
         return self.lines
 
     def generate(self, grid_args: Sequence[int] = (), reduce_outputs: bool = False, grouped: bool = False,
-                 pixel_args: Sequence[int] = (), accumulate: bool = False) -> KernelSource:
+                 pixel_args: Sequence[int] = (), accumulate: bool = False, vec: int = 1) -> KernelSource:
         """grid_args: argument indices of (x_lb, x_ub, y_lb, y_ub) when they are generated from the pixel
         index (render programs, tests/plot.py:8-29) instead of being streamed from per-instance arrays.
         reduce_outputs: instead of one output stream per component, every block sums its instances'
@@ -672,7 +673,10 @@ class Emitter:
         values of the scalar arguments and its own window of pixels; launch-invariant values become one
         table row per group (global memory, staged through shared memory per block) instead of the
         constant bank.  pixel_args: arguments read from images indexed by pixel (an upstream dL).
-        accumulate: outputs are added into images (groups of one launch must not overlap)."""
+        accumulate: outputs are added into images (groups of one launch must not overlap).
+        vec: instances per thread for streaming (loop-free) programs: 16-byte vector loads/stores of ``vec``
+        consecutive instances put 4x the bytes in flight per thread, which is what an HBM-bound kernel
+        needs (a 4-byte load per thread saturates at ~2 TB/s on B200); all pointers must be 16-byte aligned."""
         sch = self.sch
         T = self.ctype
         name = self.name
@@ -817,6 +821,43 @@ class Emitter:
             else:
                 mparams = ', '.join([f'const T* __restrict__ in{a}' for a in arrs] + outs_decl + ['const long long n'])
                 src.append(f'extern "C" __global__ void __launch_bounds__({bs}) {name}_main({mparams}) {{')
+                if vec > 1:
+                    assert team == 1 and not coop and not reduce_outputs and vec == 4
+                    V = 'float4' if T == 'float' else 'double2'
+                    per = 4 if T == 'float' else 2          # elements per 16-byte vector
+                    nvec = vec // per
+                    comps = 'xyzw' if T == 'float' else 'xy'
+                    src.append('    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;')
+                    src.append(f'    const long long i0 = t * {vec};')
+                    src.append('    if (i0 >= n) return;')
+                    src.append(f'    if (i0 + {vec} <= n) {{')
+                    for a in varying:
+                        for h in range(nvec):
+                            src.append(f'        const {V} A{a}_{h} = *reinterpret_cast<const {V}*>(in{a} + i0 + {h * per});')
+                    for j in range(vec):
+                        h, c = divmod(j, per)
+                        src.append(f'        T r{j}[{K}];')
+                        src.append(f'        {name}_instance(' + ', '.join([f'A{a}_{h}.{comps[c]}' for a in varying] + [f'r{j}']) + ');')
+                    for k in range(K):
+                        for h in range(nvec):
+                            vals = ', '.join(f'r{h * per + c}[{k}]' for c in range(per))
+                            src.append(f'        *reinterpret_cast<{V}*>(out{k} + i0 + {h * per}) = make_{V}({vals});')
+                    src.append('    } else {')
+                    src.append('        for (long long i = i0; i < n; ++i) {')
+                    src.append(f'            T res[{K}];')
+                    src.append(f'            {name}_instance(' + ', '.join([f'in{a}[i]' for a in varying] + ['res']) + ');')
+                    for k in range(K):
+                        src.append(f'            out{k}[i] = res[{k}];')
+                    src.append('        }')
+                    src.append('    }')
+                    src.append('}')
+                    src.append('#endif')
+                    text = '\n'.join(src) + '\n'
+                    return KernelSource(name=name, ctype=T, num_samples=self.N, source=text,
+                                        uniform_kernel=f'{name}_uniform', main_kernel=f'{name}_main',
+                                        n_uniform=nu, scalar_args=scal, array_args=arrs, grid_args=grid,
+                                        n_outputs=K, block_size=bs, reduce_outputs=False, team=1, vec=vec,
+                                        stats={'uses_coop': False, 'loops': self.loop_counter})
                 if team == 1:
                     src.append('    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;')
                     if coop:
@@ -865,11 +906,11 @@ class Emitter:
 
 def generate(sch: Schedule, ctype: str = 'float', num_samples: int = 50, name: Optional[str] = None,
              grid_args: Sequence[int] = (), reduce_outputs: bool = False, grouped: bool = False,
-             pixel_args: Sequence[int] = (), accumulate: bool = False, **opts) -> KernelSource:
+             pixel_args: Sequence[int] = (), accumulate: bool = False, vec: int = 1, **opts) -> KernelSource:
     name = name or _c_ident(sch.dag.name)
     return Emitter(sch, ctype, num_samples, name, **opts).generate(
         grid_args=grid_args, reduce_outputs=reduce_outputs, grouped=grouped, pixel_args=pixel_args,
-        accumulate=accumulate)
+        accumulate=accumulate, vec=vec)
 
 
 def _c_ident(s: str) -> str:

@@ -457,7 +457,14 @@ extern "C" int tegb_program_launch(tegb_program *p, const double *scalars, const
     for (int i = 0; i < p->d.n_array_args; i++) { ins[i] = in_ptrs[i]; args.push_back(&ins[i]); }
     const unsigned bs = (unsigned)p->d.block_size;
     const long long team = p->d.team > 1 ? p->d.team : 1;
-    const long long blocks = (n * team + bs - 1) / bs;
+    const long long vec = p->d.vec > 1 ? p->d.vec : 1;
+    if (vec > 1) {
+        for (int i = 0; i < p->d.n_array_args; i++)
+            if (((uintptr_t)in_ptrs[i]) & 15) return fail(TEGB_ERR_INVALID, "vectorised program: input %d is not 16-byte aligned", i);
+        for (int k = 0; k < p->d.n_outputs; k++)
+            if (((uintptr_t)out_ptrs[k]) & 15) return fail(TEGB_ERR_INVALID, "vectorised program: output %d is not 16-byte aligned", k);
+    }
+    const long long blocks = (((n + vec - 1) / vec) * team + bs - 1) / bs;
     if (blocks > 2147483647LL) return fail(TEGB_ERR_INVALID, "too many instances for one launch");
     if (p->d.reduce_outputs) {
         rc = ensure_partials(p, (unsigned long long)blocks);

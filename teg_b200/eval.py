@@ -112,16 +112,24 @@ class CUDA_EvalMode(EvalMode):
         return team
 
     def kernel_source(self, array_args: Sequence[int], grid_args: Sequence[int] = (),
-                      reduce: bool = False, team: int = 1) -> KernelSource:
+                      reduce: bool = False, team: int = 1, vec: int = 1) -> KernelSource:
         sch = self.schedule(array_args, grid_args)
         block = team if team > 32 else self.block_size
         return generate(sch, self.float_width, self.num_samples, grid_args=list(grid_args),
-                        reduce_outputs=reduce, block_size=block, team=team, **self.codegen_opts)
+                        reduce_outputs=reduce, block_size=block, team=team, vec=vec, **self.codegen_opts)
+
+    def pick_vec(self, array_args: Sequence[int], reduce: bool, team: int, ptrs: Sequence[int]) -> int:
+        """4 instances per thread (16-byte vector loads/stores) for streaming programs: no sample loop left
+        after delta elimination (e.g. the README derivative), plain per-instance arrays, aligned buffers."""
+        if reduce or team != 1 or not array_args or any(p & 15 for p in ptrs):
+            return 1
+        return 4 if self.schedule(array_args).loop_depth() == 0 else 1
 
     def compiled(self, array_args: Sequence[int], grid_args: Sequence[int] = (), reduce: bool = False,
-                 team: int = 1, grouped: bool = False, pixel_args: Sequence[int] = (), accumulate: bool = False):
+                 team: int = 1, grouped: bool = False, pixel_args: Sequence[int] = (), accumulate: bool = False,
+                 vec: int = 1):
         key = (tuple(sorted(array_args)), tuple(grid_args), bool(reduce), int(team), bool(grouped),
-               tuple(pixel_args), bool(accumulate))
+               tuple(pixel_args), bool(accumulate), int(vec))
         hit = self._variants.get(key)
         if hit is None:
             if grouped:
@@ -130,7 +138,7 @@ class CUDA_EvalMode(EvalMode):
                               reduce_outputs=reduce, grouped=True, pixel_args=list(pixel_args),
                               accumulate=accumulate, block_size=self.block_size, **self.codegen_opts)
             else:
-                ks = self.kernel_source(array_args, grid_args, reduce, team)
+                ks = self.kernel_source(array_args, grid_args, reduce, team, vec)
             mod = runtime.Module(ks.source, opts=self.nvrtc_opts, use_cache=self.use_cache)
             prog = runtime.Program(mod, ks, device=self.device)
             hit = (ks, prog)
@@ -178,10 +186,12 @@ class CUDA_EvalMode(EvalMode):
             n = ln
         array_args = [i for i, f in enumerate(is_arr) if f]
         team = self.pick_team(1 if n is None else n, array_args)
-        ks, prog = self.compiled(array_args, reduce=reduce, team=team)
-        scalars = [float(args[a]) for a in ks.scalar_args]
         if any_torch:
-            return self._eval_torch(ks, prog, args, scalars, n, reduce)
+            return self._eval_torch(args, array_args, n, reduce, team)
+        # host path: the library stages through its own (256-byte aligned) device buffers
+        vec = self.pick_vec(array_args, reduce, team, [])
+        ks, prog = self.compiled(array_args, reduce=reduce, team=team, vec=vec)
+        scalars = [float(args[a]) for a in ks.scalar_args]
         batched = n is not None
         n = 1 if n is None else n
         ins = [np.ascontiguousarray(np.asarray(args[a], dtype=dt).reshape(-1)) for a in ks.array_args]
@@ -197,23 +207,28 @@ class CUDA_EvalMode(EvalMode):
             return vals if self.out_is_tuple and len(vals) > 1 else vals[0]
         return out if self.out_is_tuple and ks.n_outputs > 1 else out[0]
 
-    def _eval_torch(self, ks, prog, args, scalars, n, reduce=False):
+    def _eval_torch(self, args, array_args, n, reduce, team):
         import torch
         tdt = torch.float32 if self.float_width == 'float' else torch.float64
         dev = torch.device('cuda', self.device)
-        ins = []
-        for a in ks.array_args:
+        ins = {}
+        for a in array_args:
             t = args[a]
             if not _is_torch(t):
                 t = torch.as_tensor(np.asarray(t), device=dev)
-            t = t.to(device=dev, dtype=tdt).contiguous().view(-1)
-            ins.append(t)
+            ins[a] = t.to(device=dev, dtype=tdt).contiguous().view(-1)
+        k_out = len(self.dag.outputs)
+        out = None if reduce else torch.empty((k_out, n), dtype=tdt, device=dev)
+        ptrs = [t.data_ptr() for t in ins.values()] + ([] if reduce else [out[k].data_ptr() for k in range(k_out)])
+        vec = self.pick_vec(array_args, reduce, team, ptrs)
+        ks, prog = self.compiled(array_args, reduce=reduce, team=team, vec=vec)
+        scalars = [float(args[a]) for a in ks.scalar_args]
+        ins = [ins[a] for a in ks.array_args]
         stream = torch.cuda.current_stream(dev).cuda_stream
         if reduce:
             sums = torch.empty(ks.n_outputs, dtype=tdt, device=dev)
             prog.launch(scalars, [t.data_ptr() for t in ins], [sums.data_ptr()], n, stream=stream)
             return sums if self.out_is_tuple and ks.n_outputs > 1 else sums[0]
-        out = torch.empty((ks.n_outputs, n), dtype=tdt, device=dev)
         prog.launch(scalars, [t.data_ptr() for t in ins], [out[k].data_ptr() for k in range(ks.n_outputs)],
                     n, stream=stream)
         return out if self.out_is_tuple and ks.n_outputs > 1 else out[0]
@@ -293,15 +308,19 @@ class CUDA_EvalMode(EvalMode):
             array_args.append(i)
         n_eff = 1 if n is None else n
         team = self.pick_team(n_eff, array_args)
-        ks, prog = self.compiled(array_args, reduce=reduce, team=team)
-        ins = []
-        for a in ks.array_args:
+        tens = {}
+        for a in array_args:
             t = args[a]
             if not _is_torch(t):
                 t = torch.as_tensor(np.asarray(t))
-            ins.append(t.to(device=dev, dtype=tdt).contiguous().view(-1))
-        out = (torch.empty(ks.n_outputs, dtype=tdt, device=dev) if reduce
-               else torch.empty((ks.n_outputs, n_eff), dtype=tdt, device=dev))
+            tens[a] = t.to(device=dev, dtype=tdt).contiguous().view(-1)
+        k_out = len(self.dag.outputs)
+        out = (torch.empty(k_out, dtype=tdt, device=dev) if reduce
+               else torch.empty((k_out, n_eff), dtype=tdt, device=dev))
+        ptrs = [t.data_ptr() for t in tens.values()] + ([] if reduce else [out[k].data_ptr() for k in range(k_out)])
+        ks, prog = self.compiled(array_args, reduce=reduce, team=team,
+                                 vec=self.pick_vec(array_args, reduce, team, ptrs))
+        ins = [tens[a] for a in ks.array_args]
         scalars = [float(args[a]) for a in ks.scalar_args]
         return PreparedCall(self, ks, prog, scalars, ins, out, n_eff, reduce)
 

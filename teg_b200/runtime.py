@@ -22,7 +22,7 @@ class ProgramDesc(ctypes.Structure):
     _fields_ = [('uniform_kernel', ctypes.c_char_p), ('main_kernel', ctypes.c_char_p),
                 ('uniform_symbol', ctypes.c_char_p), ('elem_size', ctypes.c_int), ('n_uniform', ctypes.c_int),
                 ('n_scalar_args', ctypes.c_int), ('n_array_args', ctypes.c_int), ('n_grid_args', ctypes.c_int),
-                ('n_outputs', ctypes.c_int), ('block_size', ctypes.c_int), ('reduce_outputs', ctypes.c_int), ('team', ctypes.c_int), ('grouped', ctypes.c_int),
+                ('n_outputs', ctypes.c_int), ('block_size', ctypes.c_int), ('reduce_outputs', ctypes.c_int), ('team', ctypes.c_int), ('vec', ctypes.c_int), ('grouped', ctypes.c_int),
                 ('n_pixel_args', ctypes.c_int), ('accumulate', ctypes.c_int)]
 
 
@@ -184,7 +184,7 @@ class Program:
         desc = ProgramDesc(self._names[0], self._names[1], self._names[2], self.elem_size, ks.n_uniform,
                            len(ks.scalar_args), len(ks.array_args), len(getattr(ks, 'grid_args', ())),
                            ks.n_outputs, ks.block_size, int(getattr(ks, 'reduce_outputs', False)),
-                           int(getattr(ks, 'team', 1)), int(getattr(ks, 'grouped', False)),
+                           int(getattr(ks, 'team', 1)), int(getattr(ks, 'vec', 1)), int(getattr(ks, 'grouped', False)),
                            len(getattr(ks, 'pixel_args', None) or ()), int(getattr(ks, 'accumulate', False)))
         self.handle = ctypes.c_void_p()
         check(L.tegb_program_create(module.handle, ctypes.byref(desc), device, ctypes.byref(self.handle)))
