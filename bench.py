@@ -173,6 +173,7 @@ def main() -> int:
     ap.add_argument('--cpu-rows', type=int, default=256, help='pixel rows in the bounded CPU sample')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--fused', type=int, default=0, help='1: value and reverse derivative in ONE kernel (program bundle)')
     ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'], help='working precision of the programs')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
@@ -210,6 +211,7 @@ def main() -> int:
     esz = 4 if args.dtype == 'f32' else 8
     m_primal = CUDA_EvalMode(primal, num_samples=NUM_SAMPLES, device=local_rank, float_width=fw)
     m_grad = CUDA_EvalMode(grad, num_samples=NUM_SAMPLES, device=local_rank, float_width=fw)
+    m_fused = CUDA_EvalMode([primal, grad], num_samples=NUM_SAMPLES, device=local_rank, float_width=fw) if args.fused else None
     box = primal.args[:4]
     params = {lab: TRIANGLE[lab.rsplit('_', 1)[0]] for lab in primal.args[4:]}
     gparams = {lab: TRIANGLE[lab.rsplit('_', 1)[0]] for lab in grad.args[4:]}
@@ -229,6 +231,18 @@ def main() -> int:
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if record else None
         if record:
             e[0].record(stream)
+        if m_fused is not None:
+            m_fused.render(box, (res_x_total, res), bounds, gparams, rows=rows, out=(imgs[buf], gsums[buf]),
+                           stream=sptr, reduce=6)
+            if record:
+                e[1].record(stream)
+                e[2].record(stream)
+            if world > 1:
+                dist.all_reduce(gsums[buf])
+            if record:
+                ev['primal'].append((e[0], e[1]))
+                ev['grad'].append((e[1], e[2]))
+            return
         m_primal.render(box, (res_x_total, res), bounds, params, rows=rows, out=imgs[buf], stream=sptr)
         if record:
             e[1].record(stream)
@@ -397,7 +411,7 @@ def main() -> int:
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'res_per_gpu': [res, res], 'num_samples': NUM_SAMPLES,
-                   'programs': ['tri_primal', 'tri_grad'], 'outputs': 'value image [4096,4096] + per-parameter '
+                   'programs': ['tri_primal', 'tri_grad'], 'fused_kernel': bool(args.fused), 'outputs': 'value image [4096,4096] + per-parameter '
                    'gradient sum [6] (reduced in-kernel)', 'l2': 'L2 flushed between timed steps by writing a '
                    '256 MB buffer (outside the per-step event pairs); inputs are generated from the pixel index',
                    'parallelism': f'rows sharded over {world} GPU(s), one NCCL all-reduce of the [6] gradient'},

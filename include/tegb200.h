@@ -59,8 +59,10 @@ typedef struct {
     int n_grid_args;              /* arguments generated from the pixel index (0 unless a render program) */
     int n_outputs;                /* output streams of the main kernel */
     int block_size;               /* threads per block the main kernel was generated for */
-    int reduce_outputs;           /* 1: the main kernel writes per-block partial sums; launches then deliver the
-                                     n_outputs per-component sums over all instances to out_ptrs[0] (device) */
+    int reduce_outputs;           /* number R of TRAILING outputs that are summed over the instances (0 = none,
+                                     n_outputs = all): the main kernel writes per-block partial sums for them and
+                                     launches deliver the R sums to out_ptrs[n_outputs - R] (one device pointer);
+                                     out_ptrs[0 .. n_outputs - R) stay ordinary per-instance output streams */
     int team;                     /* threads cooperating on one instance (power of two, 1 = thread per instance);
                                      > 32 means one block of `team` threads per instance (block_size == team) */
     int vec;                      /* instances per thread of a streaming program (1 or 4); > 1 requires every
@@ -101,8 +103,8 @@ void tegb_program_destroy(tegb_program *p);
 
 /* Device buffers.  scalars[n_scalar_args] are converted to the program's element type.
  * in_ptrs[n_array_args], out_ptrs[n_outputs]: device pointers to n elements each.  Asynchronous on
- * `stream` (a cudaStream_t; NULL = default stream).  For reduce_outputs programs only out_ptrs[0] is
- * used: a device pointer to n_outputs elements that receive the sums over the n instances (fixed
+ * `stream` (a cudaStream_t; NULL = default stream).  With reduce_outputs = R > 0 the last R outputs are
+ * delivered as sums over the n instances to out_ptrs[n_outputs - R] (a device pointer to R elements; fixed
  * summation order for a given n: deterministic). */
 int tegb_program_launch(tegb_program *p, const double *scalars, const void *const *in_ptrs,
                         void *const *out_ptrs, int64_t n, void *stream);

@@ -59,7 +59,7 @@ class KernelSource:
     grid_args: List[int]            # (x_lb, x_ub, y_lb, y_ub) argument indices generated from the pixel index
     n_outputs: int
     block_size: int
-    reduce_outputs: bool            # main kernel writes per-block partial sums instead of per-instance outputs
+    reduce_outputs: int             # number of trailing outputs summed over the instances (per-block partial sums)
     team: int                       # threads cooperating on one instance (1 = thread per instance)
     grouped: bool = False           # grouped render launch: per-group scalar arguments + pixel windows
     pixel_args: List[int] = None    # arguments read from pixel-indexed images (grouped launches)
@@ -681,6 +681,11 @@ class Emitter:
         T = self.ctype
         name = self.name
         K = len(sch.outputs)
+        # number of TRAILING outputs that are summed over the instances (True = all of them)
+        nr = K if reduce_outputs is True else int(reduce_outputs)
+        assert 0 <= nr <= K
+        ns_out = K - nr
+        reduce_outputs = nr > 0
         nu = max(1, len(sch.uniform_slots))
         scal = list(sch.scalar_args)
         grid = list(grid_args)
@@ -699,10 +704,7 @@ class Emitter:
         bs = self.block_size
 
         ubody_params = ', '.join([f'const T a{a}' for a in scal] + ['T* __restrict__ U'])
-        if reduce_outputs:
-            outs_decl = ['T* __restrict__ partials']
-        else:
-            outs_decl = [f'T* __restrict__ out{k}' for k in range(K)]
+        outs_decl = [f'T* __restrict__ out{k}' for k in range(ns_out)] + (['T* __restrict__ partials'] if nr else [])
         coop = self.uses_coop
         iparams = ', '.join((['const T* __restrict__ tegU'] if grouped else []) +
                             (['const bool live'] if coop else []) +
@@ -733,6 +735,7 @@ class Emitter:
         zero = literal('0', T)
         if grouped:
             assert team == 1, 'render programs are thread-per-pixel'
+            assert nr in (0, K), 'grouped launches reduce all outputs or none'
             uparams = ', '.join([f'const T* __restrict__ g{a}' for a in scal] +
                                 ['const int group_begin', 'const int group_count', 'T* __restrict__ U'])
             src.append(f'extern "C" __global__ void {name}_uniform({uparams}) {{')
@@ -822,7 +825,7 @@ class Emitter:
                 mparams = ', '.join([f'const T* __restrict__ in{a}' for a in arrs] + outs_decl + ['const long long n'])
                 src.append(f'extern "C" __global__ void __launch_bounds__({bs}) {name}_main({mparams}) {{')
                 if vec > 1:
-                    assert team == 1 and not coop and not reduce_outputs and vec == 4
+                    assert team == 1 and not coop and nr == 0 and vec == 4
                     V = 'float4' if T == 'float' else 'double2'
                     per = 4 if T == 'float' else 2          # elements per 16-byte vector
                     nvec = vec // per
@@ -856,7 +859,7 @@ class Emitter:
                     return KernelSource(name=name, ctype=T, num_samples=self.N, source=text,
                                         uniform_kernel=f'{name}_uniform', main_kernel=f'{name}_main',
                                         n_uniform=nu, scalar_args=scal, array_args=arrs, grid_args=grid,
-                                        n_outputs=K, block_size=bs, reduce_outputs=False, team=1, vec=vec,
+                                        n_outputs=K, block_size=bs, reduce_outputs=0, team=1, vec=vec,
                                         stats={'uses_coop': False, 'loops': self.loop_counter})
                 if team == 1:
                     src.append('    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;')
@@ -873,16 +876,20 @@ class Emitter:
                     call = ', '.join(['team_rank'] + [f'in{a}[i]' for a in varying] + ['res'])
                 src.append('    const bool live = i < n;')
             src.append(f'    T res[{K}];')
-            if reduce_outputs:
+            if nr:
+                # every thread of the block reaches the block sum: dead lanes contribute zeros
                 src.append(f'    for (int k = 0; k < {K}; k++) res[k] = {zero};')
                 if coop:
                     src.append(f'    {name}_instance({call});')
-                    src.append(f'    if (!live) {{ for (int k = 0; k < {K}; k++) res[k] = {zero}; }}')
                 else:
                     src.append(f'    if (live) {name}_instance({call});')
-                if team > 1:
-                    src.append(f'    if (team_rank != 0) {{ for (int k = 0; k < {K}; k++) res[k] = {zero}; }}')
-                src.append(f'    tegb_block_sum_store<T, {K}, {bs}>(res, partials);')
+                owner = 'live' if team == 1 else '(live && team_rank == 0)'
+                for k in range(ns_out):
+                    src.append(f'    if ({owner}) out{k}[i] = res[{k}];')
+                src.append(f'    T rr[{nr}];')
+                for j in range(nr):
+                    src.append(f'    rr[{j}] = {owner} ? res[{ns_out + j}] : {zero};')
+                src.append(f'    tegb_block_sum_store<T, {nr}, {bs}>(rr, partials);')
             else:
                 if coop:
                     src.append(f'    {name}_instance({call});')
@@ -899,7 +906,7 @@ class Emitter:
         return KernelSource(name=name, ctype=T, num_samples=self.N, source=text,
                             uniform_kernel=f'{name}_uniform', main_kernel=f'{name}_main',
                             n_uniform=nu, scalar_args=scal, array_args=arrs, grid_args=grid,
-                            n_outputs=K, block_size=bs, reduce_outputs=bool(reduce_outputs), team=team,
+                            n_outputs=K, block_size=bs, reduce_outputs=nr, team=team,
                             grouped=bool(grouped), pixel_args=pix, accumulate=bool(accumulate),
                             stats={'uses_coop': self.uses_coop, 'loops': self.loop_counter})
 

@@ -290,6 +290,10 @@ extern "C" int tegb_program_create(tegb_module *m, const tegb_program_desc *desc
     if (desc->elem_size != 4 && desc->elem_size != 8) return fail(TEGB_ERR_INVALID, "elem_size must be 4 or 8");
     if (desc->n_outputs < 1 || desc->block_size < 32 || desc->block_size > 1024)
         return fail(TEGB_ERR_INVALID, "bad program description");
+    if (desc->reduce_outputs < 0 || desc->reduce_outputs > desc->n_outputs)
+        return fail(TEGB_ERR_INVALID, "reduce_outputs must be in [0, n_outputs]");
+    if (desc->grouped && desc->reduce_outputs != 0 && desc->reduce_outputs != desc->n_outputs)
+        return fail(TEGB_ERR_INVALID, "grouped programs reduce all outputs or none");
     if (desc->team > 1 && ((desc->team & (desc->team - 1)) != 0 || desc->team > 1024 ||
                            (desc->team > 32 && desc->team != desc->block_size) ||
                            (desc->team <= 32 && desc->block_size % desc->team != 0)))
@@ -391,7 +395,7 @@ __global__ void __launch_bounds__(RED_THREADS) colsum_stage2(const T *partials, 
 
 // partials buffer of a reduce_outputs program: n_outputs x n_blocks elements
 static int ensure_partials(tegb_program *p, unsigned long long n_blocks) {
-    const size_t need = (size_t)p->d.n_outputs * (n_blocks + RED_SLICES) * p->d.elem_size;
+    const size_t need = (size_t)p->d.reduce_outputs * (n_blocks + RED_SLICES) * p->d.elem_size;
     if (need <= p->partials_bytes) return TEGB_OK;
     if (p->d_partials) { cudaFree(p->d_partials); p->d_partials = nullptr; p->partials_bytes = 0; }
     RT_CHECK(cudaMalloc(&p->d_partials, need));
@@ -432,11 +436,11 @@ static void sum_columns(const T *partials, int n_cols, unsigned long long n_bloc
 
 static int finish_partials(tegb_program *p, unsigned long long n_blocks, void *out, cudaStream_t st) {
     // slice sums live behind the partials (ensure_partials reserves the room)
-    char *slices = (char *)p->d_partials + (size_t)p->d.n_outputs * n_blocks * p->d.elem_size;
+    char *slices = (char *)p->d_partials + (size_t)p->d.reduce_outputs * n_blocks * p->d.elem_size;
     if (p->d.elem_size == 4)
-        sum_columns<float>((const float *)p->d_partials, p->d.n_outputs, n_blocks, (float *)out, (float *)slices, st);
+        sum_columns<float>((const float *)p->d_partials, p->d.reduce_outputs, n_blocks, (float *)out, (float *)slices, st);
     else
-        sum_columns<double>((const double *)p->d_partials, p->d.n_outputs, n_blocks, (double *)out, (double *)slices, st);
+        sum_columns<double>((const double *)p->d_partials, p->d.reduce_outputs, n_blocks, (double *)out, (double *)slices, st);
     RT_CHECK(cudaGetLastError());
     return TEGB_OK;
 }
@@ -466,18 +470,18 @@ extern "C" int tegb_program_launch(tegb_program *p, const double *scalars, const
     }
     const long long blocks = (((n + vec - 1) / vec) * team + bs - 1) / bs;
     if (blocks > 2147483647LL) return fail(TEGB_ERR_INVALID, "too many instances for one launch");
+    const int n_store = p->d.n_outputs - p->d.reduce_outputs;
+    for (int k = 0; k < n_store; k++) { outs[k] = out_ptrs[k]; args.push_back(&outs[k]); }
     if (p->d.reduce_outputs) {
         rc = ensure_partials(p, (unsigned long long)blocks);
         if (rc) return rc;
         args.push_back(&p->d_partials);
-    } else {
-        for (int k = 0; k < p->d.n_outputs; k++) { outs[k] = out_ptrs[k]; args.push_back(&outs[k]); }
     }
     long long nn = n;
     args.push_back(&nn);
     CU_CHECK(drv::LaunchKernel(p->f_main, (unsigned)blocks, 1, 1, bs, 1, 1, 0, st, args.data(), nullptr));
     g_launches++;
-    if (p->d.reduce_outputs) return finish_partials(p, (unsigned long long)blocks, out_ptrs[0], (cudaStream_t)st);
+    if (p->d.reduce_outputs) return finish_partials(p, (unsigned long long)blocks, out_ptrs[n_store], (cudaStream_t)st);
     return TEGB_OK;
 }
 
@@ -512,14 +516,12 @@ extern "C" int tegb_program_eval_host(tegb_program *p, const double *scalars, co
         RT_CHECK(cudaMemcpyAsync(p->d_in[i], host_in[i], bytes, cudaMemcpyHostToDevice, st));
     rc = tegb_program_launch(p, scalars, (const void *const *)p->d_in.data(), p->d_out.data(), n, st);
     if (rc) return rc;
-    if (p->d.reduce_outputs) {
-        // the n_outputs sums were written to the start of d_out[0]; host_out[0] receives them
-        RT_CHECK(cudaMemcpyAsync(host_out[0], p->d_out[0], (size_t)p->d.n_outputs * p->d.elem_size,
+    const int n_store = p->d.n_outputs - p->d.reduce_outputs;
+    for (int k = 0; k < n_store; k++)
+        RT_CHECK(cudaMemcpyAsync(host_out[k], p->d_out[k], bytes, cudaMemcpyDeviceToHost, st));
+    if (p->d.reduce_outputs)    // the sums were written to the start of d_out[n_store]; host_out[n_store] receives them
+        RT_CHECK(cudaMemcpyAsync(host_out[n_store], p->d_out[n_store], (size_t)p->d.reduce_outputs * p->d.elem_size,
                                  cudaMemcpyDeviceToHost, st));
-    } else {
-        for (int k = 0; k < p->d.n_outputs; k++)
-            RT_CHECK(cudaMemcpyAsync(host_out[k], p->d_out[k], bytes, cudaMemcpyDeviceToHost, st));
-    }
     RT_CHECK(cudaStreamSynchronize(st));
     return TEGB_OK;
 }
@@ -664,16 +666,16 @@ extern "C" int tegb_render_launch(tegb_program *p, const double *scalars, const 
     const unsigned gx = (unsigned)((g->res_y + bs - 1) / bs);
     const unsigned gy = (unsigned)(g->row_end - g->row_begin);
     if (gy > 65535u) return fail(TEGB_ERR_INVALID, "more than 65535 rows in one render launch");
+    const int n_store = p->d.n_outputs - p->d.reduce_outputs;
+    for (int k = 0; k < n_store; k++) { outs[k] = out_ptrs[k]; args.push_back(&outs[k]); }
     if (p->d.reduce_outputs) {
         rc = ensure_partials(p, (unsigned long long)gx * gy);
         if (rc) return rc;
         args.push_back(&p->d_partials);
-    } else {
-        for (int k = 0; k < p->d.n_outputs; k++) { outs[k] = out_ptrs[k]; args.push_back(&outs[k]); }
     }
     CU_CHECK(drv::LaunchKernel(p->f_main, gx, gy, 1, bs, 1, 1, 0, st, args.data(), nullptr));
     g_launches++;
-    if (p->d.reduce_outputs) return finish_partials(p, (unsigned long long)gx * gy, out_ptrs[0], (cudaStream_t)st);
+    if (p->d.reduce_outputs) return finish_partials(p, (unsigned long long)gx * gy, out_ptrs[n_store], (cudaStream_t)st);
     return TEGB_OK;
 }
 

@@ -55,6 +55,7 @@ class Dag:
         self.defaults = dict(defaults)
         self.outputs: Tuple[int, ...] = ()
         self.out_is_tuple = False
+        self.out_groups: List[int] = []      # bundles: number of outputs of each member program
         self._fv: Dict[int, FrozenSet[int]] = {}
         self._has_quad: Dict[int, bool] = {}
 
@@ -282,6 +283,16 @@ def build_dag(prog: Program) -> Dag:
                 assert isinstance(e, int), 'Teg IR currently does not support multidimensional packing'
                 elems.append(e)
             return tuple(elems)
+        if op == 'J':               # bundle root: concatenate the members' results
+            flat: List[int] = []
+            sizes = []
+            for kdx in n.kids:
+                v = conv(kdx, env, depth)
+                v = (v,) if isinstance(v, int) else tuple(v)
+                sizes.append(len(v))
+                flat.extend(v)
+            dag.out_groups = sizes
+            return tuple(flat)
         if op == 'L':
             k = len(n.attr)
             vals = [conv(e, env, depth) for e in n.kids[:k]]       # parallel let: outer scope
@@ -313,4 +324,6 @@ def build_dag(prog: Program) -> Dag:
     else:
         dag.outputs = tuple(out)
         dag.out_is_tuple = True
+    if not dag.out_groups:
+        dag.out_groups = [len(dag.outputs)]
     return dag

@@ -66,6 +66,11 @@ class CUDA_EvalMode(EvalMode):
         if float_width in ('f64', np.float64):
             float_width = 'double'
         assert float_width in ('float', 'double'), f'Invalid precision setting {float_width}'
+        if isinstance(expr, (list, tuple)):
+            # several programs over the same variables, evaluated together by one kernel (tegp.bundle)
+            from .tegp import bundle
+            expr = bundle([e if isinstance(e, Program) else from_teg(e, arglist, name=f'{name}{k}')
+                           for k, e in enumerate(expr)], name=name if name != 'teg_method' else None)
         self.program: Program = expr if isinstance(expr, Program) else from_teg(expr, arglist, name=name)
         self.dag: Dag = build_dag(self.program)
         self.num_samples = int(num_samples)
@@ -96,6 +101,14 @@ class CUDA_EvalMode(EvalMode):
         if key not in self._schedules:
             self._schedules[key] = make_schedule(self.dag, list(key))
         return self._schedules[key]
+
+    def _n_reduce(self, reduce) -> int:
+        """reduce: False / True (all outputs) / int (that many TRAILING outputs, e.g. the derivative part of a
+        value + derivative bundle)."""
+        k = len(self.dag.outputs)
+        nr = k if reduce is True else int(reduce)
+        assert 0 <= nr <= k
+        return nr
 
     def pick_team(self, n: int, array_args: Sequence[int]) -> int:
         if self.team != 'auto':
@@ -128,7 +141,8 @@ class CUDA_EvalMode(EvalMode):
     def compiled(self, array_args: Sequence[int], grid_args: Sequence[int] = (), reduce: bool = False,
                  team: int = 1, grouped: bool = False, pixel_args: Sequence[int] = (), accumulate: bool = False,
                  vec: int = 1):
-        key = (tuple(sorted(array_args)), tuple(grid_args), bool(reduce), int(team), bool(grouped),
+        reduce = self._n_reduce(reduce)
+        key = (tuple(sorted(array_args)), tuple(grid_args), reduce, int(team), bool(grouped),
                tuple(pixel_args), bool(accumulate), int(vec))
         hit = self._variants.get(key)
         if hit is None:
@@ -330,8 +344,9 @@ class CUDA_EvalMode(EvalMode):
         """Evaluate over the pixel grid of tests/plot.py:8-29 with on-device pixel boxes.
 
         box_vars: (x_lb, x_ub, y_lb, y_ub) Vars or labels.  Returns a torch CUDA tensor
-        [k, rows, res_y] (k = program outputs), or [k] sums over the pixels when ``reduce``;
-        asynchronous on ``stream``."""
+        [k, rows, res_y] (k = program outputs), or [k] sums over the pixels when ``reduce`` is True; with
+        ``reduce=r`` (an int < k, for value + derivative bundles) the pair (images [k - r, rows, res_y],
+        sums [r]).  Asynchronous on ``stream``."""
         import torch
         labels = [v if isinstance(v, str) else label_of(v) for v in box_vars]
         pos = {lab: i for i, (lab, _) in enumerate(self.arglist)}
@@ -349,12 +364,23 @@ class CUDA_EvalMode(EvalMode):
         r0, r1 = (0, res[0]) if rows is None else rows
         tdt = torch.float32 if self.float_width == 'float' else torch.float64
         dev = torch.device('cuda', self.device)
-        if out is None:
-            out = (torch.empty(ks.n_outputs, dtype=tdt, device=dev) if reduce
-                   else torch.empty((ks.n_outputs, r1 - r0, res[1]), dtype=tdt, device=dev))
+        nr = ks.reduce_outputs
+        n_store = ks.n_outputs - nr
         grid = runtime.Grid(float(bounds[0][0]), float(bounds[0][1]), float(bounds[1][0]), float(bounds[1][1]),
                             int(res[0]), int(res[1]), int(r0), int(r1))
-        ptrs = [out.data_ptr()] if reduce else [out[k].data_ptr() for k in range(ks.n_outputs)]
+        if 0 < nr < ks.n_outputs:
+            # bundle: the leading outputs are images, the trailing ``reduce`` outputs are summed over the pixels
+            imgs, sums = out if out is not None else (None, None)
+            if imgs is None:
+                imgs = torch.empty((n_store, r1 - r0, res[1]), dtype=tdt, device=dev)
+            if sums is None:
+                sums = torch.empty(nr, dtype=tdt, device=dev)
+            prog.render(scalars, grid, [imgs[k].data_ptr() for k in range(n_store)] + [sums.data_ptr()], stream=stream)
+            return imgs, sums
+        if out is None:
+            out = (torch.empty(ks.n_outputs, dtype=tdt, device=dev) if nr
+                   else torch.empty((ks.n_outputs, r1 - r0, res[1]), dtype=tdt, device=dev))
+        ptrs = [out.data_ptr()] if nr else [out[k].data_ptr() for k in range(ks.n_outputs)]
         prog.render(scalars, grid, ptrs, stream=stream)
         return out
 

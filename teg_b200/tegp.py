@@ -33,6 +33,8 @@ Text form (one node per line, children always precede parents):
     L <k> <label0> <e0> ... <body>   LetIn (parallel)    (compile.py:154-180)
     B <a> <b>                        Bool: strict a < b, allow_eq ignored (compile.py:210-211)
     & <a> <b>     | <a> <b>          And / Or            (compile.py:205-208)
+    J <n> <r0> ... <rn-1>            (backend-only) root of a *bundle*: the results of several programs that
+                                     share arguments, evaluated together in one kernel (see ``bundle``)
     root <id>
     args <n> <label0> ... <labeln-1>   input order (teg/__main__.py:86-88 semantics)
 """
@@ -42,7 +44,7 @@ import sys
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
-OPS = ('C', 'V', 'A', 'M', 'I', 'F', 'S', 'T', 'U', 'L', 'B', '&', '|')
+OPS = ('C', 'V', 'A', 'M', 'I', 'F', 'S', 'T', 'U', 'L', 'B', '&', '|', 'J')
 
 SMOOTH_FUNCS = ('Sqr', 'Sqrt', 'Sin', 'Cos', 'ASin', 'ATan2', 'Exp')
 
@@ -105,8 +107,8 @@ class Program:
                 out.append(f'F {n.attr} {n.kids[0]}')
             elif n.op == 'T':
                 out.append(f'T {n.kids[0]} {n.kids[1]} {n.kids[2]} {n.attr}')
-            elif n.op == 'U':
-                out.append('U ' + ' '.join(map(str, (len(n.kids), *n.kids))))
+            elif n.op in ('U', 'J'):
+                out.append(n.op + ' ' + ' '.join(map(str, (len(n.kids), *n.kids))))
             elif n.op == 'L':
                 k = len(n.attr)
                 parts = [str(k)]
@@ -154,6 +156,9 @@ class Program:
                 labels = tuple(t[2 + 2 * i] for i in range(k))
                 exprs = tuple(int(t[3 + 2 * i]) for i in range(k))
                 prog.nodes.append(Node('L', (*exprs, int(t[2 + 2 * k])), labels))
+            elif op == 'J':
+                k = int(t[1])
+                prog.nodes.append(Node('J', tuple(int(v) for v in t[2:2 + k])))
             elif op in ('A', 'M', 'B', '&', '|'):
                 prog.nodes.append(Node(op, (int(t[1]), int(t[2]))))
             elif op == 'I':
@@ -326,3 +331,34 @@ def from_teg(expr, arglist: Sequence = (), name: str = 'teg_method') -> Program:
             prog.defaults.setdefault(lab, None)
     prog.args = list(ordered) + [lab for lab in free if lab not in ordered]
     return prog
+
+
+def bundle(programs: Sequence[Program], name: Optional[str] = None) -> Program:
+    """Several programs over the same variables (matched by label) as ONE program whose result is the
+    concatenation of theirs -- e.g. a value and its reverse derivative, evaluated by one kernel that shares
+    the argument loads and every common sub-expression.  The bundle root is the backend-only node ``J``."""
+    out = Program(name=name or '_'.join(p.name for p in programs))
+    table: Dict[tuple, int] = {}
+    roots = []
+    for p in programs:
+        remap: List[int] = []
+        for n in p.nodes:
+            key = (n.op, tuple(remap[k] for k in n.kids), n.attr)
+            idx = table.get(key)
+            if idx is None:
+                idx = len(out.nodes)
+                out.nodes.append(Node(n.op, key[1], n.attr))
+                table[key] = idx
+            remap.append(idx)
+        roots.append(remap[p.root])
+        for lab in p.args:
+            if lab not in out.args:
+                out.args.append(lab)
+        for lab, d in p.defaults.items():
+            if out.defaults.get(lab) is None:
+                out.defaults[lab] = d
+        for lab, v in p.live.items():
+            out.live.setdefault(lab, v)
+    out.nodes.append(Node('J', tuple(roots)))
+    out.root = len(out.nodes) - 1
+    return out

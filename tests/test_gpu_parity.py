@@ -245,3 +245,26 @@ def test_unroll_and_jam_is_bit_exact_on_device(cuda_device, scene, ns):
     assert np.array_equal(got, want, equal_nan=True)
     got, want = _run_both(scene, np.float64, res=(12, 12), n=128, ns=ns)
     assert np.array_equal(got, want, equal_nan=True)
+
+
+def test_program_bundle_value_and_gradient_in_one_kernel(cuda_device):
+    """[tri_primal, tri_grad] as one kernel: the image is bit-identical to the value program alone, the summed
+    gradient equals the separately reduced one bit for bit (same block geometry, same fold order)."""
+    import torch
+    from teg_b200 import CUDA_EvalMode
+    primal, grad = load_program('tri_primal'), load_program('tri_grad')
+    res = (200, 136)
+    par = {lab: v for lab, v in zip(grad.args, bind(grad.args, scene_values('tri_grad', res=res))) if np.ndim(v) == 0}
+    both = CUDA_EvalMode([primal, grad], num_samples=16)
+    assert both.out_size == 7 and both.dag.out_groups == [1, 6]
+    imgs, sums = both.render(grad.args[:4], res, ((0, 1), (0, 1)), par, reduce=6)
+    img1 = CUDA_EvalMode(primal, num_samples=16).render(primal.args[:4], res, ((0, 1), (0, 1)), par)
+    sum1 = CUDA_EvalMode(grad, num_samples=16).render(grad.args[:4], res, ((0, 1), (0, 1)), par, reduce=True)
+    torch.cuda.synchronize()
+    assert torch.equal(imgs, img1) and torch.equal(sums, sum1)
+    # the bundle through the array API: all 7 outputs per instance
+    vals = bind(grad.args, scene_values('tri_grad', res=(40, 40)))
+    a = np.asarray(both.eval(dict(zip(grad.args, vals))))
+    from oracle import Oracle
+    assert np.array_equal(a[:1], Oracle(program_text('tri_primal')).eval(vals, 16, np.float32))
+    assert np.array_equal(a[1:], Oracle(program_text('tri_grad')).eval(vals, 16, np.float32))
