@@ -51,11 +51,11 @@ def _load():
         lib.tego_last_error.restype = ctypes.c_char_p
         lib.tego_num_args.argtypes = [ctypes.c_void_p]
         lib.tego_out_size.argtypes = [ctypes.c_void_p]
-        for name, ct in (('tego_eval_f32', ctypes.c_float), ('tego_eval_f64', ctypes.c_double)):
+        for name, ct in (('tego_eval_f32_q', ctypes.c_float), ('tego_eval_f64_q', ctypes.c_double)):
             fn = getattr(lib, name)
             fn.restype = ctypes.c_int
             fn.argtypes = [ctypes.c_void_p, ctypes.POINTER(ct), ctypes.c_long, ctypes.c_int,
-                           ctypes.POINTER(ct), ctypes.c_int, ctypes.c_int]
+                           ctypes.POINTER(ct), ctypes.c_int, ctypes.c_int, ctypes.c_int]
         _lib = lib
     return _lib
 
@@ -92,8 +92,9 @@ class Oracle:
             self._h = None
 
     def eval(self, inputs: Sequence, num_samples: int, dtype=np.float32, n: Optional[int] = None,
-             threads: int = 1) -> np.ndarray:
+             threads: int = 1, quadrature: str = 'midpoint') -> np.ndarray:
         """inputs: one scalar or length-n array per program argument (in ``args`` order).
+        quadrature: 'midpoint' (the C backend's rule) or 'trapezoid' (the numpy backend's, numpy_eval.py:57-68).
         Returns an array [out_size, n] in ``dtype``."""
         dtype = np.dtype(dtype)
         assert len(inputs) == self.n_args, f'expected {self.n_args} inputs, got {len(inputs)}'
@@ -101,13 +102,14 @@ class Oracle:
         n = soa.shape[1]
         out = np.empty((self.out_size, n), dtype=dtype)
         if dtype == np.float32:
-            fn, ct = self._lib.tego_eval_f32, ctypes.c_float
+            fn, ct = self._lib.tego_eval_f32_q, ctypes.c_float
         elif dtype == np.float64:
-            fn, ct = self._lib.tego_eval_f64, ctypes.c_double
+            fn, ct = self._lib.tego_eval_f64_q, ctypes.c_double
         else:
             raise ValueError('dtype must be float32 or float64')
+        q = {'midpoint': 0, 'trapezoid': 1}[quadrature]
         rc = fn(self._h, soa.ctypes.data_as(ctypes.POINTER(ct)), n, int(num_samples),
-                out.ctypes.data_as(ctypes.POINTER(ct)), self.out_size, int(threads))
+                out.ctypes.data_as(ctypes.POINTER(ct)), self.out_size, int(threads), q)
         if rc != 0:
             raise RuntimeError(f'oracle: {self._lib.tego_last_error().decode()}')
         return out

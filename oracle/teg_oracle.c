@@ -288,16 +288,25 @@ int tego_num_args(const Prog *p) { return p->nargs; }
 #undef SUF
 
 int tego_eval_f32(const Prog *p, const float *in, long n, int num_samples, float *out, int k, int nthreads) {
-    return tego_eval_f(p, in, n, num_samples, out, k, nthreads);
+    return tego_eval_f(p, in, n, num_samples, out, k, nthreads, 0);
 }
 
 int tego_eval_f64(const Prog *p, const double *in, long n, int num_samples, double *out, int k, int nthreads) {
-    return tego_eval_d(p, in, n, num_samples, out, k, nthreads);
+    return tego_eval_d(p, in, n, num_samples, out, k, nthreads, 0);
+}
+
+/* quadrature: 0 = midpoint rule of the C backend, 1 = trapezoid rule of the numpy backend (numpy_eval.py:57-68) */
+int tego_eval_f32_q(const Prog *p, const float *in, long n, int num_samples, float *out, int k, int nthreads, int q) {
+    return tego_eval_f(p, in, n, num_samples, out, k, nthreads, q);
+}
+
+int tego_eval_f64_q(const Prog *p, const double *in, long n, int num_samples, double *out, int k, int nthreads, int q) {
+    return tego_eval_d(p, in, n, num_samples, out, k, nthreads, q);
 }
 
 /* size of the program's result (1 for scalars, k for Tup programs), probed on one dummy instance */
 int tego_out_size(const Prog *p) {
-    Ctxd *c = ctx_newd(p, 1);
+    Ctxd *c = ctx_newd(p, 1, 0);
     for (int a = 0; a < p->nlabels; a++) {   /* bind everything so unbound inputs cannot fail the probe */
         c->bind_val[a].n = 1; c->bind_val[a].v[0] = 0.5; c->bind_stamp[a] = ++c->clock;
     }

@@ -11,6 +11,7 @@ typedef struct { int n; T v[TEGO_MAXV]; } SUF(Val);
 typedef struct {
     const Prog *p;
     int num_samples;
+    int quadrature;             /* 0 = midpoint (the C backend), 1 = trapezoid on linspace (the numpy backend) */
     /* current binding of every label (program inputs, let variables, integration variables) */
     SUF(Val) *bind_val;
     long *bind_stamp;           /* 0 = unbound */
@@ -173,9 +174,32 @@ static SUF(Val) SUF(eval)(SUF(Ctx) *c, int id) {
         if (lo.n != 1 || hi.n != 1) { c->err = "Bounds are of different types"; return r; }
         int lab = nd->label;
         SUF(Val) saved = c->bind_val[lab]; long saved_stamp = c->bind_stamp[lab];
+        SUF(Val) out; out.n = 1; out.v[0] = 0;
+        if (c->quadrature == 1) {
+            /* numpy backend, /root/reference/teg/eval/numpy_eval.py:57-68:
+             *   samples, step = np.linspace(lower, upper, N, retstep=True)   (N points, end points included,
+             *                    x_i = i*step + lower, x_{N-1} = upper exactly)
+             *   value = (1 if lower < upper else -1) * step * sum(y[:-1] + y[1:]) / 2
+             * restated with a left fold of the pair sums (numpy's pairwise np.sum differs by rounding only) */
+            const int N = c->num_samples;
+            T step = (hi.v[0] - lo.v[0]) / (T)(N - 1);
+            SUF(Val) prev; prev.n = 1; prev.v[0] = 0;
+            int first = 1;
+            for (int i = 0; i < N; i++) {
+                SUF(Val) x; x.n = 1;
+                x.v[0] = (i == N - 1) ? hi.v[0] : (T)i * step + lo.v[0];
+                c->bind_val[lab] = x; c->bind_stamp[lab] = ++c->clock;
+                SUF(Val) f = SUF(eval)(c, nd->kids[2]);
+                if (c->err) break;
+                if (first) { out.n = f.n; for (int j = 0; j < f.n; j++) out.v[j] = 0; first = 0; }
+                else for (int j = 0; j < f.n; j++) out.v[j] = out.v[j] + (prev.v[j] + f.v[j]);
+                prev = f;
+            }
+            T sgn = (lo.v[0] < hi.v[0]) ? (T)1 : (T)-1;
+            for (int j = 0; j < out.n; j++) out.v[j] = ((sgn * step) * out.v[j]) / (T)2;
+        } else {
         T step = ((T)(hi.v[0] - lo.v[0])) / c->num_samples;
         int first = 1;
-        SUF(Val) out; out.n = 1; out.v[0] = 0;
         for (unsigned int i = 0; i < (unsigned int)c->num_samples; i++) {
             SUF(Val) x; x.n = 1;
             x.v[0] = lo.v[0] + step * (i + (T)(0.5));
@@ -184,6 +208,7 @@ static SUF(Val) SUF(eval)(SUF(Ctx) *c, int id) {
             if (c->err) break;
             if (first) { out.n = f.n; for (int j = 0; j < f.n; j++) out.v[j] = 0; first = 0; }
             for (int j = 0; j < f.n; j++) out.v[j] = out.v[j] + f.v[j] * step;
+        }
         }
         c->bind_val[lab] = saved;
         c->bind_stamp[lab] = saved_stamp ? ++c->clock : 0;
@@ -199,9 +224,9 @@ static SUF(Val) SUF(eval)(SUF(Ctx) *c, int id) {
     return r;
 }
 
-static SUF(Ctx) *SUF(ctx_new)(const Prog *p, int num_samples) {
+static SUF(Ctx) *SUF(ctx_new)(const Prog *p, int num_samples, int quadrature) {
     SUF(Ctx) *c = (SUF(Ctx) *)calloc(1, sizeof(SUF(Ctx)));
-    c->p = p; c->num_samples = num_samples;
+    c->p = p; c->num_samples = num_samples; c->quadrature = quadrature;
     c->bind_val = (SUF(Val) *)calloc(p->nlabels ? p->nlabels : 1, sizeof(SUF(Val)));
     c->bind_stamp = (long *)calloc(p->nlabels ? p->nlabels : 1, sizeof(long));
     c->memo_val = (SUF(Val) *)calloc(p->nnodes, sizeof(SUF(Val)));
@@ -217,7 +242,8 @@ static void SUF(ctx_free)(SUF(Ctx) *c) {
 /* Batch driver.  in: SoA [n_args][n] (argument a of instance i at in[a*n+i]); out: SoA [k][n].
  * Plays the role of C_EvalMode.eval (c_eval.py:129-157) called once per instance, minus the
  * process spawn and the 6-digit stdout round trip. */
-int SUF(tego_eval_)(const Prog *p, const T *in, long n, int num_samples, T *out, int k, int nthreads) {
+int SUF(tego_eval_)(const Prog *p, const T *in, long n, int num_samples, T *out, int k, int nthreads,
+                    int quadrature) {
     int failed = 0;
     const char *msg = NULL;
     if (nthreads < 1) nthreads = 1;
@@ -225,7 +251,7 @@ int SUF(tego_eval_)(const Prog *p, const T *in, long n, int num_samples, T *out,
 #pragma omp parallel num_threads(nthreads)
 #endif
     {
-        SUF(Ctx) *c = SUF(ctx_new)(p, num_samples);
+        SUF(Ctx) *c = SUF(ctx_new)(p, num_samples, quadrature);
 #ifdef _OPENMP
 #pragma omp for schedule(static)
 #endif

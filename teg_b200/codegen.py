@@ -35,6 +35,9 @@ _MATH = {
 }
 
 
+INTEGRATION_MODES = ('rectangular_quadrature', 'trapezoidal_quadrature')
+
+
 def literal(text: str, ctype: str) -> str:
     """Decimal constant in working precision, the way to_c.py:231-247 prints it (``1.0f`` / ``1``)."""
     t = text.strip()
@@ -75,8 +78,16 @@ class KernelSource:
 class Emitter:
     def __init__(self, sch: Schedule, ctype: str, num_samples: int, name: str,
                  block_size: int = 128, unroll_inner: int = 32, unroll_outer: int = 1, pred_accum: bool = True, use_asm: bool = True, team: int = 1, coop: bool = True,
-                 pred_mix: float = 0.25, jam: int = 4, coop_max_lanes: int = 4):
+                 pred_mix: float = 0.25, jam: int = 4, coop_max_lanes: int = 4,
+                 integration_mode: str = 'rectangular_quadrature'):
         assert ctype in ('float', 'double')
+        # the reference names three modes (to_c.py:389-393) and ships a template for the first only
+        assert integration_mode in INTEGRATION_MODES, f'unknown integration mode {integration_mode}'
+        self.mode = integration_mode
+        if self.mode != 'rectangular_quadrature':
+            # the sample-parallel / blocked / predicated loop forms are derived for the midpoint left fold
+            assert team == 1, 'teams are defined for rectangular_quadrature only'
+            coop, jam, pred_accum = False, 0, False
         self.sch = sch
         self.dag: Dag = sch.dag
         self.nodes = sch.dag.nodes
@@ -201,6 +212,8 @@ class Emitter:
 
     def loop(self, st: LoopGroup, known: Dict[int, bool], ind: int, depth: int, declare: bool = True):
         """data/templates/rectangular_rule.template.c:1-11, several accumulators per pass."""
+        if self.mode == 'trapezoidal_quadrature':
+            return self._trapezoid_loop(st, known, ind, depth, declare)
         if self._jam_ok(st, depth):
             return self._jam_loop(st, known, ind, depth, declare)
         k = self.loop_counter
@@ -270,6 +283,46 @@ class Emitter:
         for q in fixups:
             # skipped terms were `0 * step`: identical for every finite step; keeps NaN/inf steps poisonous
             self.emit(f'v{q} = v{q} + {literal("0", self.ctype)} * step{k};', ind + 1)
+        self.emit('}', ind)
+
+    def _trapezoid_loop(self, st: LoopGroup, known: Dict[int, bool], ind: int, depth: int, declare: bool = True):
+        """The numpy backend's rule (teg/eval/numpy_eval.py:57-68), the semantics of the reference's
+        ``trapezoidal_quadrature`` mode (to_c.py:389-393 names a template that is not shipped):
+        ``x, step = np.linspace(lo, hi, N, retstep=True)``, i.e. ``x_i = i * step + lo`` with ``step = (hi - lo) /
+        (N - 1)`` and the last point set to ``hi`` exactly; ``(1 if lo < hi else -1) * step * sum(y[:-1] + y[1:]) / 2``
+        with the pair sums folded left to right."""
+        k = self.loop_counter
+        self.loop_counter += 1
+        N, T = self.N, self.ctype
+        zero = literal('0', T)
+        innermost = not any(isinstance(s, LoopGroup) for s in st.body.walk())
+        for q in st.quads:
+            self._define(q)
+            if declare:
+                self.emit(f'T v{q} = {zero};', ind)
+        self._define(st.bvar)
+        self.emit('{', ind)
+        self.emit(f'const T lo{k} = {self.ref(st.lo, known)};', ind + 1)
+        self.emit(f'const T hi{k} = {self.ref(st.hi, known)};', ind + 1)
+        self.emit(f'const T step{k} = (hi{k} - lo{k}) / (T){N - 1};', ind + 1)
+        for q in st.quads:
+            self.emit(f'T prev{k}_{q} = {zero};', ind + 1)
+            if not declare:
+                self.emit(f'v{q} = {zero};', ind + 1)
+        unroll = N if (innermost and N <= self.unroll_inner) else 1
+        self.emit(f'#pragma unroll {unroll}', ind + 1)
+        self.emit(f'for (unsigned int s{k} = 0; s{k} < {N}u; ++s{k}) {{', ind + 1)
+        self.emit(f'const T x{st.bvar} = (s{k} == {N - 1}u) ? hi{k} : (T)s{k} * step{k} + lo{k};', ind + 2)
+        self.block(st.body, ind + 2, depth + 1)
+        for q in st.quads:
+            body = self.ref(self.nodes[q].args[2], st.body.known)
+            self.emit(f'const T f{k}_{q} = {body};', ind + 2)
+            self.emit(f'if (s{k} > 0u) v{q} = v{q} + (prev{k}_{q} + f{k}_{q});', ind + 2)
+            self.emit(f'prev{k}_{q} = f{k}_{q};', ind + 2)
+        self.emit('}', ind + 1)
+        one = literal('1', T)
+        for q in st.quads:
+            self.emit(f'v{q} = ((((lo{k} < hi{k}) ? {one} : -{one}) * step{k}) * v{q}) / {literal("2", T)};', ind + 1)
         self.emit('}', ind)
 
     # ------------------------------------------------------------ outer-loop blocking (unroll and jam)

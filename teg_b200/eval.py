@@ -55,11 +55,14 @@ class CUDA_EvalMode(EvalMode):
     num_samples: midpoint samples per integral (reference default 50, c_eval.py:26).
     float_width: 'float' (what C_EvalMode hard-wires, c_eval.py:32) or 'double'
                  (the CLI's ``-f double``, teg/__main__.py:49-52).
+    integration_mode: 'rectangular_quadrature' (default, the C backend) or 'trapezoidal_quadrature'
+                 (the numpy backend's rule); names from to_c.py:389-393.
     """
 
     def __init__(self, expr, num_samples: int = 50, float_width: str = 'float', device: int = 0,
                  arglist: Sequence = (), name: str = 'teg_method', use_cache: bool = True,
-                 block_size: int = 128, team=1, nvrtc_opts: str = '', **codegen_opts):
+                 block_size: int = 128, team=1, nvrtc_opts: str = '',
+                 integration_mode: str = 'rectangular_quadrature', **codegen_opts):
         super().__init__(name='CUDA')
         if float_width in ('single', 'f32', np.float32):
             float_width = 'float'
@@ -86,6 +89,16 @@ class CUDA_EvalMode(EvalMode):
         # C backend's own left fold is accurate (~N*eps/2 relative in the working precision).
         assert team == 'auto' or (isinstance(team, int) and team >= 1 and team & (team - 1) == 0 and team <= 1024)
         self.team = team
+        # integration_mode: 'rectangular_quadrature' = the C backend's midpoint rule (the only template the
+        # reference ships, to_c.py:389-393); 'trapezoidal_quadrature' = the numpy backend's rule
+        # (numpy_eval.py:57-68: linspace end points included).
+        from .codegen import INTEGRATION_MODES
+        assert integration_mode in INTEGRATION_MODES, f'unknown integration mode {integration_mode}'
+        self.integration_mode = integration_mode
+        if integration_mode != 'rectangular_quadrature':
+            codegen_opts = dict(codegen_opts, integration_mode=integration_mode)
+            assert team in (1, 'auto'), 'teams are defined for rectangular_quadrature only'
+            self.team = 1
         self.codegen_opts = codegen_opts
         self.nvrtc_opts = nvrtc_opts
         self.arglist: List[Tuple[str, Optional[float]]] = [

@@ -76,3 +76,15 @@ def test_compact_c_target_is_bit_identical_to_the_oracle(tmp_path):
     P = ctypes.POINTER(ctypes.c_float)
     lib.run(soa.ctypes.data_as(P), out.ctypes.data_as(P), ctypes.c_long(n))
     assert np.array_equal(out, Oracle(program_text('tri_grad')).eval(inputs, 16, np.float32))
+
+
+def test_integration_mode_flag_selects_the_trapezoid_rule(tmp_path):
+    """--integration-mode takes the names of to_c.py:389-393; unknown names are refused."""
+    (tmp_path / 'prog.py').write_text(PROG)
+    out = tmp_path / 'trap.cu'
+    r = _run(['-c', '-t', 'CUDA', '-s', '9', '-m', 'trap', '-o', str(out), '--integration-mode',
+              'trapezoidal_quadrature', 'prog.py'], tmp_path)
+    assert r.returncode == 0, r.stderr
+    text = out.read_text()
+    assert '/ (T)8;' in text and '== 8u) ? hi' in text        # step = (hi - lo) / (N - 1); last point = hi
+    assert _run(['-c', '--integration-mode', 'simpson', 'prog.py'], tmp_path).returncode != 0

@@ -268,3 +268,43 @@ def test_program_bundle_value_and_gradient_in_one_kernel(cuda_device):
     from oracle import Oracle
     assert np.array_equal(a[:1], Oracle(program_text('tri_primal')).eval(vals, 16, np.float32))
     assert np.array_equal(a[1:], Oracle(program_text('tri_grad')).eval(vals, 16, np.float32))
+
+
+# ---- trapezoidal_quadrature: the numpy backend's rule on the GPU ------------------------------
+import glob  # noqa: E402
+import os  # noqa: E402
+
+NUMPY_VECTORS = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'vectors_numpy',
+                                              '*.npz')))
+
+
+@pytest.mark.parametrize('path', NUMPY_VECTORS, ids=[os.path.basename(p)[:-4] for p in NUMPY_VECTORS])
+def test_trapezoid_mode_matches_numpy_backend_vectors(cuda_device, path):
+    """fp64 kernels against the committed outputs of the reference's numpy backend (1e-12 bar; observed <= 1e-15:
+    np.sum adds pairwise, the kernel left to right), and bit-exact against the oracle's trapezoid restatement."""
+    from oracle import Oracle
+    from teg_b200 import CUDA_EvalMode
+    z = np.load(path)
+    scene, ns = os.path.basename(path)[:-4].rsplit('_N', 1)
+    prog = load_program(scene)
+    inputs = list(z['inputs'])
+    mode = CUDA_EvalMode(prog, num_samples=int(ns), float_width='double', integration_mode='trapezoidal_quadrature')
+    got = np.asarray(mode.eval(dict(zip(prog.args, inputs)))).reshape(z['outputs'].shape)
+    ref = z['outputs']
+    assert np.all(np.abs(got - ref) <= 1e-12 * np.maximum(1.0, np.abs(ref).max()))
+    libm = scene.startswith('circle')
+    want = Oracle(program_text(scene)).eval(inputs, int(ns), np.float64, quadrature='trapezoid')
+    assert np.allclose(got, want, rtol=0, atol=1e-13) if libm else np.array_equal(got, want, equal_nan=True)
+
+
+@pytest.mark.parametrize('scene', ['tri_primal', 'tri_grad', 'shaded_grad', 'nested2d_grad', 'readme_deriv'])
+def test_trapezoid_mode_bit_exact_fp32_at_scale(cuda_device, scene):
+    from oracle import Oracle
+    from teg_b200 import CUDA_EvalMode
+    prog = load_program(scene)
+    inputs = bind(prog.args, scene_values(scene, res=(64, 64), n=4096))
+    want = Oracle(program_text(scene)).eval(inputs, 12, np.float32, threads=8, quadrature='trapezoid')
+    mode = CUDA_EvalMode(prog, num_samples=12, float_width='float', integration_mode='trapezoidal_quadrature')
+    got = np.asarray(mode.eval(dict(zip(prog.args, inputs)))).reshape(want.shape)
+    assert np.array_equal(got, want, equal_nan=True)
+    # the render path (pixel boxes generated on device) uses the same loops

@@ -3,6 +3,9 @@
 None of these run a kernel.  The lowering is checked for *value* parity by compiling the generated
 instance functions for the host (tests/host_harness.py, a checker) and comparing with the oracle.
 """
+import glob
+import os
+
 import numpy as np
 import pytest
 
@@ -184,3 +187,33 @@ def test_unroll_and_jam_keeps_every_fold_exact(scene):
         off = generate(sch, 'float', ns, use_asm=False, coop=False, jam=1)
         assert '_3 = ' not in off.source
         assert np.array_equal(run_on_host(off, inputs, n, np.float32), want, equal_nan=True)
+
+
+NUMPY_VECTORS = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'vectors_numpy',
+                                              '*.npz')))
+
+
+@pytest.mark.parametrize('path', NUMPY_VECTORS, ids=[os.path.basename(p)[:-4] for p in NUMPY_VECTORS])
+def test_trapezoid_lowering_matches_oracle_and_numpy_backend_on_host(path):
+    """``integration_mode='trapezoidal_quadrature'`` (to_c.py:389-393 names it, numpy_eval.py:57-68 defines it):
+    the generated code is bit-identical to the oracle's trapezoid restatement and reproduces the committed
+    outputs of the reference's numpy backend (np.sum is pairwise, the fold here is left to right: <= 4 ulp)."""
+    from oracle import Oracle
+    z = np.load(path)
+    scene, ns = os.path.basename(path)[:-4].rsplit('_N', 1)
+    ns = int(ns)
+    prog = load_program(scene)
+    inputs = list(z['inputs'])
+    n = inputs[0].shape[0]
+    sch = make_schedule(build_dag(prog), list(range(len(inputs))))
+    ks = generate(sch, 'double', ns, use_asm=False, integration_mode='trapezoidal_quadrature')
+    got = run_on_host(ks, inputs, n, np.float64)
+    want = Oracle(program_text(scene)).eval(inputs, ns, np.float64, quadrature='trapezoid')
+    assert np.array_equal(got, want, equal_nan=True)
+    ref = z['outputs']
+    assert np.all(np.abs(got - ref) <= 1e-15 * np.maximum(1.0, np.abs(ref).max()))
+    # fp32 lowering against the fp32 oracle
+    ks32 = generate(sch, 'float', ns, use_asm=False, integration_mode='trapezoidal_quadrature')
+    in32 = [np.asarray(v, np.float32) for v in inputs]
+    assert np.array_equal(run_on_host(ks32, in32, n, np.float32),
+                          Oracle(program_text(scene)).eval(in32, ns, np.float32, quadrature='trapezoid'), equal_nan=True)

@@ -96,3 +96,23 @@ def test_oracle_rejects_exp_like_the_reference():
     text = 'TEGP 1\nname e\nnodes 2\nC 1\nF Exp 0\nroot 1\nargs 0\n'
     with pytest.raises((RuntimeError, ValueError)):
         Oracle(text).eval([], 1)
+
+
+NUMPY_VECTORS = sorted(glob.glob(os.path.join(ROOT, 'tests', 'golden', 'vectors_numpy', '*.npz')))
+
+
+@pytest.mark.parametrize('path', NUMPY_VECTORS, ids=[os.path.basename(p)[:-4] for p in NUMPY_VECTORS])
+def test_trapezoid_oracle_reproduces_numpy_backend_vectors(path):
+    """The oracle's trapezoid mode against outputs of the reference's numpy backend (numpy_eval.py:57-68,
+    recorded by tests/golden/make_numpy_golden.py).  float64; np.sum adds pairwise, the oracle left to right,
+    so agreement is to a few ulp of the largest term rather than bit for bit."""
+    z = np.load(path)
+    scene, ns = os.path.basename(path)[:-4].rsplit('_N', 1)
+    got = Oracle(program_text(scene)).eval(list(z['inputs']), int(ns), np.float64, quadrature='trapezoid')
+    want = z['outputs']
+    assert got.shape == want.shape and np.count_nonzero(want) > 0
+    assert np.all(np.abs(got - want) <= 1e-15 * np.maximum(1.0, np.abs(want).max()))
+
+
+def test_numpy_fixtures_present():
+    assert len(NUMPY_VECTORS) >= 10
