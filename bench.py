@@ -175,6 +175,8 @@ def main() -> int:
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--fused', type=int, default=0, help='1: value and reverse derivative in ONE kernel (program bundle)')
     ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'], help='working precision of the programs')
+    ap.add_argument('--cull', type=int, default=1, help='0: dense kernels (every comparison at every sample); '
+                    '1: domain culling (teg_b200/cull.py, bit-identical results)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
 
@@ -209,9 +211,10 @@ def main() -> int:
     fw = 'float' if args.dtype == 'f32' else 'double'
     tdt = torch.float32 if args.dtype == 'f32' else torch.float64
     esz = 4 if args.dtype == 'f32' else 8
-    m_primal = CUDA_EvalMode(primal, num_samples=NUM_SAMPLES, device=local_rank, float_width=fw)
-    m_grad = CUDA_EvalMode(grad, num_samples=NUM_SAMPLES, device=local_rank, float_width=fw)
-    m_fused = CUDA_EvalMode([primal, grad], num_samples=NUM_SAMPLES, device=local_rank, float_width=fw) if args.fused else None
+    m_primal = CUDA_EvalMode(primal, num_samples=NUM_SAMPLES, device=local_rank, float_width=fw, cull=bool(args.cull))
+    m_grad = CUDA_EvalMode(grad, num_samples=NUM_SAMPLES, device=local_rank, float_width=fw, cull=bool(args.cull))
+    m_fused = CUDA_EvalMode([primal, grad], num_samples=NUM_SAMPLES, device=local_rank, float_width=fw,
+                            cull=bool(args.cull)) if args.fused else None
     box = primal.args[:4]
     params = {lab: TRIANGLE[lab.rsplit('_', 1)[0]] for lab in primal.args[4:]}
     gparams = {lab: TRIANGLE[lab.rsplit('_', 1)[0]] for lab in grad.args[4:]}
@@ -411,7 +414,7 @@ def main() -> int:
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'res_per_gpu': [res, res], 'num_samples': NUM_SAMPLES,
-                   'programs': ['tri_primal', 'tri_grad'], 'fused_kernel': bool(args.fused), 'outputs': 'value image [4096,4096] + per-parameter '
+                   'programs': ['tri_primal', 'tri_grad'], 'fused_kernel': bool(args.fused), 'cull': bool(args.cull), 'outputs': 'value image [4096,4096] + per-parameter '
                    'gradient sum [6] (reduced in-kernel)', 'l2': 'L2 flushed between timed steps by writing a '
                    '256 MB buffer (outside the per-step event pairs); inputs are generated from the pixel index',
                    'parallelism': f'rows sharded over {world} GPU(s), one NCCL all-reduce of the [6] gradient'},

@@ -169,6 +169,9 @@ class Emitter:
             return f'{m[op]}({r(n.args[0])}, {r(n.args[1])})'
         if op == 'in':
             return f'a{n.attr}'
+        if op == 'domis':
+            code = {'T': 1, 'F': 0, 'U': 2}[n.attr]
+            return f'{r(n.args[0])} == {literal(str(code), self.ctype)}'
         raise NotImplementedError(f'CUDA backend does not support instruction class "{op}"')
 
     def decl(self, i: int) -> str:
@@ -184,7 +187,10 @@ class Emitter:
             if isinstance(st, Eval):
                 i = st.node
                 self._define(i)
-                self.emit(f'const {self.decl(i)} v{i} = {self.expr(i, known)};', ind)
+                if self.nodes[i].op == 'domtri':
+                    self._emit_domtri(i, known, ind)
+                else:
+                    self.emit(f'const {self.decl(i)} v{i} = {self.expr(i, known)};', ind)
             elif isinstance(st, IfGroup) and self._coop_ok(st, depth):
                 self._coop_if(st, known, ind, depth)
             elif isinstance(st, IfGroup):
@@ -283,6 +289,129 @@ class Emitter:
         for q in fixups:
             # skipped terms were `0 * step`: identical for every finite step; keeps NaN/inf steps poisonous
             self.emit(f'v{q} = v{q} + {literal("0", self.ctype)} * step{k};', ind + 1)
+        self.emit('}', ind)
+
+    # ------------------------------------------------------------ domain culling (cull.py)
+    def _emit_domtri(self, i: int, known: Dict[int, bool], ind: int):
+        """Interval evaluation of one select condition over the sampled box of its loop nest -> ``v{i}`` =
+        1 (true at every sample), 0 (false at every sample) or 2 (unresolved).  Every bound is computed with the
+        same individually rounded operations as the per-sample code (round-to-nearest is monotone).  Corner
+        values of products / quotients / square roots and the box abscissae are also summed into a poison
+        accumulator: one non-finite term anywhere in the cone leaves the condition unresolved, so a NaN that
+        ``fmin`` / ``fmax`` drop (or an infinity that could hide one downstream) can never support a decision.
+        Sums need no poison: an overflowed sum bound is +-inf on the side no decision can use."""
+        assert self.mode == 'rectangular_quadrature', 'culling is derived for the midpoint sample placement'
+        root, B = self.nodes[i].attr
+        fv = self.dag.free_bvars
+        T, N = self.ctype, self.N
+        half, zero = literal('0.5', T), literal('0', T)
+        fmin, fmax = ('fminf', 'fmaxf') if T == 'float' else ('fmin', 'fmax')
+        pre = f'd{i}_'
+        pz = f'{pre}pz'
+
+        def interior(j: int) -> bool:
+            return bool(fv(j) & B)
+
+        order: List[int] = []
+        seen = set()
+        stack = [(root, False)]
+        while stack:
+            j, done = stack.pop()
+            if done:
+                order.append(j)
+                continue
+            if j in seen or not interior(j):
+                continue
+            seen.add(j)
+            stack.append((j, True))
+            for a in self.nodes[j].args:
+                stack.append((a, False))
+
+        def lo(j: int) -> str:
+            return f'{pre}l{j}' if interior(j) else self.ref(j, known)
+
+        def hi(j: int) -> str:
+            return f'{pre}h{j}' if interior(j) else self.ref(j, known)
+
+        def is_t(j: int) -> str:
+            return f'{pre}t{j}' if interior(j) else f'({self.ref(j, known)})'
+
+        def is_f(j: int) -> str:
+            return f'{pre}f{j}' if interior(j) else f'(!({self.ref(j, known)}))'
+
+        def const_value(j: int):
+            m = self.nodes[self.helper.resolve(j, known)]
+            return float(m.attr) if m.op == 'const' else None
+
+        self.emit(f'T v{i};', ind)
+        self.emit('{', ind)
+        e = lambda line: self.emit(line, ind + 1)     # noqa: E731
+        e(f'T {pz} = {zero};')
+        for j in order:
+            n = self.nodes[j]
+            op = n.op
+            L, H = f'{pre}l{j}', f'{pre}h{j}'
+            if op == 'bvar':
+                a, b = self.ref(n.args[0], known), self.ref(n.args[1], known)
+                e(f'const T {pre}s{j} = ((T)({b} - {a})) / (T){N};')
+                e(f'const T {pre}a{j} = {a} + {pre}s{j} * ((T)0u + {half});')
+                e(f'const T {pre}b{j} = {a} + {pre}s{j} * ((T){N - 1}u + {half});')
+                e(f'const T {L} = {fmin}({pre}a{j}, {pre}b{j}), {H} = {fmax}({pre}a{j}, {pre}b{j});')
+                e(f'{pz} = {pz} + {pre}a{j}; {pz} = {pz} + {pre}b{j};')
+            elif op == 'add':
+                x, y = n.args
+                e(f'const T {L} = {lo(x)} + {lo(y)}, {H} = {hi(x)} + {hi(y)};')
+            elif op in ('mul', 'div'):
+                x, y = n.args
+                o = '*' if op == 'mul' else '/'
+                kx, ky = const_value(x), const_value(y)
+                if op == 'mul' and (kx == -1.0 or ky == -1.0) and interior(y if kx == -1.0 else x):
+                    w = y if kx == -1.0 else x              # negation is exact: swap the bounds
+                    first = kx == -1.0
+                    neg = (lambda t: f'{self.ref(x, known)} * {t}') if first else (lambda t: f'{t} * {self.ref(y, known)}')
+                    e(f'const T {L} = {neg(hi(w))}, {H} = {neg(lo(w))};')
+                    continue
+                if interior(x) and interior(y):
+                    corners = [f'{lo(x)} {o} {lo(y)}', f'{lo(x)} {o} {hi(y)}', f'{hi(x)} {o} {lo(y)}', f'{hi(x)} {o} {hi(y)}']
+                elif interior(x):
+                    corners = [f'{lo(x)} {o} {lo(y)}', f'{hi(x)} {o} {lo(y)}']
+                else:
+                    corners = [f'{lo(x)} {o} {lo(y)}', f'{lo(x)} {o} {hi(y)}']
+                ps = [f'{pre}p{j}_{c}' for c in range(len(corners))]
+                for nm, txt in zip(ps, corners):
+                    e(f'const T {nm} = {txt};')
+                if len(ps) == 2:
+                    e(f'const T {L} = {fmin}({ps[0]}, {ps[1]}), {H} = {fmax}({ps[0]}, {ps[1]});')
+                else:
+                    e(f'const T {L} = {fmin}({fmin}({ps[0]}, {ps[1]}), {fmin}({ps[2]}, {ps[3]}));')
+                    e(f'const T {H} = {fmax}({fmax}({ps[0]}, {ps[1]}), {fmax}({ps[2]}, {ps[3]}));')
+                e(' '.join(f'{pz} = {pz} + {nm};' for nm in ps))
+                if op == 'div' and interior(y):
+                    # a divisor interval that touches zero bounds nothing
+                    e(f'if (!({lo(y)} > {zero} || {hi(y)} < {zero})) {pz} = TEGB_IV_NAN;')
+            elif op == 'sqrt':
+                x = n.args[0]
+                fn = _MATH[T]['sqrt']
+                e(f'const T {L} = {fn}({lo(x)}), {H} = {fn}({hi(x)});')
+                e(f'{pz} = {pz} + {L}; {pz} = {pz} + {H};')
+            elif op == 'sel':
+                c, x, y = n.args
+                e(f'const T {L} = {is_t(c)} ? {lo(x)} : ({is_f(c)} ? {lo(y)} : {fmin}({lo(x)}, {lo(y)}));')
+                e(f'const T {H} = {is_t(c)} ? {hi(x)} : ({is_f(c)} ? {hi(y)} : {fmax}({hi(x)}, {hi(y)}));')
+                e(f'if (!({is_t(c)} || {is_f(c)})) {pz} = {pz} + (({lo(x)} + {lo(y)}) + ({hi(x)} + {hi(y)}));')
+            elif op == 'lt':
+                x, y = n.args
+                e(f'const bool {pre}t{j} = {hi(x)} < {lo(y)}, {pre}f{j} = {lo(x)} >= {hi(y)};')
+            elif op == 'and':
+                x, y = n.args
+                e(f'const bool {pre}t{j} = {is_t(x)} && {is_t(y)}, {pre}f{j} = {is_f(x)} || {is_f(y)};')
+            elif op == 'or':
+                x, y = n.args
+                e(f'const bool {pre}t{j} = {is_t(x)} || {is_t(y)}, {pre}f{j} = {is_f(x)} && {is_f(y)};')
+            else:  # pragma: no cover  (cull.py admits interval-evaluable cones only)
+                raise NotImplementedError(f'no interval rule for "{op}"')
+        two, one = literal('2', T), literal('1', T)
+        e(f'v{i} = ({pz} * {zero} == {zero}) ? ({pre}t{root} ? {one} : ({pre}f{root} ? {zero} : {two})) : {two};')
         self.emit('}', ind)
 
     def _trapezoid_loop(self, st: LoopGroup, known: Dict[int, bool], ind: int, depth: int, declare: bool = True):
@@ -448,16 +577,35 @@ class Emitter:
             return False
         if not self._has_loop(st.then_block):
             return False
-        # the else side must be straight-line code: it is evaluated unconditionally
-        return not any(isinstance(s, (LoopGroup, IfGroup)) for s in st.else_block.walk())
+        # a straight-line else side is evaluated unconditionally (speculation); one with structure of its own is
+        # accepted only for the culling guards (cull.py), whose else side is the cheap specialised nest
+        if not any(isinstance(s, (LoopGroup, IfGroup)) for s in st.else_block.walk()):
+            return True
+        return self._is_cull_guard(st.cond)
+
+    def _is_cull_guard(self, c: int) -> bool:
+        n = self.nodes[c]
+        return n.op == 'domis' or (n.op == 'or' and all(self._is_cull_guard(a) for a in n.args))
 
     def _coop_if(self, st: IfGroup, known: Dict[int, bool], ind: int, depth: int):
         self.uses_coop = True
-        self.block(st.else_block, ind, depth)
-        for s in st.sels:
-            self._define(s)
-            self.emit(f'T v{s} = {self.ref(self.nodes[s].args[2], st.else_block.known)};', ind)
         cond = self.ref(st.cond, known)
+        if any(isinstance(s, (LoopGroup, IfGroup)) for s in st.else_block.walk()):
+            for s in st.sels:
+                self._define(s)
+                self.emit(f'T v{s} = {literal("0", self.ctype)};', ind)
+            self.emit(f'if (!({cond})) {{', ind)
+            self.divergent += 1
+            self.block(st.else_block, ind + 1, depth)
+            self.divergent -= 1
+            for s in st.sels:
+                self.emit(f'v{s} = {self.ref(self.nodes[s].args[2], st.else_block.known)};', ind + 1)
+            self.emit('}', ind)
+        else:
+            self.block(st.else_block, ind, depth)
+            for s in st.sels:
+                self._define(s)
+                self.emit(f'T v{s} = {self.ref(self.nodes[s].args[2], st.else_block.known)};', ind)
         ctx = ' && '.join(self.guard_ctx + [f'({cond})'])
         self.emit(f'if (__any_sync(0xffffffffu, {ctx})) {{', ind)
         self.guard_ctx.append(f'({cond})')
@@ -699,7 +847,10 @@ class Emitter:
         self.lines = []
         for i in self.sch.uniform_nodes:
             n = self.nodes[i]
-            self.emit(f'const {self.decl(i)} v{i} = {self.expr(i, {})};', 1)
+            if n.op == 'domtri':
+                self._emit_domtri(i, {}, 1)
+            else:
+                self.emit(f'const {self.decl(i)} v{i} = {self.expr(i, {})};', 1)
         for i, slot in sorted(self.sch.uniform_slots.items(), key=lambda kv: kv[1]):
             n = self.nodes[i]
             val = f'(v{i} ? {literal("1", self.ctype)} : {literal("0", self.ctype)})' if n.is_bool else f'v{i}'
@@ -768,6 +919,9 @@ class Emitter:
         src.append('#include "teg_b200_runtime.cuh"')
         src.append(f'typedef {T} T;')
         src.append(f'#define TEGB_NUM_UNIFORM {nu}')
+        if any(self.nodes[i].op == 'domtri' for i in self.dag.reachable(sch.outputs)):
+            # the poison value of the domain-culling prologue (cull.py)
+            src.append(f'#define TEGB_IV_NAN {"nanf" if T == "float" else "nan"}("")')
         if not grouped:
             src.append('TEGB_UNIFORM_TABLE(T, tegU, TEGB_NUM_UNIFORM);')
         src.append('')

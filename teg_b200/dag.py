@@ -29,8 +29,9 @@ from .tegp import Program
 
 Value = Union[int, Tuple[int, ...]]          # scalar node id, or a vector of scalar node ids
 
-FLOAT_OPS = ('const', 'in', 'bvar', 'add', 'mul', 'div', 'sel', 'sqrt', 'sin', 'cos', 'asin', 'atan2', 'quad')
-BOOL_OPS = ('lt', 'and', 'or')
+FLOAT_OPS = ('const', 'in', 'bvar', 'add', 'mul', 'div', 'sel', 'sqrt', 'sin', 'cos', 'asin', 'atan2', 'quad',
+             'domtri')                       # domtri / domis: cull.py
+BOOL_OPS = ('lt', 'and', 'or', 'domis')
 
 _UNARY = {'Sqrt': 'sqrt', 'Sin': 'sin', 'Cos': 'cos', 'ASin': 'asin'}
 
@@ -58,6 +59,18 @@ class Dag:
         self.out_groups: List[int] = []      # bundles: number of outputs of each member program
         self._fv: Dict[int, FrozenSet[int]] = {}
         self._has_quad: Dict[int, bool] = {}
+
+    def clone(self) -> "Dag":
+        """Independent copy (node ids are preserved) for transforms that add nodes and replace the outputs."""
+        d = Dag(self.name, self.arg_labels, self.defaults)
+        d.nodes = list(self.nodes)
+        d._table = dict(self._table)
+        d.outputs = self.outputs
+        d.out_is_tuple = self.out_is_tuple
+        d.out_groups = list(self.out_groups)
+        d._fv = dict(self._fv)
+        d._has_quad = dict(self._has_quad)
+        return d
 
     # ------------------------------------------------------------ building
     def intern(self, op: str, args: Tuple[int, ...] = (), attr=None) -> int:

@@ -57,12 +57,13 @@ class CUDA_EvalMode(EvalMode):
                  (the CLI's ``-f double``, teg/__main__.py:49-52).
     integration_mode: 'rectangular_quadrature' (default, the C backend) or 'trapezoidal_quadrature'
                  (the numpy backend's rule); names from to_c.py:389-393.
+    cull: domain culling (cull.py, default on): bit-identical results, far fewer evaluated comparisons.
     """
 
     def __init__(self, expr, num_samples: int = 50, float_width: str = 'float', device: int = 0,
                  arglist: Sequence = (), name: str = 'teg_method', use_cache: bool = True,
                  block_size: int = 128, team=1, nvrtc_opts: str = '',
-                 integration_mode: str = 'rectangular_quadrature', **codegen_opts):
+                 integration_mode: str = 'rectangular_quadrature', cull: bool = True, **codegen_opts):
         super().__init__(name='CUDA')
         if float_width in ('single', 'f32', np.float32):
             float_width = 'float'
@@ -100,6 +101,13 @@ class CUDA_EvalMode(EvalMode):
             assert team in (1, 'auto'), 'teams are defined for rectangular_quadrature only'
             self.team = 1
         self.codegen_opts = codegen_opts
+        # cull: per-instance interval evaluation of the select conditions over the sampled box; instances whose
+        # discontinuities miss the box run comparison-free specialised nests (bit-identical results, cull.py)
+        self.cull = bool(cull) and integration_mode == 'rectangular_quadrature'
+        self.sched_dag: Dag = self.dag
+        if self.cull:
+            from .cull import cull as _cull
+            self.sched_dag = _cull(self.dag, self.num_samples)
         self.nvrtc_opts = nvrtc_opts
         self.arglist: List[Tuple[str, Optional[float]]] = [
             (lab, self.program.defaults.get(lab)) for lab in self.program.args]
@@ -112,7 +120,7 @@ class CUDA_EvalMode(EvalMode):
     def schedule(self, array_args: Sequence[int], grid_args: Sequence[int] = ()):
         key = tuple(sorted(set(array_args) | set(grid_args)))
         if key not in self._schedules:
-            self._schedules[key] = make_schedule(self.dag, list(key))
+            self._schedules[key] = make_schedule(self.sched_dag, list(key))
         return self._schedules[key]
 
     def _n_reduce(self, reduce) -> int:

@@ -217,3 +217,86 @@ def test_trapezoid_lowering_matches_oracle_and_numpy_backend_on_host(path):
     in32 = [np.asarray(v, np.float32) for v in inputs]
     assert np.array_equal(run_on_host(ks32, in32, n, np.float32),
                           Oracle(program_text(scene)).eval(in32, ns, np.float32, quadrature='trapezoid'), equal_nan=True)
+
+
+# ---- domain culling (teg_b200/cull.py): interval-resolved instances run comparison-free nests, same bits ----------
+CULLED_SCENES = ['tri_primal', 'raster_theta_primal', 'shaded_primal', 'shaded_grad', 'tri_color_grad',
+                 'nested2d_value', 'nested3d_value', 'nested3d_grad', 'simple_line', 'circle', 'rect_hyperbola',
+                 'bilinear_lerp']
+
+
+@pytest.mark.parametrize('scene', CULLED_SCENES)
+def test_culled_lowering_is_bit_identical_to_the_oracle_on_host(scene):
+    from oracle import Oracle
+    from teg_b200.cull import cull
+    prog = load_program(scene)
+    ns = SCENE_SAMPLES[scene]
+    inputs = bind(prog.args, scene_values(scene, res=(40, 40), n=600))
+    n = max(np.size(v) for v in inputs)
+    arr = [i for i, v in enumerate(inputs) if np.ndim(v) > 0]
+    dag = cull(build_dag(prog), ns)
+    assert dag.culled, 'nothing was culled'
+    assert any(nd.op == 'domtri' for nd in dag.nodes)
+    sch = make_schedule(dag, arr)
+    for dtype, ctype in ((np.float32, 'float'), (np.float64, 'double')):
+        ks = generate(sch, ctype, ns, use_asm=False, coop=False)
+        assert 'pz' in ks.source
+        got = run_on_host(ks, inputs, n, dtype)
+        want = Oracle(program_text(scene)).eval(inputs, ns, dtype)
+        assert np.array_equal(got, want, equal_nan=True), f'{scene}/{ctype}'
+
+
+def test_culling_decision_boundary_on_host():
+    """Edges through pixel corners / sample abscissae, slivers, reversed, empty and non-finite boxes, huge
+    coordinates: the interval decisions must never disagree with the per-sample comparisons."""
+    from oracle import Oracle
+    from teg_b200.cull import cull
+    res = 32
+    e = np.linspace(0, 1, res + 1, dtype=np.float32)
+    xl, yl = np.meshgrid(e[:-1], e[:-1], indexing='ij')
+    xu, yu = np.meshgrid(e[1:], e[1:], indexing='ij')
+    big = np.float32(3e38)
+    odd_xl = np.array([0.2, 0.3, 0.3, np.nan, 0.1, np.inf, 0.5, -big, 0.3], dtype=np.float32)
+    odd_xu = np.array([0.3, 0.3, 0.2, 0.4, np.inf, 0.2, 0.5, big, 0.2], dtype=np.float32)
+    odd_yl = np.array([0.2, 0.3, 0.4, 0.3, 0.2, 0.3, -np.inf, -big, 0.5], dtype=np.float32)
+    odd_yu = np.array([0.3, 0.4, 0.3, 0.4, 0.3, np.nan, 0.1, big, 0.4], dtype=np.float32)
+    boxes = [np.concatenate([a.ravel(), b]) for a, b in ((xl, odd_xl), (xu, odd_xu), (yl, odd_yl), (yu, odd_yu))]
+    n = boxes[0].size
+    cases = [(0.25, 0.25, 0.75, 0.25, 0.25, 0.75), (0.0, 0.0, 1.0, 0.0, 0.0, 1.0),
+             (0.5, 0.5, 0.5 + 2 ** -12, 0.5, 0.5, 0.5 + 2 ** -12), (0.1, 0.1, 0.9, 0.1000001, 0.5, 0.10000005),
+             (0.15, 0.2, 0.4, 0.9, 0.85, 0.3), (0.3, 0.3, 0.3, 0.3, 0.3, 0.3),
+             (0.515625, 0.515625, 0.546875, 0.515625, 0.515625, 0.546875), (0.0, 0.0, big, 0.0, 0.0, big),
+             (np.nan, 0.2, 0.8, 0.3, 0.4, 0.9), (np.inf, 0.2, 0.8, 0.3, 0.4, 0.9)]
+    prog = load_program('tri_primal')
+    dag = cull(build_dag(prog), 16)
+    for arr in ([0, 1, 2, 3], list(range(10))):
+        ks = generate(make_schedule(dag, arr), 'float', 16, use_asm=False, coop=False)
+        for verts in cases:
+            inputs = boxes + [np.float32(v) for v in verts]
+            got = run_on_host(ks, inputs, n, np.float32)
+            want = Oracle(program_text('tri_primal')).eval(inputs, 16, np.float32)
+            assert np.array_equal(got, want, equal_nan=True), (arr, verts, np.count_nonzero(got != want))
+
+
+def test_cull_transform_structure():
+    from teg_b200.cull import cull
+    dag0 = build_dag(load_program('tri_primal'))
+    n0, out0 = len(dag0.nodes), dag0.outputs
+    dag = cull(dag0, 16)
+    assert len(dag0.nodes) == n0 and dag0.outputs == out0            # the input DAG is left alone
+    (q, roots), = dag.culled
+    assert len(roots) == 1
+    top = dag.nodes[dag.outputs[0]]
+    assert top.op == 'sel' and dag.nodes[top.args[0]].op == 'domis' and top.args[1] == q
+    spec = dag.nodes[top.args[2]]
+    assert spec.op == 'sel' and dag.nodes[spec.args[0]].attr == 'T'
+    # the specialised "true" nest has no comparison left; the "false" nest collapsed to 0 + 0 * step
+    ops_true = {dag.nodes[i].op for i in dag.reachable([spec.args[1]])}
+    ops_false = {dag.nodes[i].op for i in dag.reachable([spec.args[2]])}
+    assert 'lt' not in ops_true and 'quad' in ops_true
+    assert 'quad' not in ops_false and 'lt' not in ops_false
+    # short nests are left alone (N^depth below the threshold), and so are gradient programs made of 1-D delta loops
+    assert not cull(build_dag(load_program('tri_primal')), 4).culled
+    assert not cull(build_dag(load_program('tri_grad')), 16).culled
+    # transcendental conditions have no interval rule: left alone
+    assert all(len(r) for _, r in cull(build_dag(load_program('circle')), 20).culled)
