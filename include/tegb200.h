@@ -71,6 +71,12 @@ typedef struct {
                                      per-group arrays, the uniform table has one row per group */
     int n_pixel_args;             /* grouped programs: arguments read from images indexed by pixel */
     int accumulate;               /* grouped programs: outputs are added into the images in out_ptrs */
+    int n_tile_conds;             /* plain render programs: tile conditions classified by `tile_kernel` before every
+                                     launch (0 = none).  A tile is block_size pixel columns x tile_rows pixel rows;
+                                     the kernel writes one tri-state (0 false / 1 true for every pixel of the tile,
+                                     2 unresolved) per condition and tile, which the main kernel reads per block */
+    int tile_rows;
+    const char *tile_kernel;      /* <name>_tiles, or NULL when n_tile_conds == 0 */
 } tegb_program_desc;
 
 /* pixel grid of tests/plot.py:11-16: np.linspace(lo, hi, res+1) per axis, instance = nx * res_y + ny */
@@ -118,6 +124,9 @@ int tegb_program_eval_host(tegb_program *p, const double *scalars, const void *c
  * index; out_ptrs[k] receive (row_end-row_begin)*res_y elements. */
 int tegb_render_launch(tegb_program *p, const double *scalars, const tegb_grid *grid,
                        void *const *out_ptrs, void *stream);
+/* diagnostics: copies the tri-states written by the last tegb_render_launch of a program with tile conditions
+ * (condition-major, [n_tile_conds][tiles], element type of the program) to host memory */
+int tegb_program_tile_table(tegb_program *p, void *host_out, size_t nbytes, void *stream);
 
 /* Grouped render: groups [group_begin, group_begin + group_count) (e.g. triangles) are evaluated over their
  * own pixel windows in ONE launch.  group_ptrs[n_scalar_args]: device arrays with one value per group

@@ -68,6 +68,9 @@ class KernelSource:
     pixel_args: List[int] = None    # arguments read from pixel-indexed images (grouped launches)
     accumulate: bool = False        # outputs are added into images
     vec: int = 1                    # instances per thread (16-byte vector loads/stores), streaming programs
+    tile_conds: int = 0             # tile conditions classified by <name>_tiles before a render launch (cull.tile_cull)
+    tile_rows: int = 0              # pixel rows per tile (a tile is block_size columns wide)
+    tile_kernel: str = ''
     stats: Dict[str, float] = None
 
     @property
@@ -79,8 +82,9 @@ class Emitter:
     def __init__(self, sch: Schedule, ctype: str, num_samples: int, name: str,
                  block_size: int = 128, unroll_inner: int = 32, unroll_outer: int = 1, pred_accum: bool = True, use_asm: bool = True, team: int = 1, coop: bool = True,
                  pred_mix: float = 0.25, jam: int = 4, coop_max_lanes: int = 4,
-                 integration_mode: str = 'rectangular_quadrature'):
+                 integration_mode: str = 'rectangular_quadrature', tile_rows: int = 16):
         assert ctype in ('float', 'double')
+        self.tile_rows = int(tile_rows)
         # the reference names three modes (to_c.py:389-393) and ships a template for the first only
         assert integration_mode in INTEGRATION_MODES, f'unknown integration mode {integration_mode}'
         self.mode = integration_mode
@@ -294,23 +298,39 @@ class Emitter:
     # ------------------------------------------------------------ domain culling (cull.py)
     def _emit_domtri(self, i: int, known: Dict[int, bool], ind: int):
         """Interval evaluation of one select condition over the sampled box of its loop nest -> ``v{i}`` =
-        1 (true at every sample), 0 (false at every sample) or 2 (unresolved).  Every bound is computed with the
-        same individually rounded operations as the per-sample code (round-to-nearest is monotone).  Corner
-        values of products / quotients / square roots and the box abscissae are also summed into a poison
-        accumulator: one non-finite term anywhere in the cone leaves the condition unresolved, so a NaN that
-        ``fmin`` / ``fmax`` drop (or an infinity that could hide one downstream) can never support a decision.
-        Sums need no poison: an overflowed sum bound is +-inf on the side no decision can use."""
-        assert self.mode == 'rectangular_quadrature', 'culling is derived for the midpoint sample placement'
+        1 (true at every sample), 0 (false at every sample) or 2 (unresolved); see ``_iv_cone``."""
         root, B = self.nodes[i].attr
         fv = self.dag.free_bvars
+        zero = literal('0', self.ctype)
+        pre = f'd{i}_'
+        self.emit(f'T v{i};', ind)
+        self.emit('{', ind)
+        self.emit(f'T {pre}pz = {zero};', ind + 1)
+        t, f = self._iv_cone(root, lambda j: bool(fv(j) & B), {}, known, ind + 1, pre)
+        self.emit(f'v{i} = {self._iv_result(t, f, pre)};', ind + 1)
+        self.emit('}', ind)
+
+    def _iv_result(self, t: str, f: str, pre: str) -> str:
+        T = self.ctype
+        zero, one, two = literal('0', T), literal('1', T), literal('2', T)
+        return f'({pre}pz * {zero} == {zero}) ? ({t} ? {one} : ({f} ? {zero} : {two})) : {two}'
+
+    def _iv_cone(self, root: int, interior, leaf: Dict[int, tuple], known: Dict[int, bool], ind: int, pre: str):
+        """Emit the interval evaluation of the bool node ``root``; returns the names of its (always-true,
+        always-false) flags.  ``interior(j)``: node j varies over the box (everything else is a point, read through
+        ``ref``); ``leaf``: interior nodes whose (lo, hi) names are already defined.
+
+        Every bound is computed with the same individually rounded operations as the per-sample code
+        (round-to-nearest is monotone).  Corner values of products / quotients / square roots and the box abscissae
+        are also summed into the poison accumulator ``{pre}pz``: one non-finite term anywhere in the cone leaves
+        the condition unresolved, so a NaN that ``fmin`` / ``fmax`` drop (or an infinity that could hide one
+        downstream) can never support a decision.  Sums need no poison: an overflowed sum bound is +-inf on the
+        side no decision can use."""
+        assert self.mode == 'rectangular_quadrature', 'culling is derived for the midpoint sample placement'
         T, N = self.ctype, self.N
         half, zero = literal('0.5', T), literal('0', T)
         fmin, fmax = ('fminf', 'fmaxf') if T == 'float' else ('fmin', 'fmax')
-        pre = f'd{i}_'
         pz = f'{pre}pz'
-
-        def interior(j: int) -> bool:
-            return bool(fv(j) & B)
 
         order: List[int] = []
         seen = set()
@@ -320,7 +340,7 @@ class Emitter:
             if done:
                 order.append(j)
                 continue
-            if j in seen or not interior(j):
+            if j in seen or j in leaf or not interior(j):
                 continue
             seen.add(j)
             stack.append((j, True))
@@ -328,9 +348,13 @@ class Emitter:
                 stack.append((a, False))
 
         def lo(j: int) -> str:
+            if j in leaf:
+                return leaf[j][0]
             return f'{pre}l{j}' if interior(j) else self.ref(j, known)
 
         def hi(j: int) -> str:
+            if j in leaf:
+                return leaf[j][1]
             return f'{pre}h{j}' if interior(j) else self.ref(j, known)
 
         def is_t(j: int) -> str:
@@ -339,25 +363,26 @@ class Emitter:
         def is_f(j: int) -> str:
             return f'{pre}f{j}' if interior(j) else f'(!({self.ref(j, known)}))'
 
+        def is_point(j: int) -> bool:
+            return j not in leaf and not interior(j)
+
         def const_value(j: int):
             m = self.nodes[self.helper.resolve(j, known)]
             return float(m.attr) if m.op == 'const' else None
 
-        self.emit(f'T v{i};', ind)
-        self.emit('{', ind)
-        e = lambda line: self.emit(line, ind + 1)     # noqa: E731
-        e(f'T {pz} = {zero};')
+        e = lambda line: self.emit(line, ind)     # noqa: E731
         for j in order:
             n = self.nodes[j]
             op = n.op
             L, H = f'{pre}l{j}', f'{pre}h{j}'
             if op == 'bvar':
-                a, b = self.ref(n.args[0], known), self.ref(n.args[1], known)
-                e(f'const T {pre}s{j} = ((T)({b} - {a})) / (T){N};')
-                e(f'const T {pre}a{j} = {a} + {pre}s{j} * ((T)0u + {half});')
-                e(f'const T {pre}b{j} = {a} + {pre}s{j} * ((T){N - 1}u + {half});')
-                e(f'const T {L} = {fmin}({pre}a{j}, {pre}b{j}), {H} = {fmax}({pre}a{j}, {pre}b{j});')
-                e(f'{pz} = {pz} + {pre}a{j}; {pz} = {pz} + {pre}b{j};')
+                # samples lo + step * (i + 0.5), i = 0 .. N-1, step = (hi - lo) / N: every factor is monotone
+                a, b = n.args
+                e(f'const T {pre}sl{j} = ((T)({lo(b)} - {hi(a)})) / (T){N}, {pre}sh{j} = ((T)({hi(b)} - {lo(a)})) / (T){N};')
+                c0, c1 = f'((T)0u + {half})', f'((T){N - 1}u + {half})'
+                e(f'const T {L} = {lo(a)} + {fmin}({pre}sl{j} * {c0}, {pre}sl{j} * {c1});')
+                e(f'const T {H} = {hi(a)} + {fmax}({pre}sh{j} * {c0}, {pre}sh{j} * {c1});')
+                e(f'{pz} = {pz} + {L}; {pz} = {pz} + {H};')
             elif op == 'add':
                 x, y = n.args
                 e(f'const T {L} = {lo(x)} + {lo(y)}, {H} = {hi(x)} + {hi(y)};')
@@ -365,15 +390,15 @@ class Emitter:
                 x, y = n.args
                 o = '*' if op == 'mul' else '/'
                 kx, ky = const_value(x), const_value(y)
-                if op == 'mul' and (kx == -1.0 or ky == -1.0) and interior(y if kx == -1.0 else x):
-                    w = y if kx == -1.0 else x              # negation is exact: swap the bounds
-                    first = kx == -1.0
+                if op == 'mul' and ((kx == -1.0 and not is_point(y)) or (ky == -1.0 and not is_point(x))):
+                    first = kx == -1.0 and not is_point(y)     # negation is exact: swap the bounds
+                    w = y if first else x
                     neg = (lambda t: f'{self.ref(x, known)} * {t}') if first else (lambda t: f'{t} * {self.ref(y, known)}')
                     e(f'const T {L} = {neg(hi(w))}, {H} = {neg(lo(w))};')
                     continue
-                if interior(x) and interior(y):
+                if not is_point(x) and not is_point(y):
                     corners = [f'{lo(x)} {o} {lo(y)}', f'{lo(x)} {o} {hi(y)}', f'{hi(x)} {o} {lo(y)}', f'{hi(x)} {o} {hi(y)}']
-                elif interior(x):
+                elif not is_point(x):
                     corners = [f'{lo(x)} {o} {lo(y)}', f'{hi(x)} {o} {lo(y)}']
                 else:
                     corners = [f'{lo(x)} {o} {lo(y)}', f'{lo(x)} {o} {hi(y)}']
@@ -386,7 +411,7 @@ class Emitter:
                     e(f'const T {L} = {fmin}({fmin}({ps[0]}, {ps[1]}), {fmin}({ps[2]}, {ps[3]}));')
                     e(f'const T {H} = {fmax}({fmax}({ps[0]}, {ps[1]}), {fmax}({ps[2]}, {ps[3]}));')
                 e(' '.join(f'{pz} = {pz} + {nm};' for nm in ps))
-                if op == 'div' and interior(y):
+                if op == 'div' and not is_point(y):
                     # a divisor interval that touches zero bounds nothing
                     e(f'if (!({lo(y)} > {zero} || {hi(y)} < {zero})) {pz} = TEGB_IV_NAN;')
             elif op == 'sqrt':
@@ -410,9 +435,107 @@ class Emitter:
                 e(f'const bool {pre}t{j} = {is_t(x)} || {is_t(y)}, {pre}f{j} = {is_f(x)} && {is_f(y)};')
             else:  # pragma: no cover  (cull.py admits interval-evaluable cones only)
                 raise NotImplementedError(f'no interval rule for "{op}"')
-        two, one = literal('2', T), literal('1', T)
-        e(f'v{i} = ({pz} * {zero} == {zero}) ? ({pre}t{root} ? {one} : ({pre}f{root} ? {zero} : {two})) : {two};')
-        self.emit('}', ind)
+        return is_t(root), is_f(root)
+
+    # ---------------------------------------------------------------------- tile classification kernel
+    def tiles_body(self, grid: Sequence[int]) -> List[str]:
+        """Body of ``<name>_tiles`` (cull.tile_cull): one thread per tile of BLOCK columns x ``tile_rows`` rows
+        bounds the pixel-box arguments and the sample abscissae over its pixels (by walking its rows and columns:
+        exact, no reasoning about rounding) and evaluates every tile condition with ``_iv_cone``."""
+        T, N = self.ctype, self.N
+        dag, nodes = self.dag, self.nodes
+        conds = dag.tile_conds
+        half, zero = literal('0.5', T), literal('0', T)
+        fmin, fmax = ('fminf', 'fmaxf') if T == 'float' else ('fmin', 'fmax')
+        gset = set(grid)
+        saved_main = getattr(self, 'in_main', True)
+        self.in_main = False
+        self.lines = []
+        dep: Dict[int, bool] = {}
+        for j in sorted(dag.reachable([c for _, c in conds] + [nodes[c].attr[0] for k, c in conds if k == 'dom'])):
+            n = nodes[j]
+            dep[j] = (n.op == 'in' and n.attr in gset) or any(dep.get(a, False) for a in n.args)
+        fv = dag.free_bvars
+        # grid leaves: [min, max] of each pixel-box argument over the rows / columns of the tile
+        in_node = {a: dag.intern('in', (), a) for a in grid}
+        xl, xu, yl, yu = (in_node[a] for a in grid)
+        leaf: Dict[int, tuple] = {xl: ('g_xl_lo', 'g_xl_hi'), xu: ('g_xu_lo', 'g_xu_hi'),
+                                  yl: ('g_yl_lo', 'g_yl_hi'), yu: ('g_yu_lo', 'g_yu_hi')}
+        # integration variables whose bounds are exactly a pixel-box pair: exact range of their abscissae
+        roots = [(k, c, nodes[c].attr[0] if k == 'dom' else c, nodes[c].attr[1] if k == 'dom' else frozenset())
+                 for k, c in conds]
+        bx, by = [], []
+        for _, _, r, B in roots:
+            for j in dag.reachable([r]):
+                if nodes[j].op == 'bvar' and j in B:
+                    pair = tuple(self.helper.resolve(a, {}) for a in nodes[j].args)
+                    if pair == (xl, xu) and j not in bx:
+                        bx.append(j)
+                    elif pair == (yl, yu) and j not in by:
+                        by.append(j)
+        for j in bx + by:
+            leaf[j] = (f'g_b{j}_lo', f'g_b{j}_hi')
+        e = lambda line, ind=1: self.emit(line, ind)     # noqa: E731
+        e(f'T g_pz = {zero};')
+        for axis, tab, first, last, lo_n, hi_n, bvs in (('x', 'xe', 'r0', 'r1', 'xl', 'xu', bx),
+                                                      ('y', 'ye', 'c0', 'c1', 'yl', 'yu', by)):
+            e(f'T g_{lo_n}_lo = {tab}[{first}], g_{lo_n}_hi = {tab}[{first}], g_{hi_n}_lo = {tab}[{first} + 1], '
+              f'g_{hi_n}_hi = {tab}[{first} + 1];')
+            for j in bvs:
+                e(f'T g_b{j}_lo = {tab}[{first}], g_b{j}_hi = {tab}[{first}];')
+            e(f'for (int q = {first}; q < {last}; ++q) {{')
+            e(f'const T lb = {tab}[q], ub = {tab}[q + 1];', 2)
+            e(f'g_{lo_n}_lo = {fmin}(g_{lo_n}_lo, lb); g_{lo_n}_hi = {fmax}(g_{lo_n}_hi, lb);', 2)
+            e(f'g_{hi_n}_lo = {fmin}(g_{hi_n}_lo, ub); g_{hi_n}_hi = {fmax}(g_{hi_n}_hi, ub);', 2)
+            e('g_pz = g_pz + lb; g_pz = g_pz + ub;', 2)
+            if bvs:
+                e(f'const T st = ((T)(ub - lb)) / (T){N};', 2)
+                e(f'const T sa = lb + st * ((T)0u + {half}), sb = lb + st * ((T){N - 1}u + {half});', 2)
+                e('g_pz = g_pz + sa; g_pz = g_pz + sb;', 2)
+                for j in bvs:
+                    e(f'g_b{j}_lo = {fmin}(g_b{j}_lo, {fmin}(sa, sb)); g_b{j}_hi = {fmax}(g_b{j}_hi, {fmax}(sa, sb));', 2)
+            e('}')
+        # launch-invariant values the cones read (points), from the scalar arguments
+        need: List[int] = []
+        seen = set()
+        for _, _, r, B in roots:
+            interior = (lambda j, B=B: bool(fv(j) & B) or dep.get(j, False))
+            stack = [r]
+            visited = set()
+            while stack:
+                j = stack.pop()
+                if j in visited:
+                    continue
+                visited.add(j)
+                if j in leaf:
+                    continue
+                if interior(j):
+                    stack.extend(nodes[j].args)
+                    continue
+                # a point: emit its whole (launch-invariant) cone
+                sub = [(j, False)]
+                while sub:
+                    m, done = sub.pop()
+                    if done:
+                        need.append(m)
+                        continue
+                    if m in seen or nodes[m].op == 'const':
+                        continue
+                    seen.add(m)
+                    sub.append((m, True))
+                    for a2 in reversed(nodes[m].args):
+                        sub.append((a2, False))
+        for m in need:
+            e(f'const {self.decl(m)} v{m} = {self.expr(m, {})};')
+        for k, (kind, c, r, B) in enumerate(roots):
+            pre = f'k{k}_'
+            e('{')
+            e(f'T {pre}pz = g_pz;', 2)
+            t, f = self._iv_cone(r, (lambda j, B=B: bool(fv(j) & B) or dep.get(j, False)), leaf, {}, 2, pre)
+            e(f'tiles[(size_t){k} * n_tiles + t] = {self._iv_result(t, f, pre)};', 2)
+            e('}')
+        self.in_main = saved_main
+        return self.lines
 
     def _trapezoid_loop(self, st: LoopGroup, known: Dict[int, bool], ind: int, depth: int, declare: bool = True):
         """The numpy backend's rule (teg/eval/numpy_eval.py:57-68), the semantics of the reference's
@@ -898,7 +1021,11 @@ class Emitter:
         assert not grid or len(grid) == 4, 'a render program takes exactly x_lb, x_ub, y_lb, y_ub on the grid'
         assert not grouped or grid, 'grouped launches are render launches'
         assert not pix or grouped, 'pixel-indexed arguments need a grouped render launch'
-        arrs = [a for a in sch.array_args if a not in grid and a not in pix]
+        n_prog_args = len(self.dag.arg_labels)
+        tile = [a for a in sch.array_args if a >= n_prog_args]      # tile conditions (pseudo arguments, cull.tile_cull)
+        assert not tile or (grid and not grouped and self.team == 1), 'tile conditions belong to plain render launches'
+        assert len(tile) == len(getattr(self.dag, 'tile_conds', []) if tile else [])
+        arrs = [a for a in sch.array_args if a not in grid and a not in pix and a not in tile]
         assert not (grid and arrs), 'render programs cannot also stream per-instance arrays'
         used_in = {self.nodes[i].attr for i in sch.uniform_nodes if self.nodes[i].op == 'in'}
         uni = self.uniform_body()
@@ -919,7 +1046,7 @@ class Emitter:
         src.append('#include "teg_b200_runtime.cuh"')
         src.append(f'typedef {T} T;')
         src.append(f'#define TEGB_NUM_UNIFORM {nu}')
-        if any(self.nodes[i].op == 'domtri' for i in self.dag.reachable(sch.outputs)):
+        if tile or any(self.nodes[i].op == 'domtri' for i in self.dag.reachable(sch.outputs)):
             # the poison value of the domain-culling prologue (cull.py)
             src.append(f'#define TEGB_IV_NAN {"nanf" if T == "float" else "nan"}("")')
         if not grouped:
@@ -1015,8 +1142,26 @@ class Emitter:
             if grid:
                 assert team == 1, 'render programs are thread-per-pixel'
                 # pixel (nx, ny) -> instance nx * res_y + ny; box bounds from the two np.linspace edge tables
+                if tile:
+                    tparams = ', '.join([f'const T a{a}' for a in scal] +
+                                        ['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
+                                         'const int row0', 'const int n_rows', 'const int tile_rows', 'const int n_tx',
+                                         'const int n_ty', 'T* __restrict__ tiles'])
+                    src.append(f'extern "C" __global__ void {name}_tiles({tparams}) {{')
+                    src.append('    const int t = blockIdx.x * blockDim.x + threadIdx.x;')
+                    src.append('    const size_t n_tiles = (size_t)n_tx * n_ty;')
+                    src.append('    if (t >= n_tx * n_ty) return;')
+                    src.append('    const int ty = t / n_tx, tx = t - ty * n_tx;')
+                    src.append('    const int r0 = row0 + ty * tile_rows, r1 = min(r0 + tile_rows, row0 + n_rows);')
+                    src.append(f'    const int c0 = tx * {bs}, c1 = min(c0 + {bs}, res_y);')
+                    for a in scal:
+                        src.append(f'    (void)a{a};')
+                    src += self.tiles_body(grid)
+                    src.append('}')
+                    src.append('')
                 mparams = ', '.join(['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
-                                     'const int row0'] + outs_decl)
+                                     'const int row0'] +
+                                    (['const T* __restrict__ tiles', 'const int tile_rows'] if tile else []) + outs_decl)
                 src.append(f'extern "C" __global__ void __launch_bounds__({bs}) {name}_main({mparams}) {{')
                 src.append('    const int ny = blockIdx.x * blockDim.x + threadIdx.x;')
                 src.append('    const bool live = ny < res_y;')
@@ -1027,6 +1172,11 @@ class Emitter:
                     loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye[nyc]', grid[3]: 'ye[nyc + 1]'}
                 else:
                     loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye[ny]', grid[3]: 'ye[ny + 1]'}
+                if tile:
+                    src.append('    const size_t n_tiles = (size_t)gridDim.x * ((gridDim.y + tile_rows - 1) / tile_rows);')
+                    src.append('    const size_t tile_id = (size_t)(blockIdx.y / tile_rows) * gridDim.x + blockIdx.x;')
+                    for k, a in enumerate(tile):
+                        loads[a] = f'tiles[{k} * n_tiles + tile_id]'
                 call = ', '.join((['live'] if coop else []) + [loads[a] for a in varying] + ['res'])
             else:
                 mparams = ', '.join([f'const T* __restrict__ in{a}' for a in arrs] + outs_decl + ['const long long n'])
@@ -1115,6 +1265,8 @@ class Emitter:
                             n_uniform=nu, scalar_args=scal, array_args=arrs, grid_args=grid,
                             n_outputs=K, block_size=bs, reduce_outputs=nr, team=team,
                             grouped=bool(grouped), pixel_args=pix, accumulate=bool(accumulate),
+                            tile_conds=len(tile), tile_rows=self.tile_rows if tile else 0,
+                            tile_kernel=f'{name}_tiles' if tile else '',
                             stats={'uses_coop': self.uses_coop, 'loops': self.loop_counter})
 
 

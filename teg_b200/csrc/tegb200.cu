@@ -260,7 +260,7 @@ struct tegb_program {
     tegb_program_desc d;
     int device = 0;
     CUmodule mod = nullptr;
-    CUfunction f_uniform = nullptr, f_main = nullptr;
+    CUfunction f_uniform = nullptr, f_main = nullptr, f_tiles = nullptr;
     CUdeviceptr u_const = 0;      // __constant__ table inside the module
     size_t u_const_bytes = 0;
     void *u_stage = nullptr;      // device buffer the uniform kernel writes
@@ -277,6 +277,9 @@ struct tegb_program {
     // per-block partial sums of reduce_outputs programs
     void *d_partials = nullptr;
     size_t partials_bytes = 0;
+    // tri-states of the tile conditions (render programs with n_tile_conds > 0)
+    void *d_tiles = nullptr;
+    size_t tiles_bytes = 0;
     // pixel-edge tables for tegb_render_launch
     void *d_xe = nullptr, *d_ye = nullptr;
     std::vector<char> h_xe, h_ye;
@@ -311,6 +314,12 @@ extern "C" int tegb_program_create(tegb_module *m, const tegb_program_desc *desc
     if (r != CUDA_SUCCESS) return bail(fail(TEGB_ERR_CUDA, "kernel %s: %s", desc->uniform_kernel, drv::errstr(r)));
     r = drv::ModuleGetFunction(&p->f_main, p->mod, desc->main_kernel);
     if (r != CUDA_SUCCESS) return bail(fail(TEGB_ERR_CUDA, "kernel %s: %s", desc->main_kernel, drv::errstr(r)));
+    if (desc->n_tile_conds > 0) {
+        if (!desc->tile_kernel || desc->tile_rows < 1 || desc->grouped || desc->n_grid_args != 4)
+            return bail(fail(TEGB_ERR_INVALID, "tile conditions need a plain render program, tile_rows >= 1 and a tile kernel"));
+        r = drv::ModuleGetFunction(&p->f_tiles, p->mod, desc->tile_kernel);
+        if (r != CUDA_SUCCESS) return bail(fail(TEGB_ERR_CUDA, "kernel %s: %s", desc->tile_kernel, drv::errstr(r)));
+    }
     size_t want = (size_t)(desc->n_uniform > 0 ? desc->n_uniform : 1) * desc->elem_size;
     if (!desc->grouped) {
         r = drv::ModuleGetGlobal(&p->u_const, &p->u_const_bytes, p->mod, desc->uniform_symbol);
@@ -330,6 +339,7 @@ extern "C" void tegb_program_destroy(tegb_program *p) {
     if (p->u_stage) cudaFree(p->u_stage);
     if (p->d_partials) cudaFree(p->d_partials);
     if (p->d_utab) cudaFree(p->d_utab);
+    if (p->d_tiles) cudaFree(p->d_tiles);
     if (p->d_xe) cudaFree(p->d_xe);
     if (p->d_ye) cudaFree(p->d_ye);
     if (p->mod) drv::ModuleUnload(p->mod);
@@ -666,6 +676,40 @@ extern "C" int tegb_render_launch(tegb_program *p, const double *scalars, const 
     const unsigned gx = (unsigned)((g->res_y + bs - 1) / bs);
     const unsigned gy = (unsigned)(g->row_end - g->row_begin);
     if (gy > 65535u) return fail(TEGB_ERR_INVALID, "more than 65535 rows in one render launch");
+    int tile_rows = p->d.tile_rows;
+    if (p->d.n_tile_conds > 0) {
+        // classify the tiles (block_size columns x tile_rows rows) for these launch-wide arguments and this band
+        int n_rows = (int)gy, n_tx = (int)gx, n_ty = (n_rows + tile_rows - 1) / tile_rows;
+        const size_t need = (size_t)p->d.n_tile_conds * n_tx * n_ty * p->d.elem_size;
+        if (need > p->tiles_bytes) {
+            RT_CHECK(cudaStreamSynchronize((cudaStream_t)st));      // an earlier launch may still read the old table
+            if (p->d_tiles) { cudaFree(p->d_tiles); p->d_tiles = nullptr; p->tiles_bytes = 0; }
+            RT_CHECK(cudaMalloc(&p->d_tiles, need));
+            p->tiles_bytes = need;
+        }
+        const int ns = p->d.n_scalar_args;
+        std::vector<float> sf(ns > 0 ? ns : 1);
+        std::vector<double> sd(ns > 0 ? ns : 1);
+        std::vector<void *> targs;
+        for (int i = 0; i < ns; i++) {
+            if (p->d.elem_size == 4) { sf[i] = (float)scalars[i]; targs.push_back(&sf[i]); }
+            else { sd[i] = scalars[i]; targs.push_back(&sd[i]); }
+        }
+        targs.push_back(&p->d_xe);
+        targs.push_back(&p->d_ye);
+        targs.push_back(&res_y);
+        targs.push_back(&row0);
+        targs.push_back(&n_rows);
+        targs.push_back(&tile_rows);
+        targs.push_back(&n_tx);
+        targs.push_back(&n_ty);
+        targs.push_back(&p->d_tiles);
+        const unsigned tb = 64, tg = (unsigned)((n_tx * n_ty + tb - 1) / tb);
+        CU_CHECK(drv::LaunchKernel(p->f_tiles, tg, 1, 1, tb, 1, 1, 0, st, targs.data(), nullptr));
+        g_launches++;
+        args.push_back(&p->d_tiles);
+        args.push_back(&tile_rows);
+    }
     const int n_store = p->d.n_outputs - p->d.reduce_outputs;
     for (int k = 0; k < n_store; k++) { outs[k] = out_ptrs[k]; args.push_back(&outs[k]); }
     if (p->d.reduce_outputs) {
@@ -676,6 +720,16 @@ extern "C" int tegb_render_launch(tegb_program *p, const double *scalars, const 
     CU_CHECK(drv::LaunchKernel(p->f_main, gx, gy, 1, bs, 1, 1, 0, st, args.data(), nullptr));
     g_launches++;
     if (p->d.reduce_outputs) return finish_partials(p, (unsigned long long)gx * gy, out_ptrs[n_store], (cudaStream_t)st);
+    return TEGB_OK;
+}
+
+extern "C" int tegb_program_tile_table(tegb_program *p, void *host_out, size_t nbytes, void *stream) {
+    if (!p || !host_out) return fail(TEGB_ERR_INVALID, "tegb_program_tile_table: null argument");
+    if (!p->d_tiles || nbytes > p->tiles_bytes)
+        return fail(TEGB_ERR_INVALID, "no tile table of that size (render first; n_tile_conds x tiles x elem_size bytes)");
+    RT_CHECK(cudaSetDevice(p->device));
+    RT_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    RT_CHECK(cudaMemcpy(host_out, p->d_tiles, nbytes, cudaMemcpyDeviceToHost));
     return TEGB_OK;
 }
 

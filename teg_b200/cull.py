@@ -144,7 +144,9 @@ class _Rebuilder:
             return self.dag.intern(n.op, (a, b))
         if n.op == 'lt':
             return self.dag.intern('lt', (self.value(n.args[0]), self.value(n.args[1])))
-        return i            # domis and friends
+        if n.op == 'domis':
+            return self.dag.intern('domis', (self.value(n.args[0]),), n.attr)
+        return i
 
     def value(self, root: int) -> int:
         dag, memo = self.dag, self.memo
@@ -157,7 +159,7 @@ class _Rebuilder:
                 continue
             n = nodes[i]
             if n.op in ('const', 'in', 'domtri'):
-                memo[i] = i
+                memo[i] = i                      # (a preset memo entry replaces a domtri by a tile input)
                 stack.pop()
                 continue
             if n.op == 'sel':
@@ -289,4 +291,111 @@ def cull(dag: Dag, num_samples: int, min_samples: int = 64, max_roots: int = 4, 
 
     dag.outputs = tuple(rewrite(o) for o in dag.outputs)
     dag.culled = record
+    return dag
+
+
+# ------------------------------------------------------------------------------------------ tile level
+def interval_evaluable(dag: Dag, root: int, interior) -> bool:
+    """Can the cone of ``root`` above the nodes for which ``interior`` is false be bounded by intervals?"""
+    nodes = dag.nodes
+    seen: Set[int] = set()
+    stack = [root]
+    while stack:
+        i = stack.pop()
+        if i in seen:
+            continue
+        if not interior(i):
+            # a point of the classification kernel: must be plain launch-invariant arithmetic
+            if dag.has_quad(i) or any(nodes[j].op in ('domtri', 'domis') for j in dag.reachable([i])):
+                return False
+            continue
+        seen.add(i)
+        n = nodes[i]
+        if n.op == 'in':
+            continue
+        if n.op not in IV_FLOAT_OPS and n.op not in IV_BOOL_OPS:
+            return False
+        stack.extend(n.args)
+    return len(seen) <= 160
+
+
+def tile_cull(dag: Dag, grid_args: Sequence[int], num_samples: int, max_conds: int = 12) -> Dag:
+    """Second level of culling for render launches (pixel boxes generated from the pixel index): the same interval
+    evaluation, but over a whole TILE of pixels, done once per tile by a small classification kernel.
+
+    Tile conditions: (a) every ``domtri`` of the per-instance culling (now: "uniform over every sample of every
+    pixel of the tile"), (b) every per-instance guard of an integral (the bound checks around the delta terms of
+    reverse-mode programs: "true / false for every pixel of the tile").  Condition k becomes the pseudo argument
+    ``n_args + k`` (a tri-state the main kernel loads per block), and each output becomes
+
+        any tile condition unresolved ? <the per-instance program> : <the program with the conditions substituted>
+
+    In a resolved tile no pixel evaluates an interval or a guard: interior pixels of the triangle run the 32
+    additions, exterior ones a handful of instructions, and a reverse-mode program whose guards are all false
+    reduces to its constant zeros.  Exactness as for ``cull``: the tile box contains every pixel box of the tile,
+    bounds are monotone.  Returns a copy with ``.tile_conds`` = [(kind, node)] ('dom' | 'guard'); unchanged
+    (``tile_conds`` empty) when there is nothing to classify."""
+    dag = dag.clone()
+    dag.tile_conds = []
+    nodes = dag.nodes
+    n_args = len(dag.arg_labels)
+    grid = set(grid_args)
+    live = dag.reachable(dag.outputs)
+
+    dep_cache: Dict[int, bool] = {}
+
+    def on_grid(i: int) -> bool:
+        """does node i depend on a pixel-box argument?"""
+        if i in dep_cache:
+            return dep_cache[i]
+        stack = [i]
+        while stack:
+            j = stack[-1]
+            if j in dep_cache:
+                stack.pop()
+                continue
+            n = nodes[j]
+            pend = [a for a in n.args if a not in dep_cache]
+            if pend:
+                stack.extend(pend)
+                continue
+            dep_cache[j] = (n.op == 'in' and n.attr in grid) or any(dep_cache[a] for a in n.args)
+            stack.pop()
+        return dep_cache[i]
+
+    conds: List[Tuple[str, int]] = []
+    for i in live:
+        n = nodes[i]
+        if n.op == 'domtri':
+            root, B = n.attr
+            if interval_evaluable(dag, root, lambda j, B=B: bool(dag.free_bvars(j) & B) or on_grid(j)):
+                conds.append(('dom', i))
+    for i in live:
+        n = nodes[i]
+        if n.op != 'sel' or dag.free_bvars(i):
+            continue
+        c = n.args[0]
+        if not (dag.has_quad(n.args[1]) or dag.has_quad(n.args[2])):
+            continue
+        if dag.free_bvars(c) or dag.has_quad(c) or not on_grid(c) or ('guard', c) in conds:
+            continue
+        if any(nodes[j].op in ('domis', 'domtri') for j in dag.reachable([c])):
+            continue
+        if interval_evaluable(dag, c, on_grid):
+            conds.append(('guard', c))
+    if not conds or len(conds) > max_conds:
+        return dag
+    rb = _Rebuilder(dag, num_samples, {}, {})
+    unresolved = None
+    for k, (kind, node) in enumerate(conds):
+        tin = dag.intern('in', (), n_args + k)
+        u = dag.intern('domis', (tin,), 'U')
+        unresolved = u if unresolved is None else dag.intern('or', (unresolved, u))
+        if kind == 'dom':
+            rb.memo[node] = tin
+            rb.known[dag.intern('domis', (node,), 'U')] = False
+        else:
+            rb.repl[node] = dag.intern('domis', (tin,), 'T')
+    dag.outputs = tuple(dag.sel(unresolved, o, rb.value(o)) for o in dag.outputs)
+    dag.tile_conds = conds
     return dag

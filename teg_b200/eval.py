@@ -104,6 +104,8 @@ class CUDA_EvalMode(EvalMode):
         # cull: per-instance interval evaluation of the select conditions over the sampled box; instances whose
         # discontinuities miss the box run comparison-free specialised nests (bit-identical results, cull.py)
         self.cull = bool(cull) and integration_mode == 'rectangular_quadrature'
+        self.tiles = self.cull and bool(codegen_opts.pop('tiles', True))     # tile-level classification for renders
+        self.codegen_opts = codegen_opts
         self.sched_dag: Dag = self.dag
         if self.cull:
             from .cull import cull as _cull
@@ -117,11 +119,24 @@ class CUDA_EvalMode(EvalMode):
         self._schedules: Dict[tuple, object] = {}
 
     # ------------------------------------------------------------------ compile
-    def schedule(self, array_args: Sequence[int], grid_args: Sequence[int] = ()):
+    def schedule(self, array_args: Sequence[int], grid_args: Sequence[int] = (), tiled: bool = False):
+        """tiled (plain render launches with culling): the program additionally takes one tri-state per tile
+        condition, classified per tile of pixels by ``<name>_tiles`` (cull.tile_cull)."""
         key = tuple(sorted(set(array_args) | set(grid_args)))
-        if key not in self._schedules:
-            self._schedules[key] = make_schedule(self.sched_dag, list(key))
-        return self._schedules[key]
+        tiled = bool(tiled) and self.cull and len(grid_args) == 4 and set(array_args) <= set(grid_args)
+        if (key, tiled) not in self._schedules:
+            dag, arr = self.sched_dag, list(key)
+            if tiled:
+                from .cull import tile_cull
+                dag = tile_cull(self.sched_dag, list(grid_args), self.num_samples)
+                arr += [len(self.program.args) + k for k in range(len(dag.tile_conds))]
+            self._schedules[(key, tiled)] = make_schedule(dag, arr)
+        return self._schedules[(key, tiled)]
+
+    def reference_schedule(self, array_args: Sequence[int]):
+        """Schedule of the program as the reference states it (no culling): what the algorithmic operation
+        count (opcount.py) is defined on."""
+        return make_schedule(self.dag, sorted(set(array_args)))
 
     def _n_reduce(self, reduce) -> int:
         """reduce: False / True (all outputs) / int (that many TRAILING outputs, e.g. the derivative part of a
@@ -147,7 +162,7 @@ class CUDA_EvalMode(EvalMode):
 
     def kernel_source(self, array_args: Sequence[int], grid_args: Sequence[int] = (),
                       reduce: bool = False, team: int = 1, vec: int = 1) -> KernelSource:
-        sch = self.schedule(array_args, grid_args)
+        sch = self.schedule(array_args, grid_args, tiled=bool(grid_args) and team == 1 and self.tiles)
         block = team if team > 32 else self.block_size
         return generate(sch, self.float_width, self.num_samples, grid_args=list(grid_args),
                         reduce_outputs=reduce, block_size=block, team=team, vec=vec, **self.codegen_opts)

@@ -33,7 +33,7 @@ PARAMS = ('px0', 'py0', 'px1', 'py1', 'px2', 'py2', 'col')
 
 class MultiTriangleRasterizer:
     def __init__(self, primal: Program, grad: Program, res: int, bands: int = 1, rank: int = 0,
-                 num_samples: int = 16, device: int = 0, float_width: str = 'float'):
+                 num_samples: int = 16, device: int = 0, float_width: str = 'float', cull: bool = True):
         import torch
         self.torch = torch
         self.res = int(res)
@@ -42,8 +42,9 @@ class MultiTriangleRasterizer:
         self.device = device
         self.dev = torch.device('cuda', device)
         self.tdt = torch.float32 if float_width == 'float' else torch.float64
-        self.m_primal = CUDA_EvalMode(primal, num_samples=num_samples, device=device, float_width=float_width)
-        self.m_grad = CUDA_EvalMode(grad, num_samples=num_samples, device=device, float_width=float_width)
+        self.m_primal = CUDA_EvalMode(primal, num_samples=num_samples, device=device, float_width=float_width,
+                                      cull=cull)
+        self.m_grad = CUDA_EvalMode(grad, num_samples=num_samples, device=device, float_width=float_width, cull=cull)
         self.p_lab = {base_name(lab): lab for lab in primal.args}
         self.g_lab = {base_name(lab): lab for lab in grad.args}
         self.bounds = ((0.0, float(bands)), (0.0, 1.0))

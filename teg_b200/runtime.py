@@ -23,7 +23,8 @@ class ProgramDesc(ctypes.Structure):
                 ('uniform_symbol', ctypes.c_char_p), ('elem_size', ctypes.c_int), ('n_uniform', ctypes.c_int),
                 ('n_scalar_args', ctypes.c_int), ('n_array_args', ctypes.c_int), ('n_grid_args', ctypes.c_int),
                 ('n_outputs', ctypes.c_int), ('block_size', ctypes.c_int), ('reduce_outputs', ctypes.c_int), ('team', ctypes.c_int), ('vec', ctypes.c_int), ('grouped', ctypes.c_int),
-                ('n_pixel_args', ctypes.c_int), ('accumulate', ctypes.c_int)]
+                ('n_pixel_args', ctypes.c_int), ('accumulate', ctypes.c_int), ('n_tile_conds', ctypes.c_int),
+                ('tile_rows', ctypes.c_int), ('tile_kernel', ctypes.c_char_p)]
 
 
 class Grid(ctypes.Structure):
@@ -36,7 +37,7 @@ SYMBOLS = [
     'tegb_last_error', 'tegb_version', 'tegb_nvrtc_version', 'tegb_device_count', 'tegb_compile', 'tegb_module_from_cubin',
     'tegb_module_cubin', 'tegb_module_log', 'tegb_module_destroy', 'tegb_program_create',
     'tegb_program_destroy', 'tegb_program_launch', 'tegb_program_eval_host', 'tegb_render_launch',
-    'tegb_render_groups_launch',
+    'tegb_render_groups_launch', 'tegb_program_tile_table',
     'tegb_launch_count', 'tegb_reduce_workspace_bytes', 'tegb_reduce_sum', 'tegb_nccl_unique_id',
     'tegb_nccl_comm_create', 'tegb_nccl_comm_destroy', 'tegb_allreduce_sum', 'tegb_fma_peak',
 ]
@@ -77,6 +78,7 @@ def lib():
                                      ctypes.POINTER(vp), vp]
     L.tegb_render_groups_launch.argtypes = [vp, ctypes.POINTER(vp), i32, i32, ctypes.POINTER(Grid), vp, i32, i32,
                                             ctypes.POINTER(vp), ctypes.POINTER(vp), vp]
+    L.tegb_program_tile_table.argtypes = [vp, vp, ctypes.c_size_t, vp]
     L.tegb_launch_count.restype = i64
     L.tegb_reduce_workspace_bytes.argtypes = [i32, i64, i32]
     L.tegb_reduce_workspace_bytes.restype = ctypes.c_size_t
@@ -180,14 +182,24 @@ class Program:
         self.ks = ks
         self.device = device
         self.elem_size = 4 if ks.ctype == 'float' else 8
-        self._names = (ks.uniform_kernel.encode(), ks.main_kernel.encode(), b'tegU')
+        self._names = (ks.uniform_kernel.encode(), ks.main_kernel.encode(), b'tegU',
+                       (getattr(ks, 'tile_kernel', '') or '').encode() or None)
         desc = ProgramDesc(self._names[0], self._names[1], self._names[2], self.elem_size, ks.n_uniform,
                            len(ks.scalar_args), len(ks.array_args), len(getattr(ks, 'grid_args', ())),
                            ks.n_outputs, ks.block_size, int(getattr(ks, 'reduce_outputs', False)),
                            int(getattr(ks, 'team', 1)), int(getattr(ks, 'vec', 1)), int(getattr(ks, 'grouped', False)),
-                           len(getattr(ks, 'pixel_args', None) or ()), int(getattr(ks, 'accumulate', False)))
+                           len(getattr(ks, 'pixel_args', None) or ()), int(getattr(ks, 'accumulate', False)),
+                           int(getattr(ks, 'tile_conds', 0)), int(getattr(ks, 'tile_rows', 0)), self._names[3])
         self.handle = ctypes.c_void_p()
         check(L.tegb_program_create(module.handle, ctypes.byref(desc), device, ctypes.byref(self.handle)))
+
+    def tile_table(self, count: int, stream: int = 0):
+        """Tri-states of the tile conditions written by the last render (diagnostics): ndarray [count]."""
+        import numpy as np
+        out = np.empty(count, dtype=np.float32 if self.elem_size == 4 else np.float64)
+        check(self._L.tegb_program_tile_table(self.handle, ctypes.c_void_p(out.ctypes.data),
+                                              ctypes.c_size_t(out.nbytes), ctypes.c_void_p(stream)))
+        return out
 
     def launch(self, scalars: Sequence[float], in_ptrs: Sequence[int], out_ptrs: Sequence[int], n: int,
                stream: int = 0) -> None:

@@ -24,7 +24,8 @@ def compile_for_host(ks):
            '#define TEGB_UNIFORM_TABLE(T, name, n) static T name[n]\n#define __restrict__\n')
     uargs = ', '.join([f'sc[{j}]' for j in range(len(ks.scalar_args))] + ['tegU'])
     varying = list(ks.array_args) + list(ks.grid_args)
-    margs = ', '.join([f'in[{j}][i]' for j in range(len(sorted(varying)))] + ['res'])
+    n_in = len(varying) + int(getattr(ks, 'tile_conds', 0))        # tile tri-states come last (pseudo arguments)
+    margs = ', '.join([f'in[{j}][i]' for j in range(n_in)] + ['res'])
     stores = ' '.join(f'out[{k}][i] = res[{k}];' for k in range(ks.n_outputs))
     drv = (f'\nextern "C" void run(const {T}* sc, const {T}* const* in, {T}* const* out, long long n) {{\n'
            f'  {ks.name}_uniform_body({uargs});\n'
@@ -42,13 +43,16 @@ def compile_for_host(ks):
     return ctypes.CDLL(so)
 
 
-def run_on_host(ks, inputs, n, dtype):
+def run_on_host(ks, inputs, n, dtype, tile_inputs=()):
+    """tile_inputs: one per-instance array of tri-states (0 / 1 / 2) per tile condition of a tiled render unit."""
     lib = compile_for_host(ks)
+    assert len(tile_inputs) == int(getattr(ks, 'tile_conds', 0))
     ct = ctypes.c_float if dtype == np.float32 else ctypes.c_double
     P = ctypes.POINTER(ct)
     sc = np.array([inputs[a] for a in ks.scalar_args] + [0], dtype=dtype)
     varying = sorted(list(ks.array_args) + list(ks.grid_args))
     arrs = [np.ascontiguousarray(np.broadcast_to(np.asarray(inputs[a], dtype=dtype), (n,))) for a in varying]
+    arrs += [np.ascontiguousarray(np.broadcast_to(np.asarray(t, dtype=dtype), (n,))) for t in tile_inputs]
     outs = [np.empty(n, dtype=dtype) for _ in range(ks.n_outputs)]
     inp = (P * max(1, len(arrs)))(*[a.ctypes.data_as(P) for a in arrs])
     outp = (P * len(outs))(*[o.ctypes.data_as(P) for o in outs])

@@ -169,3 +169,97 @@ def test_culling_resolves_what_it_should(cuda_device):
     unresolved = int((tri == 2).sum())
     assert int(partial.sum()) <= unresolved <= 3 * int(partial.sum()) + 64, (unresolved, int(partial.sum()))
     assert px > 0
+
+
+# ---- tile-level classification (cull.tile_cull + <name>_tiles) ------------------------------------------------------
+def _render_all_ways(scene, res, bounds, params, rows=None, reduce=False):
+    """render with tiles, with per-pixel culling only, and dense: three tensors that must be identical"""
+    import torch
+    from teg_b200 import CUDA_EvalMode
+    prog = load_program(scene)
+    names = [a.rsplit('_', 1)[0] for a in prog.args]
+    box = [prog.args[names.index(b)] for b in ('x_lb', 'x_ub', 'y_lb', 'y_ub')]
+    outs = []
+    for opts in (dict(), dict(tiles=False), dict(cull=False)):
+        mode = CUDA_EvalMode(prog, num_samples=16, **opts)
+        ks, _ = mode.compiled([prog.args.index(b) for b in box], [prog.args.index(b) for b in box], reduce=reduce)
+        assert (ks.tile_conds > 0) == (not opts), (scene, opts, ks.tile_conds)
+        outs.append(mode.render(box, res, bounds, params, rows=rows, reduce=reduce))
+    torch.cuda.synchronize()
+    return outs
+
+
+def test_tiled_render_equals_untiled_and_dense_at_full_size(cuda_device):
+    import torch
+    for scene, res, reduce in (('tri_primal', (4096, 4096), False), ('tri_grad', (4096, 4096), True),
+                               ('tri_grad', (2048, 2048), False), ('shaded_grad', (1024, 1024), False),
+                               ('shaded_grad', (1024, 1024), True)):
+        prog = load_program(scene)
+        vals = dict(zip(prog.args, bind(prog.args, scene_values(scene, res=(2, 2)))))
+        params = {lab: float(v) for lab, v in vals.items() if np.ndim(v) == 0}
+        a, b, c = _render_all_ways(scene, res, ((0, 1), (0, 1)), params, reduce=reduce)
+        assert torch.equal(a, b) and torch.equal(b, c), (scene, res, reduce)
+
+
+def test_tiled_render_random_triangles_odd_grids_and_bands(cuda_device):
+    """Random triangles (slivers, clockwise, sub-pixel, far outside), grids that are not multiples of the block or the
+    tile, shifted / reversed bounds, and row bands that start inside a tile: tiles + per-pixel culling + dense
+    renders agree bit for bit, and rows agree with the array path that the oracle tests cover."""
+    import torch
+    rng = np.random.default_rng(11)
+    geoms = [((300, 200), ((0, 1), (0, 1)), None), ((257, 391), ((-0.5, 1.5), (0.25, 0.75)), (37, 200)),
+             ((64, 1000), ((1, 0), (0, 1)), (5, 64)), ((1000, 130), ((0, 1), (2, -1)), (990, 1000))]
+    for t in range(24):
+        kind = t % 6
+        if kind == 0:
+            v = rng.uniform(0, 1, 6)
+        elif kind == 1:
+            c = rng.uniform(0.2, 0.8, 2)
+            v = np.concatenate([c + rng.normal(scale=0.002, size=2) for _ in range(3)])
+        elif kind == 2:
+            p, q = rng.uniform(0, 1, 2), rng.uniform(0, 1, 2)
+            v = np.concatenate([p, q, (p + q) / 2 + rng.normal(scale=1e-4, size=2)])
+        elif kind == 3:
+            v = rng.uniform(-3, 4, 6)
+        elif kind == 4:
+            v = np.array([0.25, 0.25, 0.75, 0.25, 0.25, 0.75]) + (rng.integers(0, 8, 6) / 64.0)
+        else:
+            v = rng.uniform(0.4, 0.6, 6)
+        res, bounds, rows = geoms[t % len(geoms)]
+        for scene in ('tri_primal', 'tri_grad'):
+            prog = load_program(scene)
+            params = {lab: float(np.float32(x)) for lab, x in zip(prog.args[4:], v)}
+            a, b, c = _render_all_ways(scene, res, bounds, params, rows=rows)
+            assert torch.equal(a, b) and torch.equal(b, c), (scene, t, res, bounds, rows)
+            if scene == 'tri_grad':
+                a, b, c = _render_all_ways(scene, res, bounds, params, rows=rows, reduce=True)
+                assert torch.equal(a, b) and torch.equal(b, c), (scene, t, 'reduce')
+    # one geometry against the oracle through the array path
+    from teg_b200.workloads import pixel_boxes
+    res, bounds, rows = (257, 391), ((-0.5, 1.5), (0.25, 0.75)), (37, 200)
+    prog = load_program('tri_grad')
+    v = np.float32([0.15, 0.3, 0.95, 0.35, 0.4, 0.7])
+    params = {lab: float(x) for lab, x in zip(prog.args[4:], v)}
+    a, _, _ = _render_all_ways('tri_grad', res, bounds, params, rows=rows)
+    box = pixel_boxes(res, bounds=bounds, rows=rows)
+    inputs = list(box) + [np.float32(x) for x in v]
+    want = _oracle('tri_grad', inputs, 16)
+    assert np.array_equal(a.cpu().numpy().reshape(want.shape), want)
+
+
+def test_tile_classification_resolves_most_tiles(cuda_device):
+    """4096 x 4096 triangle: the classification leaves only the tiles an edge passes through (or near) unresolved."""
+    import ctypes
+    import torch
+    from teg_b200 import CUDA_EvalMode
+    prog = load_program('tri_primal')
+    mode = CUDA_EvalMode(prog, num_samples=16)
+    params = {lab: TRIANGLE[lab.rsplit('_', 1)[0]] for lab in prog.args[4:]}
+    mode.render(prog.args[:4], (4096, 4096), ((0, 1), (0, 1)), params)
+    torch.cuda.synchronize()
+    ks, p = mode.compiled([0, 1, 2, 3], [0, 1, 2, 3])
+    n_tiles = (4096 // ks.block_size) * (4096 // ks.tile_rows)
+    tiles = p.tile_table(n_tiles * ks.tile_conds)
+    frac = float(np.mean(tiles == 2))
+    assert set(np.unique(tiles)) <= {0.0, 1.0, 2.0} and 0.01 < frac < 0.2, frac
+    assert 0.1 < float(np.mean(tiles == 1)) < 0.3           # the triangle covers 23 % of the square

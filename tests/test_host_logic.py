@@ -300,3 +300,45 @@ def test_cull_transform_structure():
     assert not cull(build_dag(load_program('tri_grad')), 16).culled
     # transcendental conditions have no interval rule: left alone
     assert all(len(r) for _, r in cull(build_dag(load_program('circle')), 20).culled)
+
+
+def test_tile_cull_structure_and_spec_path_on_host(tmp_path, monkeypatch):
+    """cull.tile_cull: render programs read one tri-state per tile condition.  With every tile 'unresolved' the
+    program is the per-instance one; with a (brute-force) valid classification the substituted program must give
+    the same bits.  The classification kernel itself is checked on the GPU (tests/test_gpu_cull.py)."""
+    from oracle import Oracle
+    from teg_b200 import runtime
+    from teg_b200.cull import cull, tile_cull
+    monkeypatch.setenv('TEGB200_CACHE_DIR', str(tmp_path))
+    res = 48
+    for scene, kinds in (('tri_primal', ['dom']), ('tri_grad', ['guard'] * 3), ('shaded_grad', ['dom'] + ['guard'] * 3)):
+        prog = load_program(scene)
+        names = [a.rsplit('_', 1)[0] for a in prog.args]
+        box = [names.index(b) for b in ('x_lb', 'x_ub', 'y_lb', 'y_ub')]
+        dag = tile_cull(cull(build_dag(prog), 16), box, 16)
+        assert [k for k, _ in dag.tile_conds] == kinds
+        n_args = len(prog.args)
+        arr = box + [n_args + k for k in range(len(kinds))]
+        sch = make_schedule(dag, arr)
+        inputs = bind(prog.args, scene_values(scene, res=(res, res)))
+        n = res * res
+        want = Oracle(program_text(scene)).eval(inputs, 16, np.float32)
+        ks = generate(sch, 'float', 16, grid_args=box, use_asm=False, coop=False)
+        assert ks.tile_conds == len(kinds) and ks.tile_kernel == f'{scene}_tiles' and f'{scene}_tiles(' in ks.source
+        # (1) everything unresolved -> the per-instance program
+        got = run_on_host(ks, inputs, n, np.float32, tile_inputs=[np.full(n, 2.0)] * len(kinds))
+        assert np.array_equal(got, want, equal_nan=True), scene
+        # (2) the device unit compiles for sm_100a (tile kernel included)
+        dev = generate(sch, 'float', 16, grid_args=box, reduce_outputs=scene.endswith('grad'))
+        assert len(runtime.Module(dev.source).cubin()) > 1000
+    # (3) a valid classification for the triangle value: pixels that are exactly full / exactly empty
+    prog = load_program('tri_primal')
+    dag = tile_cull(cull(build_dag(prog), 16), [0, 1, 2, 3], 16)
+    ks = generate(make_schedule(dag, [0, 1, 2, 3, 10]), 'float', 16, grid_args=[0, 1, 2, 3], use_asm=False, coop=False)
+    inputs = bind(prog.args, scene_values('tri_primal', res=(res, res)))
+    want = Oracle(program_text('tri_primal')).eval(inputs, 16, np.float32)[0]
+    tri = np.where(want == want.max(), 1.0, np.where(want == 0, 0.0, 2.0))
+    # (a pixel with value 0 has every sample outside, one with the maximal value every sample inside)
+    got = run_on_host(ks, inputs, res * res, np.float32, tile_inputs=[tri])
+    assert np.array_equal(got[0], want)
+    assert 0 < np.count_nonzero(tri == 1) and 0 < np.count_nonzero(tri == 0) and 0 < np.count_nonzero(tri == 2)

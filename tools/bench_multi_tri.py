@@ -30,6 +30,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--res', type=int, default=4096)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--cull', type=int, default=1)
     args = ap.parse_args()
 
     import torch
@@ -54,7 +55,7 @@ def main():
     grad = Program.load(os.path.join(pdir, 'tri_color_grad.tegp'))
     scene = multi_triangle_scene(bands=world, res=res)
     K = scene['verts'].shape[0]
-    r = MultiTriangleRasterizer(primal, grad, res, bands=world, rank=rank, device=local)
+    r = MultiTriangleRasterizer(primal, grad, res, bands=world, rank=rank, device=local, cull=bool(args.cull))
     br = scene['band_ranges']
     active = (br[max(rank - 1, 0)][0], br[min(rank + 1, world - 1)][1])      # own band and its neighbours
     r.set_scene(scene['verts'], scene['col'], scene['windows'], scene['classes'], scene['max_rows'],
@@ -130,7 +131,7 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    sch = r.m_primal.schedule([0, 1, 2, 3])
+    sch = r.m_primal.reference_schedule([0, 1, 2, 3])
     oc = op_count(sch, 16)
     peak, _ = runtime.fma_peak(4, local)
     achieved = oc.unguarded * pairs_local / (phase['forward'] * 1e-3) / 1e12
