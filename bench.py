@@ -175,6 +175,8 @@ def main() -> int:
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--fused', type=int, default=0, help='1: value and reverse derivative in ONE kernel (program bundle)')
     ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'], help='working precision of the programs')
+    ap.add_argument('--maxreg', type=int, default=0, help='experiment: --maxrregcount for the generated kernels')
+    ap.add_argument('--tile-rows', type=int, default=16, help='pixel rows per render block / classification tile')
     ap.add_argument('--cull', type=int, default=1, help='0: dense kernels (every comparison at every sample); '
                     '1: domain culling (teg_b200/cull.py, bit-identical results)')
     args = ap.parse_args()
@@ -211,8 +213,11 @@ def main() -> int:
     fw = 'float' if args.dtype == 'f32' else 'double'
     tdt = torch.float32 if args.dtype == 'f32' else torch.float64
     esz = 4 if args.dtype == 'f32' else 8
-    m_primal = CUDA_EvalMode(primal, num_samples=NUM_SAMPLES, device=local_rank, float_width=fw, cull=bool(args.cull))
-    m_grad = CUDA_EvalMode(grad, num_samples=NUM_SAMPLES, device=local_rank, float_width=fw, cull=bool(args.cull))
+    xopts = dict(nvrtc_opts=f'--maxrregcount={args.maxreg}' if args.maxreg else '', tile_rows=args.tile_rows)
+    m_primal = CUDA_EvalMode(primal, num_samples=NUM_SAMPLES, device=local_rank, float_width=fw, cull=bool(args.cull),
+                             **xopts)
+    m_grad = CUDA_EvalMode(grad, num_samples=NUM_SAMPLES, device=local_rank, float_width=fw, cull=bool(args.cull),
+                           **xopts)
     m_fused = CUDA_EvalMode([primal, grad], num_samples=NUM_SAMPLES, device=local_rank, float_width=fw,
                             cull=bool(args.cull)) if args.fused else None
     box = primal.args[:4]
@@ -246,17 +251,20 @@ def main() -> int:
                 ev['primal'].append((e[0], e[1]))
                 ev['grad'].append((e[1], e[2]))
             return
-        m_primal.render(box, (res_x_total, res), bounds, params, rows=rows, out=imgs[buf], stream=sptr)
-        if record:
-            e[1].record(stream)
+        # reverse derivative first: its [6]-vector all-reduce (N > 1) then runs on NCCL's stream underneath the value
+        # kernel instead of after it
         m_grad.render(box, (res_x_total, res), bounds, gparams, rows=rows, out=gsums[buf], stream=sptr, reduce=True)
         if record:
-            e[2].record(stream)
-        if world > 1:
-            dist.all_reduce(gsums[buf])
+            e[1].record(stream)
+        work = dist.all_reduce(gsums[buf], async_op=True) if world > 1 else None
+        m_primal.render(box, (res_x_total, res), bounds, params, rows=rows, out=imgs[buf], stream=sptr)
         if record:
-            ev['primal'].append((e[0], e[1]))
-            ev['grad'].append((e[1], e[2]))
+            e[2].record(stream)
+        if work is not None:
+            work.wait()                 # stream-ordered: the current stream waits for the reduced gradient
+        if record:
+            ev['grad'].append((e[0], e[1]))
+            ev['primal'].append((e[1], e[2]))
 
     def sync_all():
         if world > 1:
@@ -362,35 +370,76 @@ def main() -> int:
         return 0
 
     # ------------------------------------------------------------------------------------- roofline
-    sch = make_schedule(m_primal.dag, [0, 1, 2, 3])
+    # The reference program's operation count (SURVEY 8(d) rule) is defined on the un-culled program.
+    sch = m_primal.reference_schedule([0, 1, 2, 3])
     oc = op_count(sch, NUM_SAMPLES)
     flops_per_launch = oc.unguarded * n_local           # primal has no guards: exact
     peak_tflops, clk_mhz = runtime.fma_peak(esz, local_rank)
     nominal = 2 * (128 if esz == 4 else 64) * 148 * 1965e6 / 1e12
-    achieved = flops_per_launch / (phase_ms['primal'] * 1e-3) / 1e12
-    traffic = None
     try:
-        if esz != 4:
-            raise KeyError('the committed ncu capture is of the fp32 kernel')
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            hbm_peak, hbm_src = float(json.load(f)['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)'
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, 'fallback stated in B200_PROFILING.md (MEASURED_PEAKS.json absent)'
+    traffic_tab = {}
+    try:
         import glob
         latest = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_traffic.json')))[-1]
         with open(latest) as f:
-            tj = json.load(f)['tri_primal_main']
-        traffic = tj['dram_bytes_read'] + tj['dram_bytes_write']     # from the committed ncu --set full capture
+            traffic_tab = json.load(f)
     except Exception:
         pass
-    roofline = {'bound': 'fp32_fma' if esz == 4 else 'fp64_fma', 'kernel': 'tri_primal_main', 'achieved': achieved, 'peak': peak_tflops,
-                'unit': 'TFLOP/s', 'frac': achieved / peak_tflops, 'traffic': traffic,
-                'traffic_unit': 'bytes per launch (dram read + write, ncu)', 'algorithmic_bytes': n_local * esz,
-                'peak_source': 'FFMA micro-benchmark (tegb_fma_peak) measured in this run; MEASURED_PEAKS.json '
-                               'has no fp32 figure', 'peak_nominal': nominal,
-                'algorithmic_ops_per_instance': oc.unguarded, 'ops_per_inner_sample': oc.per_sample_inner,
-                'kernel_ms': phase_ms['primal'],
-                'note': 'achieved counts the reference program\'s operations (SURVEY 8(d) rule: 17 per inner sample); '
-                        'ptxas tabulates the inner-variable-only terms, so fewer instructions execute and the '
-                        'fraction can exceed 1; the kernel is bound by the ALU pipe (3 FSETP per sample, '
-                        'ncu: alu 84 %, fma 30 %, issue 76 %; profiles/)',
-                'hbm_GBps_out': (n_local * esz) / (ms_per_step * 1e-3) / 1e9}
+
+    def traffic_of(key):
+        tj = traffic_tab.get(key)
+        return None if (tj is None or esz != 4) else tj['dram_bytes_read'] + tj['dram_bytes_write']
+
+    # dense leg (always measured, same run): the value kernel that evaluates every comparison at every sample --
+    # the FP32 roofline statement of BASELINE.json's north_star
+    m_dense = m_primal if not args.cull else CUDA_EvalMode(primal, num_samples=NUM_SAMPLES, device=local_rank,
+                                                           float_width=fw, cull=False)
+    dense_ev = []
+    for k in range(3 + max(5, min(args.steps, 20))):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.fill_(k & 0xff)
+        a.record(stream)
+        m_dense.render(box, (res_x_total, res), bounds, params, rows=rows, out=imgs[1], stream=sptr)
+        b.record(stream)
+        if k >= 3:
+            dense_ev.append((a, b))
+    torch.cuda.synchronize(dev)
+    dense_ms = float(np.mean([a.elapsed_time(b) for a, b in dense_ev]))
+    assert torch.equal(imgs[1], imgs[0]), 'dense and culled value images differ'
+    dense_achieved = flops_per_launch / (dense_ms * 1e-3) / 1e12
+    roofline_dense = {
+        'bound': 'fp32_fma' if esz == 4 else 'fp64_fma', 'kernel': 'tri_primal_main (cull=0)', 'achieved': dense_achieved,
+        'peak': peak_tflops, 'unit': 'TFLOP/s', 'frac': dense_achieved / peak_tflops, 'traffic': traffic_of('tri_primal_main_dense'),
+        'peak_source': 'FFMA micro-benchmark (tegb_fma_peak) measured in this run; MEASURED_PEAKS.json has no fp32 figure',
+        'peak_nominal': nominal, 'algorithmic_ops_per_instance': oc.unguarded, 'ops_per_inner_sample': oc.per_sample_inner,
+        'kernel_ms': dense_ms, 'launches_timed': len(dense_ev),
+        'note': 'achieved counts the reference program\'s operations (SURVEY 8(d) rule: 17 per inner sample); ptxas '
+                'tabulates the inner-variable-only terms, so fewer instructions execute and the fraction can exceed 1; '
+                'the kernel is bound by the ALU pipe (3 FSETP per sample; ncu: alu 81 %, fma 42 %, issue 87 %; profiles/)'}
+    if args.cull:
+        # default path: after culling almost no sample is evaluated; what bounds the value kernel is its output stream
+        kern_ms = phase_ms['primal']
+        bytes_per_launch = n_local * esz
+        ach = bytes_per_launch / (kern_ms * 1e-3) / 1e9
+        roofline = {
+            'bound': 'hbm', 'kernel': 'tri_primal_tiles + tri_primal_main (cull=1)', 'achieved': ach, 'peak': hbm_peak,
+            'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': traffic_of('tri_primal_main'),
+            'traffic_unit': 'bytes per launch (dram read + write, ncu)', 'algorithmic_bytes': bytes_per_launch,
+            'peak_source': hbm_src, 'kernel_ms': kern_ms,
+            'algorithmic_tflops': flops_per_launch / (kern_ms * 1e-3) / 1e12,
+            'algorithmic_frac_of_fp32_peak': flops_per_launch / (kern_ms * 1e-3) / 1e12 / peak_tflops,
+            'note': 'culled kernels (teg_b200/cull.py) evaluate the comparisons only where an edge crosses a pixel: '
+                    'the algorithmic bytes are the value image (one store per pixel, no input stream); kernel_ms is '
+                    'the CUDA-event time of the tile classification + main kernel; algorithmic_tflops applies the '
+                    'reference program\'s operation count to this time (the culled kernel skips that work, so the '
+                    'figure exceeds the FFMA peak); the FP32 statement for the sample loop itself is roofline_dense'}
+    else:
+        roofline = dict(roofline_dense, kernel='tri_primal_main')
+    roofline['hbm_GBps_out'] = (n_local * esz) / (ms_per_step * 1e-3) / 1e9
 
     # ----------------------------------------------------------------------------------- cpu baseline
     cpu = None
@@ -417,8 +466,9 @@ def main() -> int:
                    'programs': ['tri_primal', 'tri_grad'], 'fused_kernel': bool(args.fused), 'cull': bool(args.cull), 'outputs': 'value image [4096,4096] + per-parameter '
                    'gradient sum [6] (reduced in-kernel)', 'l2': 'L2 flushed between timed steps by writing a '
                    '256 MB buffer (outside the per-step event pairs); inputs are generated from the pixel index',
-                   'parallelism': f'rows sharded over {world} GPU(s), one NCCL all-reduce of the [6] gradient'},
-        'phase_ms': phase_ms, 'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e,
+                   'parallelism': f'rows sharded over {world} GPU(s), one NCCL all-reduce of the [6] gradient, '
+                                  'issued after the gradient kernel and overlapped with the value kernel'},
+        'phase_ms': phase_ms, 'roofline': roofline, 'roofline_dense': roofline_dense, 'cpu_baseline': cpu, 'e2e': e2e,
         'gpu_launches': int(launches_timed), 'clocks': clocks,
         'check': {'sum_value': area, 'expected_area_per_rank': 0.2325 if world == 1 else None,
                   'grad_sum': gvec.tolist()},

@@ -75,7 +75,7 @@ typedef struct {
                                      launch (0 = none).  A tile is block_size pixel columns x tile_rows pixel rows;
                                      the kernel writes one tri-state (0 false / 1 true for every pixel of the tile,
                                      2 unresolved) per condition and tile, which the main kernel reads per block */
-    int tile_rows;
+    int tile_rows;                /* plain render programs: pixel rows walked by one block (>= 1) */
     const char *tile_kernel;      /* <name>_tiles, or NULL when n_tile_conds == 0 */
 } tegb_program_desc;
 

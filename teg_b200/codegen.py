@@ -483,7 +483,7 @@ class Emitter:
               f'g_{hi_n}_hi = {tab}[{first} + 1];')
             for j in bvs:
                 e(f'T g_b{j}_lo = {tab}[{first}], g_b{j}_hi = {tab}[{first}];')
-            e(f'for (int q = {first}; q < {last}; ++q) {{')
+            e(f'for (int q = {first} + lane; q < {last}; q += 32) {{')
             e(f'const T lb = {tab}[q], ub = {tab}[q + 1];', 2)
             e(f'g_{lo_n}_lo = {fmin}(g_{lo_n}_lo, lb); g_{lo_n}_hi = {fmax}(g_{lo_n}_hi, lb);', 2)
             e(f'g_{hi_n}_lo = {fmin}(g_{hi_n}_lo, ub); g_{hi_n}_hi = {fmax}(g_{hi_n}_hi, ub);', 2)
@@ -494,6 +494,14 @@ class Emitter:
                 e('g_pz = g_pz + sa; g_pz = g_pz + sb;', 2)
                 for j in bvs:
                     e(f'g_b{j}_lo = {fmin}(g_b{j}_lo, {fmin}(sa, sb)); g_b{j}_hi = {fmax}(g_b{j}_hi, {fmax}(sa, sb));', 2)
+            e('}')
+            mins = [f'g_{lo_n}_lo', f'g_{hi_n}_lo'] + [f'g_b{j}_lo' for j in bvs]
+            maxs = [f'g_{lo_n}_hi', f'g_{hi_n}_hi'] + [f'g_b{j}_hi' for j in bvs]
+            e('for (int off = 16; off > 0; off >>= 1) {')
+            for v in mins:
+                e(f'{v} = {fmin}({v}, __shfl_xor_sync(0xffffffffu, {v}, off));', 2)
+            for v in maxs:
+                e(f'{v} = {fmax}({v}, __shfl_xor_sync(0xffffffffu, {v}, off));', 2)
             e('}')
         # launch-invariant values the cones read (points), from the scalar arguments
         need: List[int] = []
@@ -525,6 +533,7 @@ class Emitter:
                     sub.append((m, True))
                     for a2 in reversed(nodes[m].args):
                         sub.append((a2, False))
+        e('for (int off = 16; off > 0; off >>= 1) g_pz = g_pz + __shfl_xor_sync(0xffffffffu, g_pz, off);')
         for m in need:
             e(f'const {self.decl(m)} v{m} = {self.expr(m, {})};')
         for k, (kind, c, r, B) in enumerate(roots):
@@ -532,7 +541,7 @@ class Emitter:
             e('{')
             e(f'T {pre}pz = g_pz;', 2)
             t, f = self._iv_cone(r, (lambda j, B=B: bool(fv(j) & B) or dep.get(j, False)), leaf, {}, 2, pre)
-            e(f'tiles[(size_t){k} * n_tiles + t] = {self._iv_result(t, f, pre)};', 2)
+            e(f'if (lane == 0) tiles[(size_t){k} * n_tiles + t] = {self._iv_result(t, f, pre)};', 2)
             e('}')
         self.in_main = saved_main
         return self.lines
@@ -1148,7 +1157,9 @@ class Emitter:
                                          'const int row0', 'const int n_rows', 'const int tile_rows', 'const int n_tx',
                                          'const int n_ty', 'T* __restrict__ tiles'])
                     src.append(f'extern "C" __global__ void {name}_tiles({tparams}) {{')
-                    src.append('    const int t = blockIdx.x * blockDim.x + threadIdx.x;')
+                    src.append('    // one warp per tile: lanes share the walk over the tile\'s rows and columns')
+                    src.append('    const int t = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);')
+                    src.append('    const int lane = threadIdx.x & 31;')
                     src.append('    const size_t n_tiles = (size_t)n_tx * n_ty;')
                     src.append('    if (t >= n_tx * n_ty) return;')
                     src.append('    const int ty = t / n_tx, tx = t - ty * n_tx;')
@@ -1159,25 +1170,62 @@ class Emitter:
                     src += self.tiles_body(grid)
                     src.append('}')
                     src.append('')
+                # one block = one tile: block_size columns x tile_rows rows; every thread walks its column's rows
+                # (the per-block set-up, the tile tri-states and the block sum are paid once per tile)
                 mparams = ', '.join(['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
-                                     'const int row0'] +
-                                    (['const T* __restrict__ tiles', 'const int tile_rows'] if tile else []) + outs_decl)
+                                     'const int row0', 'const int n_rows', 'const int tile_rows'] +
+                                    (['const T* __restrict__ tiles'] if tile else []) + outs_decl)
                 src.append(f'extern "C" __global__ void __launch_bounds__({bs}) {name}_main({mparams}) {{')
                 src.append('    const int ny = blockIdx.x * blockDim.x + threadIdx.x;')
                 src.append('    const bool live = ny < res_y;')
-                src.append('    const int nx = row0 + blockIdx.y;')
-                src.append('    const long long i = (long long)blockIdx.y * res_y + ny;')
+                ycol = 'nyc' if coop else 'ny'
                 if coop:
                     src.append('    const int nyc = live ? ny : 0;')
-                    loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye[nyc]', grid[3]: 'ye[nyc + 1]'}
-                else:
-                    loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye[ny]', grid[3]: 'ye[ny + 1]'}
+                src.append(f'    const T ye_lo = ye[{ycol}], ye_hi = ye[{ycol} + 1];' if coop else
+                           '    const T ye_lo = live ? ye[ny] : ye[0], ye_hi = live ? ye[ny + 1] : ye[1];')
+                loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye_lo', grid[3]: 'ye_hi'}
                 if tile:
-                    src.append('    const size_t n_tiles = (size_t)gridDim.x * ((gridDim.y + tile_rows - 1) / tile_rows);')
-                    src.append('    const size_t tile_id = (size_t)(blockIdx.y / tile_rows) * gridDim.x + blockIdx.x;')
+                    src.append('    const size_t n_tiles = (size_t)gridDim.x * gridDim.y;')
+                    src.append('    const size_t tile_id = (size_t)blockIdx.y * gridDim.x + blockIdx.x;')
                     for k, a in enumerate(tile):
-                        loads[a] = f'tiles[{k} * n_tiles + tile_id]'
+                        src.append(f'    const T tile{k} = tiles[{k} * n_tiles + tile_id];')
+                        loads[a] = f'tile{k}'
                 call = ', '.join((['live'] if coop else []) + [loads[a] for a in varying] + ['res'])
+                if nr:
+                    src.append(f'    T rr[{nr}];')
+                    src.append(f'    for (int k = 0; k < {nr}; k++) rr[k] = {zero};')
+                src.append('    #pragma unroll 1')
+                src.append('    for (int r = 0; r < tile_rows; ++r) {')
+                src.append('        const int rel = blockIdx.y * tile_rows + r;')
+                src.append('        if (rel >= n_rows) break;')
+                src.append('        const int nx = row0 + rel;')
+                src.append('        const long long i = (long long)rel * res_y + ny;')
+                src.append(f'        T res[{K}];')
+                if nr:
+                    src.append(f'        for (int k = 0; k < {K}; k++) res[k] = {zero};')
+                if coop:
+                    src.append(f'        {name}_instance({call});')
+                else:
+                    src.append(f'        if (live) {name}_instance({call});')
+                for k in range(ns_out):
+                    src.append(f'        if (live) out{k}[i] = res[{k}];')
+                for j in range(nr):
+                    # rows are added in order: a fixed summation order per thread, then the fixed block sum
+                    src.append(f'        if (live) rr[{j}] = rr[{j}] + res[{ns_out + j}];')
+                src.append('    }')
+                if nr:
+                    src.append(f'    tegb_block_sum_store<T, {nr}, {bs}>(rr, partials);')
+                src.append('}')
+                src.append('#endif')
+                text = '\n'.join(src) + '\n'
+                return KernelSource(name=name, ctype=T, num_samples=self.N, source=text,
+                                    uniform_kernel=f'{name}_uniform', main_kernel=f'{name}_main',
+                                    n_uniform=nu, scalar_args=scal, array_args=arrs, grid_args=grid,
+                                    n_outputs=K, block_size=bs, reduce_outputs=nr, team=team,
+                                    grouped=False, pixel_args=pix, accumulate=False,
+                                    tile_conds=len(tile), tile_rows=self.tile_rows,
+                                    tile_kernel=f'{name}_tiles' if tile else '',
+                                    stats={'uses_coop': self.uses_coop, 'loops': self.loop_counter})
             else:
                 mparams = ', '.join([f'const T* __restrict__ in{a}' for a in arrs] + outs_decl + ['const long long n'])
                 src.append(f'extern "C" __global__ void __launch_bounds__({bs}) {name}_main({mparams}) {{')

@@ -674,12 +674,16 @@ extern "C" int tegb_render_launch(tegb_program *p, const double *scalars, const 
     args.push_back(&row0);
     const unsigned bs = (unsigned)p->d.block_size;
     const unsigned gx = (unsigned)((g->res_y + bs - 1) / bs);
-    const unsigned gy = (unsigned)(g->row_end - g->row_begin);
-    if (gy > 65535u) return fail(TEGB_ERR_INVALID, "more than 65535 rows in one render launch");
-    int tile_rows = p->d.tile_rows;
+    // one block per tile of block_size columns x tile_rows rows
+    int tile_rows = p->d.tile_rows > 0 ? p->d.tile_rows : 1;
+    int n_rows = g->row_end - g->row_begin;
+    const unsigned gy = (unsigned)((n_rows + tile_rows - 1) / tile_rows);
+    if (gy > 65535u) return fail(TEGB_ERR_INVALID, "more than 65535 tile rows in one render launch");
+    args.push_back(&n_rows);
+    args.push_back(&tile_rows);
     if (p->d.n_tile_conds > 0) {
-        // classify the tiles (block_size columns x tile_rows rows) for these launch-wide arguments and this band
-        int n_rows = (int)gy, n_tx = (int)gx, n_ty = (n_rows + tile_rows - 1) / tile_rows;
+        // classify the tiles for these launch-wide arguments and this band
+        int n_tx = (int)gx, n_ty = (int)gy;
         const size_t need = (size_t)p->d.n_tile_conds * n_tx * n_ty * p->d.elem_size;
         if (need > p->tiles_bytes) {
             RT_CHECK(cudaStreamSynchronize((cudaStream_t)st));      // an earlier launch may still read the old table
@@ -704,11 +708,10 @@ extern "C" int tegb_render_launch(tegb_program *p, const double *scalars, const 
         targs.push_back(&n_tx);
         targs.push_back(&n_ty);
         targs.push_back(&p->d_tiles);
-        const unsigned tb = 64, tg = (unsigned)((n_tx * n_ty + tb - 1) / tb);
+        const unsigned tb = 128, tg = (unsigned)(((size_t)n_tx * n_ty * 32 + tb - 1) / tb);      // a warp per tile
         CU_CHECK(drv::LaunchKernel(p->f_tiles, tg, 1, 1, tb, 1, 1, 0, st, targs.data(), nullptr));
         g_launches++;
         args.push_back(&p->d_tiles);
-        args.push_back(&tile_rows);
     }
     const int n_store = p->d.n_outputs - p->d.reduce_outputs;
     for (int k = 0; k < n_store; k++) { outs[k] = out_ptrs[k]; args.push_back(&outs[k]); }

@@ -186,10 +186,11 @@ class _Rebuilder:
                 lo, hi, body = (memo[a] for a in n.args)
                 bv = memo[n.attr] if n.attr in memo else n.attr
                 if self.is_zeroish(body):
-                    # left fold of N terms (zero * step) from +0: exactly 0 + zero * step
-                    step = dag.intern('div', (dag.intern('add', (hi, dag.intern('mul', (dag.const('-1'), lo)))),
-                                              dag.const(str(self.N))))
-                    r = dag.intern('add', (self._zero(), dag.intern('mul', (body, step))))
+                    # left fold of N terms (zero * step) from +0: exactly 0 + zero * step.  zero * ((hi - lo) / N) and
+                    # zero * (hi - lo) are the same value (a zero of the sign of hi - lo, or NaN when hi - lo is not
+                    # finite), so the division is not emitted
+                    width = dag.intern('add', (hi, dag.intern('mul', (dag.const('-1'), lo))))
+                    r = dag.intern('add', (self._zero(), dag.intern('mul', (body, width))))
                     self.zeroish.add(r)
                     memo[i] = r
                 else:
