@@ -218,7 +218,8 @@ def _extend_known(nodes: Sequence[DNode], cond: int, value: bool) -> Dict[int, b
     return k
 
 
-def cull(dag: Dag, num_samples: int, min_samples: int = 64, max_roots: int = 4, max_cone: int = 96) -> Dag:
+def cull(dag: Dag, num_samples: int, min_samples: int = 64, max_roots: int = 4, max_cone: int = 96,
+         min_depth: int = 2) -> Dag:
     """Rewrite every closed top-level integral of ``dag`` whose select conditions admit interval evaluation.
     Returns a copy of ``dag`` (outputs replaced); ``.culled`` lists (integral, conditions) for the record."""
     dag = dag.clone()
@@ -229,7 +230,9 @@ def cull(dag: Dag, num_samples: int, min_samples: int = 64, max_roots: int = 4, 
 
     def wrap(q: int) -> int:
         nest = _Nest(dag, q)
-        if float(N) ** nest.depth < min_samples:
+        # one-dimensional nests (the delta integrals of reverse-mode programs) are short and usually straddle their
+        # discontinuity: the test would cost more than it saves
+        if nest.depth < min_depth or float(N) ** nest.depth < min_samples:
             return q
         roots = nest.roots()
         if not roots or len(roots) > max_roots:
