@@ -71,6 +71,7 @@ class KernelSource:
     tile_conds: int = 0             # tile conditions classified by <name>_tiles before a render launch (cull.tile_cull)
     tile_rows: int = 0              # pixel rows per tile (a tile is block_size columns wide)
     tile_kernel: str = ''
+    tile_bodies: List = None        # [(label, {condition: admitted states})]: bodies <name>_tile_<label> for resolved tiles
     stats: Dict[str, float] = None
 
     @property
@@ -487,7 +488,7 @@ class Emitter:
             e(f'const T lb = {tab}[q], ub = {tab}[q + 1];', 2)
             e(f'g_{lo_n}_lo = {fmin}(g_{lo_n}_lo, lb); g_{lo_n}_hi = {fmax}(g_{lo_n}_hi, lb);', 2)
             e(f'g_{hi_n}_lo = {fmin}(g_{hi_n}_lo, ub); g_{hi_n}_hi = {fmax}(g_{hi_n}_hi, ub);', 2)
-            e('g_pz = g_pz + lb; g_pz = g_pz + ub;', 2)
+            e('g_pz = g_pz + lb; g_pz = g_pz + ub; g_pz = g_pz + (ub - lb);', 2)
             if bvs:
                 e(f'const T st = ((T)(ub - lb)) / (T){N};', 2)
                 e(f'const T sa = lb + st * ((T)0u + {half}), sb = lb + st * ((T){N - 1}u + {half});', 2)
@@ -990,12 +991,15 @@ class Emitter:
         return self.lines
 
     def main_body(self) -> List[str]:
+        return self.body_lines(self.sch.main, self.sch.outputs)
+
+    def body_lines(self, block: Block, outputs: Sequence[int]) -> List[str]:
         self.in_main = True
         self.lines = []
         self.guard_ctx = ['live'] if self.coop else []
-        self.block(self.sch.main, 1, 0)
-        for k, o in enumerate(self.sch.outputs):
-            self.emit(f'res[{k}] = {self.ref(o, self.sch.main.known)};', 1)
+        self.block(block, 1, 0)
+        for k, o in enumerate(outputs):
+            self.emit(f'res[{k}] = {self.ref(o, block.known)};', 1)
         return self.lines
 
     def generate(self, grid_args: Sequence[int] = (), reduce_outputs: bool = False, grouped: bool = False,
@@ -1074,6 +1078,27 @@ class Emitter:
         src += main
         src.append('}')
         src.append('')
+        # tile-culled render programs: the bodies for resolved tiles (cull.tile_cull); the kernel picks one per tile
+        tile_bodies = []
+        if tile:
+            general_coop = self.uses_coop
+            for label, match, blk, outs in sch.bodies:
+                if match is None:
+                    continue
+                self.uses_coop = False
+                lines = self.body_lines(blk, outs)
+                b_coop = self.uses_coop
+                bparams = ', '.join((['const bool live'] if b_coop else []) +
+                                    [f'const T a{a}' for a in varying] + [f'T (&res)[{K}]'])
+                src.append(f'TEGB_FN void {name}_tile_{label}({bparams}) {{')
+                for a in varying:
+                    src.append(f'    (void)a{a};')
+                src += lines
+                src.append('}')
+                src.append('')
+                tile_bodies.append((label, match, b_coop))
+            self.uses_coop = general_coop
+            coop = general_coop
         src.append('#ifdef __CUDACC__')
         zero = literal('0', T)
         if grouped:
@@ -1190,29 +1215,49 @@ class Emitter:
                     for k, a in enumerate(tile):
                         src.append(f'    const T tile{k} = tiles[{k} * n_tiles + tile_id];')
                         loads[a] = f'tile{k}'
-                call = ', '.join((['live'] if coop else []) + [loads[a] for a in varying] + ['res'])
                 if nr:
                     src.append(f'    T rr[{nr}];')
                     src.append(f'    for (int k = 0; k < {nr}; k++) rr[k] = {zero};')
-                src.append('    #pragma unroll 1')
-                src.append('    for (int r = 0; r < tile_rows; ++r) {')
-                src.append('        const int rel = blockIdx.y * tile_rows + r;')
-                src.append('        if (rel >= n_rows) break;')
-                src.append('        const int nx = row0 + rel;')
-                src.append('        const long long i = (long long)rel * res_y + ny;')
-                src.append(f'        T res[{K}];')
-                if nr:
-                    src.append(f'        for (int k = 0; k < {K}; k++) res[k] = {zero};')
-                if coop:
-                    src.append(f'        {name}_instance({call});')
+
+                def row_loop(fn: str, with_live: bool, ind: str):
+                    call = ', '.join((['live'] if with_live else []) + [loads[a] for a in varying] + ['res'])
+                    src.append(f'{ind}#pragma unroll 1')
+                    src.append(f'{ind}for (int r = 0; r < tile_rows; ++r) {{')
+                    src.append(f'{ind}    const int rel = blockIdx.y * tile_rows + r;')
+                    src.append(f'{ind}    if (rel >= n_rows) break;')
+                    src.append(f'{ind}    const int nx = row0 + rel;')
+                    src.append(f'{ind}    const long long i = (long long)rel * res_y + ny;')
+                    src.append(f'{ind}    T res[{K}];')
+                    if nr:
+                        src.append(f'{ind}    for (int k = 0; k < {K}; k++) res[k] = {zero};')
+                    if with_live:
+                        src.append(f'{ind}    {fn}({call});')
+                    else:
+                        src.append(f'{ind}    if (live) {fn}({call});')
+                    for k in range(ns_out):
+                        src.append(f'{ind}    if (live) out{k}[i] = res[{k}];')
+                    for j in range(nr):
+                        # rows are added in order: a fixed summation order per thread, then the fixed block sum
+                        src.append(f'{ind}    if (live) rr[{j}] = rr[{j}] + res[{ns_out + j}];')
+                    src.append(f'{ind}}}')
+
+                if tile_bodies:
+                    # the tile's conditions are the same for every thread of the block: a uniform branch picks the body
+                    first = True
+                    for label, match, b_coop in tile_bodies:
+                        terms = []
+                        for k2 in sorted(match):
+                            alts = ' || '.join(f'tile{k2} == {literal(str(v), T)}' for v in match[k2])
+                            terms.append(f'({alts})')
+                        src.append(f'    {"if" if first else "else if"} ({" && ".join(terms)}) {{')
+                        row_loop(f'{name}_tile_{label}', b_coop, '        ')
+                        src.append('    }')
+                        first = False
+                    src.append('    else {')
+                    row_loop(f'{name}_instance', coop, '        ')
+                    src.append('    }')
                 else:
-                    src.append(f'        if (live) {name}_instance({call});')
-                for k in range(ns_out):
-                    src.append(f'        if (live) out{k}[i] = res[{k}];')
-                for j in range(nr):
-                    # rows are added in order: a fixed summation order per thread, then the fixed block sum
-                    src.append(f'        if (live) rr[{j}] = rr[{j}] + res[{ns_out + j}];')
-                src.append('    }')
+                    row_loop(f'{name}_instance', coop, '    ')
                 if nr:
                     src.append(f'    tegb_block_sum_store<T, {nr}, {bs}>(rr, partials);')
                 src.append('}')
@@ -1225,6 +1270,7 @@ class Emitter:
                                     grouped=False, pixel_args=pix, accumulate=False,
                                     tile_conds=len(tile), tile_rows=self.tile_rows,
                                     tile_kernel=f'{name}_tiles' if tile else '',
+                                    tile_bodies=[(lb, mt) for lb, mt, _ in tile_bodies],
                                     stats={'uses_coop': self.uses_coop, 'loops': self.loop_counter})
             else:
                 mparams = ', '.join([f'const T* __restrict__ in{a}' for a in arrs] + outs_decl + ['const long long n'])

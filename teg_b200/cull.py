@@ -103,7 +103,12 @@ class _Nest:
 class _Rebuilder:
     """Copy of a cone with some conditions replaced by constants (``known``) or by other bool nodes (``repl``)."""
 
-    def __init__(self, dag: Dag, num_samples: int, known: Dict[int, bool], repl: Dict[int, int]):
+    def __init__(self, dag: Dag, num_samples: int, known: Dict[int, bool], repl: Dict[int, int],
+                 finite_pairs: Sequence[Tuple[int, int]] = ()):
+        # finite_pairs: (lo, hi) bound pairs whose width is known to be finite where the copy runs (tile-resolved
+        # code: the classification kernel poisons on every edge and width of the tile), so ``0 + 0 * (hi - lo)``
+        # is the literal zero there
+        self.finite_pairs = set(finite_pairs)
         self.dag = dag
         self.N = int(num_samples)
         self.known = known
@@ -185,7 +190,9 @@ class _Rebuilder:
             elif n.op == 'quad':
                 lo, hi, body = (memo[a] for a in n.args)
                 bv = memo[n.attr] if n.attr in memo else n.attr
-                if self.is_zeroish(body):
+                if self.is_zeroish(body) and (lo, hi) in self.finite_pairs:
+                    memo[i] = self._zero()
+                elif self.is_zeroish(body):
                     # left fold of N terms (zero * step) from +0: exactly 0 + zero * step.  zero * ((hi - lo) / N) and
                     # zero * (hi - lo) are the same value (a zero of the sign of hi - lo, or NaN when hi - lo is not
                     # finite), so the division is not emitted
@@ -330,9 +337,12 @@ def tile_cull(dag: Dag, grid_args: Sequence[int], num_samples: int, max_conds: i
     Tile conditions: (a) every ``domtri`` of the per-instance culling (now: "uniform over every sample of every
     pixel of the tile"), (b) every per-instance guard of an integral (the bound checks around the delta terms of
     reverse-mode programs: "true / false for every pixel of the tile").  Condition k becomes the pseudo argument
-    ``n_args + k`` (a tri-state the main kernel loads per block), and each output becomes
+    ``n_args + k`` (a tri-state the main kernel loads per block), and the program gets several *bodies*, chosen per
+    tile by the kernel (``.bodies`` = [(label, {condition: admitted states} | None, outputs)], first match wins):
 
-        any tile condition unresolved ? <the per-instance program> : <the program with the conditions substituted>
+        quiet / quiet0 / quiet1   every guard false over the tile (a single domain condition fixed to 0 / 1): static
+        resolved                  every condition resolved: conditions substituted by the tile's values
+        general                   some condition unresolved: the per-instance program, untouched
 
     In a resolved tile no pixel evaluates an interval or a guard: interior pixels of the triangle run the 32
     additions, exterior ones a handful of instructions, and a reverse-mode program whose guards are all false
@@ -389,17 +399,45 @@ def tile_cull(dag: Dag, grid_args: Sequence[int], num_samples: int, max_conds: i
             conds.append(('guard', c))
     if not conds or len(conds) > max_conds:
         return dag
-    rb = _Rebuilder(dag, num_samples, {}, {})
-    unresolved = None
-    for k, (kind, node) in enumerate(conds):
-        tin = dag.intern('in', (), n_args + k)
-        u = dag.intern('domis', (tin,), 'U')
-        unresolved = u if unresolved is None else dag.intern('or', (unresolved, u))
-        if kind == 'dom':
-            rb.memo[node] = tin
-            rb.known[dag.intern('domis', (node,), 'U')] = False
-        else:
-            rb.repl[node] = dag.intern('domis', (tin,), 'T')
-    dag.outputs = tuple(dag.sel(unresolved, o, rb.value(o)) for o in dag.outputs)
+    tins = [dag.intern('in', (), n_args + k) for k in range(len(conds))]
+    in_node = {a: dag.intern('in', (), a) for a in grid_args}
+    gl = list(grid_args)
+    pairs = [(in_node[gl[0]], in_node[gl[1]]), (in_node[gl[2]], in_node[gl[3]])] if len(gl) == 4 else []
+
+    def build(states: Dict[int, Optional[int]]) -> Tuple[int, ...]:
+        """outputs with condition k fixed to states[k] (0 / 1), or read from its tile input (None)"""
+        rb = _Rebuilder(dag, num_samples, {}, {}, finite_pairs=pairs)
+        for k, (kind, node) in enumerate(conds):
+            st = states[k]
+            if kind == 'dom':
+                if st is None:
+                    rb.known[dag.intern('domis', (node,), 'U')] = False
+                    rb.memo[node] = tins[k]
+                else:
+                    # specialise the original nest again (not cull's copy): zero nests become the literal zero here
+                    rb.known[dag.intern('domis', (node,), 'U')] = True
+                    rb.known.update(_extend_known(nodes, nodes[node].attr[0], bool(st)))
+            elif st is None:
+                rb.repl[node] = dag.intern('domis', (tins[k],), 'T')
+            else:
+                rb.known.update(_extend_known(nodes, node, bool(st)))
+        return tuple(rb.value(o) for o in dag.outputs)
+
+    doms = [k for k, (kind, _) in enumerate(conds) if kind == 'dom']
+    guards = [k for k, (kind, _) in enumerate(conds) if kind == 'guard']
+    every = list(range(len(conds)))
+    bodies: List[Tuple[str, Optional[Dict[int, Tuple[int, ...]]], Tuple[int, ...]]] = []
+    # most tiles: no guard holds anywhere in the tile (no discontinuity line crosses it)
+    quiet = {k: 0 for k in guards}
+    if len(doms) == 1:
+        for st in (0, 1):
+            bodies.append((f'quiet{st}', {**{k: (0,) for k in guards}, doms[0]: (st,)}, build({**quiet, doms[0]: st})))
+    elif guards:
+        bodies.append(('quiet', {**{k: (0,) for k in guards}, **{k: (0, 1) for k in doms}},
+                       build({**quiet, **{k: None for k in doms}})))
+    if guards or len(doms) != 1:
+        bodies.append(('resolved', {k: (0, 1) for k in every}, build({k: None for k in every})))
+    bodies.append(('general', None, tuple(dag.outputs)))
+    dag.bodies = bodies
     dag.tile_conds = conds
     return dag

@@ -78,6 +78,9 @@ class Schedule:
     array_args: List[int]           # argument indices that are per-instance arrays
     scalar_args: List[int]          # argument indices bound to one scalar for the whole launch
     outputs: Tuple[int, ...]
+    # tile-culled render programs (cull.tile_cull): alternative bodies chosen per tile, [(label, match, block, outputs)];
+    # the last one is the general body (== main)
+    bodies: List[Tuple[str, Optional[Dict[int, Tuple[int, ...]]], Block, Tuple[int, ...]]] = field(default_factory=list)
 
     def loops(self) -> List[LoopGroup]:
         return [s for s in self.main.walk() if isinstance(s, LoopGroup)]
@@ -431,6 +434,16 @@ def make_schedule(dag: Dag, array_args: Sequence[int], **opts) -> Schedule:
     for o in dag.outputs:
         if sch.is_uniform(o):
             sch.uniform_used.add(o)
+    bodies = []
+    for label, match, outs in getattr(dag, 'bodies', []):
+        if match is None:
+            bodies.append((label, None, main, tuple(outs)))
+            continue
+        blk = sch.region(list(outs), set(), {})
+        for o in outs:
+            if sch.is_uniform(o):
+                sch.uniform_used.add(o)
+        bodies.append((label, dict(match), blk, tuple(outs)))
     # prologue: every uniform value referenced from per-instance code, with its (uniform) dependencies
     need: List[int] = []
     seen: Set[int] = set()
@@ -456,4 +469,4 @@ def make_schedule(dag: Dag, array_args: Sequence[int], **opts) -> Schedule:
     arr = set(sch.array_args)
     return Schedule(dag=dag, main=main, uniform_nodes=need, uniform_slots=slots,
                     array_args=sorted(arr), scalar_args=[a for a in range(n_args) if a not in arr],
-                    outputs=tuple(dag.outputs))
+                    outputs=tuple(dag.outputs), bodies=bodies)

@@ -27,9 +27,16 @@ def compile_for_host(ks):
     n_in = len(varying) + int(getattr(ks, 'tile_conds', 0))        # tile tri-states come last (pseudo arguments)
     margs = ', '.join([f'in[{j}][i]' for j in range(n_in)] + ['res'])
     stores = ' '.join(f'out[{k}][i] = res[{k}];' for k in range(ks.n_outputs))
+    # tile-culled units: pick the body the kernel would pick for the tile states of this instance
+    n_var = len(varying)
+    call = ''
+    for label, match in (getattr(ks, 'tile_bodies', None) or []):
+        cond = ' && '.join('(' + ' || '.join(f'in[{n_var + k}][i] == {v}' for v in match[k]) + ')' for k in sorted(match))
+        call += f'if ({cond}) {ks.name}_tile_{label}({margs}); else '
+    call += f'{ks.name}_instance({margs});'
     drv = (f'\nextern "C" void run(const {T}* sc, const {T}* const* in, {T}* const* out, long long n) {{\n'
            f'  {ks.name}_uniform_body({uargs});\n'
-           f'  for (long long i = 0; i < n; i++) {{ {T} res[{ks.n_outputs}]; {ks.name}_instance({margs}); {stores} }}\n}}\n')
+           f'  for (long long i = 0; i < n; i++) {{ {T} res[{ks.n_outputs}]; {call} {stores} }}\n}}\n')
     text = pre + ks.source + drv
     os.makedirs(_DIR, exist_ok=True)
     key = hashlib.sha256(text.encode()).hexdigest()[:20]
