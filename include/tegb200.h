@@ -76,6 +76,8 @@ typedef struct {
                                      the kernel writes one tri-state (0 false / 1 true for every pixel of the tile,
                                      2 unresolved) per condition and tile, which the main kernel reads per block */
     int tile_rows;                /* plain render programs: pixel rows walked by one block (>= 1) */
+    int tile_samples;             /* samples per integral the unit was generated for (the classification bounds the
+                                     midpoint abscissae lb + step * (i + 0.5), i < tile_samples, of every pixel) */
     const char *tile_kernel;      /* <name>_tiles, or NULL when n_tile_conds == 0 */
 } tegb_program_desc;
 

@@ -477,33 +477,19 @@ class Emitter:
         for j in bx + by:
             leaf[j] = (f'g_b{j}_lo', f'g_b{j}_hi')
         e = lambda line, ind=1: self.emit(line, ind)     # noqa: E731
-        e(f'T g_pz = {zero};')
-        for axis, tab, first, last, lo_n, hi_n, bvs in (('x', 'xe', 'r0', 'r1', 'xl', 'xu', bx),
-                                                      ('y', 'ye', 'c0', 'c1', 'yl', 'yu', by)):
-            e(f'T g_{lo_n}_lo = {tab}[{first}], g_{lo_n}_hi = {tab}[{first}], g_{hi_n}_lo = {tab}[{first} + 1], '
-              f'g_{hi_n}_hi = {tab}[{first} + 1];')
-            for j in bvs:
-                e(f'T g_b{j}_lo = {tab}[{first}], g_b{j}_hi = {tab}[{first}];')
-            e(f'for (int q = {first} + lane; q < {last}; q += 32) {{')
-            e(f'const T lb = {tab}[q], ub = {tab}[q + 1];', 2)
-            e(f'g_{lo_n}_lo = {fmin}(g_{lo_n}_lo, lb); g_{lo_n}_hi = {fmax}(g_{lo_n}_hi, lb);', 2)
-            e(f'g_{hi_n}_lo = {fmin}(g_{hi_n}_lo, ub); g_{hi_n}_hi = {fmax}(g_{hi_n}_hi, ub);', 2)
-            e('g_pz = g_pz + lb; g_pz = g_pz + ub; g_pz = g_pz + (ub - lb);', 2)
-            if bvs:
-                e(f'const T st = ((T)(ub - lb)) / (T){N};', 2)
-                e(f'const T sa = lb + st * ((T)0u + {half}), sb = lb + st * ((T){N - 1}u + {half});', 2)
-                e('g_pz = g_pz + sa; g_pz = g_pz + sb;', 2)
-                for j in bvs:
-                    e(f'g_b{j}_lo = {fmin}(g_b{j}_lo, {fmin}(sa, sb)); g_b{j}_hi = {fmax}(g_b{j}_hi, {fmax}(sa, sb));', 2)
-            e('}')
-            mins = [f'g_{lo_n}_lo', f'g_{hi_n}_lo'] + [f'g_b{j}_lo' for j in bvs]
-            maxs = [f'g_{lo_n}_hi', f'g_{hi_n}_hi'] + [f'g_b{j}_hi' for j in bvs]
-            e('for (int off = 16; off > 0; off >>= 1) {')
-            for v in mins:
-                e(f'{v} = {fmin}({v}, __shfl_xor_sync(0xffffffffu, {v}, off));', 2)
-            for v in maxs:
-                e(f'{v} = {fmax}({v}, __shfl_xor_sync(0xffffffffu, {v}, off));', 2)
-            e('}')
+        # [min, max] of the box edges and of the sample abscissae over the tile's rows / columns: computed once per
+        # grid by the runtime's tile_ranges kernel (exact walk over the rows / columns), 7 values per tile row / column
+        e('const T* __restrict__ rx = ranges + (size_t)ty * 7;')
+        e('const T* __restrict__ ry = ranges + ((size_t)n_ty + tx) * 7;')
+        for nm, tab in (('xl', 'rx'), ('yl', 'ry')):
+            e(f'const T g_{nm}_lo = {tab}[0], g_{nm}_hi = {tab}[1];')
+        for nm, tab in (('xu', 'rx'), ('yu', 'ry')):
+            e(f'const T g_{nm}_lo = {tab}[2], g_{nm}_hi = {tab}[3];')
+        for j in bx:
+            e(f'const T g_b{j}_lo = rx[4], g_b{j}_hi = rx[5];')
+        for j in by:
+            e(f'const T g_b{j}_lo = ry[4], g_b{j}_hi = ry[5];')
+        e('const T g_pz = rx[6] + ry[6];')
         # launch-invariant values the cones read (points), from the scalar arguments
         need: List[int] = []
         seen = set()
@@ -534,7 +520,6 @@ class Emitter:
                     sub.append((m, True))
                     for a2 in reversed(nodes[m].args):
                         sub.append((a2, False))
-        e('for (int off = 16; off > 0; off >>= 1) g_pz = g_pz + __shfl_xor_sync(0xffffffffu, g_pz, off);')
         for m in need:
             e(f'const {self.decl(m)} v{m} = {self.expr(m, {})};')
         for k, (kind, c, r, B) in enumerate(roots):
@@ -542,7 +527,7 @@ class Emitter:
             e('{')
             e(f'T {pre}pz = g_pz;', 2)
             t, f = self._iv_cone(r, (lambda j, B=B: bool(fv(j) & B) or dep.get(j, False)), leaf, {}, 2, pre)
-            e(f'if (lane == 0) tiles[(size_t){k} * n_tiles + t] = {self._iv_result(t, f, pre)};', 2)
+            e(f'tiles[(size_t){k} * n_tiles + t] = {self._iv_result(t, f, pre)};', 2)
             e('}')
         self.in_main = saved_main
         return self.lines
@@ -1178,18 +1163,13 @@ class Emitter:
                 # pixel (nx, ny) -> instance nx * res_y + ny; box bounds from the two np.linspace edge tables
                 if tile:
                     tparams = ', '.join([f'const T a{a}' for a in scal] +
-                                        ['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
-                                         'const int row0', 'const int n_rows', 'const int tile_rows', 'const int n_tx',
-                                         'const int n_ty', 'T* __restrict__ tiles'])
+                                        ['const T* __restrict__ ranges', 'const int n_tx', 'const int n_ty',
+                                         'T* __restrict__ tiles'])
                     src.append(f'extern "C" __global__ void {name}_tiles({tparams}) {{')
-                    src.append('    // one warp per tile: lanes share the walk over the tile\'s rows and columns')
-                    src.append('    const int t = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);')
-                    src.append('    const int lane = threadIdx.x & 31;')
+                    src.append('    const int t = blockIdx.x * blockDim.x + threadIdx.x;       // one thread per tile')
                     src.append('    const size_t n_tiles = (size_t)n_tx * n_ty;')
                     src.append('    if (t >= n_tx * n_ty) return;')
                     src.append('    const int ty = t / n_tx, tx = t - ty * n_tx;')
-                    src.append('    const int r0 = row0 + ty * tile_rows, r1 = min(r0 + tile_rows, row0 + n_rows);')
-                    src.append(f'    const int c0 = tx * {bs}, c1 = min(c0 + {bs}, res_y);')
                     for a in scal:
                         src.append(f'    (void)a{a};')
                     src += self.tiles_body(grid)

@@ -280,6 +280,11 @@ struct tegb_program {
     // tri-states of the tile conditions (render programs with n_tile_conds > 0)
     void *d_tiles = nullptr;
     size_t tiles_bytes = 0;
+    // per tile row / tile column: [min, max] of the box edges and sample abscissae (valid for ranges_grid)
+    void *d_ranges = nullptr;
+    size_t ranges_bytes = 0;
+    tegb_grid ranges_grid{};
+    bool ranges_valid = false;
     // pixel-edge tables for tegb_render_launch
     void *d_xe = nullptr, *d_ye = nullptr;
     std::vector<char> h_xe, h_ye;
@@ -315,7 +320,7 @@ extern "C" int tegb_program_create(tegb_module *m, const tegb_program_desc *desc
     r = drv::ModuleGetFunction(&p->f_main, p->mod, desc->main_kernel);
     if (r != CUDA_SUCCESS) return bail(fail(TEGB_ERR_CUDA, "kernel %s: %s", desc->main_kernel, drv::errstr(r)));
     if (desc->n_tile_conds > 0) {
-        if (!desc->tile_kernel || desc->tile_rows < 1 || desc->grouped || desc->n_grid_args != 4)
+        if (!desc->tile_kernel || desc->tile_rows < 1 || desc->tile_samples < 1 || desc->grouped || desc->n_grid_args != 4)
             return bail(fail(TEGB_ERR_INVALID, "tile conditions need a plain render program, tile_rows >= 1 and a tile kernel"));
         r = drv::ModuleGetFunction(&p->f_tiles, p->mod, desc->tile_kernel);
         if (r != CUDA_SUCCESS) return bail(fail(TEGB_ERR_CUDA, "kernel %s: %s", desc->tile_kernel, drv::errstr(r)));
@@ -340,6 +345,7 @@ extern "C" void tegb_program_destroy(tegb_program *p) {
     if (p->d_partials) cudaFree(p->d_partials);
     if (p->d_utab) cudaFree(p->d_utab);
     if (p->d_tiles) cudaFree(p->d_tiles);
+    if (p->d_ranges) cudaFree(p->d_ranges);
     if (p->d_xe) cudaFree(p->d_xe);
     if (p->d_ye) cudaFree(p->d_ye);
     if (p->mod) drv::ModuleUnload(p->mod);
@@ -569,6 +575,75 @@ static int ensure_edges(tegb_program *p, const tegb_grid *g, CUstream st) {
     RT_CHECK(cudaMemcpyAsync(p->d_ye, p->h_ye.data(), p->h_ye.size(), cudaMemcpyHostToDevice, (cudaStream_t)st));
     p->grid_cached = *g;
     p->grid_valid = true;
+    p->ranges_valid = false;
+    return TEGB_OK;
+}
+
+// Tile classification support (generated <name>_tiles kernels read this table): for every tile row (x axis, entries
+// [0, n_ty)) and every tile column (y axis, entries [n_ty, n_ty + n_tx)) the exact [min, max] over its pixels of the
+// lower box edge, the upper box edge and the first / last midpoint abscissa -- computed by walking the pixels with
+// the very operations the generated code uses (lb + step * (i + 0.5), step = (ub - lb) / N; this file is compiled
+// with --fmad=false like the generated units) -- plus a poison sum that is finite iff every edge, width and abscissa
+// of the walk is.  7 values per entry: lb_lo lb_hi ub_lo ub_hi s_lo s_hi poison.  One warp per entry.
+template <typename T>
+__global__ void tile_ranges(const T *__restrict__ xe, const T *__restrict__ ye, int res_y, int row0, int n_rows,
+                            int tile_rows, int tile_cols, int num_samples, int n_tx, int n_ty, T *__restrict__ out) {
+    const int e = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (e >= n_tx + n_ty) return;
+    const bool is_x = e < n_ty;
+    const T *tab = is_x ? xe : ye;
+    int first, last;
+    if (is_x) { first = row0 + e * tile_rows; last = min(first + tile_rows, row0 + n_rows); }
+    else { first = (e - n_ty) * tile_cols; last = min(first + tile_cols, res_y); }
+    T lb_lo = tab[first], lb_hi = tab[first], ub_lo = tab[first + 1], ub_hi = tab[first + 1];
+    T s_lo = tab[first], s_hi = tab[first], pz = (T)0;
+    const T half = (T)0.5;
+    for (int q = first + lane; q < last; q += 32) {
+        const T lb = tab[q], ub = tab[q + 1];
+        lb_lo = fmin(lb_lo, lb); lb_hi = fmax(lb_hi, lb);
+        ub_lo = fmin(ub_lo, ub); ub_hi = fmax(ub_hi, ub);
+        const T st = ((T)(ub - lb)) / (T)num_samples;
+        const T sa = lb + st * ((T)0u + half), sb = lb + st * ((T)(unsigned)(num_samples - 1) + half);
+        s_lo = fmin(s_lo, fmin(sa, sb)); s_hi = fmax(s_hi, fmax(sa, sb));
+        pz = pz + lb; pz = pz + ub; pz = pz + (ub - lb); pz = pz + sa; pz = pz + sb;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        lb_lo = fmin(lb_lo, __shfl_xor_sync(0xffffffffu, lb_lo, off)); lb_hi = fmax(lb_hi, __shfl_xor_sync(0xffffffffu, lb_hi, off));
+        ub_lo = fmin(ub_lo, __shfl_xor_sync(0xffffffffu, ub_lo, off)); ub_hi = fmax(ub_hi, __shfl_xor_sync(0xffffffffu, ub_hi, off));
+        s_lo = fmin(s_lo, __shfl_xor_sync(0xffffffffu, s_lo, off)); s_hi = fmax(s_hi, __shfl_xor_sync(0xffffffffu, s_hi, off));
+        pz = pz + __shfl_xor_sync(0xffffffffu, pz, off);
+    }
+    if (lane == 0) {
+        T *o = out + (size_t)e * 7;
+        o[0] = lb_lo; o[1] = lb_hi; o[2] = ub_lo; o[3] = ub_hi; o[4] = s_lo; o[5] = s_hi; o[6] = pz;
+    }
+}
+
+static int ensure_ranges(tegb_program *p, const tegb_grid *g, int n_tx, int n_ty, cudaStream_t st) {
+    const tegb_grid &c = p->ranges_grid;
+    if (p->ranges_valid && c.x_lo == g->x_lo && c.x_hi == g->x_hi && c.y_lo == g->y_lo && c.y_hi == g->y_hi &&
+        c.res_x == g->res_x && c.res_y == g->res_y && c.row_begin == g->row_begin && c.row_end == g->row_end)
+        return TEGB_OK;
+    const size_t need = (size_t)(n_tx + n_ty) * 7 * p->d.elem_size;
+    if (need > p->ranges_bytes) {
+        RT_CHECK(cudaStreamSynchronize(st));
+        if (p->d_ranges) { cudaFree(p->d_ranges); p->d_ranges = nullptr; p->ranges_bytes = 0; }
+        RT_CHECK(cudaMalloc(&p->d_ranges, need));
+        p->ranges_bytes = need;
+    }
+    const int n_rows = g->row_end - g->row_begin;
+    const unsigned tb = 128, tg = (unsigned)(((size_t)(n_tx + n_ty) * 32 + tb - 1) / tb);
+    if (p->d.elem_size == 4)
+        tile_ranges<float><<<tg, tb, 0, st>>>((const float *)p->d_xe, (const float *)p->d_ye, g->res_y, g->row_begin, n_rows,
+                                             p->d.tile_rows, p->d.block_size, p->d.tile_samples, n_tx, n_ty, (float *)p->d_ranges);
+    else
+        tile_ranges<double><<<tg, tb, 0, st>>>((const double *)p->d_xe, (const double *)p->d_ye, g->res_y, g->row_begin, n_rows,
+                                              p->d.tile_rows, p->d.block_size, p->d.tile_samples, n_tx, n_ty, (double *)p->d_ranges);
+    RT_CHECK(cudaGetLastError());
+    g_launches++;
+    p->ranges_grid = *g;
+    p->ranges_valid = true;
     return TEGB_OK;
 }
 
@@ -699,16 +774,13 @@ extern "C" int tegb_render_launch(tegb_program *p, const double *scalars, const 
             if (p->d.elem_size == 4) { sf[i] = (float)scalars[i]; targs.push_back(&sf[i]); }
             else { sd[i] = scalars[i]; targs.push_back(&sd[i]); }
         }
-        targs.push_back(&p->d_xe);
-        targs.push_back(&p->d_ye);
-        targs.push_back(&res_y);
-        targs.push_back(&row0);
-        targs.push_back(&n_rows);
-        targs.push_back(&tile_rows);
+        rc = ensure_ranges(p, g, n_tx, n_ty, (cudaStream_t)st);
+        if (rc) return rc;
+        targs.push_back(&p->d_ranges);
         targs.push_back(&n_tx);
         targs.push_back(&n_ty);
         targs.push_back(&p->d_tiles);
-        const unsigned tb = 128, tg = (unsigned)(((size_t)n_tx * n_ty * 32 + tb - 1) / tb);      // a warp per tile
+        const unsigned tb = 128, tg = (unsigned)(((size_t)n_tx * n_ty + tb - 1) / tb);      // a thread per tile
         CU_CHECK(drv::LaunchKernel(p->f_tiles, tg, 1, 1, tb, 1, 1, 0, st, targs.data(), nullptr));
         g_launches++;
         args.push_back(&p->d_tiles);
