@@ -522,13 +522,19 @@ class Emitter:
                         sub.append((a2, False))
         for m in need:
             e(f'const {self.decl(m)} v{m} = {self.expr(m, {})};')
+        e('bool unresolved = false;')
         for k, (kind, c, r, B) in enumerate(roots):
             pre = f'k{k}_'
             e('{')
             e(f'T {pre}pz = g_pz;', 2)
             t, f = self._iv_cone(r, (lambda j, B=B: bool(fv(j) & B) or dep.get(j, False)), leaf, {}, 2, pre)
-            e(f'tiles[(size_t){k} * n_tiles + t] = {self._iv_result(t, f, pre)};', 2)
+            e(f'const T {pre}tri = {self._iv_result(t, f, pre)};', 2)
+            e(f'tiles[(size_t){k} * n_tiles + t] = {pre}tri;', 2)
+            e(f'unresolved = unresolved || {pre}tri == {literal("2", T)};', 2)
             e('}')
+        # launch order of the main kernel: unresolved tiles from the front, resolved ones from the back
+        e('if (unresolved) order[atomicAdd(&counters[0], 1)] = t;')
+        e('else order[n_tx * n_ty - 1 - atomicAdd(&counters[1], 1)] = t;')
         self.in_main = saved_main
         return self.lines
 
@@ -1164,7 +1170,7 @@ class Emitter:
                 if tile:
                     tparams = ', '.join([f'const T a{a}' for a in scal] +
                                         ['const T* __restrict__ ranges', 'const int n_tx', 'const int n_ty',
-                                         'T* __restrict__ tiles'])
+                                         'T* __restrict__ tiles', 'int* __restrict__ order', 'int* __restrict__ counters'])
                     src.append(f'extern "C" __global__ void {name}_tiles({tparams}) {{')
                     src.append('    const int t = blockIdx.x * blockDim.x + threadIdx.x;       // one thread per tile')
                     src.append('    const size_t n_tiles = (size_t)n_tx * n_ty;')
@@ -1179,9 +1185,17 @@ class Emitter:
                 # (the per-block set-up, the tile tri-states and the block sum are paid once per tile)
                 mparams = ', '.join(['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
                                      'const int row0', 'const int n_rows', 'const int tile_rows'] +
-                                    (['const T* __restrict__ tiles'] if tile else []) + outs_decl)
+                                    (['const T* __restrict__ tiles', 'const int* __restrict__ order'] if tile else []) +
+                                    outs_decl)
                 src.append(f'extern "C" __global__ void __launch_bounds__({bs}) {name}_main({mparams}) {{')
-                src.append('    const int ny = blockIdx.x * blockDim.x + threadIdx.x;')
+                if tile:
+                    # blocks take the tiles in the order the classification listed them: unresolved (expensive) tiles
+                    # first, so that they all start in the first wave instead of trailing the launch
+                    src.append('    const int tile_lin = order[blockIdx.y * gridDim.x + blockIdx.x];')
+                    src.append('    const int tby = tile_lin / (int)gridDim.x, tbx = tile_lin - tby * (int)gridDim.x;')
+                else:
+                    src.append('    const int tby = blockIdx.y, tbx = blockIdx.x;')
+                src.append('    const int ny = tbx * blockDim.x + threadIdx.x;')
                 src.append('    const bool live = ny < res_y;')
                 ycol = 'nyc' if coop else 'ny'
                 if coop:
@@ -1191,7 +1205,7 @@ class Emitter:
                 loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye_lo', grid[3]: 'ye_hi'}
                 if tile:
                     src.append('    const size_t n_tiles = (size_t)gridDim.x * gridDim.y;')
-                    src.append('    const size_t tile_id = (size_t)blockIdx.y * gridDim.x + blockIdx.x;')
+                    src.append('    const size_t tile_id = (size_t)tile_lin;')
                     for k, a in enumerate(tile):
                         src.append(f'    const T tile{k} = tiles[{k} * n_tiles + tile_id];')
                         loads[a] = f'tile{k}'
@@ -1203,7 +1217,7 @@ class Emitter:
                     call = ', '.join((['live'] if with_live else []) + [loads[a] for a in varying] + ['res'])
                     src.append(f'{ind}#pragma unroll 1')
                     src.append(f'{ind}for (int r = 0; r < tile_rows; ++r) {{')
-                    src.append(f'{ind}    const int rel = blockIdx.y * tile_rows + r;')
+                    src.append(f'{ind}    const int rel = tby * tile_rows + r;')
                     src.append(f'{ind}    if (rel >= n_rows) break;')
                     src.append(f'{ind}    const int nx = row0 + rel;')
                     src.append(f'{ind}    const long long i = (long long)rel * res_y + ny;')
@@ -1239,7 +1253,9 @@ class Emitter:
                 else:
                     row_loop(f'{name}_instance', coop, '    ')
                 if nr:
-                    src.append(f'    tegb_block_sum_store<T, {nr}, {bs}>(rr, partials);')
+                    # the partial of a tile lives at the tile's own index: the sums do not depend on the block order
+                    src.append(f'    tegb_block_sum_store<T, {nr}, {bs}>(rr, partials, (unsigned long long)gridDim.x * gridDim.y, '
+                               '(unsigned long long)tby * gridDim.x + tbx);')
                 src.append('}')
                 src.append('#endif')
                 text = '\n'.join(src) + '\n'

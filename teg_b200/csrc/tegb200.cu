@@ -281,6 +281,8 @@ struct tegb_program {
     void *d_tiles = nullptr;
     size_t tiles_bytes = 0;
     // per tile row / tile column: [min, max] of the box edges and sample abscissae (valid for ranges_grid)
+    int *d_order = nullptr;       // [n_tiles] tile indices in launch order, then 2 counters
+    size_t order_count = 0;
     void *d_ranges = nullptr;
     size_t ranges_bytes = 0;
     tegb_grid ranges_grid{};
@@ -346,6 +348,7 @@ extern "C" void tegb_program_destroy(tegb_program *p) {
     if (p->d_utab) cudaFree(p->d_utab);
     if (p->d_tiles) cudaFree(p->d_tiles);
     if (p->d_ranges) cudaFree(p->d_ranges);
+    if (p->d_order) cudaFree(p->d_order);
     if (p->d_xe) cudaFree(p->d_xe);
     if (p->d_ye) cudaFree(p->d_ye);
     if (p->mod) drv::ModuleUnload(p->mod);
@@ -776,14 +779,26 @@ extern "C" int tegb_render_launch(tegb_program *p, const double *scalars, const 
         }
         rc = ensure_ranges(p, g, n_tx, n_ty, (cudaStream_t)st);
         if (rc) return rc;
+        const size_t n_tiles = (size_t)n_tx * n_ty;
+        if (n_tiles > p->order_count) {
+            RT_CHECK(cudaStreamSynchronize((cudaStream_t)st));
+            if (p->d_order) { cudaFree(p->d_order); p->d_order = nullptr; p->order_count = 0; }
+            RT_CHECK(cudaMalloc((void **)&p->d_order, (n_tiles + 2) * sizeof(int)));
+            p->order_count = n_tiles;
+        }
+        int *d_counters = p->d_order + p->order_count;
+        RT_CHECK(cudaMemsetAsync(d_counters, 0, 2 * sizeof(int), (cudaStream_t)st));
         targs.push_back(&p->d_ranges);
         targs.push_back(&n_tx);
         targs.push_back(&n_ty);
         targs.push_back(&p->d_tiles);
+        targs.push_back(&p->d_order);
+        targs.push_back(&d_counters);
         const unsigned tb = 128, tg = (unsigned)(((size_t)n_tx * n_ty + tb - 1) / tb);      // a thread per tile
         CU_CHECK(drv::LaunchKernel(p->f_tiles, tg, 1, 1, tb, 1, 1, 0, st, targs.data(), nullptr));
         g_launches++;
         args.push_back(&p->d_tiles);
+        args.push_back(&p->d_order);
     }
     const int n_store = p->d.n_outputs - p->d.reduce_outputs;
     for (int k = 0; k < n_store; k++) { outs[k] = out_ptrs[k]; args.push_back(&outs[k]); }
