@@ -375,6 +375,34 @@ class CUDA_EvalMode(EvalMode):
         return PreparedCall(self, ks, prog, scalars, ins, out, n_eff, reduce)
 
     # ------------------------------------------------------------------- render
+    def prepare_render(self, box_vars, res: Tuple[int, int], bounds=((0, 1), (0, 1)), bindings=None,
+                       rows: Optional[Tuple[int, int]] = None, out=None, reduce: bool = False) -> "PreparedRender":
+        """``render`` bound once (arguments resolved, output allocated): the returned object's ``run(stream)`` costs
+        one C call.  Same arguments and output conventions as ``render`` (bundles with 0 < reduce < k excluded)."""
+        import torch
+        labels = [v if isinstance(v, str) else label_of(v) for v in box_vars]
+        pos = {lab: i for i, (lab, _) in enumerate(self.arglist)}
+        grid_args = [pos[lab] for lab in labels]
+        by_label = {(k if isinstance(k, str) else label_of(k)): v for k, v in (bindings or {}).items()}
+        ks, prog = self.compiled(grid_args, grid_args, reduce=reduce)
+        assert ks.reduce_outputs in (0, ks.n_outputs), 'prepare_render: all outputs are images, or all are sums'
+        scalars = []
+        for a in ks.scalar_args:
+            lab, default = self.arglist[a]
+            v = by_label.get(lab, default)
+            assert v is not None, f'No bindings found for {[lab]}'
+            scalars.append(float(v))
+        r0, r1 = (0, res[0]) if rows is None else rows
+        tdt = torch.float32 if self.float_width == 'float' else torch.float64
+        dev = torch.device('cuda', self.device)
+        if out is None:
+            out = (torch.empty(ks.n_outputs, dtype=tdt, device=dev) if ks.reduce_outputs
+                   else torch.empty((ks.n_outputs, r1 - r0, res[1]), dtype=tdt, device=dev))
+        ptrs = [out.data_ptr()] if ks.reduce_outputs else [out[k].data_ptr() for k in range(ks.n_outputs)]
+        grid = runtime.Grid(float(bounds[0][0]), float(bounds[0][1]), float(bounds[1][0]), float(bounds[1][1]),
+                            int(res[0]), int(res[1]), int(r0), int(r1))
+        return PreparedRender(self, ks, prog, scalars, grid, out, ptrs)
+
     def render(self, box_vars, res: Tuple[int, int], bounds=((0, 1), (0, 1)), bindings=None,
                rows: Optional[Tuple[int, int]] = None, out=None, stream: int = 0, reduce: bool = False):
         """Evaluate over the pixel grid of tests/plot.py:8-29 with on-device pixel boxes.
@@ -419,6 +447,27 @@ class CUDA_EvalMode(EvalMode):
         ptrs = [out.data_ptr()] if nr else [out[k].data_ptr() for k in range(ks.n_outputs)]
         prog.render(scalars, grid, ptrs, stream=stream)
         return out
+
+
+class PreparedRender:
+    """A bound ``render`` (see ``CUDA_EvalMode.prepare_render``): ``run(stream)`` is one C-ABI call
+    (``tegb_render_launch``) with pre-marshalled arguments; ``set_scalars`` rebinds the launch-wide arguments."""
+
+    def __init__(self, mode, ks, prog, scalars, grid, out, ptrs):
+        self.mode, self.ks, self.prog, self.out = mode, ks, prog, out
+        self._grid = grid
+        self._scalars = runtime._dbl_array(scalars)
+        self._ptrs = runtime._ptr_array(ptrs)
+        self._fn = runtime.lib().tegb_render_launch
+        self._h = prog.handle
+
+    def set_scalars(self, values: Sequence[float]) -> None:
+        """New values for the scalar arguments, in ``ks.scalar_args`` order."""
+        self._scalars = runtime._dbl_array(values)
+
+    def run(self, stream: int = 0):
+        runtime.check(self._fn(self._h, self._scalars, ctypes.byref(self._grid), self._ptrs, ctypes.c_void_p(stream)))
+        return self.out
 
 
 class PreparedCall:
