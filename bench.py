@@ -177,6 +177,8 @@ def main() -> int:
     ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'], help='working precision of the programs')
     ap.add_argument('--maxreg', type=int, default=0, help='experiment: --maxrregcount for the generated kernels')
     ap.add_argument('--tile-rows', type=int, default=16, help='pixel rows per render block / classification tile')
+    ap.add_argument('--allreduce', default='peer', choices=['peer', 'nccl'], help='N > 1: gradient all-reduce fused '
+                    'into the column-sum kernel over NVLink peer memory (default), or a separate NCCL all-reduce')
     ap.add_argument('--cull', type=int, default=1, help='0: dense kernels (every comparison at every sample); '
                     '1: domain culling (teg_b200/cull.py, bit-identical results)')
     args = ap.parse_args()
@@ -238,7 +240,14 @@ def main() -> int:
                for b in range(2)]
     pr_primal = [m_primal.prepare_render(box, (res_x_total, res), bounds, params, rows=rows, out=imgs[b])
                  for b in range(2)]
-    side = torch.cuda.Stream(dev)
+    # the gradient pipeline is the longer one (and ends in the all-reduce): its blocks get priority
+    side = torch.cuda.Stream(dev, priority=-1)
+    peers = None
+    if world > 1 and args.allreduce == 'peer' and m_fused is None:
+        from teg_b200.parallel import PeerGroup
+        peers = PeerGroup(local_rank, max_values=16)
+        for pr in pr_grad:
+            peers.attach(pr.prog)            # the last column-sum kernel of the gradient does the exchange itself
     side_ptr = side.cuda_stream
 
     def step(record: bool, buf: int = 0):
@@ -266,7 +275,7 @@ def main() -> int:
             if record:
                 e[2].record(side)
             pr_grad[buf].run(side_ptr)
-            if world > 1:
+            if world > 1 and peers is None:
                 dist.all_reduce(gsums[buf])        # enqueued behind the gradient on `side`
             if record:
                 e[3].record(side)
@@ -309,22 +318,24 @@ def main() -> int:
         step_ev.append((a, b))
     sync_all()
     total_ms = float(sum(a.elapsed_time(b) for a, b in step_ev))
-    # the timed region lasts only tens of milliseconds: keep the same steps running (untimed) for ~1.2 s so that
-    # nvidia-smi (100 ms period) sees the clocks and throttle reasons under this very load
-    t_hold = time.perf_counter()
-    while time.perf_counter() - t_hold < 1.2:
-        for _ in range(20):
-            step(False)
-        torch.cuda.synchronize(dev)
-    clocks = sampler.stop() if rank == 0 else None
-    if clocks is not None:
-        clocks['window'] = 'timed steps + 1.2 s untimed continuation of the same steps'
-    sync_all()
     launches_timed = runtime.launch_count() - launches_warm
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
+    # the timed region lasts only milliseconds: keep the same steps running (untimed) for ~1.2 s so that nvidia-smi
+    # (100 ms period) sees the clocks and throttle reasons under this very load.  The number of extra steps is derived
+    # from the all-reduced time, i.e. it is the same on every rank (the steps contain a collective).
+    n_hold = int(min(60000, max(20, 1200.0 / max(total_ms / args.steps, 1e-3))))
+    for k in range(n_hold):
+        step(False)
+        if k % 64 == 63:
+            torch.cuda.synchronize(dev)
+    torch.cuda.synchronize(dev)
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks['window'] = f'timed steps + {n_hold} untimed repetitions of the same step (~1.2 s)'
+    sync_all()
     ms_per_step = total_ms / args.steps
     value = n_local * world * args.steps / (total_ms * 1e-3)
 
@@ -380,6 +391,8 @@ def main() -> int:
                       'every step on a second stream, double-buffered', 'steps': k_e2e,
                'ms_per_step': float(te.item()) / k_e2e * 1e3}
 
+    if peers is not None:
+        peers.close()                # checks the time-out flag, then a barrier before the mailboxes go away
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -494,8 +507,9 @@ def main() -> int:
                    'programs': ['tri_primal', 'tri_grad'], 'fused_kernel': bool(args.fused), 'cull': bool(args.cull), 'outputs': 'value image [4096,4096] + per-parameter '
                    'gradient sum [6] (reduced in-kernel)', 'l2': 'L2 flushed between timed steps by writing a '
                    '256 MB buffer (outside the per-step event pairs); inputs are generated from the pixel index',
-                   'parallelism': f'rows sharded over {world} GPU(s), one NCCL all-reduce of the [6] gradient, '
-                                  'on the gradient stream, next to the value kernel'},
+                   'parallelism': f'rows sharded over {world} GPU(s), one all-reduce of the [6] gradient per step ('
+                                  + ('fused into the column-sum kernel over NVLink peer memory' if peers is not None else 'NCCL')
+                                  + '), on the gradient stream next to the value kernel'},
         'phase_ms': phase_ms, 'phase_note': 'the value and the gradient pipelines run concurrently on two streams: '
         'their phase times overlap and each is longer than the same pipeline alone', 'roofline': roofline, 'roofline_dense': roofline_dense, 'cpu_baseline': cpu, 'e2e': e2e,
         'gpu_launches': int(launches_timed), 'clocks': clocks,

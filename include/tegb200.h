@@ -130,6 +130,24 @@ int tegb_render_launch(tegb_program *p, const double *scalars, const tegb_grid *
  * (condition-major, [n_tile_conds][tiles], element type of the program) to host memory */
 int tegb_program_tile_table(tegb_program *p, void *host_out, size_t nbytes, void *stream);
 
+/* --- all-reduce over NVLink peer memory (one node) --------------------------------------------------------------
+ * Replaces "column sums, then ncclAllReduce" for the per-parameter gradients of a sharded render:
+ * every rank owns a mailbox mapped by all peers (CUDA IPC); the last column-sum kernel writes its sums into every
+ * mailbox and adds the ranks' contributions in rank order (bit-identical on every rank).
+ *   tegb_peer_create   allocates this rank's mailbox (up to max_values numbers per call) and returns its 64-byte handle
+ *   tegb_peer_connect  maps the other ranks' mailboxes; `handles` = world x 64 bytes in rank order (the caller gathers
+ *                      them, e.g. with torch.distributed.all_gather)
+ *   tegb_program_set_peer  reduce_outputs launches of the program then deliver the all-reduced sums
+ *   tegb_peer_allreduce_sum  stand-alone in-place all-reduce of a device vector (every rank must call it, same order)
+ *   tegb_peer_error    1 if an exchange timed out (a peer never arrived); tegb_peer_destroy after a barrier */
+typedef struct tegb_peer tegb_peer;
+int tegb_peer_create(int rank, int world, int max_values, int device, tegb_peer **out, void *handle64);
+int tegb_peer_connect(tegb_peer *p, const void *handles);
+int tegb_peer_allreduce_sum(tegb_peer *p, void *buf, int count, int elem_size, void *stream);
+int tegb_peer_error(tegb_peer *p);
+void tegb_peer_destroy(tegb_peer *p);
+int tegb_program_set_peer(tegb_program *prog, tegb_peer *peer);
+
 /* Grouped render: groups [group_begin, group_begin + group_count) (e.g. triangles) are evaluated over their
  * own pixel windows in ONE launch.  group_ptrs[n_scalar_args]: device arrays with one value per group
  * (indexed by absolute group number).  windows: device int32 [n_groups][4] = (row_begin, row_end, col_begin,

@@ -256,6 +256,7 @@ extern "C" const char *tegb_module_log(const tegb_module *m) { return m ? m->log
 extern "C" void tegb_module_destroy(tegb_module *m) { delete m; }
 
 // ------------------------------------------------------------------------------------------- programs
+struct tegb_peer;
 struct tegb_program {
     tegb_program_desc d;
     int device = 0;
@@ -277,6 +278,8 @@ struct tegb_program {
     // per-block partial sums of reduce_outputs programs
     void *d_partials = nullptr;
     size_t partials_bytes = 0;
+    // set by tegb_program_set_peer: the sums of reduce_outputs launches are all-reduced over the peer mailboxes
+    struct tegb_peer *peer = nullptr;
     // tri-states of the tile conditions (render programs with n_tile_conds > 0)
     void *d_tiles = nullptr;
     size_t tiles_bytes = 0;
@@ -402,6 +405,79 @@ __device__ __forceinline__ T block_sum_fixed(T v, T *smem) {
     return r;   // valid in thread 0
 }
 
+// ---------------------------------------------------------------------- all-reduce over NVLink peer memory
+// The reverse-mode gradient of a sharded render is a handful of numbers per rank.  Instead of handing them to a
+// collective library after the column sums, the last column-sum kernel does the exchange itself: every rank owns a
+// mailbox (cudaMalloc + CUDA IPC, mapped by every peer of the node), block c writes its column sum into slot
+// [bank][my rank][c] of EVERY mailbox (value, fence, sequence number), then polls its own mailbox until all ranks'
+// slots for column c carry this call's sequence number and adds them in rank order.  One NVLink store latency plus one
+// poll; every rank forms the same sum in the same order (bit-identical across ranks and runs).  Two banks alternate
+// with the sequence number: a rank can run at most one call ahead of the slowest peer, because finishing call s needs
+// every peer's call-s slot, which a peer writes only after its call s-1 kernel completed (stream order).
+#define TEGB_MAX_PEERS 16
+struct PeerSlot { unsigned long long bits; unsigned long long seq; };
+struct PeerView {
+    PeerSlot *box[TEGB_MAX_PEERS];      // mailbox of every rank, mapped here
+    int rank, world, maxv;
+    int *err;                           // set when a peer did not answer within the time-out
+};
+
+template <typename T>
+__device__ __forceinline__ T peer_exchange_sum(const PeerView &v, int col, T value, unsigned long long seq) {
+    const int bank = (int)(seq & 1ull);
+    unsigned long long bits = 0;
+    if (sizeof(T) == 4) bits = (unsigned long long)__float_as_uint((float)value);
+    else bits = (unsigned long long)__double_as_longlong((double)value);
+    const size_t mine = ((size_t)bank * v.world + v.rank) * v.maxv + col;
+    for (int p = 0; p < v.world; ++p) *(volatile unsigned long long *)&v.box[p][mine].bits = bits;
+    __threadfence_system();
+    for (int p = 0; p < v.world; ++p) *(volatile unsigned long long *)&v.box[p][mine].seq = seq;
+    T acc = 0;
+    for (int r = 0; r < v.world; ++r) {
+        PeerSlot *s = &v.box[v.rank][((size_t)bank * v.world + r) * v.maxv + col];
+        const long long t0 = clock64();
+        while (*(volatile unsigned long long *)&s->seq != seq) {
+            if (clock64() - t0 > 4000000000ll) { *v.err = 1; break; }     // ~2 s: a peer is gone; do not hang the GPU
+        }
+        __threadfence_system();
+        const unsigned long long b = *(volatile unsigned long long *)&s->bits;
+        T x;
+        if (sizeof(T) == 4) x = (T)__uint_as_float((unsigned int)b);
+        else x = (T)__longlong_as_double((long long)b);
+        acc = (r == 0) ? x : acc + x;
+    }
+    return acc;
+}
+
+// column sums fused with the peer all-reduce: out[c] = sum over ranks (in rank order) of this rank's column sum
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS) colsum_stage2_peer(const T *partials, long long n_blocks, T *out,
+                                                                  PeerView view, unsigned long long seq) {
+    __shared__ T smem[32];
+    const int c = blockIdx.x;
+    T acc = 0;
+    for (long long i = threadIdx.x; i < n_blocks; i += RED_THREADS) acc = acc + partials[(long long)c * n_blocks + i];
+    T s = block_sum_fixed(acc, smem);
+    if (threadIdx.x == 0) out[c] = peer_exchange_sum<T>(view, c, s, seq);
+}
+
+// stand-alone form: in-place all-reduce of a device vector (count <= maxv)
+template <typename T>
+__global__ void peer_allreduce_kernel(T *buf, int count, PeerView view, unsigned long long seq) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < count) buf[c] = peer_exchange_sum<T>(view, c, buf[c], seq);
+}
+
+struct tegb_peer {
+    PeerView view{};
+    int device = 0;
+    void *d_box = nullptr;
+    size_t box_bytes = 0;
+    std::vector<void *> opened;
+    unsigned long long seq = 0;
+    int h_err = 0;
+};
+
 template <typename T>
 __global__ void __launch_bounds__(RED_THREADS) colsum_stage2(const T *partials, long long n_blocks, T *out) {
     __shared__ T smem[32];
@@ -453,9 +529,33 @@ static void sum_columns(const T *partials, int n_cols, unsigned long long n_bloc
     }
 }
 
+template <typename T>
+static void sum_columns_peer(const T *partials, int n_cols, unsigned long long n_blocks, T *out, T *slices, cudaStream_t st,
+                             tegb_peer *peer) {
+    const unsigned long long seq = ++peer->seq;
+    if (n_blocks >= 4096) {
+        const long long chunk = (long long)((n_blocks + RED_SLICES - 1) / RED_SLICES);
+        colsum_slices<T><<<dim3(RED_SLICES, n_cols), RED_THREADS, 0, st>>>(partials, (long long)n_blocks, chunk, slices);
+        colsum_stage2_peer<T><<<n_cols, RED_THREADS, 0, st>>>(slices, (long long)RED_SLICES, out, peer->view, seq);
+        g_launches += 2;
+    } else {
+        colsum_stage2_peer<T><<<n_cols, RED_THREADS, 0, st>>>(partials, (long long)n_blocks, out, peer->view, seq);
+        g_launches++;
+    }
+}
+
 static int finish_partials(tegb_program *p, unsigned long long n_blocks, void *out, cudaStream_t st) {
     // slice sums live behind the partials (ensure_partials reserves the room)
     char *slices = (char *)p->d_partials + (size_t)p->d.reduce_outputs * n_blocks * p->d.elem_size;
+    if (p->peer) {
+        if (p->d.reduce_outputs > p->peer->view.maxv) return fail(TEGB_ERR_INVALID, "peer mailbox smaller than the gradient");
+        if (p->d.elem_size == 4)
+            sum_columns_peer<float>((const float *)p->d_partials, p->d.reduce_outputs, n_blocks, (float *)out, (float *)slices, st, p->peer);
+        else
+            sum_columns_peer<double>((const double *)p->d_partials, p->d.reduce_outputs, n_blocks, (double *)out, (double *)slices, st, p->peer);
+        RT_CHECK(cudaGetLastError());
+        return TEGB_OK;
+    }
     if (p->d.elem_size == 4)
         sum_columns<float>((const float *)p->d_partials, p->d.reduce_outputs, n_blocks, (float *)out, (float *)slices, st);
     else
@@ -875,6 +975,88 @@ extern "C" int tegb_reduce_sum(const void *const *in_ptrs, int n_cols, int64_t n
     }
     g_launches += 2;
     RT_CHECK(cudaGetLastError());
+    return TEGB_OK;
+}
+
+// --------------------------------------------------------------------------------------- peer mailboxes
+extern "C" int tegb_peer_create(int rank, int world, int max_values, int device, tegb_peer **out, void *handle64) {
+    if (!out || !handle64 || world < 1 || world > TEGB_MAX_PEERS || rank < 0 || rank >= world || max_values < 1)
+        return fail(TEGB_ERR_INVALID, "tegb_peer_create: bad argument (world <= %d)", TEGB_MAX_PEERS);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    RT_CHECK(cudaSetDevice(device));
+    tegb_peer *p = new tegb_peer();
+    p->device = device;
+    p->view.rank = rank; p->view.world = world; p->view.maxv = max_values;
+    p->box_bytes = sizeof(PeerSlot) * 2 * (size_t)world * max_values + 256;
+    if (cudaMalloc(&p->d_box, p->box_bytes) != cudaSuccess) { delete p; return fail(TEGB_ERR_CUDA, "cudaMalloc(mailbox) failed"); }
+    cudaMemset(p->d_box, 0, p->box_bytes);
+    cudaDeviceSynchronize();
+    p->view.err = (int *)((char *)p->d_box + sizeof(PeerSlot) * 2 * (size_t)world * max_values);
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, p->d_box) != cudaSuccess) {
+        cudaFree(p->d_box); delete p;
+        return fail(TEGB_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    memcpy(handle64, &h, 64);
+    *out = p;
+    return TEGB_OK;
+}
+
+/* handles: world x 64 bytes, the handle of rank r at offset 64 r (gathered by the caller, e.g. torch.distributed) */
+extern "C" int tegb_peer_connect(tegb_peer *p, const void *handles) {
+    if (!p || !handles) return fail(TEGB_ERR_INVALID, "tegb_peer_connect: null argument");
+    RT_CHECK(cudaSetDevice(p->device));
+    for (int r = 0; r < p->view.world; r++) {
+        if (r == p->view.rank) { p->view.box[r] = (PeerSlot *)p->d_box; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + 64 * r, 64);
+        void *ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(TEGB_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        p->opened.push_back(ptr);
+        p->view.box[r] = (PeerSlot *)ptr;
+    }
+    return TEGB_OK;
+}
+
+extern "C" int tegb_peer_allreduce_sum(tegb_peer *p, void *buf, int count, int elem_size, void *stream) {
+    if (!p || !buf || count < 0 || count > p->view.maxv || (elem_size != 4 && elem_size != 8))
+        return fail(TEGB_ERR_INVALID, "tegb_peer_allreduce_sum: bad argument");
+    if (count == 0) return TEGB_OK;
+    RT_CHECK(cudaSetDevice(p->device));
+    const unsigned long long seq = ++p->seq;
+    const int tb = 64, tg = (count + tb - 1) / tb;
+    if (elem_size == 4) peer_allreduce_kernel<float><<<tg, tb, 0, (cudaStream_t)stream>>>((float *)buf, count, p->view, seq);
+    else peer_allreduce_kernel<double><<<tg, tb, 0, (cudaStream_t)stream>>>((double *)buf, count, p->view, seq);
+    RT_CHECK(cudaGetLastError());
+    g_launches++;
+    return TEGB_OK;
+}
+
+/* 1 when some exchange gave up waiting for a peer (results of that call are invalid); synchronises the device */
+extern "C" int tegb_peer_error(tegb_peer *p) {
+    if (!p) return 1;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    int e = 0;
+    cudaMemcpy(&e, p->view.err, sizeof(int), cudaMemcpyDeviceToHost);
+    return e;
+}
+
+/* all ranks must have finished using the mailboxes (barrier) before any rank destroys its own */
+extern "C" void tegb_peer_destroy(tegb_peer *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    for (void *q : p->opened) cudaIpcCloseMemHandle(q);
+    if (p->d_box) cudaFree(p->d_box);
+    delete p;
+}
+
+/* reduce_outputs launches of `prog` deliver the sum over all ranks of `peer` (NULL restores local sums) */
+extern "C" int tegb_program_set_peer(tegb_program *prog, tegb_peer *peer) {
+    if (!prog) return fail(TEGB_ERR_INVALID, "tegb_program_set_peer: null program");
+    prog->peer = peer;
     return TEGB_OK;
 }
 

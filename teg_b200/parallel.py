@@ -5,6 +5,12 @@ blocks with no data-path collective; the value image stays sh
 per-parameter gradient vector [P] (P = 6..2304 numbers) is combined, with ONE all-reduce per step.
 ``torch.distributed`` (NCCL over NVLink on GPUs, gloo in the CPU tests) carries it; the C ABI offers the
 same operation without torch (tegb_nccl_comm_create / tegb_allreduce_sum).
+
+On one node the collective library can be left out of the step altogether: ``PeerGroup`` maps a small mailbox of
+every rank into every peer (CUDA IPC over NVLink / NVSwitch) and the runtime's last column-sum kernel writes the local
+sums straight into all mailboxes and adds the ranks' contributions in rank order (csrc/tegb200.cu,
+``colsum_stage2_peer``): no extra launch, a few microseconds instead of a collective's latency, and the same bits on
+every rank.  ``torch.distributed`` is used once, to gather the 64-byte IPC handles.
 """
 from __future__ import annotations
 
@@ -29,3 +35,66 @@ def allreduce_gradients(grad_sum, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(grad_sum, op=dist.ReduceOp.SUM, group=group)
     return grad_sum
+
+
+class PeerGroup:
+    """Mailboxes for the fused column-sum + all-reduce over NVLink peer memory (one node, <= 16 ranks).
+
+    ``attach(program)``: ``reduce`` launches of that compiled program return the sum over all ranks.
+    ``allreduce_(tensor)``: stand-alone in-place all-reduce of a small CUDA vector.
+    Every rank must make the same sequence of reducing calls.  ``close()`` synchronises the ranks first."""
+
+    def __init__(self, device: int, max_values: int = 64, group=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import runtime
+        assert dist.is_initialized(), 'PeerGroup needs an initialised torch.distributed process group'
+        self._L = runtime.lib()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = device
+        self.handle = ctypes.c_void_p()
+        mine = (ctypes.c_ubyte * 64)()
+        runtime.check(self._L.tegb_peer_create(self.rank, self.world, int(max_values), int(device),
+                                               ctypes.byref(self.handle), ctypes.cast(mine, ctypes.c_void_p)))
+        on_gpu = dist.get_backend(group) == 'nccl'
+        dev = torch.device('cuda', device) if on_gpu else torch.device('cpu')
+        t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=dev)
+        gathered = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(gathered, t, group=group)
+        blob = b''.join(bytes(g.cpu().tolist()) for g in gathered)
+        self._blob = ctypes.create_string_buffer(blob, len(blob))
+        runtime.check(self._L.tegb_peer_connect(self.handle, ctypes.cast(self._blob, ctypes.c_void_p)))
+        dist.barrier(group=group)           # every mailbox is mapped everywhere before anyone writes
+
+    def attach(self, program) -> None:
+        """program: a ``runtime.Program`` (``CUDA_EvalMode.compiled(...)[1]``, ``PreparedRender.prog``)"""
+        from . import runtime
+        runtime.check(self._L.tegb_program_set_peer(program.handle, self.handle))
+
+    def detach(self, program) -> None:
+        from . import runtime
+        runtime.check(self._L.tegb_program_set_peer(program.handle, None))
+
+    def allreduce_(self, tensor, stream: int = 0):
+        import ctypes
+        from . import runtime
+        assert tensor.is_cuda and tensor.is_contiguous() and tensor.element_size() in (4, 8)
+        runtime.check(self._L.tegb_peer_allreduce_sum(self.handle, ctypes.c_void_p(tensor.data_ptr()),
+                                                      int(tensor.numel()), int(tensor.element_size()),
+                                                      ctypes.c_void_p(stream)))
+        return tensor
+
+    def check(self) -> None:
+        """Raises if an exchange timed out waiting for a peer (synchronises the device)."""
+        if self._L.tegb_peer_error(self.handle):
+            raise RuntimeError('peer all-reduce: a rank did not arrive within the time-out')
+
+    def close(self) -> None:
+        import torch.distributed as dist
+        if self.handle:
+            self.check()
+            dist.barrier(group=self.group)
+            self._L.tegb_peer_destroy(self.handle)
+            self.handle = None

@@ -37,7 +37,8 @@ SYMBOLS = [
     'tegb_last_error', 'tegb_version', 'tegb_nvrtc_version', 'tegb_device_count', 'tegb_compile', 'tegb_module_from_cubin',
     'tegb_module_cubin', 'tegb_module_log', 'tegb_module_destroy', 'tegb_program_create',
     'tegb_program_destroy', 'tegb_program_launch', 'tegb_program_eval_host', 'tegb_render_launch',
-    'tegb_render_groups_launch', 'tegb_program_tile_table',
+    'tegb_render_groups_launch', 'tegb_program_tile_table', 'tegb_peer_create', 'tegb_peer_connect',
+    'tegb_peer_allreduce_sum', 'tegb_peer_error', 'tegb_peer_destroy', 'tegb_program_set_peer',
     'tegb_launch_count', 'tegb_reduce_workspace_bytes', 'tegb_reduce_sum', 'tegb_nccl_unique_id',
     'tegb_nccl_comm_create', 'tegb_nccl_comm_destroy', 'tegb_allreduce_sum', 'tegb_fma_peak',
 ]
@@ -79,6 +80,13 @@ def lib():
     L.tegb_render_groups_launch.argtypes = [vp, ctypes.POINTER(vp), i32, i32, ctypes.POINTER(Grid), vp, i32, i32,
                                             ctypes.POINTER(vp), ctypes.POINTER(vp), vp]
     L.tegb_program_tile_table.argtypes = [vp, vp, ctypes.c_size_t, vp]
+    L.tegb_peer_create.argtypes = [i32, i32, i32, i32, ctypes.POINTER(vp), vp]
+    L.tegb_peer_connect.argtypes = [vp, vp]
+    L.tegb_peer_allreduce_sum.argtypes = [vp, vp, i32, i32, vp]
+    L.tegb_peer_error.argtypes = [vp]
+    L.tegb_peer_destroy.argtypes = [vp]
+    L.tegb_peer_destroy.restype = None
+    L.tegb_program_set_peer.argtypes = [vp, vp]
     L.tegb_launch_count.restype = i64
     L.tegb_reduce_workspace_bytes.argtypes = [i32, i64, i32]
     L.tegb_reduce_workspace_bytes.restype = ctypes.c_size_t
