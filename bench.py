@@ -242,6 +242,8 @@ def main() -> int:
                  for b in range(2)]
     # the gradient pipeline is the longer one (and ends in the all-reduce): its blocks get priority
     side = torch.cuda.Stream(dev, priority=-1)
+    forks = [torch.cuda.Event() for _ in range(2)]
+    joins = [torch.cuda.Event() for _ in range(2)]
     peers = None
     if world > 1 and args.allreduce == 'peer' and m_fused is None:
         from teg_b200.parallel import PeerGroup
@@ -268,19 +270,18 @@ def main() -> int:
                 ev['primal'].append((e[0], e[1]))
                 ev['grad'].append((e[0], e[1]))
             return
-        fork = torch.cuda.Event()
+        fork, join = forks[buf], joins[buf]
         fork.record(stream)
         side.wait_event(fork)
-        with torch.cuda.stream(side):
-            if record:
-                e[2].record(side)
-            pr_grad[buf].run(side_ptr)
-            if world > 1 and peers is None:
+        if record:
+            e[2].record(side)
+        pr_grad[buf].run(side_ptr)
+        if world > 1 and peers is None:
+            with torch.cuda.stream(side):
                 dist.all_reduce(gsums[buf])        # enqueued behind the gradient on `side`
-            if record:
-                e[3].record(side)
-            join = torch.cuda.Event()
-            join.record(side)
+        if record:
+            e[3].record(side)
+        join.record(side)
         if record:
             e[0].record(stream)
         pr_primal[buf].run(sptr)
