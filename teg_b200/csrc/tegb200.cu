@@ -422,30 +422,34 @@ struct PeerView {
     int *err;                           // set when a peer did not answer within the time-out
 };
 
+// called by all 32 lanes of one warp; `value` is taken from lane 0; every lane returns the sum.  Lane p serves peer p
+// (stores / polls run in parallel over the ranks), the contributions are then added in rank order.
 template <typename T>
 __device__ __forceinline__ T peer_exchange_sum(const PeerView &v, int col, T value, unsigned long long seq) {
+    const int lane = threadIdx.x & 31;
     const int bank = (int)(seq & 1ull);
+    value = __shfl_sync(0xffffffffu, value, 0);
     unsigned long long bits = 0;
     if (sizeof(T) == 4) bits = (unsigned long long)__float_as_uint((float)value);
     else bits = (unsigned long long)__double_as_longlong((double)value);
     const size_t mine = ((size_t)bank * v.world + v.rank) * v.maxv + col;
-    for (int p = 0; p < v.world; ++p) *(volatile unsigned long long *)&v.box[p][mine].bits = bits;
+    if (lane < v.world) *(volatile unsigned long long *)&v.box[lane][mine].bits = bits;
     __threadfence_system();
-    for (int p = 0; p < v.world; ++p) *(volatile unsigned long long *)&v.box[p][mine].seq = seq;
-    T acc = 0;
-    for (int r = 0; r < v.world; ++r) {
-        PeerSlot *s = &v.box[v.rank][((size_t)bank * v.world + r) * v.maxv + col];
+    if (lane < v.world) *(volatile unsigned long long *)&v.box[lane][mine].seq = seq;
+    T x = 0;
+    if (lane < v.world) {
+        PeerSlot *s = &v.box[v.rank][((size_t)bank * v.world + lane) * v.maxv + col];
         const long long t0 = clock64();
         while (*(volatile unsigned long long *)&s->seq != seq) {
             if (clock64() - t0 > 4000000000ll) { *v.err = 1; break; }     // ~2 s: a peer is gone; do not hang the GPU
         }
         __threadfence_system();
         const unsigned long long b = *(volatile unsigned long long *)&s->bits;
-        T x;
         if (sizeof(T) == 4) x = (T)__uint_as_float((unsigned int)b);
         else x = (T)__longlong_as_double((long long)b);
-        acc = (r == 0) ? x : acc + x;
     }
+    T acc = __shfl_sync(0xffffffffu, x, 0);
+    for (int r = 1; r < v.world; ++r) acc = acc + __shfl_sync(0xffffffffu, x, r);
     return acc;
 }
 
@@ -458,14 +462,19 @@ __global__ void __launch_bounds__(RED_THREADS) colsum_stage2_peer(const T *parti
     T acc = 0;
     for (long long i = threadIdx.x; i < n_blocks; i += RED_THREADS) acc = acc + partials[(long long)c * n_blocks + i];
     T s = block_sum_fixed(acc, smem);
-    if (threadIdx.x == 0) out[c] = peer_exchange_sum<T>(view, c, s, seq);
+    if (threadIdx.x < 32) {
+        const T total = peer_exchange_sum<T>(view, c, s, seq);
+        if (threadIdx.x == 0) out[c] = total;
+    }
 }
 
-// stand-alone form: in-place all-reduce of a device vector (count <= maxv)
+// stand-alone form: in-place all-reduce of a device vector (count <= maxv), one warp per element
 template <typename T>
 __global__ void peer_allreduce_kernel(T *buf, int count, PeerView view, unsigned long long seq) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < count) buf[c] = peer_exchange_sum<T>(view, c, buf[c], seq);
+    const int c = blockIdx.x;
+    if (c >= count) return;
+    const T total = peer_exchange_sum<T>(view, c, buf[c], seq);
+    if (threadIdx.x == 0) buf[c] = total;
 }
 
 struct tegb_peer {
@@ -533,7 +542,7 @@ template <typename T>
 static void sum_columns_peer(const T *partials, int n_cols, unsigned long long n_blocks, T *out, T *slices, cudaStream_t st,
                              tegb_peer *peer) {
     const unsigned long long seq = ++peer->seq;
-    if (n_blocks >= 4096) {
+    if (n_blocks >= 16384 && slices) {
         const long long chunk = (long long)((n_blocks + RED_SLICES - 1) / RED_SLICES);
         colsum_slices<T><<<dim3(RED_SLICES, n_cols), RED_THREADS, 0, st>>>(partials, (long long)n_blocks, chunk, slices);
         colsum_stage2_peer<T><<<n_cols, RED_THREADS, 0, st>>>(slices, (long long)RED_SLICES, out, peer->view, seq);
@@ -983,6 +992,7 @@ extern "C" int tegb_peer_create(int rank, int world, int max_values, int device,
     if (!out || !handle64 || world < 1 || world > TEGB_MAX_PEERS || rank < 0 || rank >= world || max_values < 1)
         return fail(TEGB_ERR_INVALID, "tegb_peer_create: bad argument (world <= %d)", TEGB_MAX_PEERS);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    static_assert(TEGB_MAX_PEERS <= 32, "one lane per peer");
     RT_CHECK(cudaSetDevice(device));
     tegb_peer *p = new tegb_peer();
     p->device = device;
@@ -1025,7 +1035,7 @@ extern "C" int tegb_peer_allreduce_sum(tegb_peer *p, void *buf, int count, int e
     if (count == 0) return TEGB_OK;
     RT_CHECK(cudaSetDevice(p->device));
     const unsigned long long seq = ++p->seq;
-    const int tb = 64, tg = (count + tb - 1) / tb;
+    const int tb = 32, tg = count;
     if (elem_size == 4) peer_allreduce_kernel<float><<<tg, tb, 0, (cudaStream_t)stream>>>((float *)buf, count, p->view, seq);
     else peer_allreduce_kernel<double><<<tg, tb, 0, (cudaStream_t)stream>>>((double *)buf, count, p->view, seq);
     RT_CHECK(cudaGetLastError());
