@@ -11,7 +11,8 @@ integral (256 samples per pixel for the value, 16 per active delta term for the 
 One *step* = one pass over the whole batch: value image, per-pixel gradients, and the per-parameter
 gradient sum (+ one NCCL all-reduce of the 6-vector when N > 1).  One *integral evaluation* = one
 pixel instance (value + its reverse derivative).  Multi-GPU is weak scaling: the image grows to
-(4096 N) x 4096 pixels over the same domain and rank r owns rows [4096 r, 4096 (r+1)).
+(4096 N) x 4096 pixels over the same domain and rank r owns the tile rows r, r + N, ... (16 pixel rows each;
+--shard band gives it the contiguous rows [4096 r, 4096 (r+1)) instead).
 
 Nothing here reads /root/reference: programs come from tests/golden/programs/*.tegp, the CPU
 baseline from oracle/_ref/*.so (the reference's own generated C, built where the reference exists)
@@ -179,6 +180,8 @@ def main() -> int:
     ap.add_argument('--tile-rows', type=int, default=16, help='pixel rows per render block / classification tile')
     ap.add_argument('--allreduce', default='peer', choices=['peer', 'nccl'], help='N > 1: gradient all-reduce fused '
                     'into the column-sum kernel over NVLink peer memory (default), or a separate NCCL all-reduce')
+    ap.add_argument('--shard', default='interleave', choices=['interleave', 'band'],
+                    help='N > 1: how the pixel rows are split over the ranks')
     ap.add_argument('--cull', type=int, default=1, help='0: dense kernels (every comparison at every sample); '
                     '1: domain culling (teg_b200/cull.py, bit-identical results)')
     args = ap.parse_args()
@@ -207,8 +210,14 @@ def main() -> int:
         dist.init_process_group('nccl', device_id=dev)
 
     res = args.res
-    res_x_total = res * world                  # weak scaling: rank r owns rows [res*r, res*(r+1))
-    rows = (res * rank, res * (rank + 1))
+    res_x_total = res * world                  # weak scaling: the image grows to (res * world) x res pixels
+    # --shard band: rank r owns rows [res*r, res*(r+1)); --shard interleave (default): rank r owns the tile rows
+    # r, r + world, ... (16 pixel rows each), so every rank gets the same mix of interior / exterior / edge tiles
+    if args.shard == 'band' or world == 1:
+        rows, inter = (res * rank, res * (rank + 1)), (1, 0)
+    else:
+        assert res % args.tile_rows == 0, 'interleaved sharding wants res divisible by the tile height'
+        rows, inter = (0, res_x_total), (world, rank)
     n_local = res * res
     primal = Program.loads(load_text('tri_primal'))
     grad = Program.loads(load_text('tri_grad'))
@@ -236,9 +245,10 @@ def main() -> int:
     ev = {k: [] for k in ('primal', 'grad')}
 
     # bound launches (one C-ABI call each); the fused bundle keeps the generic render() call
-    pr_grad = [m_grad.prepare_render(box, (res_x_total, res), bounds, gparams, rows=rows, out=gsums[b], reduce=True)
+    pr_grad = [m_grad.prepare_render(box, (res_x_total, res), bounds, gparams, rows=rows, out=gsums[b], reduce=True,
+                                     interleave=inter)
                for b in range(2)]
-    pr_primal = [m_primal.prepare_render(box, (res_x_total, res), bounds, params, rows=rows, out=imgs[b])
+    pr_primal = [m_primal.prepare_render(box, (res_x_total, res), bounds, params, rows=rows, out=imgs[b], interleave=inter)
                  for b in range(2)]
     # the gradient pipeline is the longer one (and ends in the all-reduce): its blocks get priority
     side = torch.cuda.Stream(dev, priority=-1)
@@ -261,7 +271,7 @@ def main() -> int:
             if record:
                 e[0].record(stream)
             m_fused.render(box, (res_x_total, res), bounds, gparams, rows=rows, out=(imgs[buf], gsums[buf]),
-                           stream=sptr, reduce=6)
+                           stream=sptr, reduce=6, interleave=inter)
             if record:
                 e[1].record(stream)
             if world > 1:
@@ -433,7 +443,7 @@ def main() -> int:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         flush.fill_(k & 0xff)
         a.record(stream)
-        m_dense.render(box, (res_x_total, res), bounds, params, rows=rows, out=imgs[1], stream=sptr)
+        m_dense.render(box, (res_x_total, res), bounds, params, rows=rows, out=imgs[1], stream=sptr, interleave=inter)
         b.record(stream)
         if k >= 3:
             dense_ev.append((a, b))
@@ -508,7 +518,7 @@ def main() -> int:
                    'programs': ['tri_primal', 'tri_grad'], 'fused_kernel': bool(args.fused), 'cull': bool(args.cull), 'outputs': 'value image [4096,4096] + per-parameter '
                    'gradient sum [6] (reduced in-kernel)', 'l2': 'L2 flushed between timed steps by writing a '
                    '256 MB buffer (outside the per-step event pairs); inputs are generated from the pixel index',
-                   'parallelism': f'rows sharded over {world} GPU(s), one all-reduce of the [6] gradient per step ('
+                   'parallelism': f'rows sharded over {world} GPU(s) ({args.shard if world > 1 else "all"}), one all-reduce of the [6] gradient per step ('
                                   + ('fused into the column-sum kernel over NVLink peer memory' if peers is not None else 'NCCL')
                                   + '), on the gradient stream next to the value kernel'},
         'phase_ms': phase_ms, 'phase_note': 'the value and the gradient pipelines run concurrently on two streams: '

@@ -126,6 +126,12 @@ int tegb_program_eval_host(tegb_program *p, const double *scalars, const void *c
  * index; out_ptrs[k] receive (row_end-row_begin)*res_y elements. */
 int tegb_render_launch(tegb_program *p, const double *scalars, const tegb_grid *grid,
                        void *const *out_ptrs, void *stream);
+/* the same, restricted to the tile rows tile_phase, tile_phase + tile_stride, ... of the row range (a tile row =
+ * tile_rows consecutive pixel rows): interleaved sharding over ranks (tile_stride = world size, tile_phase = rank), which
+ * gives every rank the same mix of cheap and expensive tiles.  The output images hold the rendered rows only, compact
+ * and in order. */
+int tegb_render_launch_strided(tegb_program *p, const double *scalars, const tegb_grid *grid, int tile_stride,
+                               int tile_phase, void *const *out_ptrs, void *stream);
 /* diagnostics: copies the tri-states written by the last tegb_render_launch of a program with tile conditions
  * (condition-major, [n_tile_conds][tiles], element type of the program) to host memory */
 int tegb_program_tile_table(tegb_program *p, void *host_out, size_t nbytes, void *stream);

@@ -1184,7 +1184,8 @@ class Emitter:
                 # one block = one tile: block_size columns x tile_rows rows; every thread walks its column's rows
                 # (the per-block set-up, the tile tri-states and the block sum are paid once per tile)
                 mparams = ', '.join(['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
-                                     'const int row0', 'const int n_rows', 'const int tile_rows'] +
+                                     'const int row0', 'const int n_rows', 'const int tile_rows', 'const int row_stride',
+                                     'const int row_phase'] +
                                     (['const T* __restrict__ tiles', 'const int* __restrict__ order'] if tile else []) +
                                     outs_decl)
                 src.append(f'extern "C" __global__ void __launch_bounds__({bs}) {name}_main({mparams}) {{')
@@ -1217,10 +1218,12 @@ class Emitter:
                     call = ', '.join((['live'] if with_live else []) + [loads[a] for a in varying] + ['res'])
                     src.append(f'{ind}#pragma unroll 1')
                     src.append(f'{ind}for (int r = 0; r < tile_rows; ++r) {{')
-                    src.append(f'{ind}    const int rel = tby * tile_rows + r;')
+                    # local tile row tby is tile row tby * row_stride + row_phase of the row range (interleaved
+                    # sharding: rank r renders tile rows r, r + world, ...); the local image is compact
+                    src.append(f'{ind}    const int rel = (tby * row_stride + row_phase) * tile_rows + r;')
                     src.append(f'{ind}    if (rel >= n_rows) break;')
                     src.append(f'{ind}    const int nx = row0 + rel;')
-                    src.append(f'{ind}    const long long i = (long long)rel * res_y + ny;')
+                    src.append(f'{ind}    const long long i = (long long)(tby * tile_rows + r) * res_y + ny;')
                     src.append(f'{ind}    T res[{K}];')
                     if nr:
                         src.append(f'{ind}    for (int k = 0; k < {K}; k++) res[k] = {zero};')

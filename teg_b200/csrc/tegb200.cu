@@ -289,6 +289,7 @@ struct tegb_program {
     void *d_ranges = nullptr;
     size_t ranges_bytes = 0;
     tegb_grid ranges_grid{};
+    int ranges_stride = 1, ranges_phase = 0;
     bool ranges_valid = false;
     // pixel-edge tables for tegb_render_launch
     void *d_xe = nullptr, *d_ye = nullptr;
@@ -699,14 +700,15 @@ static int ensure_edges(tegb_program *p, const tegb_grid *g, CUstream st) {
 // of the walk is.  7 values per entry: lb_lo lb_hi ub_lo ub_hi s_lo s_hi poison.  One warp per entry.
 template <typename T>
 __global__ void tile_ranges(const T *__restrict__ xe, const T *__restrict__ ye, int res_y, int row0, int n_rows,
-                            int tile_rows, int tile_cols, int num_samples, int n_tx, int n_ty, T *__restrict__ out) {
+                            int tile_rows, int tile_cols, int num_samples, int n_tx, int n_ty, int row_stride,
+                            int row_phase, T *__restrict__ out) {
     const int e = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (e >= n_tx + n_ty) return;
     const bool is_x = e < n_ty;
     const T *tab = is_x ? xe : ye;
     int first, last;
-    if (is_x) { first = row0 + e * tile_rows; last = min(first + tile_rows, row0 + n_rows); }
+    if (is_x) { first = row0 + (e * row_stride + row_phase) * tile_rows; last = min(first + tile_rows, row0 + n_rows); }
     else { first = (e - n_ty) * tile_cols; last = min(first + tile_cols, res_y); }
     T lb_lo = tab[first], lb_hi = tab[first], ub_lo = tab[first + 1], ub_hi = tab[first + 1];
     T s_lo = tab[first], s_hi = tab[first], pz = (T)0;
@@ -732,9 +734,10 @@ __global__ void tile_ranges(const T *__restrict__ xe, const T *__restrict__ ye, 
     }
 }
 
-static int ensure_ranges(tegb_program *p, const tegb_grid *g, int n_tx, int n_ty, cudaStream_t st) {
+static int ensure_ranges(tegb_program *p, const tegb_grid *g, int n_tx, int n_ty, int row_stride, int row_phase,
+                         cudaStream_t st) {
     const tegb_grid &c = p->ranges_grid;
-    if (p->ranges_valid && c.x_lo == g->x_lo && c.x_hi == g->x_hi && c.y_lo == g->y_lo && c.y_hi == g->y_hi &&
+    if (p->ranges_valid && p->ranges_stride == row_stride && p->ranges_phase == row_phase && c.x_lo == g->x_lo && c.x_hi == g->x_hi && c.y_lo == g->y_lo && c.y_hi == g->y_hi &&
         c.res_x == g->res_x && c.res_y == g->res_y && c.row_begin == g->row_begin && c.row_end == g->row_end)
         return TEGB_OK;
     const size_t need = (size_t)(n_tx + n_ty) * 7 * p->d.elem_size;
@@ -748,13 +751,15 @@ static int ensure_ranges(tegb_program *p, const tegb_grid *g, int n_tx, int n_ty
     const unsigned tb = 128, tg = (unsigned)(((size_t)(n_tx + n_ty) * 32 + tb - 1) / tb);
     if (p->d.elem_size == 4)
         tile_ranges<float><<<tg, tb, 0, st>>>((const float *)p->d_xe, (const float *)p->d_ye, g->res_y, g->row_begin, n_rows,
-                                             p->d.tile_rows, p->d.block_size, p->d.tile_samples, n_tx, n_ty, (float *)p->d_ranges);
+                                             p->d.tile_rows, p->d.block_size, p->d.tile_samples, n_tx, n_ty, row_stride, row_phase, (float *)p->d_ranges);
     else
         tile_ranges<double><<<tg, tb, 0, st>>>((const double *)p->d_xe, (const double *)p->d_ye, g->res_y, g->row_begin, n_rows,
-                                              p->d.tile_rows, p->d.block_size, p->d.tile_samples, n_tx, n_ty, (double *)p->d_ranges);
+                                              p->d.tile_rows, p->d.block_size, p->d.tile_samples, n_tx, n_ty, row_stride, row_phase, (double *)p->d_ranges);
     RT_CHECK(cudaGetLastError());
     g_launches++;
     p->ranges_grid = *g;
+    p->ranges_stride = row_stride;
+    p->ranges_phase = row_phase;
     p->ranges_valid = true;
     return TEGB_OK;
 }
@@ -838,9 +843,19 @@ extern "C" int tegb_render_groups_launch(tegb_program *p, const void *const *gro
     return TEGB_OK;
 }
 
+extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars, const tegb_grid *g, int tile_stride,
+                                          int tile_phase, void *const *out_ptrs, void *stream);
+
 extern "C" int tegb_render_launch(tegb_program *p, const double *scalars, const tegb_grid *g,
                                   void *const *out_ptrs, void *stream) {
+    return tegb_render_launch_strided(p, scalars, g, 1, 0, out_ptrs, stream);
+}
+
+extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars, const tegb_grid *g, int tile_stride,
+                                          int tile_phase, void *const *out_ptrs, void *stream) {
     if (!p || !g || !out_ptrs) return fail(TEGB_ERR_INVALID, "tegb_render_launch: bad argument");
+    if (tile_stride < 1 || tile_phase < 0 || tile_phase >= tile_stride)
+        return fail(TEGB_ERR_INVALID, "tegb_render_launch_strided: need 0 <= tile_phase < tile_stride");
     if (p->d.n_grid_args != 4 || p->d.n_array_args != 0 || p->d.grouped)
         return fail(TEGB_ERR_INVALID, "not a plain render program (needs exactly the 4 pixel-box arguments on the grid)");
     if (g->res_x < 1 || g->res_y < 1 || g->row_begin < 0 || g->row_end > g->res_x || g->row_begin > g->row_end)
@@ -864,10 +879,15 @@ extern "C" int tegb_render_launch(tegb_program *p, const double *scalars, const 
     // one block per tile of block_size columns x tile_rows rows
     int tile_rows = p->d.tile_rows > 0 ? p->d.tile_rows : 1;
     int n_rows = g->row_end - g->row_begin;
-    const unsigned gy = (unsigned)((n_rows + tile_rows - 1) / tile_rows);
+    // tile rows tile_phase, tile_phase + tile_stride, ... of the row range are rendered by this launch
+    const int n_tr = (n_rows + tile_rows - 1) / tile_rows;
+    if (tile_phase >= n_tr) return TEGB_OK;
+    const unsigned gy = (unsigned)((n_tr - tile_phase + tile_stride - 1) / tile_stride);
     if (gy > 65535u) return fail(TEGB_ERR_INVALID, "more than 65535 tile rows in one render launch");
     args.push_back(&n_rows);
     args.push_back(&tile_rows);
+    args.push_back(&tile_stride);
+    args.push_back(&tile_phase);
     if (p->d.n_tile_conds > 0) {
         // classify the tiles for these launch-wide arguments and this band
         int n_tx = (int)gx, n_ty = (int)gy;
@@ -886,7 +906,7 @@ extern "C" int tegb_render_launch(tegb_program *p, const double *scalars, const 
             if (p->d.elem_size == 4) { sf[i] = (float)scalars[i]; targs.push_back(&sf[i]); }
             else { sd[i] = scalars[i]; targs.push_back(&sd[i]); }
         }
-        rc = ensure_ranges(p, g, n_tx, n_ty, (cudaStream_t)st);
+        rc = ensure_ranges(p, g, n_tx, n_ty, tile_stride, tile_phase, (cudaStream_t)st);
         if (rc) return rc;
         const size_t n_tiles = (size_t)n_tx * n_ty;
         if (n_tiles > p->order_count) {

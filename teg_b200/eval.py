@@ -376,7 +376,8 @@ class CUDA_EvalMode(EvalMode):
 
     # ------------------------------------------------------------------- render
     def prepare_render(self, box_vars, res: Tuple[int, int], bounds=((0, 1), (0, 1)), bindings=None,
-                       rows: Optional[Tuple[int, int]] = None, out=None, reduce: bool = False) -> "PreparedRender":
+                       rows: Optional[Tuple[int, int]] = None, out=None, reduce: bool = False,
+                       interleave: Tuple[int, int] = (1, 0)) -> "PreparedRender":
         """``render`` bound once (arguments resolved, output allocated): the returned object's ``run(stream)`` costs
         one C call.  Same arguments and output conventions as ``render`` (bundles with 0 < reduce < k excluded)."""
         import torch
@@ -395,22 +396,28 @@ class CUDA_EvalMode(EvalMode):
         r0, r1 = (0, res[0]) if rows is None else rows
         tdt = torch.float32 if self.float_width == 'float' else torch.float64
         dev = torch.device('cuda', self.device)
+        n_local = len(interleaved_rows(r1 - r0, ks.tile_rows, *interleave)) if tuple(interleave) != (1, 0) else r1 - r0
         if out is None:
             out = (torch.empty(ks.n_outputs, dtype=tdt, device=dev) if ks.reduce_outputs
-                   else torch.empty((ks.n_outputs, r1 - r0, res[1]), dtype=tdt, device=dev))
+                   else torch.empty((ks.n_outputs, n_local, res[1]), dtype=tdt, device=dev))
+        assert ks.reduce_outputs or (out.shape[1] == n_local and out.is_contiguous()), 'output image has the wrong rows'
         ptrs = [out.data_ptr()] if ks.reduce_outputs else [out[k].data_ptr() for k in range(ks.n_outputs)]
         grid = runtime.Grid(float(bounds[0][0]), float(bounds[0][1]), float(bounds[1][0]), float(bounds[1][1]),
                             int(res[0]), int(res[1]), int(r0), int(r1))
-        return PreparedRender(self, ks, prog, scalars, grid, out, ptrs)
+        return PreparedRender(self, ks, prog, scalars, grid, out, ptrs, interleave)
 
     def render(self, box_vars, res: Tuple[int, int], bounds=((0, 1), (0, 1)), bindings=None,
-               rows: Optional[Tuple[int, int]] = None, out=None, stream: int = 0, reduce: bool = False):
+               rows: Optional[Tuple[int, int]] = None, out=None, stream: int = 0, reduce: bool = False,
+               interleave: Tuple[int, int] = (1, 0)):
         """Evaluate over the pixel grid of tests/plot.py:8-29 with on-device pixel boxes.
 
         box_vars: (x_lb, x_ub, y_lb, y_ub) Vars or labels.  Returns a torch CUDA tensor
         [k, rows, res_y] (k = program outputs), or [k] sums over the pixels when ``reduce`` is True; with
         ``reduce=r`` (an int < k, for value + derivative bundles) the pair (images [k - r, rows, res_y],
-        sums [r]).  Asynchronous on ``stream``."""
+        sums [r]).  Asynchronous on ``stream``.
+        interleave=(stride, phase): only the tile rows phase, phase + stride, ... of the row range (interleaved
+        sharding over ranks: every rank gets the same mix of tiles); the image then holds those rows, compact
+        (``interleaved_rows`` lists them)."""
         import torch
         labels = [v if isinstance(v, str) else label_of(v) for v in box_vars]
         pos = {lab: i for i, (lab, _) in enumerate(self.arglist)}
@@ -430,43 +437,57 @@ class CUDA_EvalMode(EvalMode):
         dev = torch.device('cuda', self.device)
         nr = ks.reduce_outputs
         n_store = ks.n_outputs - nr
+        n_local = len(interleaved_rows(r1 - r0, ks.tile_rows, *interleave)) if tuple(interleave) != (1, 0) else r1 - r0
         grid = runtime.Grid(float(bounds[0][0]), float(bounds[0][1]), float(bounds[1][0]), float(bounds[1][1]),
                             int(res[0]), int(res[1]), int(r0), int(r1))
         if 0 < nr < ks.n_outputs:
             # bundle: the leading outputs are images, the trailing ``reduce`` outputs are summed over the pixels
             imgs, sums = out if out is not None else (None, None)
             if imgs is None:
-                imgs = torch.empty((n_store, r1 - r0, res[1]), dtype=tdt, device=dev)
+                imgs = torch.empty((n_store, n_local, res[1]), dtype=tdt, device=dev)
             if sums is None:
                 sums = torch.empty(nr, dtype=tdt, device=dev)
-            prog.render(scalars, grid, [imgs[k].data_ptr() for k in range(n_store)] + [sums.data_ptr()], stream=stream)
+            prog.render(scalars, grid, [imgs[k].data_ptr() for k in range(n_store)] + [sums.data_ptr()], stream=stream,
+                        interleave=interleave)
             return imgs, sums
         if out is None:
             out = (torch.empty(ks.n_outputs, dtype=tdt, device=dev) if nr
-                   else torch.empty((ks.n_outputs, r1 - r0, res[1]), dtype=tdt, device=dev))
+                   else torch.empty((ks.n_outputs, n_local, res[1]), dtype=tdt, device=dev))
         ptrs = [out.data_ptr()] if nr else [out[k].data_ptr() for k in range(ks.n_outputs)]
-        prog.render(scalars, grid, ptrs, stream=stream)
+        prog.render(scalars, grid, ptrs, stream=stream, interleave=interleave)
         return out
+
+
+def interleaved_rows(n_rows: int, tile_rows: int, stride: int, phase: int) -> List[int]:
+    """Row indices (relative to the row range) rendered with ``interleave=(stride, phase)``: tile rows phase,
+    phase + stride, ... of ``tile_rows`` pixel rows each, in the order of the compact output image."""
+    out: List[int] = []
+    n_tr = -(-n_rows // tile_rows)
+    for t in range(phase, n_tr, stride):
+        out.extend(range(t * tile_rows, min((t + 1) * tile_rows, n_rows)))
+    return out
 
 
 class PreparedRender:
     """A bound ``render`` (see ``CUDA_EvalMode.prepare_render``): ``run(stream)`` is one C-ABI call
     (``tegb_render_launch``) with pre-marshalled arguments; ``set_scalars`` rebinds the launch-wide arguments."""
 
-    def __init__(self, mode, ks, prog, scalars, grid, out, ptrs):
+    def __init__(self, mode, ks, prog, scalars, grid, out, ptrs, interleave=(1, 0)):
         self.mode, self.ks, self.prog, self.out = mode, ks, prog, out
         self._grid = grid
         self._scalars = runtime._dbl_array(scalars)
         self._ptrs = runtime._ptr_array(ptrs)
-        self._fn = runtime.lib().tegb_render_launch
+        self._fn = runtime.lib().tegb_render_launch_strided
         self._h = prog.handle
+        self._stride, self._phase = int(interleave[0]), int(interleave[1])
 
     def set_scalars(self, values: Sequence[float]) -> None:
         """New values for the scalar arguments, in ``ks.scalar_args`` order."""
         self._scalars = runtime._dbl_array(values)
 
     def run(self, stream: int = 0):
-        runtime.check(self._fn(self._h, self._scalars, ctypes.byref(self._grid), self._ptrs, ctypes.c_void_p(stream)))
+        runtime.check(self._fn(self._h, self._scalars, ctypes.byref(self._grid), self._stride, self._phase, self._ptrs,
+                               ctypes.c_void_p(stream)))
         return self.out
 
 

@@ -37,7 +37,7 @@ SYMBOLS = [
     'tegb_last_error', 'tegb_version', 'tegb_nvrtc_version', 'tegb_device_count', 'tegb_compile', 'tegb_module_from_cubin',
     'tegb_module_cubin', 'tegb_module_log', 'tegb_module_destroy', 'tegb_program_create',
     'tegb_program_destroy', 'tegb_program_launch', 'tegb_program_eval_host', 'tegb_render_launch',
-    'tegb_render_groups_launch', 'tegb_program_tile_table', 'tegb_peer_create', 'tegb_peer_connect',
+    'tegb_render_launch_strided', 'tegb_render_groups_launch', 'tegb_program_tile_table', 'tegb_peer_create', 'tegb_peer_connect',
     'tegb_peer_allreduce_sum', 'tegb_peer_error', 'tegb_peer_destroy', 'tegb_program_set_peer',
     'tegb_launch_count', 'tegb_reduce_workspace_bytes', 'tegb_reduce_sum', 'tegb_nccl_unique_id',
     'tegb_nccl_comm_create', 'tegb_nccl_comm_destroy', 'tegb_allreduce_sum', 'tegb_fma_peak',
@@ -80,6 +80,8 @@ def lib():
     L.tegb_render_groups_launch.argtypes = [vp, ctypes.POINTER(vp), i32, i32, ctypes.POINTER(Grid), vp, i32, i32,
                                             ctypes.POINTER(vp), ctypes.POINTER(vp), vp]
     L.tegb_program_tile_table.argtypes = [vp, vp, ctypes.c_size_t, vp]
+    L.tegb_render_launch_strided.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(Grid), i32, i32,
+                                             ctypes.POINTER(vp), vp]
     L.tegb_peer_create.argtypes = [i32, i32, i32, i32, ctypes.POINTER(vp), vp]
     L.tegb_peer_connect.argtypes = [vp, vp]
     L.tegb_peer_allreduce_sum.argtypes = [vp, vp, i32, i32, vp]
@@ -218,9 +220,11 @@ class Program:
         check(self._L.tegb_program_eval_host(self.handle, _dbl_array(scalars), _ptr_array(host_in),
                                              _ptr_array(host_out), n))
 
-    def render(self, scalars: Sequence[float], grid: Grid, out_ptrs: Sequence[int], stream: int = 0) -> None:
-        check(self._L.tegb_render_launch(self.handle, _dbl_array(scalars), ctypes.byref(grid),
-                                         _ptr_array(out_ptrs), ctypes.c_void_p(stream)))
+    def render(self, scalars: Sequence[float], grid: Grid, out_ptrs: Sequence[int], stream: int = 0,
+               interleave=(1, 0)) -> None:
+        check(self._L.tegb_render_launch_strided(self.handle, _dbl_array(scalars), ctypes.byref(grid),
+                                                 int(interleave[0]), int(interleave[1]),
+                                                 _ptr_array(out_ptrs), ctypes.c_void_p(stream)))
 
     def render_groups(self, group_ptrs: Sequence[int], group_begin: int, group_count: int, grid: Grid,
                       windows_ptr: int, max_rows: int, max_cols: int, pixel_ptrs: Sequence[int],

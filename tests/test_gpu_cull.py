@@ -263,3 +263,36 @@ def test_tile_classification_resolves_most_tiles(cuda_device):
     frac = float(np.mean(tiles == 2))
     assert set(np.unique(tiles)) <= {0.0, 1.0, 2.0} and 0.01 < frac < 0.2, frac
     assert 0.1 < float(np.mean(tiles == 1)) < 0.3           # the triangle covers 23 % of the square
+
+
+def test_interleaved_tile_rows_tile_the_image(cuda_device):
+    """interleave=(stride, phase) renders tile rows phase, phase + stride, ...: the pieces of all phases reassemble
+    to the contiguous render bit for bit (value image, per-pixel gradients), and the summed gradients add up."""
+    import torch
+    from teg_b200 import CUDA_EvalMode
+    from teg_b200.eval import interleaved_rows
+    for scene, res, bounds, rows in (('tri_primal', (300, 200), ((0, 1), (0, 1)), None),
+                                     ('tri_grad', (257, 391), ((-0.5, 1.5), (0.25, 0.75)), (37, 200)),
+                                     ('tri_primal', (1024, 1024), ((0, 1), (0, 1)), None)):
+        prog = load_program(scene)
+        params = {lab: TRIANGLE[lab.rsplit('_', 1)[0]] for lab in prog.args[4:]}
+        for cull in (True, False):
+            mode = CUDA_EvalMode(prog, num_samples=16, cull=cull)
+            full = mode.render(prog.args[:4], res, bounds, params, rows=rows).clone()
+            n_rows = full.shape[1]
+            ks, _ = mode.compiled([0, 1, 2, 3], [0, 1, 2, 3])
+            for stride in (2, 3, 8):
+                got = torch.full_like(full, float('nan'))
+                for phase in range(stride):
+                    idx = interleaved_rows(n_rows, ks.tile_rows, stride, phase)
+                    part = mode.render(prog.args[:4], res, bounds, params, rows=rows, interleave=(stride, phase))
+                    assert part.shape[1] == len(idx)
+                    if idx:
+                        got[:, torch.as_tensor(idx, device=got.device)] = part
+                torch.cuda.synchronize()
+                assert torch.equal(got, full), (scene, cull, stride)
+            if scene == 'tri_grad':
+                whole = mode.render(prog.args[:4], res, bounds, params, rows=rows, reduce=True).double()
+                parts = sum(mode.render(prog.args[:4], res, bounds, params, rows=rows, reduce=True,
+                                        interleave=(4, ph)).double().clone() for ph in range(4))
+                assert torch.allclose(parts, whole, rtol=1e-5, atol=1e-8)
