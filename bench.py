@@ -397,9 +397,10 @@ def main() -> int:
         e2e = {'value': n_local * world * k_e2e / float(te.item()), 'unit': 'integral evals/s',
                'h2d_bytes_per_step': 2 * 6 * esz,
                'd2h_bytes_per_step': int(h_imgs[0].numel() * esz + h_gs[0].numel() * esz),
-               'api': 'CUDA_EvalMode.render(...) for the value image and render(..., reduce=True) for the gradient '
-                      '(pixel boxes generated on device); image + gradient vector copied to pinned host memory '
-                      'every step on a second stream, double-buffered', 'steps': k_e2e,
+               'api': 'CUDA_EvalMode.prepare_render(...).run() for the value image and for the gradient (reduce=True): '
+                      'one tegb_render_launch_strided C-ABI call each (pixel boxes generated on device); image + '
+                      'gradient vector copied to pinned host memory every step on a copy stream, double-buffered',
+               'steps': k_e2e,
                'ms_per_step': float(te.item()) / k_e2e * 1e3}
 
     if peers is not None:
