@@ -43,6 +43,11 @@ def main():
             scal = {lab: v for lab, v in b.items() if np.ndim(v) == 0}
             m.render(prog.args[:4], (45, 70), ((0, 1), (0, 1)), scal)
             m.render(prog.args[:4], (45, 70), ((0, 1), (0, 1)), scal, reduce=True, rows=(3, 40))
+            # tile classification on grids that are not multiples of the tile, interleaved tile rows, dense kernels
+            m.render(prog.args[:4], (300, 200), ((0, 1), (0, 1)), scal, interleave=(3, 1))
+            m.render(prog.args[:4], (300, 200), ((0, 1), (0, 1)), scal, reduce=True, interleave=(2, 1), rows=(5, 290))
+            CUDA_EvalMode(prog, num_samples=ns, cull=False).render(prog.args[:4], (100, 130), ((0, 1), (0, 1)), scal)
+            CUDA_EvalMode(prog, num_samples=ns, tiles=False).render(prog.args[:4], (100, 130), ((0, 1), (0, 1)), scal)
     res = 64
     scene = multi_triangle_scene(bands=1, per_band_grid=4, res=res)
     r = MultiTriangleRasterizer(load('tri_color_primal'), load('tri_color_grad'), res)
