@@ -860,9 +860,20 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
         return fail(TEGB_ERR_INVALID, "not a plain render program (needs exactly the 4 pixel-box arguments on the grid)");
     if (g->res_x < 1 || g->res_y < 1 || g->row_begin < 0 || g->row_end > g->res_x || g->row_begin > g->row_end)
         return fail(TEGB_ERR_INVALID, "bad grid");
-    if (g->row_end == g->row_begin) return TEGB_OK;
     RT_CHECK(cudaSetDevice(p->device));
     CUstream st = (CUstream)stream;
+    {
+        // nothing to render for this rank (empty row range, or no tile row of its phase): image outputs stay untouched,
+        // summed outputs are zero -- and still take part in the peer exchange, the other ranks wait for this one
+        const int tr = p->d.tile_rows > 0 ? p->d.tile_rows : 1;
+        const int n_tr0 = (g->row_end - g->row_begin + tr - 1) / tr;
+        if (tile_phase >= n_tr0) {
+            if (!p->d.reduce_outputs) return TEGB_OK;
+            int rc0 = ensure_partials(p, 0);
+            if (rc0) return rc0;
+            return finish_partials(p, 0, out_ptrs[p->d.n_outputs - p->d.reduce_outputs], (cudaStream_t)st);
+        }
+    }
     int rc = ensure_edges(p, g, st);
     if (rc) return rc;
     rc = run_uniform(p, scalars, st);
@@ -881,7 +892,6 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
     int n_rows = g->row_end - g->row_begin;
     // tile rows tile_phase, tile_phase + tile_stride, ... of the row range are rendered by this launch
     const int n_tr = (n_rows + tile_rows - 1) / tile_rows;
-    if (tile_phase >= n_tr) return TEGB_OK;
     const unsigned gy = (unsigned)((n_tr - tile_phase + tile_stride - 1) / tile_stride);
     if (gy > 65535u) return fail(TEGB_ERR_INVALID, "more than 65535 tile rows in one render launch");
     args.push_back(&n_rows);

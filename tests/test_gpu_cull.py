@@ -296,3 +296,29 @@ def test_interleaved_tile_rows_tile_the_image(cuda_device):
                 parts = sum(mode.render(prog.args[:4], res, bounds, params, rows=rows, reduce=True,
                                         interleave=(4, ph)).double().clone() for ph in range(4))
                 assert torch.allclose(parts, whole, rtol=1e-5, atol=1e-8)
+
+
+def test_render_with_nothing_to_do_and_trapezoid_render(cuda_device):
+    """A rank whose phase has no tile row (or whose row range is empty) gets zero sums, not stale memory; and the
+    render path of the trapezoid mode (no culling there) equals its array path."""
+    import torch
+    from teg_b200 import CUDA_EvalMode
+    from teg_b200.workloads import pixel_boxes
+    prog = load_program('tri_grad')
+    params = {lab: TRIANGLE[lab.rsplit('_', 1)[0]] for lab in prog.args[4:]}
+    mode = CUDA_EvalMode(prog, num_samples=16)
+    out = torch.full((6,), 7.0, device='cuda')
+    mode.render(prog.args[:4], (40, 64), ((0, 1), (0, 1)), params, reduce=True, interleave=(8, 5), out=out)   # 3 tile rows
+    torch.cuda.synchronize()
+    assert torch.equal(out, torch.zeros(6, device='cuda'))
+    out.fill_(7.0)
+    mode.render(prog.args[:4], (40, 64), ((0, 1), (0, 1)), params, reduce=True, rows=(9, 9), out=out)
+    torch.cuda.synchronize()
+    assert torch.equal(out, torch.zeros(6, device='cuda'))
+    trap = CUDA_EvalMode(prog, num_samples=12, integration_mode='trapezoidal_quadrature')
+    res, rows = (70, 150), (3, 66)
+    img = trap.render(prog.args[:4], res, ((0, 1), (0, 1)), params, rows=rows)
+    box = pixel_boxes(res, rows=rows)
+    arr = trap.eval(dict(zip(prog.args, list(box) + [params[lab] for lab in prog.args[4:]])))
+    torch.cuda.synchronize()
+    assert np.array_equal(img.cpu().numpy().reshape(6, -1), np.asarray(arr))
