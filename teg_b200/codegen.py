@@ -1087,7 +1087,11 @@ class Emitter:
                 src += lines
                 src.append('}')
                 src.append('')
-                tile_bodies.append((label, match, b_coop))
+                consts = []
+                for o in outs:
+                    m = self.nodes[self.helper.resolve(o, blk.known)]
+                    consts.append(literal(m.attr, T) if m.op == 'const' else None)
+                tile_bodies.append((label, match, b_coop, consts if all(c is not None for c in consts) else None))
             self.uses_coop = general_coop
             coop = general_coop
         src.append('#ifdef __CUDACC__')
@@ -1241,13 +1245,30 @@ class Emitter:
                 if tile_bodies:
                     # the tile's conditions are the same for every thread of the block: a uniform branch picks the body
                     first = True
-                    for label, match, b_coop in tile_bodies:
+                    for label, match, b_coop, consts in tile_bodies:
                         terms = []
                         for k2 in sorted(match):
                             alts = ' || '.join(f'tile{k2} == {literal(str(v), T)}' for v in match[k2])
                             terms.append(f'({alts})')
                         src.append(f'    {"if" if first else "else if"} ({" && ".join(terms)}) {{')
-                        row_loop(f'{name}_tile_{label}', b_coop, '        ')
+                        zeros = consts is not None and all(float(c.rstrip('f')) == 0.0 and not c.startswith('-')
+                                                           for c in consts[ns_out:])
+                        if consts is not None and (nr == 0 or zeros):
+                            # every output of this body is a constant: fill the tile's rows (summed outputs that are
+                            # +0 leave the partial sums as they are)
+                            if ns_out:
+                                src.append('        const int rel0 = (tby * row_stride + row_phase) * tile_rows;')
+                                src.append('        const int rows_here = min(tile_rows, n_rows - rel0);')
+                                src.append('        const long long i0 = (long long)(tby * tile_rows) * res_y + ny;')
+                                src.append('        if (live) {')
+                                src.append('            #pragma unroll 4')
+                                src.append('            for (int r = 0; r < rows_here; ++r) {')
+                                for k in range(ns_out):
+                                    src.append(f'                out{k}[i0 + (long long)r * res_y] = {consts[k]};')
+                                src.append('            }')
+                                src.append('        }')
+                        else:
+                            row_loop(f'{name}_tile_{label}', b_coop, '        ')
                         src.append('    }')
                         first = False
                     src.append('    else {')
@@ -1269,7 +1290,7 @@ class Emitter:
                                     grouped=False, pixel_args=pix, accumulate=False,
                                     tile_conds=len(tile), tile_rows=self.tile_rows,
                                     tile_kernel=f'{name}_tiles' if tile else '',
-                                    tile_bodies=[(lb, mt) for lb, mt, _ in tile_bodies],
+                                    tile_bodies=[(lb, mt) for lb, mt, _, _ in tile_bodies],
                                     stats={'uses_coop': self.uses_coop, 'loops': self.loop_counter})
             else:
                 mparams = ', '.join([f'const T* __restrict__ in{a}' for a in arrs] + outs_decl + ['const long long n'])

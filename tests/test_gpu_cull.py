@@ -322,3 +322,26 @@ def test_render_with_nothing_to_do_and_trapezoid_render(cuda_device):
     arr = trap.eval(dict(zip(prog.args, list(box) + [params[lab] for lab in prog.args[4:]])))
     torch.cuda.synchronize()
     assert np.array_equal(img.cpu().numpy().reshape(6, -1), np.asarray(arr))
+
+
+def test_prepared_render_rebinds_scalars(cuda_device):
+    """A bound render re-run with other vertices must re-classify its tiles and re-publish its uniform table:
+    results equal those of a fresh render, for images and for summed gradients."""
+    import torch
+    from teg_b200 import CUDA_EvalMode
+    rng = np.random.default_rng(3)
+    for scene, reduce in (('tri_primal', False), ('tri_grad', True), ('tri_grad', False)):
+        prog = load_program(scene)
+        mode = CUDA_EvalMode(prog, num_samples=16)
+        first = {lab: TRIANGLE[lab.rsplit('_', 1)[0]] for lab in prog.args[4:]}
+        call = mode.prepare_render(prog.args[:4], (512, 384), ((0, 1), (0, 1)), first, reduce=reduce)
+        stream = torch.cuda.current_stream().cuda_stream
+        for _ in range(4):
+            v = rng.uniform(0.05, 0.95, 6)
+            params = {lab: float(np.float32(x)) for lab, x in zip(prog.args[4:], v)}
+            call.set_scalars([params[prog.args[a]] for a in call.ks.scalar_args])
+            got = call.run(stream).clone()
+            want = CUDA_EvalMode(prog, num_samples=16, cull=False).render(prog.args[:4], (512, 384), ((0, 1), (0, 1)),
+                                                                         params, reduce=reduce)
+            torch.cuda.synchronize()
+            assert torch.equal(got, want), (scene, reduce)
