@@ -194,7 +194,6 @@ def main() -> int:
     import torch.distributed as dist
     from teg_b200 import CUDA_EvalMode, runtime
     from teg_b200.opcount import count as op_count
-    from teg_b200.schedule import make_schedule
     from teg_b200.tegp import Program
     from teg_b200.workloads import TRIANGLE
 

@@ -147,7 +147,6 @@ def test_culling_resolves_what_it_should(cuda_device):
     from teg_b200 import CUDA_EvalMode
     from teg_b200.cull import cull
     from teg_b200.dag import build_dag
-    from teg_b200.tegp import Program
     prog = load_program('tri_primal')
     # a probe program: same DAG, output replaced by the tri-state of the (single) condition
     dag = cull(build_dag(prog), 16)
@@ -249,7 +248,6 @@ def test_tiled_render_random_triangles_odd_grids_and_bands(cuda_device):
 
 def test_tile_classification_resolves_most_tiles(cuda_device):
     """4096 x 4096 triangle: the classification leaves only the tiles an edge passes through (or near) unresolved."""
-    import ctypes
     import torch
     from teg_b200 import CUDA_EvalMode
     prog = load_program('tri_primal')
