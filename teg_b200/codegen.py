@@ -439,7 +439,7 @@ class Emitter:
         return is_t(root), is_f(root)
 
     # ---------------------------------------------------------------------- tile classification kernel
-    def tiles_body(self, grid: Sequence[int]) -> List[str]:
+    def tiles_body(self, grid: Sequence[int], walk: bool = False) -> List[str]:
         """Body of ``<name>_tiles`` (cull.tile_cull): one thread per tile of BLOCK columns x ``tile_rows`` rows
         bounds the pixel-box arguments and the sample abscissae over its pixels (by walking its rows and columns:
         exact, no reasoning about rounding) and evaluates every tile condition with ``_iv_cone``."""
@@ -477,19 +477,46 @@ class Emitter:
         for j in bx + by:
             leaf[j] = (f'g_b{j}_lo', f'g_b{j}_hi')
         e = lambda line, ind=1: self.emit(line, ind)     # noqa: E731
-        # [min, max] of the box edges and of the sample abscissae over the tile's rows / columns: computed once per
-        # grid by the runtime's tile_ranges kernel (exact walk over the rows / columns), 7 values per tile row / column
-        e('const T* __restrict__ rx = ranges + (size_t)ty * 7;')
-        e('const T* __restrict__ ry = ranges + ((size_t)n_ty + tx) * 7;')
-        for nm, tab in (('xl', 'rx'), ('yl', 'ry')):
-            e(f'const T g_{nm}_lo = {tab}[0], g_{nm}_hi = {tab}[1];')
-        for nm, tab in (('xu', 'rx'), ('yu', 'ry')):
-            e(f'const T g_{nm}_lo = {tab}[2], g_{nm}_hi = {tab}[3];')
-        for j in bx:
-            e(f'const T g_b{j}_lo = rx[4], g_b{j}_hi = rx[5];')
-        for j in by:
-            e(f'const T g_b{j}_lo = ry[4], g_b{j}_hi = ry[5];')
-        e('const T g_pz = rx[6] + ry[6];')
+        if walk:
+            # grouped launches (tiles are relative to each group's window): one warp per tile walks the tile's rows
+            # [r0, r1) and columns [c0, c1) itself -- exact ranges of the box edges and the midpoint abscissae
+            e(f'T g_pz = {zero};')
+            for tab, first, last, lo_n, hi_n, bvs in (('xe', 'r0', 'r1', 'xl', 'xu', bx), ('ye', 'c0', 'c1', 'yl', 'yu', by)):
+                e(f'T g_{lo_n}_lo = {tab}[{first}], g_{lo_n}_hi = {tab}[{first}], g_{hi_n}_lo = {tab}[{first} + 1], '
+                  f'g_{hi_n}_hi = {tab}[{first} + 1];')
+                e(f'T g_s{lo_n}_lo = {tab}[{first}], g_s{lo_n}_hi = {tab}[{first}];')
+                e(f'for (int q = {first} + lane; q < {last}; q += 32) {{')
+                e(f'const T lb = {tab}[q], ub = {tab}[q + 1];', 2)
+                e(f'g_{lo_n}_lo = {fmin}(g_{lo_n}_lo, lb); g_{lo_n}_hi = {fmax}(g_{lo_n}_hi, lb);', 2)
+                e(f'g_{hi_n}_lo = {fmin}(g_{hi_n}_lo, ub); g_{hi_n}_hi = {fmax}(g_{hi_n}_hi, ub);', 2)
+                e(f'const T st = ((T)(ub - lb)) / (T){N};', 2)
+                e(f'const T sa = lb + st * ((T)0u + {half}), sb = lb + st * ((T){N - 1}u + {half});', 2)
+                e(f'g_s{lo_n}_lo = {fmin}(g_s{lo_n}_lo, {fmin}(sa, sb)); g_s{lo_n}_hi = {fmax}(g_s{lo_n}_hi, {fmax}(sa, sb));', 2)
+                e('g_pz = g_pz + lb; g_pz = g_pz + ub; g_pz = g_pz + (ub - lb); g_pz = g_pz + sa; g_pz = g_pz + sb;', 2)
+                e('}')
+                e('for (int off = 16; off > 0; off >>= 1) {')
+                for v in (f'g_{lo_n}_lo', f'g_{hi_n}_lo', f'g_s{lo_n}_lo'):
+                    e(f'{v} = {fmin}({v}, __shfl_xor_sync(0xffffffffu, {v}, off));', 2)
+                for v in (f'g_{lo_n}_hi', f'g_{hi_n}_hi', f'g_s{lo_n}_hi'):
+                    e(f'{v} = {fmax}({v}, __shfl_xor_sync(0xffffffffu, {v}, off));', 2)
+                e('}')
+                for j in bvs:
+                    e(f'const T g_b{j}_lo = g_s{lo_n}_lo, g_b{j}_hi = g_s{lo_n}_hi;')
+            e('for (int off = 16; off > 0; off >>= 1) g_pz = g_pz + __shfl_xor_sync(0xffffffffu, g_pz, off);')
+        else:
+            # [min, max] of the box edges and of the sample abscissae over the tile's rows / columns: computed once per
+            # grid by the runtime's tile_ranges kernel (exact walk over the rows / columns), 7 values per tile row / column
+            e('const T* __restrict__ rx = ranges + (size_t)ty * 7;')
+            e('const T* __restrict__ ry = ranges + ((size_t)n_ty + tx) * 7;')
+            for nm, tab in (('xl', 'rx'), ('yl', 'ry')):
+                e(f'const T g_{nm}_lo = {tab}[0], g_{nm}_hi = {tab}[1];')
+            for nm, tab in (('xu', 'rx'), ('yu', 'ry')):
+                e(f'const T g_{nm}_lo = {tab}[2], g_{nm}_hi = {tab}[3];')
+            for j in bx:
+                e(f'const T g_b{j}_lo = rx[4], g_b{j}_hi = rx[5];')
+            for j in by:
+                e(f'const T g_b{j}_lo = ry[4], g_b{j}_hi = ry[5];')
+            e('const T g_pz = rx[6] + ry[6];')
         # launch-invariant values the cones read (points), from the scalar arguments
         need: List[int] = []
         seen = set()
@@ -529,12 +556,18 @@ class Emitter:
             e(f'T {pre}pz = g_pz;', 2)
             t, f = self._iv_cone(r, (lambda j, B=B: bool(fv(j) & B) or dep.get(j, False)), leaf, {}, 2, pre)
             e(f'const T {pre}tri = {self._iv_result(t, f, pre)};', 2)
-            e(f'tiles[(size_t){k} * n_tiles + t] = {pre}tri;', 2)
+            if walk:
+                e(f'if (lane == 0) tiles[(size_t){k} * n_tiles + t] = {pre}tri;', 2)
+            else:
+                e(f'tiles[(size_t){k} * n_tiles + t] = {pre}tri;', 2)
             e(f'unresolved = unresolved || {pre}tri == {literal("2", T)};', 2)
             e('}')
-        # launch order of the main kernel: unresolved tiles from the front, resolved ones from the back
-        e('if (unresolved) order[atomicAdd(&counters[0], 1)] = t;')
-        e('else order[n_tx * n_ty - 1 - atomicAdd(&counters[1], 1)] = t;')
+        if not walk:
+            # launch order of the main kernel: unresolved tiles from the front, resolved ones from the back
+            e('if (unresolved) order[atomicAdd(&counters[0], 1)] = t;')
+            e('else order[n_tx * n_ty - 1 - atomicAdd(&counters[1], 1)] = t;')
+        else:
+            e('(void)unresolved;')
         self.in_main = saved_main
         return self.lines
 
@@ -1027,7 +1060,7 @@ class Emitter:
         assert not pix or grouped, 'pixel-indexed arguments need a grouped render launch'
         n_prog_args = len(self.dag.arg_labels)
         tile = [a for a in sch.array_args if a >= n_prog_args]      # tile conditions (pseudo arguments, cull.tile_cull)
-        assert not tile or (grid and not grouped and self.team == 1), 'tile conditions belong to plain render launches'
+        assert not tile or (grid and self.team == 1), 'tile conditions belong to render launches'
         assert len(tile) == len(getattr(self.dag, 'tile_conds', []) if tile else [])
         arrs = [a for a in sch.array_args if a not in grid and a not in pix and a not in tile]
         assert not (grid and arrs), 'render programs cannot also stream per-instance arrays'
@@ -1079,7 +1112,8 @@ class Emitter:
                 self.uses_coop = False
                 lines = self.body_lines(blk, outs)
                 b_coop = self.uses_coop
-                bparams = ', '.join((['const bool live'] if b_coop else []) +
+                bparams = ', '.join((['const T* __restrict__ tegU'] if grouped else []) +
+                                    (['const bool live'] if b_coop else []) +
                                     [f'const T a{a}' for a in varying] + [f'T (&res)[{K}]'])
                 src.append(f'TEGB_FN void {name}_tile_{label}({bparams}) {{')
                 for a in varying:
@@ -1109,24 +1143,53 @@ class Emitter:
                                                              ['U + (size_t)g * TEGB_NUM_UNIFORM']) + ');')
             src.append('}')
             src.append('')
+            if tile:
+                # classification of every (group, window tile): one warp per tile, launch-wide values of the group
+                tparams = ', '.join([f'const T* __restrict__ g{a}' for a in scal] +
+                                    ['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
+                                     'const int row0', 'const int row1', 'const int* __restrict__ win',
+                                     'const int group_begin', 'const int group_count', 'const int tile_rows',
+                                     'const int n_tx', 'const int n_ty', 'T* __restrict__ tiles'])
+                src.append(f'extern "C" __global__ void {name}_tiles({tparams}) {{')
+                src.append('    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;')
+                src.append('    const int lane = threadIdx.x & 31;')
+                src.append('    const int per_group = n_tx * n_ty;')
+                src.append('    if (w >= (long long)group_count * per_group) return;')
+                src.append('    const int j = (int)(w / per_group), tt = (int)(w - (long long)j * per_group);')
+                src.append('    const int ty = tt / n_tx, tx = tt - ty * n_tx;')
+                src.append('    const int g = group_begin + j;')
+                src.append('    const int w_r0 = max(win[4 * g + 0], row0), w_r1 = min(win[4 * g + 1], row1);')
+                src.append('    const int w_c0 = win[4 * g + 2], w_c1 = min(win[4 * g + 3], res_y);')
+                src.append('    const int r0 = w_r0 + ty * tile_rows, r1 = min(r0 + tile_rows, w_r1);')
+                src.append(f'    const int c0 = w_c0 + tx * {bs}, c1 = min(c0 + {bs}, w_c1);')
+                src.append('    if (r0 >= r1 || c0 >= c1) return;              // no pixel: the main kernel skips this tile too')
+                src.append('    const size_t n_tiles = (size_t)group_count * per_group;')
+                src.append('    const size_t t = (size_t)w;')
+                for a2 in scal:
+                    src.append(f'    const T a{a2} = g{a2}[g];')
+                    src.append(f'    (void)a{a2};')
+                src += self.tiles_body(grid, walk=True)
+                src.append('}')
+                src.append('')
             mparams = ', '.join(['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
                                  'const int row0', 'const int row1', 'const int* __restrict__ win',
-                                 'const int group_begin', 'const T* __restrict__ Utab'] +
+                                 'const int group_begin', 'const T* __restrict__ Utab', 'const int tile_rows'] +
+                                (['const T* __restrict__ tiles'] if tile else []) +
                                 [f'const T* __restrict__ pix{a}' for a in pix] + outs_decl)
             src.append(f'extern "C" __global__ void __launch_bounds__({bs}) {name}_main({mparams}) {{')
-            src.append('    // block (bx, by, bz): group group_begin + bz, row by of its window, columns [bx*B, bx*B + B)')
+            src.append('    // block (bx, by, bz): group group_begin + bz, tile (bx, by) of its window: B columns x tile_rows rows')
             src.append('    const int g = group_begin + blockIdx.z;')
             src.append('    const int w_r0 = max(win[4 * g + 0], row0), w_r1 = min(win[4 * g + 1], row1);')
             src.append('    const int w_c0 = win[4 * g + 2], w_c1 = win[4 * g + 3];')
-            src.append('    const int nx = w_r0 + blockIdx.y;')
+            src.append('    const int nx0 = w_r0 + blockIdx.y * tile_rows;')
             src.append('    const int ny = w_c0 + blockIdx.x * blockDim.x + threadIdx.x;')
-            src.append('    const bool block_live = nx < w_r1 && (w_c0 + (int)(blockIdx.x * blockDim.x)) < w_c1;')
+            src.append('    const bool block_live = nx0 < w_r1 && (w_c0 + (int)(blockIdx.x * blockDim.x)) < w_c1;')
             if reduce_outputs:
-                src.append('    const unsigned long long tiles = (unsigned long long)gridDim.x * gridDim.y;')
-                src.append('    const unsigned long long tile = (unsigned long long)blockIdx.y * gridDim.x + blockIdx.x;')
-                src.append(f'    T* gp = partials + (unsigned long long)blockIdx.z * {K} * tiles;')
+                src.append('    const unsigned long long tiles_n = (unsigned long long)gridDim.x * gridDim.y;')
+                src.append('    const unsigned long long tile_i = (unsigned long long)blockIdx.y * gridDim.x + blockIdx.x;')
+                src.append(f'    T* gp = partials + (unsigned long long)blockIdx.z * {K} * tiles_n;')
                 src.append('    if (!block_live) {')
-                src.append(f'        if (threadIdx.x < {K}) gp[threadIdx.x * tiles + tile] = {zero};')
+                src.append(f'        if (threadIdx.x < {K}) gp[threadIdx.x * tiles_n + tile_i] = {zero};')
                 src.append('        return;')
                 src.append('    }')
             else:
@@ -1136,31 +1199,70 @@ class Emitter:
                        'sU[j] = Utab[(size_t)g * TEGB_NUM_UNIFORM + j];')
             src.append('    __syncthreads();')
             src.append('    const bool live = ny < w_c1;')
-            src.append('    const long long i = (long long)(nx - row0) * res_y + ny;')
-            loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye[ny]', grid[3]: 'ye[ny + 1]'}
-            if coop:
-                # every lane of the warp runs the instance (dead lanes on a clamped pixel, results dropped)
-                src.append('    const int nyc = live ? ny : w_c0 + (int)(blockIdx.x * blockDim.x);')
-                src.append('    const long long ic = (long long)(nx - row0) * res_y + nyc;')
-                loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye[nyc]', grid[3]: 'ye[nyc + 1]'}
+            # every lane of a warp runs coop bodies (dead lanes on a clamped pixel, results dropped)
+            src.append('    const int nyc = live ? ny : w_c0 + (int)(blockIdx.x * blockDim.x);')
+            src.append('    const T ye_lo = ye[nyc], ye_hi = ye[nyc + 1];')
+            loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye_lo', grid[3]: 'ye_hi'}
             for a in pix:
-                loads[a] = f'pix{a}[ic]' if coop else f'pix{a}[i]'
-            call = ', '.join(['sU'] + (['live'] if coop else []) + [loads[a] for a in varying] + ['res'])
-            src.append(f'    T res[{K}];')
-            src.append(f'    for (int k = 0; k < {K}; k++) res[k] = {zero};')
-            if coop:
-                src.append(f'    {name}_instance({call});')
-                src.append(f'    if (!live) {{ for (int k = 0; k < {K}; k++) res[k] = {zero}; }}')
-            else:
-                src.append(f'    if (live) {name}_instance({call});')
+                loads[a] = f'pix{a}[ic]'
+            if tile:
+                src.append('    const size_t n_tiles = (size_t)gridDim.x * gridDim.y * gridDim.z;')
+                src.append('    const size_t tile_id = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;')
+                for k, a in enumerate(tile):
+                    src.append(f'    const T tile{k} = tiles[{k} * n_tiles + tile_id];')
+                    loads[a] = f'tile{k}'
             if reduce_outputs:
-                src.append(f'    tegb_block_sum_store<T, {K}, {bs}>(res, gp, tiles, tile);')
-            elif accumulate:
-                for k in range(K):
-                    src.append(f'    if (live) out{k}[i] = out{k}[i] + res[{k}];')
+                src.append(f'    T rr[{K}];')
+                src.append(f'    for (int k = 0; k < {K}; k++) rr[k] = {zero};')
+
+            def g_row_loop(fn: str, with_live: bool, ind: str):
+                call = ', '.join(['sU'] + (['live'] if with_live else []) + [loads[a] for a in varying] + ['res'])
+                src.append(f'{ind}#pragma unroll 1')
+                src.append(f'{ind}for (int r = 0; r < tile_rows; ++r) {{')
+                src.append(f'{ind}    const int nx = nx0 + r;')
+                src.append(f'{ind}    if (nx >= w_r1) break;')
+                src.append(f'{ind}    const long long i = (long long)(nx - row0) * res_y + ny;')
+                src.append(f'{ind}    const long long ic = (long long)(nx - row0) * res_y + nyc;')
+                src.append(f'{ind}    (void)ic;')
+                src.append(f'{ind}    T res[{K}];')
+                src.append(f'{ind}    for (int k = 0; k < {K}; k++) res[k] = {zero};')
+                if with_live:
+                    src.append(f'{ind}    {fn}({call});')
+                else:
+                    src.append(f'{ind}    if (live) {fn}({call});')
+                if reduce_outputs:
+                    for k in range(K):
+                        src.append(f'{ind}    if (live) rr[{k}] = rr[{k}] + res[{k}];')
+                elif accumulate:
+                    for k in range(K):
+                        src.append(f'{ind}    if (live) out{k}[i] = out{k}[i] + res[{k}];')
+                else:
+                    for k in range(K):
+                        src.append(f'{ind}    if (live) out{k}[i] = res[{k}];')
+                src.append(f'{ind}}}')
+
+            if tile_bodies:
+                first = True
+                for label, match, b_coop, consts in tile_bodies:
+                    terms = []
+                    for k2 in sorted(match):
+                        alts = ' || '.join(f'tile{k2} == {literal(str(v), T)}' for v in match[k2])
+                        terms.append(f'({alts})')
+                    src.append(f'    {"if" if first else "else if"} ({" && ".join(terms)}) {{')
+                    zeros = consts is not None and all(float(c.rstrip('f')) == 0.0 and not c.startswith('-') for c in consts)
+                    if zeros and (reduce_outputs or accumulate):
+                        src.append('        // every output is +0 over this tile: nothing to add')
+                    else:
+                        g_row_loop(f'{name}_tile_{label}', b_coop, '        ')
+                    src.append('    }')
+                    first = False
+                src.append('    else {')
+                g_row_loop(f'{name}_instance', coop, '        ')
+                src.append('    }')
             else:
-                for k in range(K):
-                    src.append(f'    if (live) out{k}[i] = res[{k}];')
+                g_row_loop(f'{name}_instance', coop, '    ')
+            if reduce_outputs:
+                src.append(f'    tegb_block_sum_store<T, {K}, {bs}>(rr, gp, tiles_n, tile_i);')
             src.append('}')
         else:
             src.append(f'extern "C" __global__ void {name}_uniform({ubody_params}) {{')
@@ -1379,8 +1481,9 @@ class Emitter:
                             n_uniform=nu, scalar_args=scal, array_args=arrs, grid_args=grid,
                             n_outputs=K, block_size=bs, reduce_outputs=nr, team=team,
                             grouped=bool(grouped), pixel_args=pix, accumulate=bool(accumulate),
-                            tile_conds=len(tile), tile_rows=self.tile_rows if tile else 0,
+                            tile_conds=len(tile), tile_rows=self.tile_rows if (tile or grouped) else 0,
                             tile_kernel=f'{name}_tiles' if tile else '',
+                            tile_bodies=[(lb, mt) for lb, mt, _, _ in tile_bodies],
                             stats={'uses_coop': self.uses_coop, 'loops': self.loop_counter})
 
 

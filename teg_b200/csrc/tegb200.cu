@@ -326,8 +326,8 @@ extern "C" int tegb_program_create(tegb_module *m, const tegb_program_desc *desc
     r = drv::ModuleGetFunction(&p->f_main, p->mod, desc->main_kernel);
     if (r != CUDA_SUCCESS) return bail(fail(TEGB_ERR_CUDA, "kernel %s: %s", desc->main_kernel, drv::errstr(r)));
     if (desc->n_tile_conds > 0) {
-        if (!desc->tile_kernel || desc->tile_rows < 1 || desc->tile_samples < 1 || desc->grouped || desc->n_grid_args != 4)
-            return bail(fail(TEGB_ERR_INVALID, "tile conditions need a plain render program, tile_rows >= 1 and a tile kernel"));
+        if (!desc->tile_kernel || desc->tile_rows < 1 || desc->tile_samples < 1 || desc->n_grid_args != 4)
+            return bail(fail(TEGB_ERR_INVALID, "tile conditions need a render program, tile_rows >= 1 and a tile kernel"));
         r = drv::ModuleGetFunction(&p->f_tiles, p->mod, desc->tile_kernel);
         if (r != CUDA_SUCCESS) return bail(fail(TEGB_ERR_CUDA, "kernel %s: %s", desc->tile_kernel, drv::errstr(r)));
     }
@@ -777,7 +777,7 @@ extern "C" int tegb_render_groups_launch(tegb_program *p, const void *const *gro
     if (g->res_x < 1 || g->res_y < 1 || g->row_begin < 0 || g->row_end > g->res_x || g->row_begin > g->row_end)
         return fail(TEGB_ERR_INVALID, "bad grid");
     if (group_count == 0 || g->row_end == g->row_begin) return TEGB_OK;
-    if (group_count > 65535 || max_rows > 65535) return fail(TEGB_ERR_INVALID, "more than 65535 groups or rows in one launch");
+    if (group_count > 65535 || max_rows > 65535 * 16) return fail(TEGB_ERR_INVALID, "too many groups or rows in one launch");
     RT_CHECK(cudaSetDevice(p->device));
     CUstream st = (CUstream)stream;
     int rc = ensure_edges(p, g, st);
@@ -805,12 +805,46 @@ extern "C" int tegb_render_groups_launch(tegb_program *p, const void *const *gro
     const unsigned bs = (unsigned)p->d.block_size;
     const unsigned gx = (unsigned)((max_cols + bs - 1) / bs);
     int band_rows = g->row_end - g->row_begin;
-    const unsigned gy = (unsigned)(max_rows < band_rows ? max_rows : band_rows);
+    // one block per window tile: block_size columns x tile_rows rows
+    int tile_rows = p->d.tile_rows > 0 ? p->d.tile_rows : 1;
+    const int win_rows = max_rows < band_rows ? max_rows : band_rows;
+    const unsigned gy = (unsigned)((win_rows + tile_rows - 1) / tile_rows);
     const unsigned gz = (unsigned)group_count;
     std::vector<const void *> pix(p->d.n_pixel_args > 0 ? p->d.n_pixel_args : 1);
     std::vector<void *> outs(p->d.n_outputs);
     std::vector<void *> args;
     int res_y = g->res_y, row0 = g->row_begin, row1 = g->row_end;
+    if (p->d.n_tile_conds > 0) {
+        // classify every (group, window tile) for the groups' current parameters
+        int n_tx = (int)gx, n_ty = (int)gy;
+        const size_t need_t = (size_t)p->d.n_tile_conds * gz * n_tx * n_ty * p->d.elem_size;
+        if (need_t > p->tiles_bytes) {
+            RT_CHECK(cudaStreamSynchronize((cudaStream_t)st));
+            if (p->d_tiles) { cudaFree(p->d_tiles); p->d_tiles = nullptr; p->tiles_bytes = 0; }
+            RT_CHECK(cudaMalloc(&p->d_tiles, need_t));
+            p->tiles_bytes = need_t;
+        }
+        // (tiles without a pixel are neither written by the classification nor read by the main kernel)
+        std::vector<const void *> gp2(p->d.n_scalar_args > 0 ? p->d.n_scalar_args : 1);
+        std::vector<void *> targs;
+        for (int i = 0; i < p->d.n_scalar_args; i++) { gp2[i] = group_ptrs[i]; targs.push_back(&gp2[i]); }
+        targs.push_back(&p->d_xe);
+        targs.push_back(&p->d_ye);
+        targs.push_back(&res_y);
+        targs.push_back(&row0);
+        targs.push_back(&row1);
+        targs.push_back((void *)&windows);
+        targs.push_back(&group_begin);
+        targs.push_back(&group_count);
+        targs.push_back(&tile_rows);
+        targs.push_back(&n_tx);
+        targs.push_back(&n_ty);
+        targs.push_back(&p->d_tiles);
+        const unsigned long long warps = (unsigned long long)gz * n_tx * n_ty;
+        const unsigned tb = 128, tg = (unsigned)((warps * 32 + tb - 1) / tb);
+        CU_CHECK(drv::LaunchKernel(p->f_tiles, tg, 1, 1, tb, 1, 1, 0, st, targs.data(), nullptr));
+        g_launches++;
+    }
     args.push_back(&p->d_xe);
     args.push_back(&p->d_ye);
     args.push_back(&res_y);
@@ -819,6 +853,8 @@ extern "C" int tegb_render_groups_launch(tegb_program *p, const void *const *gro
     args.push_back((void *)&windows);
     args.push_back(&group_begin);
     args.push_back(&p->d_utab);
+    args.push_back(&tile_rows);
+    if (p->d.n_tile_conds > 0) args.push_back(&p->d_tiles);
     for (int i = 0; i < p->d.n_pixel_args; i++) { pix[i] = pixel_ptrs[i]; args.push_back(&pix[i]); }
     const unsigned long long tiles = (unsigned long long)gx * gy;
     if (p->d.reduce_outputs) {

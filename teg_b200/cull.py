@@ -306,8 +306,9 @@ def cull(dag: Dag, num_samples: int, min_samples: int = 64, max_roots: int = 4, 
 
 
 # ------------------------------------------------------------------------------------------ tile level
-def interval_evaluable(dag: Dag, root: int, interior) -> bool:
-    """Can the cone of ``root`` above the nodes for which ``interior`` is false be bounded by intervals?"""
+def interval_evaluable(dag: Dag, root: int, interior, forbidden=None) -> bool:
+    """Can the cone of ``root`` above the nodes for which ``interior`` is false be bounded by intervals?
+    ``forbidden(i)``: node i must not occur in a point (per-pixel inputs that are not box edges)."""
     nodes = dag.nodes
     seen: Set[int] = set()
     stack = [root]
@@ -317,7 +318,8 @@ def interval_evaluable(dag: Dag, root: int, interior) -> bool:
             continue
         if not interior(i):
             # a point of the classification kernel: must be plain launch-invariant arithmetic
-            if dag.has_quad(i) or any(nodes[j].op in ('domtri', 'domis') for j in dag.reachable([i])):
+            if dag.has_quad(i) or any(nodes[j].op in ('domtri', 'domis') or (forbidden is not None and forbidden(j))
+                                      for j in dag.reachable([i])):
                 return False
             continue
         seen.add(i)
@@ -330,7 +332,8 @@ def interval_evaluable(dag: Dag, root: int, interior) -> bool:
     return len(seen) <= 160
 
 
-def tile_cull(dag: Dag, grid_args: Sequence[int], num_samples: int, max_conds: int = 12) -> Dag:
+def tile_cull(dag: Dag, grid_args: Sequence[int], num_samples: int, max_conds: int = 12,
+              other_array_args: Sequence[int] = ()) -> Dag:
     """Second level of culling for render launches (pixel boxes generated from the pixel index): the same interval
     evaluation, but over a whole TILE of pixels, done once per tile by a small classification kernel.
 
@@ -354,7 +357,11 @@ def tile_cull(dag: Dag, grid_args: Sequence[int], num_samples: int, max_conds: i
     nodes = dag.nodes
     n_args = len(dag.arg_labels)
     grid = set(grid_args)
+    other = set(other_array_args) - grid          # per-pixel inputs that are not box edges (an upstream dL image)
     live = dag.reachable(dag.outputs)
+
+    def forbidden(j: int) -> bool:
+        return nodes[j].op == 'in' and nodes[j].attr in other
 
     dep_cache: Dict[int, bool] = {}
 
@@ -382,7 +389,7 @@ def tile_cull(dag: Dag, grid_args: Sequence[int], num_samples: int, max_conds: i
         n = nodes[i]
         if n.op == 'domtri':
             root, B = n.attr
-            if interval_evaluable(dag, root, lambda j, B=B: bool(dag.free_bvars(j) & B) or on_grid(j)):
+            if interval_evaluable(dag, root, lambda j, B=B: bool(dag.free_bvars(j) & B) or on_grid(j), forbidden):
                 conds.append(('dom', i))
     for i in live:
         n = nodes[i]
@@ -395,7 +402,7 @@ def tile_cull(dag: Dag, grid_args: Sequence[int], num_samples: int, max_conds: i
             continue
         if any(nodes[j].op in ('domis', 'domtri') for j in dag.reachable([c])):
             continue
-        if interval_evaluable(dag, c, on_grid):
+        if interval_evaluable(dag, c, on_grid, forbidden):
             conds.append(('guard', c))
     if not conds or len(conds) > max_conds:
         return dag

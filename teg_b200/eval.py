@@ -123,12 +123,13 @@ class CUDA_EvalMode(EvalMode):
         """tiled (plain render launches with culling): the program additionally takes one tri-state per tile
         condition, classified per tile of pixels by ``<name>_tiles`` (cull.tile_cull)."""
         key = tuple(sorted(set(array_args) | set(grid_args)))
-        tiled = bool(tiled) and self.cull and len(grid_args) == 4 and set(array_args) <= set(grid_args)
+        tiled = bool(tiled) and self.cull and len(grid_args) == 4
         if (key, tiled) not in self._schedules:
             dag, arr = self.sched_dag, list(key)
             if tiled:
                 from .cull import tile_cull
-                dag = tile_cull(self.sched_dag, list(grid_args), self.num_samples)
+                dag = tile_cull(self.sched_dag, list(grid_args), self.num_samples,
+                                other_array_args=sorted(set(array_args) - set(grid_args)))
                 arr += [len(self.program.args) + k for k in range(len(dag.tile_conds))]
             self._schedules[(key, tiled)] = make_schedule(dag, arr)
         return self._schedules[(key, tiled)]
@@ -183,7 +184,7 @@ class CUDA_EvalMode(EvalMode):
         hit = self._variants.get(key)
         if hit is None:
             if grouped:
-                sch = self.schedule(list(grid_args) + list(pixel_args))
+                sch = self.schedule(list(grid_args) + list(pixel_args), grid_args, tiled=self.tiles)
                 ks = generate(sch, self.float_width, self.num_samples, grid_args=list(grid_args),
                               reduce_outputs=reduce, grouped=True, pixel_args=list(pixel_args),
                               accumulate=accumulate, block_size=self.block_size, **self.codegen_opts)

@@ -107,3 +107,21 @@ class MultiTriangleRasterizer:
                                   pixel_bindings={self.g_lab['dL']: dL}, rows=self.rows, out=out[a0:a1], reduce=True,
                                   group_range=(a0, a1), stream=stream)
         return out
+
+    def capture(self, fn):
+        """CUDA graph of ``fn(stream_ptr)`` (any mix of ``forward`` / ``backward`` / torch ops on fixed tensors).
+
+        Grouped launches read the triangles' parameters from device arrays (``update_params`` overwrites them in
+        place), never from launch arguments, so a captured step stays valid while the parameters move: replaying it
+        is one submission instead of ~30 launches.  ``fn`` runs once outside the capture first (allocations)."""
+        torch = self.torch
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            fn(side.cuda_stream)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            fn(torch.cuda.current_stream(self.dev).cuda_stream)
+        return graph

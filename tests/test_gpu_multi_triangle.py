@@ -68,3 +68,37 @@ def test_multi_triangle_forward_backward_match_oracle(cuda_device, bands):
     # dL has random signs, so the sums cancel: the fp32 summation error scales with sum |terms|, not |sum|
     assert np.all(np.abs(got_g - want_g) <= 2e-6 * want_gabs + 1e-12)
     assert np.abs(want_g).max() > 1e-3 and np.count_nonzero(want_img) > 100
+
+
+def test_captured_step_follows_parameter_updates(cuda_device):
+    """A CUDA graph of forward + dL + backward (MultiTriangleRasterizer.capture) reads the triangles from device
+    arrays: after update_params the replay equals a fresh launch-by-launch step, bit for bit."""
+    import torch
+    from teg_b200.raster import MultiTriangleRasterizer
+    res = 128
+    scene = multi_triangle_scene(bands=1, per_band_grid=4, res=res)
+    r = MultiTriangleRasterizer(load_program('tri_color_primal'), load_program('tri_color_grad'), res)
+    r.set_scene(scene['verts'], scene['col'], scene['windows'], scene['classes'], scene['max_rows'], scene['max_cols'])
+    img = torch.empty((1, res, res), dtype=torch.float32, device='cuda')
+    dL = torch.empty((res, res), dtype=torch.float32, device='cuda')
+    g = torch.empty((scene['verts'].shape[0], 7), dtype=torch.float32, device='cuda')
+    target = torch.full((res, res), 0.25, device='cuda')
+
+    def body(sp):
+        r.forward(out=img, stream=sp)
+        torch.sub(img[0], target, out=dL)
+        r.backward(dL, out=g, stream=sp)
+
+    graph = r.capture(body)
+    rng = np.random.default_rng(9)
+    for _ in range(3):
+        verts = torch.as_tensor(scene['verts'] + rng.normal(scale=2e-3, size=scene['verts'].shape), dtype=torch.float32).cuda()
+        col = torch.as_tensor(rng.uniform(0.2, 1.0, size=scene['col'].shape), dtype=torch.float32).cuda()
+        r.update_params(verts, col)
+        graph.replay()
+        torch.cuda.synchronize()
+        got_img, got_g = img.clone(), g.clone()
+        body(torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert torch.equal(got_img, img) and torch.equal(got_g, g)
+        assert float(img.sum()) > 0 and float(g.abs().sum()) > 0

@@ -31,6 +31,8 @@ def main():
     ap.add_argument('--res', type=int, default=4096)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--cull', type=int, default=1)
+    ap.add_argument('--graph', type=int, default=1, help='1: replay the step as one CUDA graph (parameters live in '
+                    'device arrays, so the graph stays valid while they change)')
     args = ap.parse_args()
 
     import torch
@@ -101,6 +103,25 @@ def main():
     for _ in range(max(3, args.warmup)):
         step(False)
     sync_all()
+    for _ in range(3):
+        step(True)              # per-phase times, launch by launch
+    sync_all()
+    phase = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in ev.items()}
+    graph = None
+    if args.graph:
+        def body(sp):
+            r.forward(out=img, stream=sp)
+            torch.sub(img[0], target, out=dL)
+            r.backward(dL, out=g, stream=sp)
+        graph = r.capture(body)
+
+        def step(record):           # noqa: F811
+            graph.replay()
+            if world > 1:
+                dist.all_reduce(g)
+        for _ in range(3):
+            step(False)
+        sync_all()
     l0 = runtime.launch_count()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -123,7 +144,6 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    phase = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in ev.items()}
     coverage = float(img.double().sum().item()) / (res * res)
     gnorm = float(g.double().norm().item())
     if rank != 0:
@@ -169,10 +189,11 @@ def main():
         'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'multi_tri_4096', 'res_per_gpu': [res, res], 'triangles': K, 'num_samples': 16,
-                   'pixel_triangle_pairs': pairs_total, 'programs': ['tri_color_primal', 'tri_color_grad'],
+                   'pixel_triangle_pairs': pairs_total, 'programs': ['tri_color_primal', 'tri_color_grad'], 'cull': bool(args.cull), 'cuda_graph': bool(args.graph),
                    'l2': 'L2 flushed between timed steps (256 MB write, outside the event pairs)',
                    'parallelism': f'pixel rows sharded over {world} GPU(s); one NCCL all-reduce of the [{K},7] gradient'},
-        'phase_ms': phase,
+        'phase_ms': phase, 'phase_note': 'phases timed launch by launch before the timed region'
+        + ('; the timed steps replay one CUDA graph' if graph is not None else ''),
         'roofline': {'bound': 'fp32_fma', 'kernel': 'tri_color_primal_main (grouped)', 'achieved': achieved,
                      'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
                      'algorithmic_ops_per_instance': oc.unguarded},
