@@ -71,11 +71,12 @@ typedef struct {
                                      per-group arrays, the uniform table has one row per group */
     int n_pixel_args;             /* grouped programs: arguments read from images indexed by pixel */
     int accumulate;               /* grouped programs: outputs are added into the images in out_ptrs */
-    int n_tile_conds;             /* plain render programs: tile conditions classified by `tile_kernel` before every
-                                     launch (0 = none).  A tile is block_size pixel columns x tile_rows pixel rows;
+    int n_tile_conds;             /* render programs: tile conditions classified by `tile_kernel` before every
+                                     launch (0 = none).  A tile is tile_cols pixel columns x tile_rows pixel rows;
                                      the kernel writes one tri-state (0 false / 1 true for every pixel of the tile,
                                      2 unresolved) per condition and tile, which the main kernel reads per block */
-    int tile_rows;                /* plain render programs: pixel rows walked by one block (>= 1) */
+    int tile_rows;                /* render programs: pixel rows walked by one block (>= 1) */
+    int tile_cols;                /* tile width: a multiple of 32 that divides block_size (whole warps per tile) */
     int tile_samples;             /* samples per integral the unit was generated for (the classification bounds the
                                      midpoint abscissae lb + step * (i + 0.5), i < tile_samples, of every pixel) */
     const char *tile_kernel;      /* <name>_tiles, or NULL when n_tile_conds == 0 */

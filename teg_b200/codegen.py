@@ -69,7 +69,8 @@ class KernelSource:
     accumulate: bool = False        # outputs are added into images
     vec: int = 1                    # instances per thread (16-byte vector loads/stores), streaming programs
     tile_conds: int = 0             # tile conditions classified by <name>_tiles before a render launch (cull.tile_cull)
-    tile_rows: int = 0              # pixel rows per tile (a tile is block_size columns wide)
+    tile_rows: int = 0              # pixel rows per tile
+    tile_cols: int = 0              # pixel columns per tile (whole warps; divides block_size)
     tile_kernel: str = ''
     tile_bodies: List = None        # [(label, {condition: admitted states})]: bodies <name>_tile_<label> for resolved tiles
     stats: Dict[str, float] = None
@@ -83,9 +84,12 @@ class Emitter:
     def __init__(self, sch: Schedule, ctype: str, num_samples: int, name: str,
                  block_size: int = 128, unroll_inner: int = 32, unroll_outer: int = 1, pred_accum: bool = True, use_asm: bool = True, team: int = 1, coop: bool = True,
                  pred_mix: float = 0.25, jam: int = 4, coop_max_lanes: int = 4,
-                 integration_mode: str = 'rectangular_quadrature', tile_rows: int = 16):
+                 integration_mode: str = 'rectangular_quadrature', tile_rows: int = 16, tile_cols: int = 32):
         assert ctype in ('float', 'double')
         self.tile_rows = int(tile_rows)
+        # tiles are tile_cols columns wide: whole warps, so that the body choice is uniform within a warp
+        assert tile_cols % 32 == 0 and block_size % tile_cols == 0, 'tile_cols: a multiple of 32 dividing the block size'
+        self.tile_cols = int(tile_cols)
         # the reference names three modes (to_c.py:389-393) and ships a template for the first only
         assert integration_mode in INTEGRATION_MODES, f'unknown integration mode {integration_mode}'
         self.mode = integration_mode
@@ -477,6 +481,52 @@ class Emitter:
         for j in bx + by:
             leaf[j] = (f'g_b{j}_lo', f'g_b{j}_hi')
         e = lambda line, ind=1: self.emit(line, ind)     # noqa: E731
+
+        def points():
+            # launch-invariant values the cones read (points), from the scalar arguments
+            need: List[int] = []
+            seen = set()
+            for _, _, r, B in roots:
+                interior = (lambda j, B=B: bool(fv(j) & B) or dep.get(j, False))
+                stack = [r]
+                visited = set()
+                while stack:
+                    j = stack.pop()
+                    if j in visited:
+                        continue
+                    visited.add(j)
+                    if j in leaf:
+                        continue
+                    if interior(j):
+                        stack.extend(nodes[j].args)
+                        continue
+                    sub = [(j, False)]          # a point: emit its whole (launch-invariant) cone
+                    while sub:
+                        m, done = sub.pop()
+                        if done:
+                            need.append(m)
+                            continue
+                        if m in seen or nodes[m].op == 'const':
+                            continue
+                        seen.add(m)
+                        sub.append((m, True))
+                        for a2 in reversed(nodes[m].args):
+                            sub.append((a2, False))
+            for m in need:
+                e(f'const {self.decl(m)} v{m} = {self.expr(m, {})};')
+
+        def cones(ind: int, index: str, guard: str):
+            e('bool unresolved = false;', ind)
+            for k, (kind, c, r, B) in enumerate(roots):
+                pre = f'k{k}_'
+                e('{', ind)
+                e(f'T {pre}pz = g_pz;', ind + 1)
+                t, f = self._iv_cone(r, (lambda j, B=B: bool(fv(j) & B) or dep.get(j, False)), leaf, {}, ind + 1, pre)
+                e(f'const T {pre}tri = {self._iv_result(t, f, pre)};', ind + 1)
+                e(f'{guard}tiles[(size_t){k} * n_tiles + {index}] = {pre}tri;', ind + 1)
+                e(f'unresolved = unresolved || {pre}tri == {literal("2", T)};', ind + 1)
+                e('}', ind)
+
         if walk:
             # grouped launches (tiles are relative to each group's window): one warp per tile walks the tile's rows
             # [r0, r1) and columns [c0, c1) itself -- exact ranges of the box edges and the midpoint abscissae
@@ -503,71 +553,34 @@ class Emitter:
                 for j in bvs:
                     e(f'const T g_b{j}_lo = g_s{lo_n}_lo, g_b{j}_hi = g_s{lo_n}_hi;')
             e('for (int off = 16; off > 0; off >>= 1) g_pz = g_pz + __shfl_xor_sync(0xffffffffu, g_pz, off);')
+            points()
+            cones(1, 't', 'if (lane == 0) ')
+            e('(void)unresolved;')
         else:
-            # [min, max] of the box edges and of the sample abscissae over the tile's rows / columns: computed once per
-            # grid by the runtime's tile_ranges kernel (exact walk over the rows / columns), 7 values per tile row / column
+            # [min, max] of the box edges and of the sample abscissae over a tile row / tile column come from the
+            # runtime's tile_ranges kernel (exact walk over the rows / columns, cached per grid): 7 values per entry.
+            # One thread per BLOCK of the main kernel: its TEGB_TILE_SUB tiles (tile_cols columns each, one or more
+            # warps) are classified in turn, and the block goes to the front of the launch order if any is unresolved.
             e('const T* __restrict__ rx = ranges + (size_t)ty * 7;')
-            e('const T* __restrict__ ry = ranges + ((size_t)n_ty + tx) * 7;')
-            for nm, tab in (('xl', 'rx'), ('yl', 'ry')):
-                e(f'const T g_{nm}_lo = {tab}[0], g_{nm}_hi = {tab}[1];')
-            for nm, tab in (('xu', 'rx'), ('yu', 'ry')):
-                e(f'const T g_{nm}_lo = {tab}[2], g_{nm}_hi = {tab}[3];')
+            e('const T g_xl_lo = rx[0], g_xl_hi = rx[1], g_xu_lo = rx[2], g_xu_hi = rx[3];')
             for j in bx:
                 e(f'const T g_b{j}_lo = rx[4], g_b{j}_hi = rx[5];')
+            points()
+            e('bool any_unresolved = false;')
+            e('for (int sub = 0; sub < TEGB_TILE_SUB; ++sub) {')
+            e('const int txs = tx * TEGB_TILE_SUB + sub;', 2)
+            e('if (txs >= n_txs || txs * TEGB_TILE_COLS >= res_y) break;        // no pixel in this tile', 2)
+            e('const T* __restrict__ ry = ranges + ((size_t)n_ty + txs) * 7;', 2)
+            e('const T g_yl_lo = ry[0], g_yl_hi = ry[1], g_yu_lo = ry[2], g_yu_hi = ry[3];', 2)
             for j in by:
-                e(f'const T g_b{j}_lo = ry[4], g_b{j}_hi = ry[5];')
-            e('const T g_pz = rx[6] + ry[6];')
-        # launch-invariant values the cones read (points), from the scalar arguments
-        need: List[int] = []
-        seen = set()
-        for _, _, r, B in roots:
-            interior = (lambda j, B=B: bool(fv(j) & B) or dep.get(j, False))
-            stack = [r]
-            visited = set()
-            while stack:
-                j = stack.pop()
-                if j in visited:
-                    continue
-                visited.add(j)
-                if j in leaf:
-                    continue
-                if interior(j):
-                    stack.extend(nodes[j].args)
-                    continue
-                # a point: emit its whole (launch-invariant) cone
-                sub = [(j, False)]
-                while sub:
-                    m, done = sub.pop()
-                    if done:
-                        need.append(m)
-                        continue
-                    if m in seen or nodes[m].op == 'const':
-                        continue
-                    seen.add(m)
-                    sub.append((m, True))
-                    for a2 in reversed(nodes[m].args):
-                        sub.append((a2, False))
-        for m in need:
-            e(f'const {self.decl(m)} v{m} = {self.expr(m, {})};')
-        e('bool unresolved = false;')
-        for k, (kind, c, r, B) in enumerate(roots):
-            pre = f'k{k}_'
-            e('{')
-            e(f'T {pre}pz = g_pz;', 2)
-            t, f = self._iv_cone(r, (lambda j, B=B: bool(fv(j) & B) or dep.get(j, False)), leaf, {}, 2, pre)
-            e(f'const T {pre}tri = {self._iv_result(t, f, pre)};', 2)
-            if walk:
-                e(f'if (lane == 0) tiles[(size_t){k} * n_tiles + t] = {pre}tri;', 2)
-            else:
-                e(f'tiles[(size_t){k} * n_tiles + t] = {pre}tri;', 2)
-            e(f'unresolved = unresolved || {pre}tri == {literal("2", T)};', 2)
+                e(f'const T g_b{j}_lo = ry[4], g_b{j}_hi = ry[5];', 2)
+            e('const T g_pz = rx[6] + ry[6];', 2)
+            cones(2, '(size_t)ty * n_txs + txs', '')
+            e('any_unresolved = any_unresolved || unresolved;', 2)
             e('}')
-        if not walk:
-            # launch order of the main kernel: unresolved tiles from the front, resolved ones from the back
-            e('if (unresolved) order[atomicAdd(&counters[0], 1)] = t;')
+            # launch order of the main kernel: unresolved blocks from the front, resolved ones from the back
+            e('if (any_unresolved) order[atomicAdd(&counters[0], 1)] = t;')
             e('else order[n_tx * n_ty - 1 - atomicAdd(&counters[1], 1)] = t;')
-        else:
-            e('(void)unresolved;')
         self.in_main = saved_main
         return self.lines
 
@@ -1084,6 +1097,8 @@ class Emitter:
         src.append(f'typedef {T} T;')
         src.append(f'#define TEGB_NUM_UNIFORM {nu}')
         if tile or any(self.nodes[i].op == 'domtri' for i in self.dag.reachable(sch.outputs)):
+            src.append(f'#define TEGB_TILE_COLS {self.tile_cols}')
+            src.append(f'#define TEGB_TILE_SUB {self.block_size // self.tile_cols}')
             # the poison value of the domain-culling prologue (cull.py)
             src.append(f'#define TEGB_IV_NAN {"nanf" if T == "float" else "nan"}("")')
         if not grouped:
@@ -1161,8 +1176,8 @@ class Emitter:
                 src.append('    const int w_r0 = max(win[4 * g + 0], row0), w_r1 = min(win[4 * g + 1], row1);')
                 src.append('    const int w_c0 = win[4 * g + 2], w_c1 = min(win[4 * g + 3], res_y);')
                 src.append('    const int r0 = w_r0 + ty * tile_rows, r1 = min(r0 + tile_rows, w_r1);')
-                src.append(f'    const int c0 = w_c0 + tx * {bs}, c1 = min(c0 + {bs}, w_c1);')
-                src.append('    if (r0 >= r1 || c0 >= c1) return;              // no pixel: the main kernel skips this tile too')
+                src.append('    const int c0 = w_c0 + tx * TEGB_TILE_COLS, c1 = min(c0 + TEGB_TILE_COLS, w_c1);')
+                src.append('    if (r0 >= r1 || c0 >= c1) return;              // no pixel: the main kernel never reads this tile')
                 src.append('    const size_t n_tiles = (size_t)group_count * per_group;')
                 src.append('    const size_t t = (size_t)w;')
                 for a2 in scal:
@@ -1206,8 +1221,9 @@ class Emitter:
             for a in pix:
                 loads[a] = f'pix{a}[ic]'
             if tile:
-                src.append('    const size_t n_tiles = (size_t)gridDim.x * gridDim.y * gridDim.z;')
-                src.append('    const size_t tile_id = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;')
+                src.append('    const size_t n_tiles = (size_t)gridDim.x * TEGB_TILE_SUB * gridDim.y * gridDim.z;')
+                src.append('    const size_t tile_id = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * (gridDim.x * TEGB_TILE_SUB) + '
+                           'blockIdx.x * TEGB_TILE_SUB + threadIdx.x / TEGB_TILE_COLS;')
                 for k, a in enumerate(tile):
                     src.append(f'    const T tile{k} = tiles[{k} * n_tiles + tile_id];')
                     loads[a] = f'tile{k}'
@@ -1275,11 +1291,11 @@ class Emitter:
                 # pixel (nx, ny) -> instance nx * res_y + ny; box bounds from the two np.linspace edge tables
                 if tile:
                     tparams = ', '.join([f'const T a{a}' for a in scal] +
-                                        ['const T* __restrict__ ranges', 'const int n_tx', 'const int n_ty',
+                                        ['const T* __restrict__ ranges', 'const int res_y', 'const int n_tx', 'const int n_ty', 'const int n_txs',
                                          'T* __restrict__ tiles', 'int* __restrict__ order', 'int* __restrict__ counters'])
                     src.append(f'extern "C" __global__ void {name}_tiles({tparams}) {{')
-                    src.append('    const int t = blockIdx.x * blockDim.x + threadIdx.x;       // one thread per tile')
-                    src.append('    const size_t n_tiles = (size_t)n_tx * n_ty;')
+                    src.append('    const int t = blockIdx.x * blockDim.x + threadIdx.x;       // one thread per block of the main kernel')
+                    src.append('    const size_t n_tiles = (size_t)n_txs * n_ty;')
                     src.append('    if (t >= n_tx * n_ty) return;')
                     src.append('    const int ty = t / n_tx, tx = t - ty * n_tx;')
                     for a in scal:
@@ -1311,8 +1327,9 @@ class Emitter:
                            '    const T ye_lo = live ? ye[ny] : ye[0], ye_hi = live ? ye[ny + 1] : ye[1];')
                 loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye_lo', grid[3]: 'ye_hi'}
                 if tile:
-                    src.append('    const size_t n_tiles = (size_t)gridDim.x * gridDim.y;')
-                    src.append('    const size_t tile_id = (size_t)tile_lin;')
+                    src.append('    const int n_txs = gridDim.x * TEGB_TILE_SUB;')
+                    src.append('    const size_t n_tiles = (size_t)n_txs * gridDim.y;')
+                    src.append('    const size_t tile_id = (size_t)tby * n_txs + tbx * TEGB_TILE_SUB + threadIdx.x / TEGB_TILE_COLS;')
                     for k, a in enumerate(tile):
                         src.append(f'    const T tile{k} = tiles[{k} * n_tiles + tile_id];')
                         loads[a] = f'tile{k}'
@@ -1320,10 +1337,11 @@ class Emitter:
                     src.append(f'    T rr[{nr}];')
                     src.append(f'    for (int k = 0; k < {nr}; k++) rr[k] = {zero};')
 
-                def row_loop(fn: str, with_live: bool, ind: str):
+                def row_loop(fn: str, with_live: bool, ind: str, r_begin: str = '0', r_end: str = 'tile_rows',
+                             r_step: str = '1'):
                     call = ', '.join((['live'] if with_live else []) + [loads[a] for a in varying] + ['res'])
                     src.append(f'{ind}#pragma unroll 1')
-                    src.append(f'{ind}for (int r = 0; r < tile_rows; ++r) {{')
+                    src.append(f'{ind}for (int r = {r_begin}; r < {r_end}; r += {r_step}) {{')
                     # local tile row tby is tile row tby * row_stride + row_phase of the row range (interleaved
                     # sharding: rank r renders tile rows r, r + world, ...); the local image is compact
                     src.append(f'{ind}    const int rel = (tby * row_stride + row_phase) * tile_rows + r;')
@@ -1373,8 +1391,27 @@ class Emitter:
                             row_loop(f'{name}_tile_{label}', b_coop, '        ')
                         src.append('    }')
                         first = False
-                    src.append('    else {')
-                    row_loop(f'{name}_instance', coop, '        ')
+                    # Unresolved tiles of this block: the per-instance program, shared by ALL warps of the block (warp w
+                    # takes rows w, w + W, ... of each unresolved tile) -- the few expensive tiles would otherwise
+                    # each be walked by a single warp while the rest of its block waits.
+                    mine_u = ' || '.join(f'tile{k} == {literal("2", T)}' for k in range(len(tile)))
+                    src.append(f'    if (__syncthreads_or({mine_u})) {{')
+                    src.append('        const int warp_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;')
+                    src.append('        const size_t tile_base = (size_t)tby * n_txs + tbx * TEGB_TILE_SUB;')
+                    src.append('        for (int sub = 0; sub < TEGB_TILE_SUB; ++sub) {')
+                    conds_u = ' || '.join(f'tiles[{k} * n_tiles + tile_base + sub] == {literal("2", T)}' for k in range(len(tile)))
+                    src.append(f'            if (!({conds_u})) continue;                 // block-uniform')
+                    src.append('            for (int cw = 0; cw < TEGB_TILE_COLS / 32; ++cw) {')
+                    src.append(f'                const int ny = tbx * {bs} + sub * TEGB_TILE_COLS + cw * 32 + lane_;')
+                    src.append('                const bool live = ny < res_y;')
+                    src.append('                const int nyc = live ? ny : 0;')
+                    src.append('                const T ye_lo = ye[nyc], ye_hi = ye[nyc + 1];')
+                    for k in range(len(tile)):
+                        src.append(f'                const T tile{k} = {literal("2", T)};')
+                    src.append(f'                (void)nyc; (void)ye_lo; (void)ye_hi;')
+                    row_loop(f'{name}_instance', coop, '                ', 'warp_', 'tile_rows', f'{bs // 32}')
+                    src.append('            }')
+                    src.append('        }')
                     src.append('    }')
                 else:
                     row_loop(f'{name}_instance', coop, '    ')
@@ -1390,7 +1427,7 @@ class Emitter:
                                     n_uniform=nu, scalar_args=scal, array_args=arrs, grid_args=grid,
                                     n_outputs=K, block_size=bs, reduce_outputs=nr, team=team,
                                     grouped=False, pixel_args=pix, accumulate=False,
-                                    tile_conds=len(tile), tile_rows=self.tile_rows,
+                                    tile_conds=len(tile), tile_rows=self.tile_rows, tile_cols=self.tile_cols,
                                     tile_kernel=f'{name}_tiles' if tile else '',
                                     tile_bodies=[(lb, mt) for lb, mt, _, _ in tile_bodies],
                                     stats={'uses_coop': self.uses_coop, 'loops': self.loop_counter})
@@ -1481,7 +1518,7 @@ class Emitter:
                             n_uniform=nu, scalar_args=scal, array_args=arrs, grid_args=grid,
                             n_outputs=K, block_size=bs, reduce_outputs=nr, team=team,
                             grouped=bool(grouped), pixel_args=pix, accumulate=bool(accumulate),
-                            tile_conds=len(tile), tile_rows=self.tile_rows if (tile or grouped) else 0,
+                            tile_conds=len(tile), tile_rows=self.tile_rows if (tile or grouped) else 0, tile_cols=self.tile_cols,
                             tile_kernel=f'{name}_tiles' if tile else '',
                             tile_bodies=[(lb, mt) for lb, mt, _, _ in tile_bodies],
                             stats={'uses_coop': self.uses_coop, 'loops': self.loop_counter})

@@ -326,7 +326,8 @@ extern "C" int tegb_program_create(tegb_module *m, const tegb_program_desc *desc
     r = drv::ModuleGetFunction(&p->f_main, p->mod, desc->main_kernel);
     if (r != CUDA_SUCCESS) return bail(fail(TEGB_ERR_CUDA, "kernel %s: %s", desc->main_kernel, drv::errstr(r)));
     if (desc->n_tile_conds > 0) {
-        if (!desc->tile_kernel || desc->tile_rows < 1 || desc->tile_samples < 1 || desc->n_grid_args != 4)
+        if (!desc->tile_kernel || desc->tile_rows < 1 || desc->tile_samples < 1 || desc->n_grid_args != 4 ||
+            desc->tile_cols < 32 || desc->tile_cols % 32 != 0 || desc->block_size % desc->tile_cols != 0)
             return bail(fail(TEGB_ERR_INVALID, "tile conditions need a render program, tile_rows >= 1 and a tile kernel"));
         r = drv::ModuleGetFunction(&p->f_tiles, p->mod, desc->tile_kernel);
         if (r != CUDA_SUCCESS) return bail(fail(TEGB_ERR_CUDA, "kernel %s: %s", desc->tile_kernel, drv::errstr(r)));
@@ -710,6 +711,7 @@ __global__ void tile_ranges(const T *__restrict__ xe, const T *__restrict__ ye, 
     int first, last;
     if (is_x) { first = row0 + (e * row_stride + row_phase) * tile_rows; last = min(first + tile_rows, row0 + n_rows); }
     else { first = (e - n_ty) * tile_cols; last = min(first + tile_cols, res_y); }
+    if (first >= last) return;          // a padding tile column beyond the image: never read
     T lb_lo = tab[first], lb_hi = tab[first], ub_lo = tab[first + 1], ub_hi = tab[first + 1];
     T s_lo = tab[first], s_hi = tab[first], pz = (T)0;
     const T half = (T)0.5;
@@ -751,10 +753,10 @@ static int ensure_ranges(tegb_program *p, const tegb_grid *g, int n_tx, int n_ty
     const unsigned tb = 128, tg = (unsigned)(((size_t)(n_tx + n_ty) * 32 + tb - 1) / tb);
     if (p->d.elem_size == 4)
         tile_ranges<float><<<tg, tb, 0, st>>>((const float *)p->d_xe, (const float *)p->d_ye, g->res_y, g->row_begin, n_rows,
-                                             p->d.tile_rows, p->d.block_size, p->d.tile_samples, n_tx, n_ty, row_stride, row_phase, (float *)p->d_ranges);
+                                             p->d.tile_rows, p->d.tile_cols, p->d.tile_samples, n_tx, n_ty, row_stride, row_phase, (float *)p->d_ranges);
     else
         tile_ranges<double><<<tg, tb, 0, st>>>((const double *)p->d_xe, (const double *)p->d_ye, g->res_y, g->row_begin, n_rows,
-                                              p->d.tile_rows, p->d.block_size, p->d.tile_samples, n_tx, n_ty, row_stride, row_phase, (double *)p->d_ranges);
+                                              p->d.tile_rows, p->d.tile_cols, p->d.tile_samples, n_tx, n_ty, row_stride, row_phase, (double *)p->d_ranges);
     RT_CHECK(cudaGetLastError());
     g_launches++;
     p->ranges_grid = *g;
@@ -816,7 +818,7 @@ extern "C" int tegb_render_groups_launch(tegb_program *p, const void *const *gro
     int res_y = g->res_y, row0 = g->row_begin, row1 = g->row_end;
     if (p->d.n_tile_conds > 0) {
         // classify every (group, window tile) for the groups' current parameters
-        int n_tx = (int)gx, n_ty = (int)gy;
+        int n_tx = (int)gx * (p->d.block_size / p->d.tile_cols), n_ty = (int)gy;      // tiles per window row
         const size_t need_t = (size_t)p->d.n_tile_conds * gz * n_tx * n_ty * p->d.elem_size;
         if (need_t > p->tiles_bytes) {
             RT_CHECK(cudaStreamSynchronize((cudaStream_t)st));
@@ -935,9 +937,11 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
     args.push_back(&tile_stride);
     args.push_back(&tile_phase);
     if (p->d.n_tile_conds > 0) {
-        // classify the tiles for these launch-wide arguments and this band
+        // classify the tiles for these launch-wide arguments and this band (tile_cols columns x tile_rows rows each;
+        // a block of the main kernel spans block_size / tile_cols of them)
         int n_tx = (int)gx, n_ty = (int)gy;
-        const size_t need = (size_t)p->d.n_tile_conds * n_tx * n_ty * p->d.elem_size;
+        int n_txs = n_tx * (p->d.block_size / p->d.tile_cols);
+        const size_t need = (size_t)p->d.n_tile_conds * n_txs * n_ty * p->d.elem_size;
         if (need > p->tiles_bytes) {
             RT_CHECK(cudaStreamSynchronize((cudaStream_t)st));      // an earlier launch may still read the old table
             if (p->d_tiles) { cudaFree(p->d_tiles); p->d_tiles = nullptr; p->tiles_bytes = 0; }
@@ -952,7 +956,7 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
             if (p->d.elem_size == 4) { sf[i] = (float)scalars[i]; targs.push_back(&sf[i]); }
             else { sd[i] = scalars[i]; targs.push_back(&sd[i]); }
         }
-        rc = ensure_ranges(p, g, n_tx, n_ty, tile_stride, tile_phase, (cudaStream_t)st);
+        rc = ensure_ranges(p, g, n_txs, n_ty, tile_stride, tile_phase, (cudaStream_t)st);
         if (rc) return rc;
         const size_t n_tiles = (size_t)n_tx * n_ty;
         if (n_tiles > p->order_count) {
@@ -964,8 +968,10 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
         int *d_counters = p->d_order + p->order_count;
         RT_CHECK(cudaMemsetAsync(d_counters, 0, 2 * sizeof(int), (cudaStream_t)st));
         targs.push_back(&p->d_ranges);
+        targs.push_back(&res_y);
         targs.push_back(&n_tx);
         targs.push_back(&n_ty);
+        targs.push_back(&n_txs);
         targs.push_back(&p->d_tiles);
         targs.push_back(&p->d_order);
         targs.push_back(&d_counters);

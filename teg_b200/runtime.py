@@ -24,7 +24,7 @@ class ProgramDesc(ctypes.Structure):
                 ('n_scalar_args', ctypes.c_int), ('n_array_args', ctypes.c_int), ('n_grid_args', ctypes.c_int),
                 ('n_outputs', ctypes.c_int), ('block_size', ctypes.c_int), ('reduce_outputs', ctypes.c_int), ('team', ctypes.c_int), ('vec', ctypes.c_int), ('grouped', ctypes.c_int),
                 ('n_pixel_args', ctypes.c_int), ('accumulate', ctypes.c_int), ('n_tile_conds', ctypes.c_int),
-                ('tile_rows', ctypes.c_int), ('tile_samples', ctypes.c_int), ('tile_kernel', ctypes.c_char_p)]
+                ('tile_rows', ctypes.c_int), ('tile_cols', ctypes.c_int), ('tile_samples', ctypes.c_int), ('tile_kernel', ctypes.c_char_p)]
 
 
 class Grid(ctypes.Structure):
@@ -199,7 +199,8 @@ class Program:
                            ks.n_outputs, ks.block_size, int(getattr(ks, 'reduce_outputs', False)),
                            int(getattr(ks, 'team', 1)), int(getattr(ks, 'vec', 1)), int(getattr(ks, 'grouped', False)),
                            len(getattr(ks, 'pixel_args', None) or ()), int(getattr(ks, 'accumulate', False)),
-                           int(getattr(ks, 'tile_conds', 0)), int(getattr(ks, 'tile_rows', 0)), int(ks.num_samples), self._names[3])
+                           int(getattr(ks, 'tile_conds', 0)), int(getattr(ks, 'tile_rows', 0)),
+                           int(getattr(ks, 'tile_cols', 0) or 32), int(ks.num_samples), self._names[3])
         self.handle = ctypes.c_void_p()
         check(L.tegb_program_create(module.handle, ctypes.byref(desc), device, ctypes.byref(self.handle)))
 

@@ -197,7 +197,14 @@ def test_tiled_render_equals_untiled_and_dense_at_full_size(cuda_device):
         vals = dict(zip(prog.args, bind(prog.args, scene_values(scene, res=(2, 2)))))
         params = {lab: float(v) for lab, v in vals.items() if np.ndim(v) == 0}
         a, b, c = _render_all_ways(scene, res, ((0, 1), (0, 1)), params, reduce=reduce)
-        assert torch.equal(a, b) and torch.equal(b, c), (scene, res, reduce)
+        if reduce:
+            # sums: unresolved tiles are walked by all warps of their block in the tiled kernels, i.e. a different
+            # (still fixed) order of the same terms: equal up to fp32 summation rounding, and reproducible
+            assert torch.equal(b, c) and torch.allclose(a, b, rtol=2e-5, atol=1e-7), (scene, res, a, b)
+            a2, _, _ = _render_all_ways(scene, res, ((0, 1), (0, 1)), params, reduce=reduce)
+            assert torch.equal(a, a2)
+        else:
+            assert torch.equal(a, b) and torch.equal(b, c), (scene, res, reduce)
 
 
 def test_tiled_render_random_triangles_odd_grids_and_bands(cuda_device):
@@ -232,7 +239,8 @@ def test_tiled_render_random_triangles_odd_grids_and_bands(cuda_device):
             assert torch.equal(a, b) and torch.equal(b, c), (scene, t, res, bounds, rows)
             if scene == 'tri_grad':
                 a, b, c = _render_all_ways(scene, res, bounds, params, rows=rows, reduce=True)
-                assert torch.equal(a, b) and torch.equal(b, c), (scene, t, 'reduce')
+                scale = float(b.abs().max()) + 1e-12
+                assert torch.equal(b, c) and float((a - b).abs().max()) <= 2e-5 * scale, (scene, t, 'reduce')
     # one geometry against the oracle through the array path
     from teg_b200.workloads import pixel_boxes
     res, bounds, rows = (257, 391), ((-0.5, 1.5), (0.25, 0.75)), (37, 200)
@@ -256,7 +264,7 @@ def test_tile_classification_resolves_most_tiles(cuda_device):
     mode.render(prog.args[:4], (4096, 4096), ((0, 1), (0, 1)), params)
     torch.cuda.synchronize()
     ks, p = mode.compiled([0, 1, 2, 3], [0, 1, 2, 3])
-    n_tiles = (4096 // ks.block_size) * (4096 // ks.tile_rows)
+    n_tiles = (4096 // ks.tile_cols) * (4096 // ks.tile_rows)
     tiles = p.tile_table(n_tiles * ks.tile_conds)
     frac = float(np.mean(tiles == 2))
     assert set(np.unique(tiles)) <= {0.0, 1.0, 2.0} and 0.01 < frac < 0.2, frac
@@ -339,7 +347,7 @@ def test_prepared_render_rebinds_scalars(cuda_device):
             params = {lab: float(np.float32(x)) for lab, x in zip(prog.args[4:], v)}
             call.set_scalars([params[prog.args[a]] for a in call.ks.scalar_args])
             got = call.run(stream).clone()
-            want = CUDA_EvalMode(prog, num_samples=16, cull=False).render(prog.args[:4], (512, 384), ((0, 1), (0, 1)),
-                                                                         params, reduce=reduce)
+            want = CUDA_EvalMode(prog, num_samples=16).render(prog.args[:4], (512, 384), ((0, 1), (0, 1)),
+                                                              params, reduce=reduce)
             torch.cuda.synchronize()
             assert torch.equal(got, want), (scene, reduce)

@@ -12,7 +12,7 @@ for scene in ('tri_primal', 'tri_grad'):
     mode.render(prog.args[:4], (4096, 4096), ((0, 1), (0, 1)), params, reduce=red)
     torch.cuda.synchronize()
     ks, p = mode.compiled([0, 1, 2, 3], [0, 1, 2, 3], reduce=red)
-    n_tiles = (4096 // ks.block_size) * (4096 // ks.tile_rows)
+    n_tiles = (4096 // ks.tile_cols) * (4096 // ks.tile_rows)
     t = p.tile_table(n_tiles * ks.tile_conds).reshape(ks.tile_conds, -1)
     for k in range(ks.tile_conds):
         print(scene, k, {v: float(np.mean(t[k] == v)) for v in (0, 1, 2)})
