@@ -55,7 +55,8 @@ def _load():
             fn = getattr(lib, name)
             fn.restype = ctypes.c_int
             fn.argtypes = [ctypes.c_void_p, ctypes.POINTER(ct), ctypes.c_long, ctypes.c_int,
-                           ctypes.POINTER(ct), ctypes.c_int, ctypes.c_int, ctypes.c_int]
+                           ctypes.POINTER(ct), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_ulonglong,
+                           ctypes.c_long]
         _lib = lib
     return _lib
 
@@ -92,9 +93,11 @@ class Oracle:
             self._h = None
 
     def eval(self, inputs: Sequence, num_samples: int, dtype=np.float32, n: Optional[int] = None,
-             threads: int = 1, quadrature: str = 'midpoint') -> np.ndarray:
+             threads: int = 1, quadrature: str = 'midpoint', seed: int = 0, inst_base: int = 0) -> np.ndarray:
         """inputs: one scalar or length-n array per program argument (in ``args`` order).
-        quadrature: 'midpoint' (the C backend's rule) or 'trapezoid' (the numpy backend's, numpy_eval.py:57-68).
+        quadrature: 'midpoint' (the C backend's rule), 'trapezoid' (the numpy backend's, numpy_eval.py:57-68) or
+        'monte_carlo' (uniform samples from Philox4x32-10 keyed by ``seed``; ``inst_base`` = index of the first
+        instance, teg_oracle_impl.h case 'T').
         Returns an array [out_size, n] in ``dtype``."""
         dtype = np.dtype(dtype)
         assert len(inputs) == self.n_args, f'expected {self.n_args} inputs, got {len(inputs)}'
@@ -107,9 +110,10 @@ class Oracle:
             fn, ct = self._lib.tego_eval_f64_q, ctypes.c_double
         else:
             raise ValueError('dtype must be float32 or float64')
-        q = {'midpoint': 0, 'trapezoid': 1}[quadrature]
+        q = {'midpoint': 0, 'trapezoid': 1, 'monte_carlo': 2}[quadrature]
         rc = fn(self._h, soa.ctypes.data_as(ctypes.POINTER(ct)), n, int(num_samples),
-                out.ctypes.data_as(ctypes.POINTER(ct)), self.out_size, int(threads), q)
+                out.ctypes.data_as(ctypes.POINTER(ct)), self.out_size, int(threads), q,
+                ctypes.c_ulonglong(int(seed) & 0xFFFFFFFFFFFFFFFF), ctypes.c_long(int(inst_base)))
         if rc != 0:
             raise RuntimeError(f'oracle: {self._lib.tego_last_error().decode()}')
         return out

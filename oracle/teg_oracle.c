@@ -11,6 +11,11 @@
  *   vector (Tup) arithmetic     /root/reference/teg/include/teg_generic_array.h:8-69
  *   one evaluation per call     /root/reference/teg/eval/c_eval.py:129-157
  *
+ * Two further quadrature modes are restated here for the backend's `integration_mode` option: the numpy backend's
+ * trapezoid rule (/root/reference/teg/eval/numpy_eval.py:57-68; pinned to committed outputs of that backend) and
+ * `monte_carlo_uniform`, which the reference names (to_c.py:389-393) but never defines -- PARITY UNPINNED for that
+ * mode: only its generator (Philox4x32-10) is checked against published known-answer vectors.
+ *
  * Instead of generating C text and compiling it per program, this file *interprets* the
  * program (TEGP text, see teg_b200/tegp.py for the grammar), performing exactly the IEEE
  * operations the generated C performs, in working precision (float or double), with the
@@ -259,6 +264,21 @@ int tego_num_args(const Prog *p) { return p->nargs; }
 #define CAT(a, b) CAT_(a, b)
 
 /* ---- fp32 instantiation: float overloads of <math.h> as the generated C++ resolves them ---- */
+/* Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11), the published
+ * counter-based generator: key (k0, k1), counter (c0, c1, c2, c3) -> 4 x 32 random bits.  Used by the Monte Carlo
+ * integration mode only; teg_b200/codegen.py emits the same text into the generated kernels. */
+void tego_philox4x32_10(unsigned int k0, unsigned int k1, unsigned int c0, unsigned int c1, unsigned int c2,
+                               unsigned int c3, unsigned int out[4]) {
+    for (int r = 0; r < 10; r++) {
+        const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+        const unsigned int n0 = (unsigned int)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned int)p1;
+        const unsigned int n2 = (unsigned int)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned int)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
 #define T float
 #define SUF(x) CAT(x, f)
 #define M_SQRT sqrtf
@@ -288,20 +308,23 @@ int tego_num_args(const Prog *p) { return p->nargs; }
 #undef SUF
 
 int tego_eval_f32(const Prog *p, const float *in, long n, int num_samples, float *out, int k, int nthreads) {
-    return tego_eval_f(p, in, n, num_samples, out, k, nthreads, 0);
+    return tego_eval_f(p, in, n, num_samples, out, k, nthreads, 0, 0, 0);
 }
 
 int tego_eval_f64(const Prog *p, const double *in, long n, int num_samples, double *out, int k, int nthreads) {
-    return tego_eval_d(p, in, n, num_samples, out, k, nthreads, 0);
+    return tego_eval_d(p, in, n, num_samples, out, k, nthreads, 0, 0, 0);
 }
 
-/* quadrature: 0 = midpoint rule of the C backend, 1 = trapezoid rule of the numpy backend (numpy_eval.py:57-68) */
-int tego_eval_f32_q(const Prog *p, const float *in, long n, int num_samples, float *out, int k, int nthreads, int q) {
-    return tego_eval_f(p, in, n, num_samples, out, k, nthreads, q);
+/* quadrature: 0 = midpoint rule of the C backend, 1 = trapezoid rule of the numpy backend (numpy_eval.py:57-68),
+ * 2 = uniform Monte Carlo (seed = generator key, inst_base = index of the first instance of this call) */
+int tego_eval_f32_q(const Prog *p, const float *in, long n, int num_samples, float *out, int k, int nthreads, int q,
+                    unsigned long long seed, long inst_base) {
+    return tego_eval_f(p, in, n, num_samples, out, k, nthreads, q, seed, inst_base);
 }
 
-int tego_eval_f64_q(const Prog *p, const double *in, long n, int num_samples, double *out, int k, int nthreads, int q) {
-    return tego_eval_d(p, in, n, num_samples, out, k, nthreads, q);
+int tego_eval_f64_q(const Prog *p, const double *in, long n, int num_samples, double *out, int k, int nthreads, int q,
+                    unsigned long long seed, long inst_base) {
+    return tego_eval_d(p, in, n, num_samples, out, k, nthreads, q, seed, inst_base);
 }
 
 /* size of the program's result (1 for scalars, k for Tup programs), probed on one dummy instance */

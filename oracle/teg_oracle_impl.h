@@ -8,10 +8,24 @@
 
 typedef struct { int n; T v[TEGO_MAXV]; } SUF(Val);
 
+/* u in [0, 1) from the Philox words: 24 bits for float, 53 bits for double (exact conversions, exact scalings) */
+static T SUF(tego_uniform)(unsigned long long seed, unsigned long long inst, unsigned int depth, unsigned int i) {
+    unsigned int r[4];
+    tego_philox4x32_10((unsigned int)seed, (unsigned int)(seed >> 32), (unsigned int)inst, (unsigned int)(inst >> 32),
+                       depth, i, r);
+    if (sizeof(T) == 4) return (T)(r[0] >> 8) * (T)(1.0 / 16777216.0);
+    return (T)(((unsigned long long)(r[0] >> 5) << 26) | (unsigned long long)(r[1] >> 6)) * (T)(1.0 / 9007199254740992.0);
+}
+
 typedef struct {
     const Prog *p;
     int num_samples;
-    int quadrature;             /* 0 = midpoint (the C backend), 1 = trapezoid on linspace (the numpy backend) */
+    int quadrature;             /* 0 = midpoint (the C backend), 1 = trapezoid on linspace (the numpy backend),
+                                   2 = uniform Monte Carlo with a counter-based generator (see case 'T') */
+    unsigned long long seed;    /* Monte Carlo: key of the generator */
+    unsigned long long inst;    /* Monte Carlo: index of the instance being evaluated */
+    int depth;                  /* Monte Carlo: nesting depth of the integral being evaluated */
+    int *memo_depth;            /* depth at which a memoised value was computed (structurally shared integrals) */
     /* current binding of every label (program inputs, let variables, integration variables) */
     SUF(Val) *bind_val;
     long *bind_stamp;           /* 0 = unbound */
@@ -27,6 +41,7 @@ static int SUF(memo_valid)(SUF(Ctx) *c, int id) {
     const Node *nd = &c->p->nodes[id];
     long st = c->memo_stamp[id];
     if (st == 0) return 0;
+    if (c->quadrature == 2 && c->memo_depth[id] != c->depth) return 0;
     for (int i = 0; i < nd->nfree; i++)
         if (c->bind_stamp[nd->free[i]] >= st) return 0;
     return 1;
@@ -68,6 +83,7 @@ static int SUF(eval_bool)(SUF(Ctx) *c, int id) {
     }
     c->memo_bool[id] = (unsigned char)r;
     c->memo_stamp[id] = ++c->clock;
+    c->memo_depth[id] = c->depth;
     return r;
 }
 
@@ -175,7 +191,30 @@ static SUF(Val) SUF(eval)(SUF(Ctx) *c, int id) {
         int lab = nd->label;
         SUF(Val) saved = c->bind_val[lab]; long saved_stamp = c->bind_stamp[lab];
         SUF(Val) out; out.n = 1; out.v[0] = 0;
-        if (c->quadrature == 1) {
+        if (c->quadrature == 2) {
+            /* monte_carlo_uniform: the reference names the mode (to_c.py:389-393) but ships neither a template nor
+             * a definition, so the semantics are this backend's (teg_b200/codegen.py, Emitter._mc_loop, same text):
+             *   u_i = philox4x32-10(key = seed, counter = (instance lo, instance hi, depth, i)) mapped to [0, 1)
+             *   x_i = lb + (ub - lb) * u_i;  step = ((T)(ub - lb)) / N;  out = out + f(x_i) * step   (left fold)
+             * The points depend on the instance, the nesting depth and the sample index only: integrals of the same
+             * depth share their points (common random numbers), which keeps loop fusion and hoisting exact. */
+            const int N = c->num_samples;
+            T width = hi.v[0] - lo.v[0];
+            T step = ((T)width) / N;
+            int first = 1;
+            const int depth = c->depth;
+            for (unsigned int i = 0; i < (unsigned int)N; i++) {
+                SUF(Val) x; x.n = 1;
+                x.v[0] = lo.v[0] + width * SUF(tego_uniform)(c->seed, c->inst, (unsigned int)depth, i);
+                c->bind_val[lab] = x; c->bind_stamp[lab] = ++c->clock;
+                c->depth = depth + 1;
+                SUF(Val) f = SUF(eval)(c, nd->kids[2]);
+                c->depth = depth;
+                if (c->err) break;
+                if (first) { out.n = f.n; for (int j = 0; j < f.n; j++) out.v[j] = 0; first = 0; }
+                for (int j = 0; j < f.n; j++) out.v[j] = out.v[j] + f.v[j] * step;
+            }
+        } else if (c->quadrature == 1) {
             /* numpy backend, /root/reference/teg/eval/numpy_eval.py:57-68:
              *   samples, step = np.linspace(lower, upper, N, retstep=True)   (N points, end points included,
              *                    x_i = i*step + lower, x_{N-1} = upper exactly)
@@ -227,6 +266,7 @@ static SUF(Val) SUF(eval)(SUF(Ctx) *c, int id) {
 static SUF(Ctx) *SUF(ctx_new)(const Prog *p, int num_samples, int quadrature) {
     SUF(Ctx) *c = (SUF(Ctx) *)calloc(1, sizeof(SUF(Ctx)));
     c->p = p; c->num_samples = num_samples; c->quadrature = quadrature;
+    c->memo_depth = (int *)calloc(p->nnodes ? p->nnodes : 1, sizeof(int));
     c->bind_val = (SUF(Val) *)calloc(p->nlabels ? p->nlabels : 1, sizeof(SUF(Val)));
     c->bind_stamp = (long *)calloc(p->nlabels ? p->nlabels : 1, sizeof(long));
     c->memo_val = (SUF(Val) *)calloc(p->nnodes, sizeof(SUF(Val)));
@@ -236,14 +276,14 @@ static SUF(Ctx) *SUF(ctx_new)(const Prog *p, int num_samples, int quadrature) {
 }
 
 static void SUF(ctx_free)(SUF(Ctx) *c) {
-    free(c->bind_val); free(c->bind_stamp); free(c->memo_val); free(c->memo_bool); free(c->memo_stamp); free(c);
+    free(c->bind_val); free(c->bind_stamp); free(c->memo_val); free(c->memo_bool); free(c->memo_stamp); free(c->memo_depth); free(c);
 }
 
 /* Batch driver.  in: SoA [n_args][n] (argument a of instance i at in[a*n+i]); out: SoA [k][n].
  * Plays the role of C_EvalMode.eval (c_eval.py:129-157) called once per instance, minus the
  * process spawn and the 6-digit stdout round trip. */
 int SUF(tego_eval_)(const Prog *p, const T *in, long n, int num_samples, T *out, int k, int nthreads,
-                    int quadrature) {
+                    int quadrature, unsigned long long seed, long inst_base) {
     int failed = 0;
     const char *msg = NULL;
     if (nthreads < 1) nthreads = 1;
@@ -252,11 +292,14 @@ int SUF(tego_eval_)(const Prog *p, const T *in, long n, int num_samples, T *out,
 #endif
     {
         SUF(Ctx) *c = SUF(ctx_new)(p, num_samples, quadrature);
+        c->seed = seed;
 #ifdef _OPENMP
 #pragma omp for schedule(static)
 #endif
         for (long i = 0; i < n; i++) {
             if (failed) continue;
+            c->inst = (unsigned long long)(inst_base + i);
+            c->depth = 0;
             for (int a = 0; a < p->nargs; a++) {
                 int lab = p->arg_labels[a];
                 c->bind_val[lab].n = 1;

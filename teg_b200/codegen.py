@@ -29,13 +29,30 @@ from typing import Dict, List, Optional, Sequence
 from .dag import Dag
 from .schedule import Block, Eval, IfGroup, LoopGroup, Schedule, Scheduler
 
+# Philox4x32-10 (Salmon et al., SC'11) and the map to [0, 1): the same text as oracle/teg_oracle.c
+_MC_PREAMBLE = '''#define TEGB_MC_SEED @SEED@
+TEGB_FN T tegb_uniform(const unsigned long long seed, const unsigned long long inst, const unsigned int depth,
+                       const unsigned int i) {
+    unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
+    unsigned int c0 = (unsigned int)inst, c1 = (unsigned int)(inst >> 32), c2 = depth, c3 = i;
+    for (int r = 0; r < 10; r++) {
+        const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+        const unsigned int n0 = (unsigned int)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned int)p1;
+        const unsigned int n2 = (unsigned int)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned int)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    if (sizeof(T) == 4) return (T)(c0 >> 8) * (T)(1.0 / 16777216.0);
+    return (T)(((unsigned long long)(c0 >> 5) << 26) | (unsigned long long)(c1 >> 6)) * (T)(1.0 / 9007199254740992.0);
+}'''
+
 _MATH = {
     'float': {'sqrt': 'sqrtf', 'sin': 'sinf', 'cos': 'cosf', 'asin': 'asinf', 'atan2': 'atan2f'},
     'double': {'sqrt': 'sqrt', 'sin': 'sin', 'cos': 'cos', 'asin': 'asin', 'atan2': 'atan2'},
 }
 
 
-INTEGRATION_MODES = ('rectangular_quadrature', 'trapezoidal_quadrature')
+INTEGRATION_MODES = ('rectangular_quadrature', 'trapezoidal_quadrature', 'monte_carlo_uniform')
 
 
 def literal(text: str, ctype: str) -> str:
@@ -72,6 +89,7 @@ class KernelSource:
     tile_rows: int = 0              # pixel rows per tile
     tile_cols: int = 0              # pixel columns per tile (whole warps; divides block_size)
     tile_kernel: str = ''
+    takes_instance_index: bool = False     # instance functions take the instance index (monte_carlo_uniform)
     tile_bodies: List = None        # [(label, {condition: admitted states})]: bodies <name>_tile_<label> for resolved tiles
     stats: Dict[str, float] = None
 
@@ -84,9 +102,11 @@ class Emitter:
     def __init__(self, sch: Schedule, ctype: str, num_samples: int, name: str,
                  block_size: int = 128, unroll_inner: int = 32, unroll_outer: int = 1, pred_accum: bool = True, use_asm: bool = True, team: int = 1, coop: bool = True,
                  pred_mix: float = 0.25, jam: int = 4, coop_max_lanes: int = 4,
-                 integration_mode: str = 'rectangular_quadrature', tile_rows: int = 16, tile_cols: int = 32):
+                 integration_mode: str = 'rectangular_quadrature', tile_rows: int = 16, tile_cols: int = 32,
+                 mc_seed: int = 0):
         assert ctype in ('float', 'double')
         self.tile_rows = int(tile_rows)
+        self.mc_seed = int(mc_seed) & 0xFFFFFFFFFFFFFFFF
         # tiles are tile_cols columns wide: whole warps, so that the body choice is uniform within a warp
         assert tile_cols % 32 == 0 and block_size % tile_cols == 0, 'tile_cols: a multiple of 32 dividing the block size'
         self.tile_cols = int(tile_cols)
@@ -229,6 +249,8 @@ class Emitter:
         """data/templates/rectangular_rule.template.c:1-11, several accumulators per pass."""
         if self.mode == 'trapezoidal_quadrature':
             return self._trapezoid_loop(st, known, ind, depth, declare)
+        if self.mode == 'monte_carlo_uniform':
+            return self._mc_loop(st, known, ind, depth, declare)
         if self._jam_ok(st, depth):
             return self._jam_loop(st, known, ind, depth, declare)
         k = self.loop_counter
@@ -622,6 +644,37 @@ class Emitter:
         one = literal('1', T)
         for q in st.quads:
             self.emit(f'v{q} = ((((lo{k} < hi{k}) ? {one} : -{one}) * step{k}) * v{q}) / {literal("2", T)};', ind + 1)
+        self.emit('}', ind)
+
+    def _mc_loop(self, st: LoopGroup, known: Dict[int, bool], ind: int, depth: int, declare: bool = True):
+        """``monte_carlo_uniform``: the reference names the mode (to_c.py:389-393) but ships neither a template nor a
+        definition; the semantics are defined here and restated by the oracle (oracle/teg_oracle_impl.h, case 'T'):
+        ``u_i = Philox4x32-10(key = seed; counter = (instance lo, instance hi, depth, i))`` mapped to [0, 1),
+        ``x_i = lb + (ub - lb) * u_i``, ``step = (ub - lb) / N``, ``out = out + f(x_i) * step`` folded left to right.
+        The points depend on the instance, the integral's nesting depth in the program and the sample index only, so
+        integrals of the same depth share their points (common random numbers) and loop fusion / hoisting stay exact.
+        Reproducible: the same (seed, instance, program) gives the same bits on any launch geometry."""
+        k = self.loop_counter
+        self.loop_counter += 1
+        N, T = self.N, self.ctype
+        tree_depth = int(self.nodes[st.bvar].attr)
+        for q in st.quads:
+            self._define(q)
+            if declare:
+                self.emit(f'T v{q} = {literal("0", T)};', ind)
+        self._define(st.bvar)
+        self.emit('{', ind)
+        self.emit(f'const T lo{k} = {self.ref(st.lo, known)};', ind + 1)
+        self.emit(f'const T width{k} = {self.ref(st.hi, known)} - lo{k};', ind + 1)
+        self.emit(f'const T step{k} = ((T)width{k}) / (T){N};', ind + 1)
+        self.emit('#pragma unroll 1', ind + 1)
+        self.emit(f'for (unsigned int s{k} = 0; s{k} < {N}u; ++s{k}) {{', ind + 1)
+        self.emit(f'const T x{st.bvar} = lo{k} + width{k} * tegb_uniform(TEGB_MC_SEED, tegb_inst, {tree_depth}u, s{k});', ind + 2)
+        self.block(st.body, ind + 2, depth + 1)
+        for q in st.quads:
+            body = self.ref(self.nodes[q].args[2], st.body.known)
+            self.emit(f'v{q} = v{q} + {body} * step{k};', ind + 2)
+        self.emit('}', ind + 1)
         self.emit('}', ind)
 
     # ------------------------------------------------------------ outer-loop blocking (unroll and jam)
@@ -1087,10 +1140,17 @@ class Emitter:
         ubody_params = ', '.join([f'const T a{a}' for a in scal] + ['T* __restrict__ U'])
         outs_decl = [f'T* __restrict__ out{k}' for k in range(ns_out)] + (['T* __restrict__ partials'] if nr else [])
         coop = self.uses_coop
+        mc = self.mode == 'monte_carlo_uniform'          # instance functions then take the instance index
+        assert not (mc and (grouped or team != 1)), 'monte_carlo_uniform: thread-per-instance array and render launches'
+
+        def inst(expr: str) -> List[str]:
+            return [f'(unsigned long long)({expr})'] if mc else []
+
         iparams = ', '.join((['const T* __restrict__ tegU'] if grouped else []) +
                             (['const bool live'] if coop else []) +
                             ([] if team == 1 else ['const unsigned int team_rank']) +
-                            [f'const T a{a}' for a in varying] + [f'T (&res)[{K}]'])
+                            [f'const T a{a}' for a in varying] +
+                            (['const unsigned long long tegb_inst'] if mc else []) + [f'T (&res)[{K}]'])
         src: List[str] = []
         src.append(f'// generated by teg_b200.codegen for program "{self.dag.name}"  (precision {T}, {self.N} samples)')
         src.append('#include "teg_b200_runtime.cuh"')
@@ -1103,6 +1163,8 @@ class Emitter:
             src.append(f'#define TEGB_IV_NAN {"nanf" if T == "float" else "nan"}("")')
         if not grouped:
             src.append('TEGB_UNIFORM_TABLE(T, tegU, TEGB_NUM_UNIFORM);')
+        if mc:
+            src += _MC_PREAMBLE.replace('@SEED@', f'{self.mc_seed}ull').split('\n')
         src.append('')
         src.append(f'TEGB_FN void {name}_uniform_body({ubody_params}) {{')
         for a in scal:
@@ -1339,7 +1401,9 @@ class Emitter:
 
                 def row_loop(fn: str, with_live: bool, ind: str, r_begin: str = '0', r_end: str = 'tile_rows',
                              r_step: str = '1'):
-                    call = ', '.join((['live'] if with_live else []) + [loads[a] for a in varying] + ['res'])
+                    # (Monte Carlo: the instance index of a pixel is its index in the whole image, whatever the band)
+                    call = ', '.join((['live'] if with_live else []) + [loads[a] for a in varying] +
+                                     inst('(long long)nx * res_y + ny') + ['res'])
                     src.append(f'{ind}#pragma unroll 1')
                     src.append(f'{ind}for (int r = {r_begin}; r < {r_end}; r += {r_step}) {{')
                     # local tile row tby is tile row tby * row_stride + row_phase of the row range (interleaved
@@ -1422,7 +1486,7 @@ class Emitter:
                 src.append('}')
                 src.append('#endif')
                 text = '\n'.join(src) + '\n'
-                return KernelSource(name=name, ctype=T, num_samples=self.N, source=text,
+                return KernelSource(name=name, ctype=T, num_samples=self.N, source=text, takes_instance_index=mc,
                                     uniform_kernel=f'{name}_uniform', main_kernel=f'{name}_main',
                                     n_uniform=nu, scalar_args=scal, array_args=arrs, grid_args=grid,
                                     n_outputs=K, block_size=bs, reduce_outputs=nr, team=team,
@@ -1450,7 +1514,8 @@ class Emitter:
                     for j in range(vec):
                         h, c = divmod(j, per)
                         src.append(f'        T r{j}[{K}];')
-                        src.append(f'        {name}_instance(' + ', '.join([f'A{a}_{h}.{comps[c]}' for a in varying] + [f'r{j}']) + ');')
+                        src.append(f'        {name}_instance(' + ', '.join([f'A{a}_{h}.{comps[c]}' for a in varying] +
+                                                                       inst(f'i0 + {j}') + [f'r{j}']) + ');')
                     for k in range(K):
                         for h in range(nvec):
                             vals = ', '.join(f'r{h * per + c}[{k}]' for c in range(per))
@@ -1458,7 +1523,7 @@ class Emitter:
                     src.append('    } else {')
                     src.append('        for (long long i = i0; i < n; ++i) {')
                     src.append(f'            T res[{K}];')
-                    src.append(f'            {name}_instance(' + ', '.join([f'in{a}[i]' for a in varying] + ['res']) + ');')
+                    src.append(f'            {name}_instance(' + ', '.join([f'in{a}[i]' for a in varying] + inst('i') + ['res']) + ');')
                     for k in range(K):
                         src.append(f'            out{k}[i] = res[{k}];')
                     src.append('        }')
@@ -1466,7 +1531,7 @@ class Emitter:
                     src.append('}')
                     src.append('#endif')
                     text = '\n'.join(src) + '\n'
-                    return KernelSource(name=name, ctype=T, num_samples=self.N, source=text,
+                    return KernelSource(name=name, ctype=T, num_samples=self.N, source=text, takes_instance_index=mc,
                                         uniform_kernel=f'{name}_uniform', main_kernel=f'{name}_main',
                                         n_uniform=nu, scalar_args=scal, array_args=arrs, grid_args=grid,
                                         n_outputs=K, block_size=bs, reduce_outputs=0, team=1, vec=vec,
@@ -1475,9 +1540,9 @@ class Emitter:
                     src.append('    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;')
                     if coop:
                         src.append('    const long long ic = i < n ? i : 0;')
-                        call = ', '.join(['i < n'] + [f'in{a}[ic]' for a in varying] + ['res'])
+                        call = ', '.join(['i < n'] + [f'in{a}[ic]' for a in varying] + inst('ic') + ['res'])
                     else:
-                        call = ', '.join([f'in{a}[i]' for a in varying] + ['res'])
+                        call = ', '.join([f'in{a}[i]' for a in varying] + inst('i') + ['res'])
                 else:
                     # TEAM threads per instance (a slice of a warp, a warp, or a whole block)
                     src.append('    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;')
@@ -1513,7 +1578,7 @@ class Emitter:
             src.append('}')
         src.append('#endif')
         text = '\n'.join(src) + '\n'
-        return KernelSource(name=name, ctype=T, num_samples=self.N, source=text,
+        return KernelSource(name=name, ctype=T, num_samples=self.N, source=text, takes_instance_index=mc,
                             uniform_kernel=f'{name}_uniform', main_kernel=f'{name}_main',
                             n_uniform=nu, scalar_args=scal, array_args=arrs, grid_args=grid,
                             n_outputs=K, block_size=bs, reduce_outputs=nr, team=team,

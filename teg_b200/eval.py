@@ -55,15 +55,18 @@ class CUDA_EvalMode(EvalMode):
     num_samples: midpoint samples per integral (reference default 50, c_eval.py:26).
     float_width: 'float' (what C_EvalMode hard-wires, c_eval.py:32) or 'double'
                  (the CLI's ``-f double``, teg/__main__.py:49-52).
-    integration_mode: 'rectangular_quadrature' (default, the C backend) or 'trapezoidal_quadrature'
-                 (the numpy backend's rule); names from to_c.py:389-393.
+    integration_mode: 'rectangular_quadrature' (default, the C backend), 'trapezoidal_quadrature' (the numpy
+                 backend's rule) or 'monte_carlo_uniform' (uniform samples from Philox4x32-10 keyed by ``seed``, the
+                 instance index, the integral's nesting depth and the sample index: reproducible on any launch
+                 geometry; instance index = position in the batch, or the pixel's index in the whole image for
+                 ``render``); names from to_c.py:389-393.
     cull: domain culling (cull.py, default on): bit-identical results, far fewer evaluated comparisons.
     """
 
     def __init__(self, expr, num_samples: int = 50, float_width: str = 'float', device: int = 0,
                  arglist: Sequence = (), name: str = 'teg_method', use_cache: bool = True,
                  block_size: int = 128, team=1, nvrtc_opts: str = '',
-                 integration_mode: str = 'rectangular_quadrature', cull: bool = True, **codegen_opts):
+                 integration_mode: str = 'rectangular_quadrature', cull: bool = True, seed: int = 0, **codegen_opts):
         super().__init__(name='CUDA')
         if float_width in ('single', 'f32', np.float32):
             float_width = 'float'
@@ -98,6 +101,8 @@ class CUDA_EvalMode(EvalMode):
         self.integration_mode = integration_mode
         if integration_mode != 'rectangular_quadrature':
             codegen_opts = dict(codegen_opts, integration_mode=integration_mode)
+            if integration_mode == 'monte_carlo_uniform':
+                codegen_opts['mc_seed'] = int(seed)
             assert team in (1, 'auto'), 'teams are defined for rectangular_quadrature only'
             self.team = 1
         self.codegen_opts = codegen_opts

@@ -25,7 +25,8 @@ def compile_for_host(ks):
     uargs = ', '.join([f'sc[{j}]' for j in range(len(ks.scalar_args))] + ['tegU'])
     varying = list(ks.array_args) + list(ks.grid_args)
     n_in = len(varying) + int(getattr(ks, 'tile_conds', 0))        # tile tri-states come last (pseudo arguments)
-    margs = ', '.join([f'in[{j}][i]' for j in range(n_in)] + ['res'])
+    margs = ', '.join([f'in[{j}][i]' for j in range(n_in)] +
+                      (['(unsigned long long)(inst_base + i)'] if getattr(ks, 'takes_instance_index', False) else []) + ['res'])
     stores = ' '.join(f'out[{k}][i] = res[{k}];' for k in range(ks.n_outputs))
     # tile-culled units: pick the body the kernel would pick for the tile states of this instance
     n_var = len(varying)
@@ -34,7 +35,8 @@ def compile_for_host(ks):
         cond = ' && '.join('(' + ' || '.join(f'in[{n_var + k}][i] == {v}' for v in match[k]) + ')' for k in sorted(match))
         call += f'if ({cond}) {ks.name}_tile_{label}({margs}); else '
     call += f'{ks.name}_instance({margs});'
-    drv = (f'\nextern "C" void run(const {T}* sc, const {T}* const* in, {T}* const* out, long long n) {{\n'
+    drv = (f'\nstatic long long inst_base = 0;\nextern "C" void set_inst_base(long long b) {{ inst_base = b; }}\n'
+           f'extern "C" void run(const {T}* sc, const {T}* const* in, {T}* const* out, long long n) {{\n'
            f'  {ks.name}_uniform_body({uargs});\n'
            f'  for (long long i = 0; i < n; i++) {{ {T} res[{ks.n_outputs}]; {call} {stores} }}\n}}\n')
     text = pre + ks.source + drv
@@ -50,7 +52,7 @@ def compile_for_host(ks):
     return ctypes.CDLL(so)
 
 
-def run_on_host(ks, inputs, n, dtype, tile_inputs=()):
+def run_on_host(ks, inputs, n, dtype, tile_inputs=(), inst_base=0):
     """tile_inputs: one per-instance array of tri-states (0 / 1 / 2) per tile condition of a tiled render unit."""
     lib = compile_for_host(ks)
     assert len(tile_inputs) == int(getattr(ks, 'tile_conds', 0))
@@ -63,5 +65,6 @@ def run_on_host(ks, inputs, n, dtype, tile_inputs=()):
     outs = [np.empty(n, dtype=dtype) for _ in range(ks.n_outputs)]
     inp = (P * max(1, len(arrs)))(*[a.ctypes.data_as(P) for a in arrs])
     outp = (P * len(outs))(*[o.ctypes.data_as(P) for o in outs])
+    lib.set_inst_base(ctypes.c_longlong(inst_base))
     lib.run(sc.ctypes.data_as(P), inp, outp, ctypes.c_longlong(n))
     return np.stack(outs)

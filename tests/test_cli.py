@@ -88,3 +88,13 @@ def test_integration_mode_flag_selects_the_trapezoid_rule(tmp_path):
     text = out.read_text()
     assert '/ (T)8;' in text and '== 8u) ? hi' in text        # step = (hi - lo) / (N - 1); last point = hi
     assert _run(['-c', '--integration-mode', 'simpson', 'prog.py'], tmp_path).returncode != 0
+
+
+def test_monte_carlo_flag(tmp_path):
+    (tmp_path / 'prog.py').write_text(PROG)
+    out = tmp_path / 'mc.cu'
+    r = _run(['-c', '-t', 'CUDA', '-s', '32', '-m', 'mc', '-o', str(out), '--integration-mode', 'monte_carlo_uniform',
+              '--seed', '42', 'prog.py'], tmp_path)
+    assert r.returncode == 0, r.stderr
+    text = out.read_text()
+    assert '#define TEGB_MC_SEED 42ull' in text and 'tegb_uniform(TEGB_MC_SEED, tegb_inst, 0u' in text

@@ -342,3 +342,28 @@ def test_tile_cull_structure_and_spec_path_on_host(tmp_path, monkeypatch):
     got = run_on_host(ks, inputs, res * res, np.float32, tile_inputs=[tri])
     assert np.array_equal(got[0], want)
     assert 0 < np.count_nonzero(tri == 1) and 0 < np.count_nonzero(tri == 0) and 0 < np.count_nonzero(tri == 2)
+
+
+@pytest.mark.parametrize('scene,ns', [('tri_primal', 16), ('tri_grad', 16), ('shaded_grad', 8), ('nested3d_grad', 6),
+                                      ('readme_primal', 50), ('rect_hyperbola_grad', 12)])
+def test_monte_carlo_lowering_matches_oracle_on_host(scene, ns, tmp_path, monkeypatch):
+    """``integration_mode='monte_carlo_uniform'``: generated code == oracle restatement, bit for bit (fused loops,
+    hoisted integrals and Tup programs included: the points depend on instance, depth and sample index only)."""
+    from oracle import Oracle
+    from teg_b200 import runtime
+    monkeypatch.setenv('TEGB200_CACHE_DIR', str(tmp_path))
+    prog = load_program(scene)
+    inputs = bind(prog.args, scene_values(scene, res=(12, 12), n=150))
+    n = max(np.size(v) for v in inputs)
+    arr = [i for i, v in enumerate(inputs) if np.ndim(v) > 0]
+    sch = make_schedule(build_dag(prog), arr)
+    for dtype, ctype in ((np.float32, 'float'), (np.float64, 'double')):
+        ks = generate(sch, ctype, ns, use_asm=False, integration_mode='monte_carlo_uniform', mc_seed=2024)
+        assert ks.takes_instance_index
+        got = run_on_host(ks, inputs, n, dtype, inst_base=77)
+        want = Oracle(program_text(scene)).eval(inputs, ns, dtype, quadrature='monte_carlo', seed=2024, inst_base=77)
+        assert np.array_equal(got, want, equal_nan=True), (scene, ctype)
+    dev = generate(sch, 'float', ns, integration_mode='monte_carlo_uniform', mc_seed=2024)
+    assert len(runtime.Module(dev.source).cubin()) > 1000          # the device unit compiles for sm_100a
+    with pytest.raises(AssertionError):
+        generate(sch, 'float', ns, integration_mode='monte_carlo_uniform', team=4)

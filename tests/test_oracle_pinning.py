@@ -116,3 +116,42 @@ def test_trapezoid_oracle_reproduces_numpy_backend_vectors(path):
 
 def test_numpy_fixtures_present():
     assert len(NUMPY_VECTORS) >= 10
+
+
+# ---- monte_carlo_uniform: the generator is the published Philox4x32-10 ---------------------------------------------
+def test_philox_known_answers():
+    """Known-answer vectors of Random123 (kat_vectors, philox4x32 with 10 rounds): the oracle's generator is the
+    published one (the mode itself has no reference implementation: 'parity unpinned' beyond the generator)."""
+    import ctypes
+    import oracle
+    oracle.build()
+    lib = ctypes.CDLL(oracle.LIB_PATH)
+    out = (ctypes.c_uint * 4)()
+    cases = [((0, 0), (0, 0, 0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+             ((0xffffffff, 0xffffffff), (0xffffffff,) * 4, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+             ((0xa4093822, 0x299f31d0), (0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344),
+              (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for key, ctr, want in cases:
+        lib.tego_philox4x32_10(ctypes.c_uint(key[0]), ctypes.c_uint(key[1]), *[ctypes.c_uint(c) for c in ctr], out)
+        assert tuple(out) == want
+
+
+def test_monte_carlo_oracle_converges_and_is_reproducible():
+    from teg_b200.lang import IfElse, Teg, TegVar, Var
+    from teg_b200.tegp import from_teg
+    x, y, t = TegVar('x'), TegVar('y'), Var('t', 0.5)
+    prog = from_teg(Teg(0, 1, Teg(0, 1, IfElse(x + y < t, x * y, 0), y), x), [t])
+    o = Oracle(prog.dumps())
+    tv = np.full(256, 0.9)
+    exact = 0.9 ** 4 / 24                                    # integral of xy over the triangle x + y < t
+    errs = []
+    for ns in (16, 64, 256):
+        v = o.eval([tv], ns, np.float64, quadrature='monte_carlo', seed=3)[0]
+        assert np.array_equal(v, o.eval([tv], ns, np.float64, quadrature='monte_carlo', seed=3, threads=3)[0])
+        assert len(set(v.tolist())) == v.size               # every instance draws its own points
+        errs.append(np.sqrt(np.mean((v - exact) ** 2)))
+    assert errs[0] > errs[1] > errs[2] and errs[2] < 0.25 * exact
+    a = o.eval([tv[:8]], 64, np.float64, quadrature='monte_carlo', seed=3, inst_base=100)[0]
+    b = o.eval([tv[:108]], 64, np.float64, quadrature='monte_carlo', seed=3)[0]
+    assert np.array_equal(a, b[100:108])                    # the stream belongs to the instance index
+    assert not np.array_equal(a, o.eval([tv[:8]], 64, np.float64, quadrature='monte_carlo', seed=4, inst_base=100)[0])
