@@ -588,21 +588,23 @@ class Emitter:
             for j in bx:
                 e(f'const T g_b{j}_lo = rx[4], g_b{j}_hi = rx[5];')
             points()
-            e('bool any_unresolved = false;')
-            e('for (int sub = 0; sub < TEGB_TILE_SUB; ++sub) {')
-            e('const int txs = tx * TEGB_TILE_SUB + sub;', 2)
-            e('if (txs >= n_txs || txs * TEGB_TILE_COLS >= res_y) break;        // no pixel in this tile', 2)
-            e('const T* __restrict__ ry = ranges + ((size_t)n_ty + txs) * 7;', 2)
-            e('const T g_yl_lo = ry[0], g_yl_hi = ry[1], g_yu_lo = ry[2], g_yu_hi = ry[3];', 2)
+            # one thread per tile; the TEGB_TILE_SUB tiles of a block sit in adjacent lanes
+            e('const int txs_ = tx * TEGB_TILE_SUB + sub;')
+            e('const bool dead = !active || txs_ >= n_txs || txs_ * TEGB_TILE_COLS >= res_y;       // no pixel in this tile')
+            e('const int txs = dead ? 0 : txs_;')
+            e('const T* __restrict__ ry = ranges + ((size_t)n_ty + txs) * 7;')
+            e('const T g_yl_lo = ry[0], g_yl_hi = ry[1], g_yu_lo = ry[2], g_yu_hi = ry[3];')
             for j in by:
-                e(f'const T g_b{j}_lo = ry[4], g_b{j}_hi = ry[5];', 2)
-            e('const T g_pz = rx[6] + ry[6];', 2)
-            cones(2, '(size_t)ty * n_txs + txs', '')
-            e('any_unresolved = any_unresolved || unresolved;', 2)
+                e(f'const T g_b{j}_lo = ry[4], g_b{j}_hi = ry[5];')
+            e('const T g_pz = rx[6] + ry[6];')
+            cones(1, '(size_t)ty * n_txs + txs', 'if (!dead) ')
+            # launch order of the main kernel: blocks with an unresolved tile from the front, the others from the back
+            e('int any_unresolved = (!dead && unresolved) ? 1 : 0;')
+            e('for (int off = 1; off < TEGB_TILE_SUB; off <<= 1) any_unresolved |= __shfl_xor_sync(0xffffffffu, any_unresolved, off);')
+            e('if (active && sub == 0) {')
+            e('if (any_unresolved) order[atomicAdd(&counters[0], 1)] = t;', 2)
+            e('else order[n_tx * n_ty - 1 - atomicAdd(&counters[1], 1)] = t;', 2)
             e('}')
-            # launch order of the main kernel: unresolved blocks from the front, resolved ones from the back
-            e('if (any_unresolved) order[atomicAdd(&counters[0], 1)] = t;')
-            e('else order[n_tx * n_ty - 1 - atomicAdd(&counters[1], 1)] = t;')
         self.in_main = saved_main
         return self.lines
 
@@ -1356,9 +1358,11 @@ class Emitter:
                                         ['const T* __restrict__ ranges', 'const int res_y', 'const int n_tx', 'const int n_ty', 'const int n_txs',
                                          'T* __restrict__ tiles', 'int* __restrict__ order', 'int* __restrict__ counters'])
                     src.append(f'extern "C" __global__ void {name}_tiles({tparams}) {{')
-                    src.append('    const int t = blockIdx.x * blockDim.x + threadIdx.x;       // one thread per block of the main kernel')
+                    src.append('    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;    // one thread per tile')
+                    src.append('    const int t_ = gtid / TEGB_TILE_SUB, sub = gtid % TEGB_TILE_SUB;')
+                    src.append('    const bool active = t_ < n_tx * n_ty;                      // (whole warps stay: shuffles below)')
+                    src.append('    const int t = active ? t_ : 0;')
                     src.append('    const size_t n_tiles = (size_t)n_txs * n_ty;')
-                    src.append('    if (t >= n_tx * n_ty) return;')
                     src.append('    const int ty = t / n_tx, tx = t - ty * n_tx;')
                     for a in scal:
                         src.append(f'    (void)a{a};')

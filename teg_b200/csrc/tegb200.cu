@@ -975,7 +975,7 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
         targs.push_back(&p->d_tiles);
         targs.push_back(&p->d_order);
         targs.push_back(&d_counters);
-        const unsigned tb = 128, tg = (unsigned)(((size_t)n_tx * n_ty + tb - 1) / tb);      // a thread per tile
+        const unsigned tb = 128, tg = (unsigned)(((size_t)n_txs * n_ty + tb - 1) / tb);     // a thread per tile
         CU_CHECK(drv::LaunchKernel(p->f_tiles, tg, 1, 1, tb, 1, 1, 0, st, targs.data(), nullptr));
         g_launches++;
         args.push_back(&p->d_tiles);
