@@ -177,6 +177,7 @@ def main() -> int:
     ap.add_argument('--fused', type=int, default=0, help='1: value and reverse derivative in ONE kernel (program bundle)')
     ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'], help='working precision of the programs')
     ap.add_argument('--maxreg', type=int, default=0, help='experiment: --maxrregcount for the generated kernels')
+    ap.add_argument('--min-blocks', type=int, default=-1, help='experiment: __launch_bounds__(block, N) for render kernels')
     ap.add_argument('--block', type=int, default=128, help='experiment: threads per block of the generated kernels')
     ap.add_argument('--tile-rows', type=int, default=16, help='pixel rows per render block / classification tile')
     ap.add_argument('--allreduce', default='peer', choices=['peer', 'nccl'], help='N > 1: gradient all-reduce fused '
@@ -225,7 +226,7 @@ def main() -> int:
     tdt = torch.float32 if args.dtype == 'f32' else torch.float64
     esz = 4 if args.dtype == 'f32' else 8
     xopts = dict(nvrtc_opts=f'--maxrregcount={args.maxreg}' if args.maxreg else '', tile_rows=args.tile_rows,
-                 block_size=args.block)
+                 block_size=args.block, min_blocks=None if args.min_blocks < 0 else args.min_blocks)
     m_primal = CUDA_EvalMode(primal, num_samples=NUM_SAMPLES, device=local_rank, float_width=fw, cull=bool(args.cull),
                              **xopts)
     m_grad = CUDA_EvalMode(grad, num_samples=NUM_SAMPLES, device=local_rank, float_width=fw, cull=bool(args.cull),
