@@ -49,3 +49,31 @@ def test_program_create_without_device_fails_loudly(tmp_path, monkeypatch):
     prog = load_program('readme_primal')
     with pytest.raises(runtime.TegbError):
         CUDA_EvalMode(prog, num_samples=8).eval({prog.args[0]: 0.3})
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """ctypes mirrors of tegb_program_desc / tegb_grid (runtime.py) against the compiler's layout of
+    include/tegb200.h: same size, same field offsets, same field order."""
+    import subprocess
+    from teg_b200 import runtime
+    fields = [n for n, _ in runtime.ProgramDesc._fields_]
+    gfields = [n for n, _ in runtime.Grid._fields_]
+    prints = ''.join(f'    printf("%zu\\n", offsetof(tegb_program_desc, {n}));\n' for n in fields)
+    gprints = ''.join(f'    printf("%zu\\n", offsetof(tegb_grid, {n}));\n' for n in gfields)
+    src = tmp_path / 'layout.c'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "tegb200.h"\nint main(void) {\n'
+                   '    printf("%zu\\n", sizeof(tegb_program_desc));\n' + prints +
+                   '    printf("%zu\\n", sizeof(tegb_grid));\n' + gprints + '    return 0;\n}\n')
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-std=c99', f'-I{os.path.join(ROOT, "include")}', str(src), '-o', str(exe)], check=True)
+    vals = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert vals[0] == ctypes.sizeof(runtime.ProgramDesc)
+    assert vals[1:1 + len(fields)] == [getattr(runtime.ProgramDesc, n).offset for n in fields]
+    rest = vals[1 + len(fields):]
+    assert rest[0] == ctypes.sizeof(runtime.Grid)
+    assert rest[1:] == [getattr(runtime.Grid, n).offset for n in gfields]
+    # INTEGRATION.md shows the same field list
+    with open(os.path.join(ROOT, 'INTEGRATION.md')) as f:
+        doc = f.read()
+    stub = doc[doc.index('class Desc(ctypes.Structure)'):doc.index('mod, prog = ctypes.c_void_p()')]
+    assert re.findall(r"\('([a-z_]+)', ctypes", stub) == fields
