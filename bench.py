@@ -257,12 +257,15 @@ def main() -> int:
     forks = [torch.cuda.Event() for _ in range(2)]
     joins = [torch.cuda.Event() for _ in range(2)]
     peers = None
+    peer_note = None
     if world > 1 and args.allreduce == 'peer' and m_fused is None:
         from teg_b200.parallel import PeerGroup
-        peers = PeerGroup(local_rank, max_values=16)
-        for pr in pr_grad:
-            peers.attach(pr.prog)            # the last column-sum kernel of the gradient does the exchange itself
-    side_ptr = side.cuda_stream
+        try:
+            peers = PeerGroup(local_rank, max_values=16)       # raises on every rank or on none
+            for pr in pr_grad:
+                peers.attach(pr.prog)        # the last column-sum kernel of the gradient does the exchange itself
+        except RuntimeError as e:
+            peers, peer_note = None, f'peer mailboxes unavailable ({e}): NCCL all-reduce instead'
 
     def step(record: bool, buf: int = 0):
         """value image + reverse derivative of every pixel summed per parameter inside the kernels + the one
@@ -524,7 +527,7 @@ def main() -> int:
                    'parallelism': f'rows sharded over {world} GPU(s) ({args.shard if world > 1 else "all"}), one all-reduce of the [6] gradient per step ('
                                   + ('fused into the column-sum kernel over NVLink peer memory' if peers is not None else 'NCCL')
                                   + '), on the gradient stream next to the value kernel'},
-        'phase_ms': phase_ms, 'phase_note': 'the value and the gradient pipelines run concurrently on two streams: '
+        'allreduce_note': peer_note, 'phase_ms': phase_ms, 'phase_note': 'the value and the gradient pipelines run concurrently on two streams: '
         'their phase times overlap and each is longer than the same pipeline alone', 'roofline': roofline, 'roofline_dense': roofline_dense, 'cpu_baseline': cpu, 'e2e': e2e,
         'gpu_launches': int(launches_timed), 'clocks': clocks,
         'check': {'sum_value': area, 'expected_area_per_rank': 0.2325 if world == 1 else None,

@@ -56,17 +56,31 @@ class PeerGroup:
         self.device = device
         self.handle = ctypes.c_void_p()
         mine = (ctypes.c_ubyte * 64)()
-        runtime.check(self._L.tegb_peer_create(self.rank, self.world, int(max_values), int(device),
-                                               ctypes.byref(self.handle), ctypes.cast(mine, ctypes.c_void_p)))
+        # Every step that can fail locally (allocation, IPC export, IPC import) is followed by an agreement between the
+        # ranks, so that a failure anywhere raises on EVERY rank instead of leaving the others inside a collective.
+        rc = self._L.tegb_peer_create(self.rank, self.world, int(max_values), int(device),
+                                      ctypes.byref(self.handle), ctypes.cast(mine, ctypes.c_void_p))
+        why = '' if rc == 0 else runtime.last_error()
         on_gpu = dist.get_backend(group) == 'nccl'
         dev = torch.device('cuda', device) if on_gpu else torch.device('cpu')
-        t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=dev)
+        t = torch.tensor(list(bytes(mine)) + [1 if rc == 0 else 0], dtype=torch.uint8, device=dev)
         gathered = [torch.empty_like(t) for _ in range(self.world)]
         dist.all_gather(gathered, t, group=group)
-        blob = b''.join(bytes(g.cpu().tolist()) for g in gathered)
-        self._blob = ctypes.create_string_buffer(blob, len(blob))
-        runtime.check(self._L.tegb_peer_connect(self.handle, ctypes.cast(self._blob, ctypes.c_void_p)))
-        dist.barrier(group=group)           # every mailbox is mapped everywhere before anyone writes
+        rows = [bytes(g.cpu().tolist()) for g in gathered]
+        ok = all(r[64] == 1 for r in rows)
+        if ok:
+            blob = b''.join(r[:64] for r in rows)
+            self._blob = ctypes.create_string_buffer(blob, len(blob))
+            rc = self._L.tegb_peer_connect(self.handle, ctypes.cast(self._blob, ctypes.c_void_p))
+            why = '' if rc == 0 else runtime.last_error()
+        flag = torch.tensor([1 if (ok and rc == 0) else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)     # also: every mailbox is mapped before anyone writes
+        if int(flag.item()) == 0:
+            if self.handle:
+                self._L.tegb_peer_destroy(self.handle)
+                self.handle = None
+            raise RuntimeError('peer mailboxes unavailable on some rank (CUDA IPC between the GPUs of this node is '
+                               f'required){": " + why if why else ""}')
 
     def attach(self, program) -> None:
         """program: a ``runtime.Program`` (``CUDA_EvalMode.compiled(...)[1]``, ``PreparedRender.prog``)"""

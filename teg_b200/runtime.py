@@ -107,6 +107,10 @@ def check(rc: int) -> None:
         raise TegbError(lib().tegb_last_error().decode(errors='replace'))
 
 
+def last_error() -> str:
+    return lib().tegb_last_error().decode(errors='replace')
+
+
 def device_count() -> int:
     return lib().tegb_device_count()
 

@@ -128,3 +128,37 @@ def test_interleaved_sharding_tiles_the_image_and_sums_the_gradient(tmp_path):
     assert np.array_equal(img, full['tri_primal'][0].reshape(res, res))
     g0, g1 = np.load(tmp_path / 'grad_0.npy'), np.load(tmp_path / 'grad_1.npy')
     assert np.array_equal(g0, g1) and np.allclose(g0, full['tri_grad'].sum(axis=1), rtol=1e-12, atol=1e-15)
+
+
+def _peer_fail_worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from teg_b200.parallel import PeerGroup
+    outcome = 'created'
+    try:
+        PeerGroup(0, max_values=8)
+    except RuntimeError as e:
+        outcome = f'raised: {e}'
+    with open(os.path.join(out_dir, f'peer_{rank}.txt'), 'w') as f:
+        f.write(outcome)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_group_fails_on_every_rank_together_without_a_device(tmp_path):
+    """No CUDA device here: the mailbox allocation fails locally, the ranks agree on it and ALL raise (nobody is
+    left waiting inside a collective); bench.py then falls back to the NCCL all-reduce."""
+    from teg_b200 import runtime
+    if runtime.device_count() > 0:
+        import pytest
+        pytest.skip('a CUDA device is present')
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mp.spawn(_peer_fail_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        text = (tmp_path / f'peer_{r}.txt').read_text()
+        assert text.startswith('raised: peer mailboxes unavailable'), text
