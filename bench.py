@@ -256,6 +256,7 @@ def main() -> int:
     side = torch.cuda.Stream(dev, priority=-1)
     forks = [torch.cuda.Event() for _ in range(2)]
     joins = [torch.cuda.Event() for _ in range(2)]
+    side_ptr = side.cuda_stream
     peers = None
     peer_note = None
     if world > 1 and args.allreduce == 'peer' and m_fused is None:
