@@ -367,3 +367,43 @@ def test_monte_carlo_lowering_matches_oracle_on_host(scene, ns, tmp_path, monkey
     assert len(runtime.Module(dev.source).cubin()) > 1000          # the device unit compiles for sm_100a
     with pytest.raises(AssertionError):
         generate(sch, 'float', ns, integration_mode='monte_carlo_uniform', team=4)
+
+
+@pytest.mark.parametrize('scene', ['tri_grad', 'shaded_grad'])
+def test_tile_bodies_with_exact_per_pixel_states_on_host(scene):
+    """Every body of a tile-culled program (quiet / resolved / general), driven with a VALID classification: each
+    pixel is its own tile, and its states are the per-pixel truth of the tile conditions (evaluated by a probe program
+    lowered from the same DAG).  Whatever body the states select, the result is the oracle's, bit for bit."""
+    from oracle import Oracle
+    from teg_b200.cull import cull, tile_cull
+    prog = load_program(scene)
+    names = [a.rsplit('_', 1)[0] for a in prog.args]
+    box = [names.index(b) for b in ('x_lb', 'x_ub', 'y_lb', 'y_ub')]
+    ns = SCENE_SAMPLES[scene]
+    res = 40
+    inputs = bind(prog.args, scene_values(scene, res=(res, res)))
+    n = res * res
+    base = cull(build_dag(prog), ns)
+    tiled = tile_cull(base, box, ns)
+    kinds = [k for k, _ in tiled.tile_conds]
+    assert 'guard' in kinds
+    # probe: per-pixel value of every tile condition (guard -> 0 / 1, domain tri-state -> 0 / 1 / 2)
+    probe = base.clone()
+    probe.outputs = tuple(node if kind == 'dom' else probe.sel(node, probe.const('1'), probe.const('0'))
+                          for kind, node in tiled.tile_conds)
+    pks = generate(make_schedule(probe, box), 'float', ns, use_asm=False, coop=False, name='probe')
+    states = run_on_host(pks, inputs, n, np.float32)
+    assert set(np.unique(states)) <= {0.0, 1.0, 2.0} and (states == 1).any() and (states == 0).any()
+    n_args = len(prog.args)
+    sch = make_schedule(tiled, box + [n_args + k for k in range(len(kinds))])
+    ks = generate(sch, 'float', ns, grid_args=box, use_asm=False, coop=False)
+    labels = [lb for lb, _ in ks.tile_bodies]
+    assert any(lb.startswith('quiet') for lb in labels) and 'resolved' in labels
+    want = Oracle(program_text(scene)).eval(inputs, ns, np.float32)
+    got = run_on_host(ks, inputs, n, np.float32, tile_inputs=list(states))
+    assert np.array_equal(got, want, equal_nan=True), scene
+    # how the pixels were routed: all three kinds of body must have been exercised
+    guards = [i for i, k in enumerate(kinds) if k == 'guard']
+    known = np.all(states != 2, axis=0)
+    quiet = known & np.all(states[guards] == 0, axis=0)
+    assert quiet.any() and (known & ~quiet).any() and (~known).any() == ('dom' in kinds and (states == 2).any())
