@@ -43,6 +43,29 @@ def load_text(scene: str) -> str:
         return f.read()
 
 
+# --------------------------------------------------------------------------------------------- stdout
+class _StdoutToStderr:
+    """File-descriptor level redirection of stdout to stderr: libraries that print to stdout from C (NCCL announces its
+    version there when it initialises) must not get in front of the ONE JSON line this program prints."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)          # C stdio buffers too
+        except Exception:
+            pass
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
+
 # ------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler:
     QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
@@ -208,7 +231,9 @@ def main() -> int:
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        with _StdoutToStderr():
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()              # the communicator exists (and has said so) before stdout is restored
 
     res = args.res
     res_x_total = res * world                  # weak scaling: the image grows to (res * world) x res pixels

@@ -98,3 +98,14 @@ def test_monte_carlo_flag(tmp_path):
     assert r.returncode == 0, r.stderr
     text = out.read_text()
     assert '#define TEGB_MC_SEED 42ull' in text and 'tegb_uniform(TEGB_MC_SEED, tegb_inst, 0u' in text
+
+
+def test_bench_keeps_library_chatter_off_stdout():
+    """bench.py prints ONE JSON line: text written to stdout from C while NCCL initialises is sent to stderr."""
+    code = ('import sys, ctypes; sys.path.insert(0, %r); import bench\n'
+            'libc = ctypes.CDLL(None)\n'
+            'with bench._StdoutToStderr():\n'
+            '    libc.puts(b"NCCL version (from C)")\n'
+            'print(\'{"json": 1}\')\n') % ROOT
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == '{"json": 1}\n' and 'NCCL version (from C)' in r.stderr
