@@ -109,3 +109,23 @@ def test_bench_keeps_library_chatter_off_stdout():
             'print(\'{"json": 1}\')\n') % ROOT
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout == '{"json": 1}\n' and 'NCCL version (from C)' in r.stderr
+
+
+def test_bench_reference_arm_prints_one_json_line_without_a_gpu():
+    """`bench.py --impl reference`: the reference's own C (oracle/_ref) or the oracle port on the host cores, same
+    metric / unit / workload keys as the CUDA arm, plus cpu_baseline and e2e objects; rank != 0 prints nothing."""
+    import json
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                        '--warmup', '1', '--cpu-rows', '4'], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['metric'] == 'integral_evals_per_s' and d['unit'] == 'integral evals/s'
+    assert d['config']['workload'] == 'tri_raster_4096' and d['higher_is_better'] is True and d['value'] > 0
+    assert d['cpu_baseline']['kind'] in ('reference', 'port') and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                         '--warmup', '1', '--cpu-rows', '4'], capture_output=True, text=True, env=dict(env, RANK='1'))
+    assert r1.returncode == 0 and r1.stdout.strip() == ''
