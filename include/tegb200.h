@@ -41,7 +41,8 @@ typedef enum {
     TEGB_ERR_COMPILE = 2,      /* NVRTC rejected the source; tegb_last_error() holds the log */
     TEGB_ERR_CUDA = 3,         /* driver / runtime error */
     TEGB_ERR_NO_DEVICE = 4,    /* no usable CUDA device or driver */
-    TEGB_ERR_NCCL = 5
+    TEGB_ERR_NCCL = 5,
+    TEGB_ERR_PEER = 6          /* a rank of a peer group did not arrive within the time-out: sums were poisoned (NaN) */
 } tegb_status;
 
 typedef struct tegb_module tegb_module;     /* one compiled translation unit (cubin) */
@@ -91,6 +92,9 @@ typedef struct {
 
 const char *tegb_last_error(void);
 int tegb_version(void);
+/* hash of the runtime header (teg_b200_runtime.cuh) embedded in the library: generated units include it by name, so it
+ * belongs in any cache key of compiled units */
+uint64_t tegb_runtime_header_hash(void);
 /* version of the NVRTC the library loaded, major * 1000 + minor * 10 (e.g. 12090); 0 if none could be loaded */
 int tegb_nvrtc_version(void);
 
@@ -107,6 +111,11 @@ const char *tegb_module_log(const tegb_module *m);
 void tegb_module_destroy(tegb_module *m);
 
 /* --- programs ----------------------------------------------------------------------------- */
+/* Threads and streams: handles are independent of one another (each owns its copy of the module, its published
+ * uniform table and its scratch buffers), so one handle per thread / stream runs fully concurrently.  ONE handle may
+ * also be shared: its launch calls are serialised by a mutex, and a launch on another stream than the handle's
+ * previous launch first waits, on the device, for that previous launch (the scratch is single-buffered).  The
+ * reference's executor is "NOT thread-safe" (teg/eval/c_eval.py:55-56). */
 int tegb_program_create(tegb_module *m, const tegb_program_desc *desc, int device, tegb_program **out);
 void tegb_program_destroy(tegb_program *p);
 
@@ -146,7 +155,12 @@ int tegb_program_tile_table(tegb_program *p, void *host_out, size_t nbytes, void
  *                      them, e.g. with torch.distributed.all_gather)
  *   tegb_program_set_peer  reduce_outputs launches of the program then deliver the all-reduced sums
  *   tegb_peer_allreduce_sum  stand-alone in-place all-reduce of a device vector (every rank must call it, same order)
- *   tegb_peer_error    1 if an exchange timed out (a peer never arrived); tegb_peer_destroy after a barrier */
+ *   tegb_program_set_peer_groups  the same for grouped reduce programs: out_ptrs[0] of tegb_render_groups_launch then
+ *                      receives the all-reduced [n_groups_total][n_outputs] sums
+ *   tegb_peer_error    1 if an exchange timed out (a peer never arrived); tegb_peer_destroy after a barrier
+ * Time-out: an exchange waits TEGB200_PEER_TIMEOUT_S seconds (default 120; 0 = for ever) for every peer.  When it
+ * expires the sums of that call are NaN, a sticky flag is raised and EVERY later launch on the group returns
+ * TEGB_ERR_PEER (checked on the host before enqueueing, no synchronisation). */
 typedef struct tegb_peer tegb_peer;
 int tegb_peer_create(int rank, int world, int max_values, int device, tegb_peer **out, void *handle64);
 int tegb_peer_connect(tegb_peer *p, const void *handles);
@@ -154,6 +168,7 @@ int tegb_peer_allreduce_sum(tegb_peer *p, void *buf, int count, int elem_size, v
 int tegb_peer_error(tegb_peer *p);
 void tegb_peer_destroy(tegb_peer *p);
 int tegb_program_set_peer(tegb_program *prog, tegb_peer *peer);
+int tegb_program_set_peer_groups(tegb_program *prog, tegb_peer *peer, int n_groups_total);
 
 /* Grouped render: groups [group_begin, group_begin + group_count) (e.g. triangles) are evaluated over their
  * own pixel windows in ONE launch.  group_ptrs[n_scalar_args]: device arrays with one value per group

@@ -150,6 +150,7 @@ class Emitter:
         self.coop_max_lanes = int(coop_max_lanes)
         self.lines: List[str] = []
         self.loop_counter = 0
+        self.active_bvars: List[int] = []     # variables of the sample loops enclosing the code being emitted
 
     # --------------------------------------------------------------- references
     def ref(self, i: int, known: Dict[int, bool]) -> str:
@@ -243,10 +244,15 @@ class Emitter:
                 self.divergent -= 1
                 self.emit('}', ind)
             elif isinstance(st, LoopGroup):
+                # two nested loops over ONE canonical variable would make the inner integrand read the outer sample
+                # (dag.build_dag keeps such binders apart; this is the backstop)
+                assert st.bvar not in self.active_bvars, 'nested integrals share a bound variable (internal error)'
+                self.active_bvars.append(st.bvar)
                 if self.coop and depth == 0 and not self.divergent and len(self.guard_ctx) > 1:
                     self._coop_loop(st, known, ind)
                 else:
                     self.loop(st, known, ind, depth)
+                self.active_bvars.pop()
             else:  # pragma: no cover
                 raise TypeError(st)
 
@@ -717,6 +723,7 @@ class Emitter:
         self.loop_counter += 1
         teamed = self.team > 1 and depth == 0
         inner = [s for s in st.body.stmts if isinstance(s, LoopGroup)][0]
+        assert inner.bvar != st.bvar and inner.bvar not in self.active_bvars, 'nested integrals share a bound variable'
         pos = st.body.stmts.index(inner)
         pre, post = st.body.stmts[:pos], st.body.stmts[pos + 1:]
         fv = self.dag.free_bvars

@@ -46,6 +46,12 @@ static int fail(int code, const char *fmt, ...) {
 extern "C" const char *tegb_last_error(void) { return g_err; }
 extern "C" int tegb_version(void) { return 100; }
 extern "C" int64_t tegb_launch_count(void) { return g_launches.load(); }
+// FNV-1a of the embedded runtime header: part of the cubin cache key (generated units #include it by name only)
+extern "C" uint64_t tegb_runtime_header_hash(void) {
+    uint64_t h = 1469598103934665603ull;
+    for (const char *c = TEGB_RUNTIME_HEADER; *c; ++c) { h ^= (unsigned char)*c; h *= 1099511628211ull; }
+    return h;
+}
 
 // ------------------------------------------------------------------------------------- driver API shim
 namespace drv {
@@ -260,6 +266,14 @@ struct tegb_peer;
 struct tegb_program {
     tegb_program_desc d;
     int device = 0;
+    // A handle owns device scratch (the published uniform table, tile tables, partial sums, staging): its launches are
+    // serialised on the host by `mu`, and a launch on another stream than the previous one first waits (on the device)
+    // for that previous launch -- so one handle may be shared by threads and streams; independent handles overlap.
+    std::recursive_mutex mu;
+    cudaEvent_t ev_last = nullptr;    // recorded after the last launch sequence of this handle
+    bool ev_valid = false;
+    CUstream ev_stream = nullptr;
+    int n_groups_total = 0;           // grouped programs with a peer: rows of the all-reduced [groups][outputs] result
     CUmodule mod = nullptr;
     CUfunction f_uniform = nullptr, f_main = nullptr, f_tiles = nullptr;
     CUdeviceptr u_const = 0;      // __constant__ table inside the module
@@ -343,9 +357,33 @@ extern "C" int tegb_program_create(tegb_module *m, const tegb_program_desc *desc
     return TEGB_OK;
 }
 
+// Entry of every launch path (p->mu held): order this launch after the handle's previous one when the stream changed.
+static int begin_launch(tegb_program *p, CUstream st) {
+    if (p->ev_valid && p->ev_stream != st) {
+        RT_CHECK(cudaStreamWaitEvent((cudaStream_t)st, p->ev_last, 0));
+        // the published uniform table belongs to the previous stream's launch order: re-publish on this one
+        p->uniform_valid = false;
+    }
+    return TEGB_OK;
+}
+
+// Exit of every launch path: remember where the handle's scratch was last used.  (Not while the stream is being
+// captured into a CUDA graph: events recorded there cannot be waited on from outside the capture.)
+static int end_launch(tegb_program *p, CUstream st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing((cudaStream_t)st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; }
+    if (cs != cudaStreamCaptureStatusNone) { p->ev_valid = false; return TEGB_OK; }
+    if (!p->ev_last) RT_CHECK(cudaEventCreateWithFlags(&p->ev_last, cudaEventDisableTiming));
+    RT_CHECK(cudaEventRecord(p->ev_last, (cudaStream_t)st));
+    p->ev_valid = true;
+    p->ev_stream = st;
+    return TEGB_OK;
+}
+
 extern "C" void tegb_program_destroy(tegb_program *p) {
     if (!p) return;
     cudaSetDevice(p->device);
+    if (p->ev_last) cudaEventDestroy(p->ev_last);
     for (void *q : p->d_in) if (q) cudaFree(q);
     for (void *q : p->d_out) if (q) cudaFree(q);
     if (p->u_stage) cudaFree(p->u_stage);
@@ -421,8 +459,15 @@ struct PeerSlot { unsigned long long bits; unsigned long long seq; };
 struct PeerView {
     PeerSlot *box[TEGB_MAX_PEERS];      // mailbox of every rank, mapped here
     int rank, world, maxv;
-    int *err;                           // set when a peer did not answer within the time-out
+    volatile int *err;                  // (pinned host memory, mapped) set when a peer did not answer within the time-out
+    unsigned long long timeout_ns;      // 0: wait for ever
 };
+
+__device__ __forceinline__ unsigned long long tegb_globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // called by all 32 lanes of one warp; `value` is taken from lane 0; every lane returns the sum.  Lane p serves peer p
 // (stores / polls run in parallel over the ranks), the contributions are then added in rank order.
@@ -441,14 +486,23 @@ __device__ __forceinline__ T peer_exchange_sum(const PeerView &v, int col, T val
     T x = 0;
     if (lane < v.world) {
         PeerSlot *s = &v.box[v.rank][((size_t)bank * v.world + lane) * v.maxv + col];
-        const long long t0 = clock64();
+        const unsigned long long t0 = tegb_globaltimer_ns();
+        bool arrived = true;
+        unsigned int spins = 0;
         while (*(volatile unsigned long long *)&s->seq != seq) {
-            if (clock64() - t0 > 4000000000ll) { *v.err = 1; break; }     // ~2 s: a peer is gone; do not hang the GPU
+            // a peer that never arrives (crashed rank) must not hang the GPU for ever: after the time-out the sticky
+            // error flag is raised (every later launch on this peer group fails) and the result is poisoned below
+            if (v.timeout_ns && (++spins & 1023u) == 0 && tegb_globaltimer_ns() - t0 > v.timeout_ns) {
+                *v.err = 1;
+                arrived = false;
+                break;
+            }
         }
         __threadfence_system();
         const unsigned long long b = *(volatile unsigned long long *)&s->bits;
         if (sizeof(T) == 4) x = (T)__uint_as_float((unsigned int)b);
         else x = (T)__longlong_as_double((long long)b);
+        if (!arrived) x = (T)__longlong_as_double(0x7ff8000000000000ll);       // NaN: the failure shows in the data
     }
     T acc = __shfl_sync(0xffffffffu, x, 0);
     for (int r = 1; r < v.world; ++r) acc = acc + __shfl_sync(0xffffffffu, x, r);
@@ -485,9 +539,20 @@ struct tegb_peer {
     void *d_box = nullptr;
     size_t box_bytes = 0;
     std::vector<void *> opened;
-    unsigned long long seq = 0;
-    int h_err = 0;
+    std::atomic<unsigned long long> seq{0};
+    int *h_err = nullptr;               // pinned + mapped: kernels raise it, the host reads it without synchronising
 };
+
+// Checked (one host load) before every exchange is enqueued: once a peer timed out, results were poisoned and the
+// group is unusable -- fail loudly instead of handing out more sums.
+static int peer_failed(tegb_peer *peer) {
+    if (peer && peer->h_err && *(volatile int *)peer->h_err) {
+        fail(TEGB_ERR_PEER, "peer all-reduce: a rank did not arrive within the time-out (TEGB200_PEER_TIMEOUT_S); "
+                            "the affected sums were set to NaN and this peer group is unusable");
+        return 1;
+    }
+    return 0;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(RED_THREADS) colsum_stage2(const T *partials, long long n_blocks, T *out) {
@@ -560,6 +625,7 @@ static int finish_partials(tegb_program *p, unsigned long long n_blocks, void *o
     char *slices = (char *)p->d_partials + (size_t)p->d.reduce_outputs * n_blocks * p->d.elem_size;
     if (p->peer) {
         if (p->d.reduce_outputs > p->peer->view.maxv) return fail(TEGB_ERR_INVALID, "peer mailbox smaller than the gradient");
+        if (peer_failed(p->peer)) return TEGB_ERR_PEER;
         if (p->d.elem_size == 4)
             sum_columns_peer<float>((const float *)p->d_partials, p->d.reduce_outputs, n_blocks, (float *)out, (float *)slices, st, p->peer);
         else
@@ -581,9 +647,12 @@ extern "C" int tegb_program_launch(tegb_program *p, const double *scalars, const
     if (p->d.n_grid_args != 0 || p->d.grouped) return fail(TEGB_ERR_INVALID, "render program: use tegb_render_launch");
     if (p->d.n_array_args > 0 && !in_ptrs) return fail(TEGB_ERR_INVALID, "in_ptrs is NULL");
     if (n == 0) return TEGB_OK;
+    std::lock_guard<std::recursive_mutex> lock(p->mu);
     RT_CHECK(cudaSetDevice(p->device));
     CUstream st = (CUstream)stream;
-    int rc = run_uniform(p, scalars, st);
+    int rc = begin_launch(p, st);
+    if (rc) return rc;
+    rc = run_uniform(p, scalars, st);
     if (rc) return rc;
     std::vector<const void *> ins(p->d.n_array_args > 0 ? p->d.n_array_args : 1);
     std::vector<void *> outs(p->d.n_outputs);
@@ -611,8 +680,11 @@ extern "C" int tegb_program_launch(tegb_program *p, const double *scalars, const
     args.push_back(&nn);
     CU_CHECK(drv::LaunchKernel(p->f_main, (unsigned)blocks, 1, 1, bs, 1, 1, 0, st, args.data(), nullptr));
     g_launches++;
-    if (p->d.reduce_outputs) return finish_partials(p, (unsigned long long)blocks, out_ptrs[n_store], (cudaStream_t)st);
-    return TEGB_OK;
+    if (p->d.reduce_outputs) {
+        rc = finish_partials(p, (unsigned long long)blocks, out_ptrs[n_store], (cudaStream_t)st);
+        if (rc) return rc;
+    }
+    return end_launch(p, st);
 }
 
 static int ensure_staging(tegb_program *p, int64_t n) {
@@ -637,6 +709,7 @@ extern "C" int tegb_program_eval_host(tegb_program *p, const double *scalars, co
     if (!p || !host_out || n < 0) return fail(TEGB_ERR_INVALID, "tegb_program_eval_host: bad argument");
     if (p->d.n_array_args > 0 && !host_in) return fail(TEGB_ERR_INVALID, "host_in is NULL");
     if (n == 0) return TEGB_OK;
+    std::lock_guard<std::recursive_mutex> lock(p->mu);
     RT_CHECK(cudaSetDevice(p->device));
     int rc = ensure_staging(p, n);
     if (rc) return rc;
@@ -766,6 +839,55 @@ static int ensure_ranges(tegb_program *p, const tegb_grid *g, int n_tx, int n_ty
     return TEGB_OK;
 }
 
+// per-group sums of a grouped reduce launch: partials [group][component][tile] -> out[group][component].  With peer
+// mailboxes attached (tegb_program_set_peer_groups) `out` is the whole [n_groups_total][n_outputs] result: every
+// column is exchanged, the columns of groups this launch did not cover contribute zero.
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS) colsum_groups_peer(const T *partials, long long n_tiles, int col_begin,
+                                                                  int col_count, T *out, PeerView view,
+                                                                  unsigned long long seq) {
+    __shared__ T smem[32];
+    const int c = blockIdx.x;
+    const int lc = c - col_begin;
+    T acc = 0;
+    if (lc >= 0 && lc < col_count)          // block-uniform
+        for (long long i = threadIdx.x; i < n_tiles; i += RED_THREADS) acc = acc + partials[(long long)lc * n_tiles + i];
+    T s = block_sum_fixed(acc, smem);
+    if (threadIdx.x < 32) {
+        const T total = peer_exchange_sum<T>(view, c, s, seq);
+        if (threadIdx.x == 0) out[c] = total;
+    }
+}
+
+static int finish_group_partials(tegb_program *p, unsigned long long tiles, int group_begin, int group_count, void *out,
+                                 cudaStream_t st) {
+    const int K = p->d.n_outputs;
+    if (p->peer && p->n_groups_total > 0) {
+        const int total = p->n_groups_total * K;
+        if (total > p->peer->view.maxv) return fail(TEGB_ERR_INVALID, "peer mailbox smaller than the [groups][outputs] gradient");
+        if (peer_failed(p->peer)) return TEGB_ERR_PEER;
+        const unsigned long long seq = ++p->peer->seq;
+        if (p->d.elem_size == 4)
+            colsum_groups_peer<float><<<total, RED_THREADS, 0, st>>>((const float *)p->d_partials, (long long)tiles, group_begin * K,
+                                                                     group_count * K, (float *)out, p->peer->view, seq);
+        else
+            colsum_groups_peer<double><<<total, RED_THREADS, 0, st>>>((const double *)p->d_partials, (long long)tiles, group_begin * K,
+                                                                      group_count * K, (double *)out, p->peer->view, seq);
+        g_launches++;
+        RT_CHECK(cudaGetLastError());
+        return TEGB_OK;
+    }
+    if (group_count == 0) return TEGB_OK;
+    const int cols = group_count * K;
+    if (p->d.elem_size == 4)
+        colsum_stage2<float><<<cols, RED_THREADS, 0, st>>>((const float *)p->d_partials, (long long)tiles, (float *)out);
+    else
+        colsum_stage2<double><<<cols, RED_THREADS, 0, st>>>((const double *)p->d_partials, (long long)tiles, (double *)out);
+    g_launches++;
+    RT_CHECK(cudaGetLastError());
+    return TEGB_OK;
+}
+
 extern "C" int tegb_render_groups_launch(tegb_program *p, const void *const *group_ptrs, int group_begin,
                                          int group_count, const tegb_grid *g, const int32_t *windows,
                                          int max_rows, int max_cols, const void *const *pixel_ptrs,
@@ -778,11 +900,23 @@ extern "C" int tegb_render_groups_launch(tegb_program *p, const void *const *gro
         return fail(TEGB_ERR_INVALID, "bad group range or window bounds");
     if (g->res_x < 1 || g->res_y < 1 || g->row_begin < 0 || g->row_end > g->res_x || g->row_begin > g->row_end)
         return fail(TEGB_ERR_INVALID, "bad grid");
-    if (group_count == 0 || g->row_end == g->row_begin) return TEGB_OK;
+    const bool peer_groups = p->d.reduce_outputs && p->peer && p->n_groups_total > 0;
+    if (peer_groups && (group_begin + group_count > p->n_groups_total))
+        return fail(TEGB_ERR_INVALID, "group range exceeds the total declared with tegb_program_set_peer_groups");
+    if ((group_count == 0 || g->row_end == g->row_begin) && !peer_groups) return TEGB_OK;
     if (group_count > 65535 || max_rows > 65535 * 16) return fail(TEGB_ERR_INVALID, "too many groups or rows in one launch");
+    std::lock_guard<std::recursive_mutex> lock(p->mu);
     RT_CHECK(cudaSetDevice(p->device));
     CUstream st = (CUstream)stream;
-    int rc = ensure_edges(p, g, st);
+    int rc = begin_launch(p, st);
+    if (rc) return rc;
+    if (group_count == 0 || g->row_end == g->row_begin) {
+        // nothing to render on this rank, but the other ranks wait for its (zero) contribution
+        rc = finish_group_partials(p, 0, 0, 0, out_ptrs[0], (cudaStream_t)st);
+        if (rc) return rc;
+        return end_launch(p, st);
+    }
+    rc = ensure_edges(p, g, st);
     if (rc) return rc;
     const int nu = p->d.n_uniform > 0 ? p->d.n_uniform : 1;
     const size_t need = (size_t)(group_begin + group_count) * nu * p->d.elem_size;
@@ -869,16 +1003,10 @@ extern "C" int tegb_render_groups_launch(tegb_program *p, const void *const *gro
     CU_CHECK(drv::LaunchKernel(p->f_main, gx, gy, gz, bs, 1, 1, 0, st, args.data(), nullptr));
     g_launches++;
     if (p->d.reduce_outputs) {
-        // partials: [group][component][tile] -> out[group][component]
-        const int cols = (int)gz * p->d.n_outputs;
-        if (p->d.elem_size == 4)
-            colsum_stage2<float><<<cols, RED_THREADS, 0, (cudaStream_t)st>>>((const float *)p->d_partials, (long long)tiles, (float *)out_ptrs[0]);
-        else
-            colsum_stage2<double><<<cols, RED_THREADS, 0, (cudaStream_t)st>>>((const double *)p->d_partials, (long long)tiles, (double *)out_ptrs[0]);
-        g_launches++;
-        RT_CHECK(cudaGetLastError());
+        rc = finish_group_partials(p, tiles, group_begin, (int)gz, out_ptrs[0], (cudaStream_t)st);
+        if (rc) return rc;
     }
-    return TEGB_OK;
+    return end_launch(p, st);
 }
 
 extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars, const tegb_grid *g, int tile_stride,
@@ -898,8 +1026,11 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
         return fail(TEGB_ERR_INVALID, "not a plain render program (needs exactly the 4 pixel-box arguments on the grid)");
     if (g->res_x < 1 || g->res_y < 1 || g->row_begin < 0 || g->row_end > g->res_x || g->row_begin > g->row_end)
         return fail(TEGB_ERR_INVALID, "bad grid");
+    std::lock_guard<std::recursive_mutex> lock(p->mu);
     RT_CHECK(cudaSetDevice(p->device));
     CUstream st = (CUstream)stream;
+    int rc = begin_launch(p, st);
+    if (rc) return rc;
     {
         // nothing to render for this rank (empty row range, or no tile row of its phase): image outputs stay untouched,
         // summed outputs are zero -- and still take part in the peer exchange, the other ranks wait for this one
@@ -909,10 +1040,12 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
             if (!p->d.reduce_outputs) return TEGB_OK;
             int rc0 = ensure_partials(p, 0);
             if (rc0) return rc0;
-            return finish_partials(p, 0, out_ptrs[p->d.n_outputs - p->d.reduce_outputs], (cudaStream_t)st);
+            rc0 = finish_partials(p, 0, out_ptrs[p->d.n_outputs - p->d.reduce_outputs], (cudaStream_t)st);
+            if (rc0) return rc0;
+            return end_launch(p, st);
         }
     }
-    int rc = ensure_edges(p, g, st);
+    rc = ensure_edges(p, g, st);
     if (rc) return rc;
     rc = run_uniform(p, scalars, st);
     if (rc) return rc;
@@ -990,14 +1123,18 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
     }
     CU_CHECK(drv::LaunchKernel(p->f_main, gx, gy, 1, bs, 1, 1, 0, st, args.data(), nullptr));
     g_launches++;
-    if (p->d.reduce_outputs) return finish_partials(p, (unsigned long long)gx * gy, out_ptrs[n_store], (cudaStream_t)st);
-    return TEGB_OK;
+    if (p->d.reduce_outputs) {
+        rc = finish_partials(p, (unsigned long long)gx * gy, out_ptrs[n_store], (cudaStream_t)st);
+        if (rc) return rc;
+    }
+    return end_launch(p, st);
 }
 
 extern "C" int tegb_program_tile_table(tegb_program *p, void *host_out, size_t nbytes, void *stream) {
     if (!p || !host_out) return fail(TEGB_ERR_INVALID, "tegb_program_tile_table: null argument");
     if (!p->d_tiles || nbytes > p->tiles_bytes)
         return fail(TEGB_ERR_INVALID, "no tile table of that size (render first; n_tile_conds x tiles x elem_size bytes)");
+    std::lock_guard<std::recursive_mutex> lock(p->mu);
     RT_CHECK(cudaSetDevice(p->device));
     RT_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
     RT_CHECK(cudaMemcpy(host_out, p->d_tiles, nbytes, cudaMemcpyDeviceToHost));
@@ -1069,11 +1206,26 @@ extern "C" int tegb_peer_create(int rank, int world, int max_values, int device,
     tegb_peer *p = new tegb_peer();
     p->device = device;
     p->view.rank = rank; p->view.world = world; p->view.maxv = max_values;
-    p->box_bytes = sizeof(PeerSlot) * 2 * (size_t)world * max_values + 256;
+    p->box_bytes = sizeof(PeerSlot) * 2 * (size_t)world * max_values;
     if (cudaMalloc(&p->d_box, p->box_bytes) != cudaSuccess) { delete p; return fail(TEGB_ERR_CUDA, "cudaMalloc(mailbox) failed"); }
     cudaMemset(p->d_box, 0, p->box_bytes);
     cudaDeviceSynchronize();
-    p->view.err = (int *)((char *)p->d_box + sizeof(PeerSlot) * 2 * (size_t)world * max_values);
+    if (cudaHostAlloc((void **)&p->h_err, sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
+        cudaFree(p->d_box); delete p;
+        return fail(TEGB_ERR_CUDA, "cudaHostAlloc(peer error flag) failed");
+    }
+    *p->h_err = 0;
+    void *d_err = nullptr;
+    if (cudaHostGetDevicePointer(&d_err, p->h_err, 0) != cudaSuccess) {
+        cudaFreeHost(p->h_err); cudaFree(p->d_box); delete p;
+        return fail(TEGB_ERR_CUDA, "cudaHostGetDevicePointer(peer error flag) failed");
+    }
+    p->view.err = (volatile int *)d_err;
+    // how long an exchange waits for a peer: rank skew of seconds is ordinary (a JIT compile on one rank, a host stall),
+    // so the default is generous; 0 waits for ever
+    double secs = 120.0;
+    if (const char *e = getenv("TEGB200_PEER_TIMEOUT_S")) secs = atof(e);
+    p->view.timeout_ns = secs > 0 ? (unsigned long long)(secs * 1e9) : 0ull;
     cudaIpcMemHandle_t h;
     if (cudaIpcGetMemHandle(&h, p->d_box) != cudaSuccess) {
         cudaFree(p->d_box); delete p;
@@ -1105,6 +1257,7 @@ extern "C" int tegb_peer_allreduce_sum(tegb_peer *p, void *buf, int count, int e
     if (!p || !buf || count < 0 || count > p->view.maxv || (elem_size != 4 && elem_size != 8))
         return fail(TEGB_ERR_INVALID, "tegb_peer_allreduce_sum: bad argument");
     if (count == 0) return TEGB_OK;
+    if (peer_failed(p)) return TEGB_ERR_PEER;
     RT_CHECK(cudaSetDevice(p->device));
     const unsigned long long seq = ++p->seq;
     const int tb = 32, tg = count;
@@ -1115,14 +1268,12 @@ extern "C" int tegb_peer_allreduce_sum(tegb_peer *p, void *buf, int count, int e
     return TEGB_OK;
 }
 
-/* 1 when some exchange gave up waiting for a peer (results of that call are invalid); synchronises the device */
+/* 1 when some exchange gave up waiting for a peer (its sums are NaN, later launches fail); synchronises the device */
 extern "C" int tegb_peer_error(tegb_peer *p) {
     if (!p) return 1;
     cudaSetDevice(p->device);
     cudaDeviceSynchronize();
-    int e = 0;
-    cudaMemcpy(&e, p->view.err, sizeof(int), cudaMemcpyDeviceToHost);
-    return e;
+    return *(volatile int *)p->h_err;
 }
 
 /* all ranks must have finished using the mailboxes (barrier) before any rank destroys its own */
@@ -1132,13 +1283,30 @@ extern "C" void tegb_peer_destroy(tegb_peer *p) {
     cudaDeviceSynchronize();
     for (void *q : p->opened) cudaIpcCloseMemHandle(q);
     if (p->d_box) cudaFree(p->d_box);
+    if (p->h_err) cudaFreeHost(p->h_err);
     delete p;
 }
 
 /* reduce_outputs launches of `prog` deliver the sum over all ranks of `peer` (NULL restores local sums) */
 extern "C" int tegb_program_set_peer(tegb_program *prog, tegb_peer *peer) {
     if (!prog) return fail(TEGB_ERR_INVALID, "tegb_program_set_peer: null program");
+    std::lock_guard<std::recursive_mutex> lock(prog->mu);
     prog->peer = peer;
+    prog->n_groups_total = 0;
+    return TEGB_OK;
+}
+
+/* grouped reduce_outputs programs: tegb_render_groups_launch then delivers the all-reduced [n_groups_total][n_outputs]
+ * sums to out_ptrs[0] (ALL rows, whatever group range the launch covered; groups it did not cover contribute zero).
+ * Every rank must make the same sequence of such launches, also ranks with nothing to render. */
+extern "C" int tegb_program_set_peer_groups(tegb_program *prog, tegb_peer *peer, int n_groups_total) {
+    if (!prog || (peer && n_groups_total < 1)) return fail(TEGB_ERR_INVALID, "tegb_program_set_peer_groups: bad argument");
+    if (!prog->d.grouped || !prog->d.reduce_outputs) return fail(TEGB_ERR_INVALID, "not a grouped reduce program");
+    if (peer && (long long)n_groups_total * prog->d.n_outputs > peer->view.maxv)
+        return fail(TEGB_ERR_INVALID, "peer mailbox smaller than n_groups_total x n_outputs");
+    std::lock_guard<std::recursive_mutex> lock(prog->mu);
+    prog->peer = peer;
+    prog->n_groups_total = peer ? n_groups_total : 0;
     return TEGB_OK;
 }
 

@@ -16,8 +16,9 @@ teg/ir/instr/*.py) with a representation designed for batched GPU evaluation:
     ``Bool`` -> strict ``<`` whatever ``allow_eq`` says (compile.py:210-211).
 
 Only rewrites that are exact in IEEE arithmetic are applied while building:
-``x + 0 -> x`` (differs from the reference only in the sign of a zero result), ``1 * x -> x``,
-``sel(c, a, a) -> a``.  Nothing is re-associated, distributed or contracted.
+``x + 0 -> x`` **only where x is provably not -0** (the reference computes ``-0 + 0 = +0``; sums that
+start from an integral's accumulator, squares and non-zero literals can never be -0, see ``never_neg_zero``),
+``1 * x -> x``, ``sel(c, a, a) -> a``.  Nothing is re-associated, distributed or contracted.
 """
 from __future__ import annotations
 
@@ -59,6 +60,8 @@ class Dag:
         self.out_groups: List[int] = []      # bundles: number of outputs of each member program
         self._fv: Dict[int, FrozenSet[int]] = {}
         self._has_quad: Dict[int, bool] = {}
+        self._nnz: Dict[int, bool] = {}
+        self._qb: Dict[int, FrozenSet[int]] = {}
 
     def clone(self) -> "Dag":
         """Independent copy (node ids are preserved) for transforms that add nodes and replace the outputs."""
@@ -70,6 +73,8 @@ class Dag:
         d.out_groups = list(self.out_groups)
         d._fv = dict(self._fv)
         d._has_quad = dict(self._has_quad)
+        d._nnz = dict(self._nnz)
+        d._qb = dict(self._qb)
         return d
 
     # ------------------------------------------------------------ building
@@ -89,10 +94,46 @@ class Dag:
         n = self.nodes[i]
         return n.op == 'const' and float(n.attr) == value and not (value == 0 and n.attr.lstrip().startswith('-'))
 
+    def never_neg_zero(self, i: int) -> bool:
+        """Is the value of node i provably never -0?  (Round to nearest: a sum is -0 only when both operands are -0,
+        so an integral -- a left fold that starts at +0 -- never is; nor is x * x, a literal other than -0, or a
+        select between two such values.)  Conservative: False when unknown."""
+        nnz = self._nnz
+        stack = [i]
+        while stack:
+            j = stack[-1]
+            if j in nnz:
+                stack.pop()
+                continue
+            n = self.nodes[j]
+            if n.op == 'quad':
+                nnz[j] = True
+            elif n.op == 'const':
+                nnz[j] = not (float(n.attr) == 0.0 and n.attr.lstrip().startswith('-'))
+            elif n.op == 'add':
+                pend = [a for a in n.args if a not in nnz]
+                if pend:
+                    stack.extend(pend)
+                    continue
+                nnz[j] = nnz[n.args[0]] or nnz[n.args[1]]
+            elif n.op == 'sel':
+                pend = [a for a in n.args[1:] if a not in nnz]
+                if pend:
+                    stack.extend(pend)
+                    continue
+                nnz[j] = nnz[n.args[1]] and nnz[n.args[2]]
+            elif n.op == 'mul':
+                nnz[j] = n.args[0] == n.args[1]
+            else:
+                nnz[j] = False
+            stack.pop()
+        return nnz[i]
+
     def add(self, a: int, b: int) -> int:
-        if self._is_const(b, 0.0):
+        # x + 0 == x bit for bit unless x is -0 (-0 + 0 = +0): fold only where x cannot be -0
+        if self._is_const(b, 0.0) and self.never_neg_zero(a):
             return a
-        if self._is_const(a, 0.0):
+        if self._is_const(a, 0.0) and self.never_neg_zero(b):
             return b
         return self.intern('add', (a, b))
 
@@ -154,6 +195,27 @@ class Dag:
             hq[j] = n.op == 'quad' or any(hq[a] for a in n.args)
             stack.pop()
         return hq[i]
+
+    def quad_bvars(self, i: int) -> FrozenSet[int]:
+        """Bound variables of every integral contained in node i (closed or not)."""
+        qb = self._qb
+        stack = [i]
+        while stack:
+            j = stack[-1]
+            if j in qb:
+                stack.pop()
+                continue
+            n = self.nodes[j]
+            pending = [a for a in n.args if a not in qb]
+            if pending:
+                stack.extend(pending)
+                continue
+            r = frozenset().union(*(qb[a] for a in n.args)) if n.args else frozenset()
+            if n.op == 'quad':
+                r = r | {n.attr}
+            qb[j] = r
+            stack.pop()
+        return qb[i]
 
     def reachable(self, roots: Sequence[int]) -> List[int]:
         seen = set()
@@ -316,10 +378,22 @@ def build_dag(prog: Program) -> Dag:
         if op == 'T':
             lo = scalar(conv(n.kids[0], env, depth), 'integration bound')
             hi = scalar(conv(n.kids[1], env, depth), 'integration bound')
-            bvar = dag.intern('bvar', (lo, hi), depth)
+            # Canonical binder = (bounds, nesting depth) -- unless a value substituted into the body (a LetIn-bound
+            # expression, converted in an outer scope) already contains an integral over that very binder: nesting
+            # the two would make the inner integrand read the outer loop's variable.  Such a binder moves to the
+            # next free depth (it only loses sharing with integrals it must not be confused with).
+            taken = set()
+            for lab in free[n.kids[2]]:
+                v = env.get(lab) if lab != n.attr else None
+                for e in (() if v is None else ((v,) if isinstance(v, int) else v)):
+                    taken |= dag.quad_bvars(e)
+            d = depth
+            while dag._table.get(('bvar', (lo, hi), d)) in taken and taken:
+                d += 1
+            bvar = dag.intern('bvar', (lo, hi), d)
             env2 = dict(env)
             env2[n.attr] = bvar
-            body = conv(n.kids[2], env2, depth + 1)
+            body = conv(n.kids[2], env2, d + 1)
             mk = lambda b: dag.intern('quad', (lo, hi, b), bvar)   # noqa: E731
             return mk(body) if isinstance(body, int) else tuple(mk(b) for b in body)
         raise ValueError(f'The type of the expr "{op}" cannot be expressed in IR.')

@@ -182,7 +182,9 @@ class CUDA_EvalMode(EvalMode):
 
     def compiled(self, array_args: Sequence[int], grid_args: Sequence[int] = (), reduce: bool = False,
                  team: int = 1, grouped: bool = False, pixel_args: Sequence[int] = (), accumulate: bool = False,
-                 vec: int = 1):
+                 vec: int = 1, private: bool = False):
+        """(KernelSource, runtime.Program) of one variant, compiled once per mode.  private: a NEW handle on the same
+        module (own uniform table and scratch buffers) for callers that keep it to themselves."""
         reduce = self._n_reduce(reduce)
         key = (tuple(sorted(array_args)), tuple(grid_args), reduce, int(team), bool(grouped),
                tuple(pixel_args), bool(accumulate), int(vec))
@@ -199,6 +201,8 @@ class CUDA_EvalMode(EvalMode):
             prog = runtime.Program(mod, ks, device=self.device)
             hit = (ks, prog)
             self._variants[key] = hit
+        if private:
+            return hit[0], runtime.Program(hit[1].module, hit[0], device=self.device)
         return hit
 
     # --------------------------------------------------------------------- eval
@@ -218,6 +222,19 @@ class CUDA_EvalMode(EvalMode):
         assert all(a is not None for a in args), \
             f'No bindings found for {[self.arglist[i][0] for i, a in enumerate(args) if a is None]}'
         return args
+
+    def _resolve_scalars(self, bindings, arg_indices: Sequence[int]) -> List[float]:
+        """Launch-wide arguments of a render call, resolved like ``_resolve`` (c_eval.py:135-140): the binding, else
+        the Var's *current* value, else the default captured at conversion time; ``AssertionError`` when unbound."""
+        by_label = {(k if isinstance(k, str) else label_of(k)): v for k, v in (bindings or {}).items()}
+        live = self.program.live
+        out = []
+        for a in arg_indices:
+            lab, default = self.arglist[a]
+            v = by_label[lab] if lab in by_label else (live[lab].value if lab in live else default)
+            assert v is not None, f'No bindings found for {[lab]}'
+            out.append(float(v))
+        return out
 
     def eval(self, bindings={}, reduce: bool = False, **kwargs):
         """reduce=True: return the per-component SUM over the instances (reverse-mode gradients w.r.t.
@@ -289,6 +306,15 @@ class CUDA_EvalMode(EvalMode):
                     n, stream=stream)
         return out if self.out_is_tuple and ks.n_outputs > 1 else out[0]
 
+    def grouped_program(self, box_vars, pixel_vars=(), reduce: bool = False, accumulate: bool = False):
+        """(KernelSource, runtime.Program) of the grouped render variant ``render_groups`` launches for these box /
+        per-pixel arguments (e.g. to attach peer mailboxes to it: ``PeerGroup.attach_groups``)."""
+        pos = {lab: i for i, (lab, _) in enumerate(self.arglist)}
+        grid_args = [pos[v if isinstance(v, str) else label_of(v)] for v in box_vars]
+        pixel_args = sorted(pos[v if isinstance(v, str) else label_of(v)] for v in pixel_vars)
+        return self.compiled(grid_args, grid_args, reduce=reduce, grouped=True, pixel_args=pixel_args,
+                             accumulate=accumulate)
+
     def render_groups(self, box_vars, res: Tuple[int, int], bounds, group_bindings, windows, max_rows: int,
                       max_cols: int, pixel_bindings=None, rows: Optional[Tuple[int, int]] = None, out=None,
                       reduce: bool = False, accumulate: bool = False, group_range: Optional[Tuple[int, int]] = None,
@@ -304,22 +330,19 @@ class CUDA_EvalMode(EvalMode):
         Output: ``out`` images [k, rows, res_y] (assigned, or added to with ``accumulate`` -- the windows of
         one launch must then be disjoint), or with ``reduce`` a tensor [G_range, k] of per-group sums."""
         import torch
-        labels = [v if isinstance(v, str) else label_of(v) for v in box_vars]
         pos = {lab: i for i, (lab, _) in enumerate(self.arglist)}
-        grid_args = [pos[lab] for lab in labels]
         pix = {(k if isinstance(k, str) else label_of(k)): v for k, v in (pixel_bindings or {}).items()}
         grp = {(k if isinstance(k, str) else label_of(k)): v for k, v in (group_bindings or {}).items()}
-        pixel_args = sorted(pos[lab] for lab in pix)
-        ks, prog = self.compiled(grid_args, grid_args, reduce=reduce, grouped=True, pixel_args=pixel_args,
-                                 accumulate=accumulate)
+        ks, prog = self.grouped_program(box_vars, list(pix), reduce=reduce, accumulate=accumulate)
         tdt = torch.float32 if self.float_width == 'float' else torch.float64
         dev = torch.device('cuda', self.device)
         G = int(windows.shape[0])
         g0, g1 = (0, G) if group_range is None else group_range
         gptrs, keep = [], []
+        live = self.program.live
         for a in ks.scalar_args:
             lab, default = self.arglist[a]
-            v = grp.get(lab, default)
+            v = grp[lab] if lab in grp else (live[lab].value if lab in live else default)
             assert v is not None, f'No bindings found for {[lab]}'
             if not _is_torch(v) or v.dim() == 0:
                 v = torch.full((G,), float(v), dtype=tdt, device=dev)
@@ -375,7 +398,7 @@ class CUDA_EvalMode(EvalMode):
                else torch.empty((k_out, n_eff), dtype=tdt, device=dev))
         ptrs = [t.data_ptr() for t in tens.values()] + ([] if reduce else [out[k].data_ptr() for k in range(k_out)])
         ks, prog = self.compiled(array_args, reduce=reduce, team=team,
-                                 vec=self.pick_vec(array_args, reduce, team, ptrs))
+                                 vec=self.pick_vec(array_args, reduce, team, ptrs), private=True)
         ins = [tens[a] for a in ks.array_args]
         scalars = [float(args[a]) for a in ks.scalar_args]
         return PreparedCall(self, ks, prog, scalars, ins, out, n_eff, reduce)
@@ -390,15 +413,11 @@ class CUDA_EvalMode(EvalMode):
         labels = [v if isinstance(v, str) else label_of(v) for v in box_vars]
         pos = {lab: i for i, (lab, _) in enumerate(self.arglist)}
         grid_args = [pos[lab] for lab in labels]
-        by_label = {(k if isinstance(k, str) else label_of(k)): v for k, v in (bindings or {}).items()}
-        ks, prog = self.compiled(grid_args, grid_args, reduce=reduce)
+        # a prepared render owns its handle (its own uniform table and scratch): several of them -- also of the same
+        # program with different scalars, on different streams or threads -- run concurrently
+        ks, prog = self.compiled(grid_args, grid_args, reduce=reduce, private=True)
         assert ks.reduce_outputs in (0, ks.n_outputs), 'prepare_render: all outputs are images, or all are sums'
-        scalars = []
-        for a in ks.scalar_args:
-            lab, default = self.arglist[a]
-            v = by_label.get(lab, default)
-            assert v is not None, f'No bindings found for {[lab]}'
-            scalars.append(float(v))
+        scalars = self._resolve_scalars(bindings, ks.scalar_args)
         r0, r1 = (0, res[0]) if rows is None else rows
         tdt = torch.float32 if self.float_width == 'float' else torch.float64
         dev = torch.device('cuda', self.device)
@@ -428,16 +447,8 @@ class CUDA_EvalMode(EvalMode):
         labels = [v if isinstance(v, str) else label_of(v) for v in box_vars]
         pos = {lab: i for i, (lab, _) in enumerate(self.arglist)}
         grid_args = [pos[lab] for lab in labels]
-        by_label = {}
-        for k, v in (bindings or {}).items():
-            by_label[k if isinstance(k, str) else label_of(k)] = v
         ks, prog = self.compiled(grid_args, grid_args, reduce=reduce)
-        scalars = []
-        for a in ks.scalar_args:
-            lab, default = self.arglist[a]
-            v = by_label.get(lab, default)
-            assert v is not None, f'No bindings found for {[lab]}'
-            scalars.append(float(v))
+        scalars = self._resolve_scalars(bindings, ks.scalar_args)
         r0, r1 = (0, res[0]) if rows is None else rows
         tdt = torch.float32 if self.float_width == 'float' else torch.float64
         dev = torch.device('cuda', self.device)

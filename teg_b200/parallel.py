@@ -87,6 +87,13 @@ class PeerGroup:
         from . import runtime
         runtime.check(self._L.tegb_program_set_peer(program.handle, self.handle))
 
+    def attach_groups(self, program, n_groups_total: int) -> None:
+        """Grouped reduce programs (``CUDA_EvalMode.grouped_program(..., reduce=True)[1]``): their launches then
+        deliver the all-reduced ``[n_groups_total, k]`` sums -- every row, whatever group range a rank launched (the
+        groups it did not cover contribute zero).  ``max_values`` of this PeerGroup must be >= n_groups_total * k."""
+        from . import runtime
+        runtime.check(self._L.tegb_program_set_peer_groups(program.handle, self.handle, int(n_groups_total)))
+
     def detach(self, program) -> None:
         from . import runtime
         runtime.check(self._L.tegb_program_set_peer(program.handle, None))
@@ -101,7 +108,10 @@ class PeerGroup:
         return tensor
 
     def check(self) -> None:
-        """Raises if an exchange timed out waiting for a peer (synchronises the device)."""
+        """Raises if an exchange timed out waiting for a peer (synchronises the device).  A time-out
+        (``TEGB200_PEER_TIMEOUT_S``, default 120 s) also poisons the sums of that call with NaN and makes every later
+        launch on this group raise ``TegbError``, so a missed ``check()`` cannot hide it; call it on every rank
+        before trusting results that were produced without a later launch."""
         if self._L.tegb_peer_error(self.handle):
             raise RuntimeError('peer all-reduce: a rank did not arrive within the time-out')
 

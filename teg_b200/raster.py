@@ -51,6 +51,17 @@ class MultiTriangleRasterizer:
         self.grid_res = (self.res * self.bands, self.res)
         self.rows = (self.res * self.rank, self.res * (self.rank + 1))
         self.K = 0
+        self.peers = None
+
+    def set_peers(self, peers) -> None:
+        """peers: a ``parallel.PeerGroup`` with max_values >= 7 K.  ``backward`` then returns the gradient summed over
+        all ranks: the last per-triangle column-sum kernel exchanges the [K, 7] sums over NVLink peer memory itself
+        (no separate collective).  Call after ``set_scene`` on every rank; every rank must call ``backward`` the same
+        number of times."""
+        assert self.K > 0, 'set_scene first'
+        _, prog = self.m_grad.grouped_program([self.g_lab[b] for b in BOX], [self.g_lab['dL']], reduce=True)
+        peers.attach_groups(prog, self.K)
+        self.peers = peers
 
     def set_scene(self, verts, col, windows, classes: Sequence[Tuple[int, int]], max_rows: int, max_cols: int,
                   active: Optional[Tuple[int, int]] = None):
@@ -101,6 +112,12 @@ class MultiTriangleRasterizer:
         box = [self.g_lab[b] for b in BOX]
         gb = {self.g_lab[nm]: self.params[nm] for nm in PARAMS}
         a0, a1 = self.active
+        if self.peers is not None:
+            # all K rows are written by the fused exchange (groups outside the active range contribute zero)
+            self.m_grad.render_groups(box, self.grid_res, self.bounds, gb, self.windows, self.max_rows, self.max_cols,
+                                      pixel_bindings={self.g_lab['dL']: dL}, rows=self.rows, out=out, reduce=True,
+                                      group_range=(a0, a1), stream=stream)
+            return out
         if (a0, a1) != (0, self.K):
             out.zero_()
         self.m_grad.render_groups(box, self.grid_res, self.bounds, gb, self.windows, self.max_rows, self.max_cols,

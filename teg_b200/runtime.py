@@ -34,11 +34,12 @@ class Grid(ctypes.Structure):
 
 
 SYMBOLS = [
-    'tegb_last_error', 'tegb_version', 'tegb_nvrtc_version', 'tegb_device_count', 'tegb_compile', 'tegb_module_from_cubin',
+    'tegb_last_error', 'tegb_version', 'tegb_runtime_header_hash', 'tegb_nvrtc_version', 'tegb_device_count', 'tegb_compile', 'tegb_module_from_cubin',
     'tegb_module_cubin', 'tegb_module_log', 'tegb_module_destroy', 'tegb_program_create',
     'tegb_program_destroy', 'tegb_program_launch', 'tegb_program_eval_host', 'tegb_render_launch',
     'tegb_render_launch_strided', 'tegb_render_groups_launch', 'tegb_program_tile_table', 'tegb_peer_create', 'tegb_peer_connect',
     'tegb_peer_allreduce_sum', 'tegb_peer_error', 'tegb_peer_destroy', 'tegb_program_set_peer',
+    'tegb_program_set_peer_groups',
     'tegb_launch_count', 'tegb_reduce_workspace_bytes', 'tegb_reduce_sum', 'tegb_nccl_unique_id',
     'tegb_nccl_comm_create', 'tegb_nccl_comm_destroy', 'tegb_allreduce_sum', 'tegb_fma_peak',
 ]
@@ -60,6 +61,7 @@ def lib():
     vp, cp, i32, i64 = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int64
     L.tegb_last_error.restype = cp
     L.tegb_version.restype = i32
+    L.tegb_runtime_header_hash.restype = ctypes.c_uint64
     L.tegb_device_count.restype = i32
     L.tegb_compile.argtypes = [cp, cp, cp, ctypes.POINTER(vp)]
     L.tegb_module_from_cubin.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(vp)]
@@ -89,6 +91,7 @@ def lib():
     L.tegb_peer_destroy.argtypes = [vp]
     L.tegb_peer_destroy.restype = None
     L.tegb_program_set_peer.argtypes = [vp, vp]
+    L.tegb_program_set_peer_groups.argtypes = [vp, vp, i32]
     L.tegb_launch_count.restype = i64
     L.tegb_reduce_workspace_bytes.argtypes = [i32, i64, i32]
     L.tegb_reduce_workspace_bytes.restype = ctypes.c_size_t
@@ -133,7 +136,9 @@ class Module:
         L = lib()
         self._L = L
         self.handle = ctypes.c_void_p()
-        key = hashlib.sha256(f'{L.tegb_version()}|{L.tegb_nvrtc_version()}|{arch}|{opts}|{source}'.encode()).hexdigest()[:32]
+        # the unit includes the runtime header by name only: its text (embedded in the library) is part of the key
+        key = hashlib.sha256(f'{L.tegb_version()}|{L.tegb_runtime_header_hash():016x}|{L.tegb_nvrtc_version()}|{arch}|{opts}|'
+                             f'{source}'.encode()).hexdigest()[:32]
         path = os.path.join(cache_dir(), f'{key}.cubin')
         self.from_cache = False
         if use_cache and os.path.exists(path):

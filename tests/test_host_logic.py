@@ -407,3 +407,64 @@ def test_tile_bodies_with_exact_per_pixel_states_on_host(scene):
     known = np.all(states != 2, axis=0)
     quiet = known & np.all(states[guards] == 0, axis=0)
     assert quiet.any() and (known & ~quiet).any() and (~known).any() == ('dom' in kinds and (states == 2).any())
+
+
+def _host_vs_oracle(prog, ns, vals, array_args, culled=(False, True)):
+    """generated code (host-compiled) == oracle, bit for bit, with and without culling, fp32 and fp64"""
+    from oracle import Oracle
+    from teg_b200.cull import cull
+    n = max(int(np.size(v)) for v in vals)
+    for dtype, ctype in ((np.float32, 'float'), (np.float64, 'double')):
+        v = [np.asarray(x, dtype=dtype) if np.ndim(x) else dtype(x) for x in vals]
+        want = Oracle(prog.dumps()).eval(v, ns, dtype)
+        for c in culled:
+            dag = build_dag(prog)
+            dag = cull(dag, ns, min_samples=1) if c else dag
+            ks = generate(make_schedule(dag, array_args), ctype, ns, use_asm=False, coop=False)
+            got = run_on_host(ks, v, n, dtype)
+            assert np.array_equal(got, want, equal_nan=True), (ctype, c, got, want)
+
+
+def test_let_bound_integral_used_inside_an_integral_over_the_same_domain():
+    """``let w = int_0^1 x*x*t dx in int_0^1 (y*y*t < 0.3 ? w * (y*y*t) : 0) dy``.  Both integrals
+    have the bounds (0, 1) at nesting depth 0; with binders canonicalised by (bounds, depth) alone the inner
+    integrand ``x*x*t`` was hash-consed with the outer ``y*y*t`` and read the outer sample."""
+    from teg_b200.lang import Const, IfElse, LetIn, Teg, TegVar, Var
+    x, y, t = TegVar('x'), TegVar('y'), Var('t', 0.1)
+    w = Var('w')
+    inner = Teg(Const(0), Const(1), x * x * t, x)
+    body = Teg(Const(0), Const(1), IfElse(y * y * t < Const(0.3), w * (y * y * t), Const(0)), y)
+    prog = from_teg(LetIn([w], [inner], body), [t], name='let_nested')
+    dag = build_dag(prog)
+    bvars = {n.attr for n in dag.nodes if n.op == 'quad'}
+    assert len(bvars) == 2, 'the two integrals must not share a bound variable'
+    ts = np.array([0.1, 0.5, 1.0, -0.3, 2.0])
+    _host_vs_oracle(prog, 8, [ts], [0])
+    _host_vs_oracle(prog, 8, [0.1], [])
+    # one level down: the let sits inside an outer integral, its value and its body integrate over (0, 1) at depth 1
+    z = TegVar('z')
+    inner2 = Teg(Const(0), Const(1), x * z * t, x)
+    body2 = Teg(Const(0), Const(1), IfElse(y * t < Const(0.3), w * (y * z * t), Const(0)), y)
+    prog2 = from_teg(Teg(Const(0), Const(2), LetIn([w], [inner2], body2), z), [t], name='let_nested2')
+    _host_vs_oracle(prog2, 6, [ts], [0])
+    # integrals that do NOT nest still share their variable (fusion / sharing is kept)
+    both = from_teg(Teg(Const(0), Const(1), x * t, x) + Teg(Const(0), Const(1), y * y * t, y), [t], name='siblings')
+    assert len({n.attr for n in build_dag(both).nodes if n.op == 'quad'}) == 1
+
+
+def test_adding_zero_to_a_negative_zero_is_not_folded_away():
+    """the reference computes ``-0 + 0 = +0``; ``1 / (((-1 * t) * 0) + 0)`` is +inf, not -inf."""
+    from teg_b200.lang import Const, Var
+    t = Var('t', 1.0)
+    prog = from_teg(Const(1) / (((Const(-1) * t) * Const(0)) + Const(0)), [t], name='negzero')
+    _host_vs_oracle(prog, 4, [np.array([1.0, 2.0, -3.0, 0.0])], [0], culled=(False,))
+    # ... while the folds that ARE exact stay: 0 + integral, x*x + 0, literal + 0
+    from teg_b200.lang import Teg, TegVar
+    x = TegVar('x')
+    q = from_teg(Const(0) + Teg(Const(0), Const(1), x * t, x) + Const(0), [t], name='q0')
+    d = build_dag(q)
+    assert d.nodes[d.outputs[0]].op == 'quad'
+    d2 = build_dag(from_teg((t * t) + Const(0), [t], name='sq0'))
+    assert d2.nodes[d2.outputs[0]].op == 'mul'
+    d3 = build_dag(from_teg(t + Const(0), [t], name='t0'))
+    assert d3.nodes[d3.outputs[0]].op == 'add'
