@@ -46,10 +46,11 @@ VARIANTS = {
     'shaded_grad': [('f32', 16), ('f64', 16)],
     'tri_color_primal': [('f32', 16), ('f64', 16)],
     'tri_color_grad': [('f32', 16), ('f64', 16)],
-    'nested2d_value': [('f32', 16), ('f32', 64), ('f64', 16)],
-    'nested2d_grad': [('f32', 16), ('f32', 64), ('f64', 16)],
-    'nested3d_value': [('f32', 16), ('f64', 16)],
-    'nested3d_grad': [('f32', 16), ('f64', 16)],
+    # config 4: the top of the sample-count sweep as well -- N = 1024 / 4096 in 2-D, 128 / 256 in 3-D
+    'nested2d_value': [('f32', 16), ('f32', 64), ('f64', 16), ('f32', 1024), ('f32', 4096), ('f64', 1024)],
+    'nested2d_grad': [('f32', 16), ('f32', 64), ('f64', 16), ('f32', 1024), ('f32', 4096), ('f64', 1024)],
+    'nested3d_value': [('f32', 16), ('f64', 16), ('f32', 128), ('f32', 256)],
+    'nested3d_grad': [('f32', 16), ('f64', 16), ('f32', 128), ('f32', 256)],
     'simple_line': [('f32', 20)],
     'simple_line_grad': [('f32', 20), ('f64', 20)],
     'circle': [('f32', 20)],
@@ -59,6 +60,14 @@ VARIANTS = {
     'bilinear_lerp': [('f32', 20)],
     'bilinear_lerp_grad': [('f32', 20), ('f64', 20)],
 }
+
+
+# variants whose golden vectors hold fewer instances (N^2 / N^3 samples each): tests/golden/vectors_high_n/
+HIGH_N_INSTANCES = 64
+
+
+def is_high_n(scene: str, ns: int) -> bool:
+    return scene.startswith('nested') and ns >= 128
 
 
 def reference_available() -> bool:

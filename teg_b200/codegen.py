@@ -285,11 +285,17 @@ class Emitter:
         # (see _emit_pred_add) so that neither the ALU pipe (compares) nor the issue slots are the lone limit
         mixed = (innermost and not teamed and self.pred_mix > 0 and self.use_asm and N <= self.unroll_inner
                  and self.ctype == 'float')
+        zero = literal('0', self.ctype)
         if teamed:
-            # the instance's team splits the outermost sample loop: member r takes samples r, r+TEAM, ...
-            # (each member still folds its own samples left to right; partial sums are combined below)
+            # the instance's team splits the outermost sample loop: chunks of TEAM consecutive samples, member r
+            # evaluates sample chunk + r, then every member adds the chunk's terms in sample order (tegb_team_fold):
+            # the reference's left fold, bit for bit
             self.emit('#pragma unroll 1', ind + 1)
-            self.emit(f'for (unsigned int s{k} = team_rank; s{k} < {N}u; s{k} += {self.team}u) {{', ind + 1)
+            self.emit(f'for (unsigned int base{k} = 0; base{k} < {N}u; base{k} += {self.team}u) {{', ind + 1)
+            self.emit(f'const unsigned int s{k} = base{k} + team_rank;', ind + 2)
+            for q in st.quads:
+                self.emit(f'T t{k}_{q}[1] = {{{zero}}};', ind + 2)
+            self.emit(f'if (s{k} < {N}u) {{', ind + 2)
         elif mixed:
             self.emit('{', ind + 1)         # unrolled by hand below: one scope per sample, in sample order
         else:
@@ -305,12 +311,19 @@ class Emitter:
                 if pf is not None and pf[0]:
                     conds, val = pf
                     term = f'step{k}' if val is None else f'{val} * step{k}'
-                    self._emit_pred_add(f'v{q}', conds, term, st.body.known, ind2, form=form)
+                    if teamed:
+                        cond = ' && '.join(f'({self.ref(c, st.body.known)})' for c in conds)
+                        self.emit(f't{k}_{q}[0] = ({cond}) ? {term} : {zero};', ind2)
+                    else:
+                        self._emit_pred_add(f'v{q}', conds, term, st.body.known, ind2, form=form)
                     if q not in fixups:
                         fixups.append(q)
                 else:
                     body = self.ref(self.nodes[q].args[2], st.body.known)
-                    self.emit(f'v{q} = v{q} + {body} * step{k};', ind2)
+                    if teamed:
+                        self.emit(f't{k}_{q}[0] = {body} * step{k};', ind2)
+                    else:
+                        self.emit(f'v{q} = v{q} + {body} * step{k};', ind2)
 
         if mixed:
             # a fraction pred_mix of the samples (evenly spread) uses the min3 form, the rest the chained form
@@ -322,15 +335,20 @@ class Emitter:
                 self.emit('{', ind + 2)
                 sample(f'{j}u', form, ind + 3)
                 self.emit('}', ind + 2)
+        elif teamed:
+            self.divergent += 1              # (members beyond the last sample sit this out: no collectives inside)
+            sample(f's{k}', 'chain', ind + 3)
+            self.divergent -= 1
+            self.emit('}', ind + 2)
+            self.emit(f'const unsigned int cnt{k} = ({N}u - base{k}) < {self.team}u ? ({N}u - base{k}) : {self.team}u;', ind + 2)
+            for q in st.quads:
+                self.emit(f'v{q} = tegb_team_fold<T, {self.team}, 1>(v{q}, t{k}_{q}, cnt{k});', ind + 2)
         else:
             sample(f's{k}', 'chain', ind + 2)
         self.emit('}', ind + 1)
-        if teamed:
-            for q in st.quads:
-                self.emit(f'v{q} = tegb_team_sum<T, {self.team}>(v{q});', ind + 1)
         for q in fixups:
             # skipped terms were `0 * step`: identical for every finite step; keeps NaN/inf steps poisonous
-            self.emit(f'v{q} = v{q} + {literal("0", self.ctype)} * step{k};', ind + 1)
+            self.emit(f'v{q} = v{q} + {zero} * step{k};', ind + 1)
         self.emit('}', ind)
 
     # ------------------------------------------------------------ domain culling (cull.py)
@@ -739,7 +757,12 @@ class Emitter:
         self.emit(f'const T step{k} = ((T)({self.ref(st.hi, known)} - lo{k})) / (T){N};', ind + 1)
         self.emit('#pragma unroll 1', ind + 1)
         if teamed:
-            self.emit(f'for (unsigned int s{k} = team_rank * {U}u; s{k} < {N}u; s{k} += {self.team * U}u) {{', ind + 1)
+            # chunks of TEAM * U consecutive samples: member r carries the U samples chunk + r * U + u through one pass
+            # of the inner loop; the chunk's TEAM * U terms are then added in sample order by every member
+            self.emit(f'for (unsigned int base{k} = 0; base{k} < {N}u; base{k} += {self.team * U}u) {{', ind + 1)
+            self.emit(f'const unsigned int s{k} = base{k} + team_rank * {U}u;', ind + 2)
+            for q in st.quads:
+                self.emit(f'T t{k}_{q}[{U}];', ind + 2)
         else:
             self.emit(f'for (unsigned int s{k} = 0; s{k} < {N}u; s{k} += {U}u) {{', ind + 1)
         copy_nodes = [st.bvar] + [s.node for s in pre] + list(inner.quads) + [s.node for s in post]
@@ -789,12 +812,15 @@ class Emitter:
                 self.emit(f'const {self.decl(s.node)} v{s.node}_{u} = {self.expr(s.node, st.body.known)};', ind + 2)
             for q in st.quads:
                 body = self.ref(self.nodes[q].args[2], st.body.known)
-                self.emit(f'v{q} = v{q} + {body} * step{k};', ind + 2)
+                if teamed:
+                    self.emit(f't{k}_{q}[{u}] = {body} * step{k};', ind + 2)
+                else:
+                    self.emit(f'v{q} = v{q} + {body} * step{k};', ind + 2)
         self.jam_map = saved
-        self.emit('}', ind + 1)
         if teamed:
             for q in st.quads:
-                self.emit(f'v{q} = tegb_team_sum<T, {self.team}>(v{q});', ind + 1)
+                self.emit(f'v{q} = tegb_team_fold<T, {self.team}, {U}>(v{q}, t{k}_{q}, {self.team * U}u);', ind + 2)
+        self.emit('}', ind + 1)
         self.emit('}', ind)
 
     # ------------------------------------------------------ warp-cooperative guarded loops

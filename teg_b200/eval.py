@@ -65,7 +65,7 @@ class CUDA_EvalMode(EvalMode):
 
     def __init__(self, expr, num_samples: int = 50, float_width: str = 'float', device: int = 0,
                  arglist: Sequence = (), name: str = 'teg_method', use_cache: bool = True,
-                 block_size: int = 128, team=1, nvrtc_opts: str = '',
+                 block_size: int = 128, team='auto', nvrtc_opts: str = '',
                  integration_mode: str = 'rectangular_quadrature', cull: bool = True, seed: int = 0, **codegen_opts):
         super().__init__(name='CUDA')
         if float_width in ('single', 'f32', np.float32):
@@ -85,12 +85,12 @@ class CUDA_EvalMode(EvalMode):
         self.device = device
         self.use_cache = use_cache
         self.block_size = block_size
-        # team: threads cooperating on one instance.  1 (default) = thread per instance: every sum is the
-        # reference's left fold, results are bit-exact w.r.t. the C backend.  'auto' keeps 1 unless the batch
-        # is too small to fill the GPU *and* each instance carries >= 4096 samples; then the outermost sample
-        # loop is split over a team (slice of a warp / warp / block) and the partial sums are combined in a
-        # fixed order.  That re-associates one sum: deterministic, but only as close to the C backend as the
-        # C backend's own left fold is accurate (~N*eps/2 relative in the working precision).
+        # team: threads cooperating on one instance.  1 = thread per instance.  'auto' (default) keeps 1 unless the
+        # batch is too small to fill the GPU *and* each instance carries >= 4096 samples; then the outermost
+        # sample loop is split over a team (slice of a warp / warp / block): members evaluate consecutive outer
+        # samples (their inner integrals are ordinary sequential folds) and every member adds the outer terms in
+        # sample order (tegb_team_fold).  Either way every sum is the reference's left fold: bit-exact w.r.t. the
+        # C backend.
         assert team == 'auto' or (isinstance(team, int) and team >= 1 and team & (team - 1) == 0 and team <= 1024)
         self.team = team
         # integration_mode: 'rectangular_quadrature' = the C backend's midpoint rule (the only template the

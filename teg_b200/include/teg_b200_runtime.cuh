@@ -62,31 +62,34 @@ static __device__ __forceinline__ void tegb_block_sum_store(const T (&v)[K], T* 
     tegb_block_sum_store<T, K, BLOCK>(v, partials, nblk, blk);
 }
 
-/* Sum over the TEAM threads that cooperate on one instance (TEAM consecutive threads, TEAM a power of two).
- * TEAM <= 32: xor butterfly inside the team's lanes.  Every stage adds the same two numbers on both partners,
- * so all members end with the same bits, and the combination order is fixed: deterministic.
- * TEAM  > 32: the team is the whole block; warp butterflies, then every thread adds the per-warp values in
- * warp order.  Reached by all members together: guards that enclose a team loop depend only on per-instance
- * values, which are identical across the team. */
-template <typename T, int TEAM>
-static __device__ __forceinline__ T tegb_team_sum(T v) {
+/* Teams: TEAM consecutive threads (a power of two) cooperate on one instance by splitting its OUTERMOST sample loop.
+ * The reference folds the outer terms left to right (rectangular_rule.template.c:4-9), and so does the team: the
+ * loop advances in chunks of TEAM * U consecutive samples, member r evaluates the U samples chunk + r * U + u (its
+ * inner integrals are ordinary sequential folds), and then EVERY member adds the chunk's terms to its copy of the
+ * accumulator in sample order.  All members hold the same bits at all times and the result equals the sequential
+ * fold bit for bit -- no partial sums, nothing re-associated.
+ * TEAM <= 32: the terms travel by shuffles inside the team's lanes.  TEAM > 32: the team is the whole block; the terms
+ * go through shared memory.  `count` = number of valid samples in this chunk (a multiple of U; team-uniform).
+ * Reached by all members together: guards that enclose a team loop depend only on per-instance values. */
+template <typename T, int TEAM, int U>
+static __device__ __forceinline__ T tegb_team_fold(T acc, const T (&t)[U], const unsigned int count) {
     if (TEAM <= 32) {
         const unsigned lane = threadIdx.x & 31u;
-        const unsigned mask = (TEAM == 32) ? 0xffffffffu : (((1u << (TEAM & 31)) - 1u) << (lane & ~(unsigned)(TEAM - 1)));
+        const unsigned first = lane & ~(unsigned)(TEAM - 1);
+        const unsigned mask = (TEAM == 32) ? 0xffffffffu : (((1u << (TEAM & 31)) - 1u) << first);
+        for (unsigned int l = 0; l * U < count; ++l) {
 #pragma unroll
-        for (int off = TEAM / 2; off > 0; off >>= 1) v = v + __shfl_xor_sync(mask, v, off);
-        return v;
+            for (int u = 0; u < U; u++) acc = acc + __shfl_sync(mask, t[u], (int)(first + l));
+        }
+        return acc;
     } else {
-        __shared__ T sm[32];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, off);
+        __shared__ T sm[TEAM * U];
         __syncthreads();                       /* previous use of sm is over */
-        if ((threadIdx.x & 31u) == 0) sm[threadIdx.x >> 5] = v;
-        __syncthreads();
-        T t = sm[0];
 #pragma unroll
-        for (int w = 1; w < TEAM / 32; w++) t = t + sm[w];
-        return t;
+        for (int u = 0; u < U; u++) sm[threadIdx.x * U + u] = t[u];
+        __syncthreads();
+        for (unsigned int i = 0; i < count; ++i) acc = acc + sm[i];
+        return acc;
     }
 }
 #else

@@ -102,3 +102,116 @@ def test_captured_step_follows_parameter_updates(cuda_device):
         torch.cuda.synchronize()
         assert torch.equal(got_img, img) and torch.equal(got_g, g)
         assert float(img.sum()) > 0 and float(g.abs().sum()) > 0
+
+
+# ---- BASELINE size: 4096 x 4096 per band, 256 triangles per band -------------------------------
+def _oracle_rows(scene, res, bands, r_lo, r_hi):
+    """image rows [r_lo, r_hi) of the full scene, accumulated class by class like the device (fp32): every triangle
+    whose window reaches into the rows contributes; only the pixels inside the rows are evaluated."""
+    from oracle import Oracle
+    prim = Oracle(program_text('tri_color_primal'))
+    rows_total = res * bands
+    xs = np.linspace(0.0, float(bands), rows_total + 1)
+    ys = np.linspace(0.0, 1.0, res + 1)
+    img = np.zeros((r_hi - r_lo, res), dtype=np.float32)
+    used = 0
+    for g0, g1 in scene['classes']:
+        for k in range(g0, g1):
+            r0, r1, c0, c1 = scene['windows'][k]
+            a0, a1 = max(r0, r_lo), min(r1, r_hi)
+            if a0 >= a1:
+                continue
+            used += 1
+            nx = np.repeat(np.arange(a0, a1), c1 - c0)
+            ny = np.tile(np.arange(c0, c1), a1 - a0)
+            par = list(scene['verts'][k]) + [scene['col'][k]]
+            v = prim.eval([xs[nx], xs[nx + 1], ys[ny], ys[ny + 1]] + par, 16, np.float32, threads=16)[0]
+            img[nx - r_lo, ny] = img[nx - r_lo, ny] + v
+    return img, used
+
+
+def _oracle_grad(scene, res, bands, dL, ks):
+    """float64 sums (and sums of magnitudes) of the per-pixel reverse derivatives over the FULL windows of triangles ks"""
+    from oracle import Oracle
+    grad = Oracle(program_text('tri_color_grad'))
+    rows_total = res * bands
+    xs = np.linspace(0.0, float(bands), rows_total + 1)
+    ys = np.linspace(0.0, 1.0, res + 1)
+    g, gabs = {}, {}
+    for k in ks:
+        r0, r1, c0, c1 = scene['windows'][k]
+        nx = np.repeat(np.arange(r0, r1), c1 - c0)
+        ny = np.tile(np.arange(c0, c1), r1 - r0)
+        par = list(scene['verts'][k]) + [scene['col'][k]]
+        gk = grad.eval([dL[nx, ny], xs[nx], xs[nx + 1], ys[ny], ys[ny + 1]] + par, 16, np.float32, threads=16)
+        g[k] = gk.astype(np.float64).sum(axis=1)
+        gabs[k] = np.abs(gk.astype(np.float64)).sum(axis=1)
+    return g, gabs
+
+
+@pytest.mark.parametrize('bands', [1, 2])
+def test_config5_at_baseline_size_against_the_oracle(cuda_device, bands):
+    """4096 x 4096 pixels and 256 triangles per band, the grouped + tile-culled path exactly as bench.py launches it.
+    Image: a strip of 384 rows (for two bands: the strip across the band boundary, where windows are clipped to the
+    ranks' bands) equals the oracle's class-ordered accumulation bit for bit.  Gradients: the [K, 7] sums of >= 16
+    triangles over their full windows (for two bands: the triangles whose windows straddle the boundary, summed over
+    the ranks like the all-reduce does) within fp32 summation error of the oracle's float64 sums."""
+    import torch
+    from teg_b200.raster import MultiTriangleRasterizer
+    res = 4096
+    scene = multi_triangle_scene(bands=bands, res=res)
+    K = scene['verts'].shape[0]
+    assert K == 256 * bands
+    r_lo, r_hi = (1800, 2184) if bands == 1 else (res - 192, res + 192)
+    want_img, used = _oracle_rows(scene, res, bands, r_lo, r_hi)
+    assert used >= 32 and np.count_nonzero(want_img) > 10000
+    w = scene['windows']
+    if bands == 1:
+        ks = [int(k) for k in np.linspace(0, K - 1, 16).astype(int)]
+    else:
+        ks = [k for k in range(K) if w[k][0] < res < w[k][1]][:16]          # windows crossing the band boundary
+        ks += [k for k in (0, 100, 300, K - 1) if k not in ks]
+    assert len(ks) >= 16
+    rng = np.random.default_rng(11)
+    dL = rng.uniform(-1, 1, size=(res * bands, res)).astype(np.float32)
+    want_g, want_gabs = _oracle_grad(scene, res, bands, dL, ks)
+    got_rows = np.zeros_like(want_img)
+    got_g = np.zeros((K, 7))
+    for rank in range(bands):
+        r = MultiTriangleRasterizer(load_program('tri_color_primal'), load_program('tri_color_grad'), res,
+                                    bands=bands, rank=rank)
+        br = scene['band_ranges']
+        active = (br[max(rank - 1, 0)][0], br[min(rank + 1, bands - 1)][1]) if bands > 1 else None
+        r.set_scene(scene['verts'], scene['col'], scene['windows'], scene['classes'], scene['max_rows'],
+                    scene['max_cols'], active=active)
+        img = r.forward()
+        band = torch.as_tensor(dL[res * rank: res * (rank + 1)]).cuda().contiguous()
+        g = r.backward(band)
+        torch.cuda.synchronize()
+        a0, a1 = max(r_lo, res * rank), min(r_hi, res * (rank + 1))
+        got_rows[a0 - r_lo:a1 - r_lo] = img[0, a0 - res * rank:a1 - res * rank].cpu().numpy()
+        got_g += g.double().cpu().numpy()
+        if rank == 0:
+            # the same step as ONE captured CUDA graph (how bench.py replays it): identical bits at this size
+            img2 = torch.empty_like(img)
+            dl2 = torch.empty((res, res), dtype=torch.float32, device='cuda')
+            g2 = torch.empty_like(g)
+            target = torch.full((res, res), 0.25, device='cuda')
+
+            def body(sp):
+                r.forward(out=img2, stream=sp)
+                torch.sub(img2[0], target, out=dl2)
+                r.backward(dl2, out=g2, stream=sp)
+
+            graph = r.capture(body)
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(img2, img), 'captured forward differs from the launch-by-launch forward'
+            g3 = r.backward((img[0] - target).contiguous())
+            torch.cuda.synchronize()
+            assert torch.equal(g2, g3), 'captured backward differs from the launch-by-launch backward'
+            del graph
+    assert np.array_equal(got_rows, want_img), f'{np.count_nonzero(got_rows != want_img)} pixels of the strip differ'
+    for k in ks:
+        assert np.all(np.abs(got_g[k] - want_g[k]) <= 2e-6 * want_gabs[k] + 1e-12), (k, got_g[k], want_g[k])
+    assert max(np.abs(want_g[k]).max() for k in ks) > 1e-3

@@ -151,6 +151,43 @@ def test_cuda_reproduces_reference_vectors(cuda_device, path):
         assert np.array_equal(got, want, equal_nan=True), f'{name}: {np.count_nonzero(got != want)} values differ'
 
 
+# ---- config 4 at the top of its sample-count sweep: N = 1024 / 4096 in 2-D, 128 / 256 in 3-D ------------
+_HIGH_N = sorted(_glob.glob(_os.path.join(_ROOT, 'tests', 'golden', 'vectors_high_n', '*.npz')))
+
+
+def test_high_n_fixtures_present():
+    assert len(_HIGH_N) >= 10
+
+
+@pytest.mark.parametrize('team', ['auto', 32, 1])
+@pytest.mark.parametrize('path', _HIGH_N, ids=[_os.path.basename(p)[:-4] for p in _HIGH_N])
+def test_config4_high_sample_counts_are_bit_exact(cuda_device, path, team):
+    """64 instances against the outputs of the reference's own compiled C (tests/golden/make_golden.py --high-n):
+    ``array_equal``, no tolerance -- with the default policy (a block or a warp per instance), a forced warp team and
+    thread per instance.  An fp32 left fold of 4096 terms carries ~1e-4 of its own rounding error, so anything that
+    re-associated it would show here."""
+    from teg_b200 import CUDA_EvalMode
+    z = np.load(path)
+    name = _os.path.basename(path)[:-4]
+    scene, prec, ns = name.rsplit('_', 2)
+    ns = int(z['num_samples'])
+    if team == 1 and ((scene.endswith('value') and ns > 1024) or (scene == 'nested3d_value' and ns > 128)):
+        pytest.skip('thread per instance at 1.7e7 samples per instance: covered by the teamed runs')
+    prog = load_program(scene)
+    mode = CUDA_EvalMode(prog, num_samples=ns, float_width='float' if prec == 'f32' else 'double', team=team)
+    inputs = list(z['inputs'])
+    arr = [i for i, v in enumerate(inputs) if np.ptp(v) > 0]
+    if team == 'auto' and scene.endswith('value'):
+        assert mode.pick_team(64, arr) >= 128                      # the teams are what is being tested
+    b = {lab: (v if i in arr else float(v[0])) for i, (lab, v) in enumerate(zip(prog.args, inputs))}
+    got = np.asarray(mode.eval(b)).reshape(z['outputs'].shape)
+    want = z['outputs']
+    assert got.dtype == want.dtype and np.count_nonzero(want) > 0
+    assert np.array_equal(got, want, equal_nan=True), \
+        f'{name} team={team}: {np.count_nonzero(got != want)} of {got.size} differ, max rel ' \
+        f'{np.nanmax(np.abs(got - want) / np.maximum(np.abs(want), 1e-30)):.3g}'
+
+
 def test_in_kernel_gradient_sum_matches_per_pixel_gradients(cuda_device):
     """reduce=True (tegb_block_sum_store + colsum_stage2): deterministic, and equal to the float64 sum of
     the per-pixel gradients up to fp32 summation error; array path and render path both."""
@@ -185,34 +222,32 @@ TEAM_CASES = [('tri_primal', 16, 2), ('tri_primal', 16, 16), ('tri_grad', 16, 8)
               ('bilinear_lerp_grad', 20, 32)]
 
 
-@pytest.mark.parametrize('dtype,tol', [(np.float32, 1e-5), (np.float64, 1e-12)], ids=['f32', 'f64'])
-@pytest.mark.parametrize('scene,ns,team', TEAM_CASES)
-def test_team_kernels_within_stated_tolerance(cuda_device, scene, ns, team, dtype, tol):
-    """Teams re-associate the outermost sum only (fixed order): 1e-5 (fp32) / 1e-12 (fp64) relative to
-    max(|ref|, instance scale) -- the north-star tolerance; sample classification stays bit-identical."""
+@pytest.mark.parametrize('dtype', [np.float32, np.float64], ids=['f32', 'f64'])
+@pytest.mark.parametrize('scene,ns,team', TEAM_CASES + [('nested2d_value', 100, 32), ('nested2d_grad', 100, 64),
+                                                         ('nested3d_value', 24, 256), ('tri_primal', 40, 8)])
+def test_team_kernels_are_bit_exact(cuda_device, scene, ns, team, dtype):
+    """Teams split the outermost sample loop over TEAM threads and add the outer terms in sample order
+    (tegb_team_fold): the reference's left fold, bit for bit (rectangular_rule.template.c:4-9) -- also when the
+    sample count is not a multiple of the team size or the team is larger than the loop."""
     n = 96 if team >= 128 else 1024
     got, want = _run_both(scene, dtype, res=(32, 32), n=n, team=team, ns=ns)
-    scale = np.maximum(np.abs(want), np.max(np.abs(want), axis=1, keepdims=True) * 1e-2 + 1e-30)
-    err = np.abs(got - want) / scale
-    assert np.nanmax(err) <= tol, f'{scene} team={team}: max scaled error {np.nanmax(err):.3g}'
-    # determinism
-    got2, _ = _run_both(scene, dtype, res=(32, 32), n=n, team=team, ns=ns)
-    assert np.array_equal(got, got2, equal_nan=True)
+    assert np.array_equal(got, want, equal_nan=True), \
+        f'{scene} team={team}: {np.count_nonzero(got != want)} of {got.size} values differ from the oracle'
 
 
 def test_auto_team_policy_and_single_instance_big_integral(cuda_device):
-    """One instance, 2-D integral at 2000 samples per axis (4e6 samples): 'auto' picks a block team; the
-    value matches the oracle's left fold to the stated tolerance."""
+    """One instance, 2-D integral at 2000 samples per axis (4e6 samples): 'auto' (the default) picks a block team;
+    the value equals the oracle's left fold bit for bit."""
     from oracle import Oracle
     from teg_b200 import CUDA_EvalMode
     prog = load_program('nested2d_value')
     vals = dict(zip(prog.args, [0.0, 1.0, 0.0, 1.0, 0.3, -0.7, 0.2, -0.5, 0.4, 0.1]))
-    mode = CUDA_EvalMode(prog, num_samples=2000, team='auto')
+    mode = CUDA_EvalMode(prog, num_samples=2000)
     assert mode.pick_team(1, []) == 1024 and mode.pick_team(1 << 20, [0]) == 1
     got = mode.eval(vals)
     want = float(Oracle(program_text('nested2d_value')).eval(list(vals.values()), 2000, np.float32)[0, 0])
-    assert isinstance(got, float) and abs(got - want) <= 2000 * 6e-8 * abs(want)      # N * eps / 2
-    assert CUDA_EvalMode(prog, num_samples=2000).pick_team(1, []) == 1                 # default stays exact
+    assert isinstance(got, float) and got == want
+    assert CUDA_EvalMode(prog, num_samples=2000, team=1).pick_team(1, []) == 1
 
 
 def test_prepared_call_matches_eval_and_tracks_scalar_updates(cuda_device):

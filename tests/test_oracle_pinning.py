@@ -37,6 +37,29 @@ def test_oracle_reproduces_reference_vectors(path):
     assert np.array_equal(got, want, equal_nan=True), f'{name}: {np.count_nonzero(got != want)} values differ'
 
 
+HIGH_N = sorted(glob.glob(os.path.join(ROOT, 'tests', 'golden', 'vectors_high_n', '*.npz')))
+
+
+@pytest.mark.parametrize('path', HIGH_N, ids=[os.path.basename(p)[:-4] for p in HIGH_N])
+def test_oracle_reproduces_reference_vectors_at_high_sample_counts(path):
+    """config 4 at the top of its sweep (N = 1024 / 4096 in 2-D, 128 / 256 in 3-D): the interpreter against the
+    reference's compiled C.  The largest value programs (1.7e7 samples per instance) are checked on 16 of the 64
+    instances to keep the CPU suite short; the GPU tests use all 64."""
+    z = np.load(path)
+    name = os.path.basename(path)[:-4]
+    scene, prec, ns = name.rsplit('_', 2)
+    dtype = np.float32 if prec == 'f32' else np.float64
+    ns = int(z['num_samples'])
+    m = 16 if (scene.endswith('value') and ns in (4096, 256)) else 64
+    got = Oracle(program_text(scene)).eval([v[:m] for v in z['inputs']], ns, dtype, threads=os.cpu_count() or 2)
+    want = z['outputs'][:, :m]
+    assert np.array_equal(got, want, equal_nan=True), f'{name}: {np.count_nonzero(got != want)} values differ'
+
+
+def test_high_n_fixtures_present():
+    assert len(HIGH_N) >= 10
+
+
 LIVE = [(s, p) for s in SCENE_SAMPLES for p in ('f32', 'f64')
         if os.path.exists(ref_lib_path(s, np.float32 if p == 'f32' else np.float64, SCENE_SAMPLES[s]))]
 
