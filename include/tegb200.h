@@ -156,7 +156,8 @@ int tegb_program_tile_table(tegb_program *p, void *host_out, size_t nbytes, void
  *   tegb_program_set_peer  reduce_outputs launches of the program then deliver the all-reduced sums
  *   tegb_peer_allreduce_sum  stand-alone in-place all-reduce of a device vector (every rank must call it, same order)
  *   tegb_program_set_peer_groups  the same for grouped reduce programs: out_ptrs[0] of tegb_render_groups_launch then
- *                      receives the all-reduced [n_groups_total][n_outputs] sums
+ *                      receives the all-reduced [n_groups_total][n_outputs] sums; local_of (device int32
+ *                      [n_groups_total] or NULL) maps every global group to this rank's group index (-1: not held)
  *   tegb_peer_error    1 if an exchange timed out (a peer never arrived); tegb_peer_destroy after a barrier
  * Time-out: an exchange waits TEGB200_PEER_TIMEOUT_S seconds (default 120; 0 = for ever) for every peer.  When it
  * expires the sums of that call are NaN, a sticky flag is raised and EVERY later launch on the group returns
@@ -168,7 +169,7 @@ int tegb_peer_allreduce_sum(tegb_peer *p, void *buf, int count, int elem_size, v
 int tegb_peer_error(tegb_peer *p);
 void tegb_peer_destroy(tegb_peer *p);
 int tegb_program_set_peer(tegb_program *prog, tegb_peer *peer);
-int tegb_program_set_peer_groups(tegb_program *prog, tegb_peer *peer, int n_groups_total);
+int tegb_program_set_peer_groups(tegb_program *prog, tegb_peer *peer, int n_groups_total, const int32_t *local_of);
 
 /* Grouped render: groups [group_begin, group_begin + group_count) (e.g. triangles) are evaluated over their
  * own pixel windows in ONE launch.  group_ptrs[n_scalar_args]: device arrays with one value per group

@@ -8,6 +8,9 @@ behind Teg's ``evaluate()`` / ``EvalMode`` plugin interface.
     from teg_b200 import evaluate, CUDA_EvalMode, render_image
     evaluate(expr, {t: np.linspace(0, 1, 1 << 20)}, backend='CUDA', num_samples=50)
 
+``teg_b200.raster`` renders scenes of many triangles (grouped launches), ``teg_b200.optim`` runs the optimisation loop
+(loss, upstream gradient, Adam) on the device, ``teg_b200.parallel`` holds the multi-GPU exchange.
+
 Importing the package registers the ``'CUDA'`` backend with ``teg.eval.backend.BACKENDS`` when the
 reference ``teg`` package is importable.
 """

@@ -103,7 +103,7 @@ class Emitter:
                  block_size: int = 128, unroll_inner: int = 32, unroll_outer: int = 1, pred_accum: bool = True, use_asm: bool = True, team: int = 1, coop: bool = True,
                  pred_mix: float = 0.25, jam: int = 4, coop_max_lanes: int = 4,
                  integration_mode: str = 'rectangular_quadrature', tile_rows: int = 16, tile_cols: int = 32,
-                 mc_seed: int = 0, min_blocks: Optional[int] = None):
+                 mc_seed: int = 0, min_blocks: Optional[int] = None, coop_groups: int = 4):
         assert ctype in ('float', 'double')
         self.tile_rows = int(tile_rows)
         self.mc_seed = int(mc_seed) & 0xFFFFFFFFFFFFFFFF
@@ -148,6 +148,7 @@ class Emitter:
         self.jam_map: Dict[int, str] = {}     # node -> per-copy name while emitting an unroll-and-jam copy
         self.jam = int(jam)
         self.coop_max_lanes = int(coop_max_lanes)
+        self.coop_groups = max(1, int(coop_groups))      # owners served per cooperative pass (short loops), at most
         self.lines: List[str] = []
         self.loop_counter = 0
         self.active_bvars: List[int] = []     # variables of the sample loops enclosing the code being emitted
@@ -570,10 +571,11 @@ class Emitter:
             e('bool unresolved = false;', ind)
             for k, (kind, c, r, B) in enumerate(roots):
                 pre = f'k{k}_'
+                e(f'T {pre}tri;', ind)
                 e('{', ind)
                 e(f'T {pre}pz = g_pz;', ind + 1)
                 t, f = self._iv_cone(r, (lambda j, B=B: bool(fv(j) & B) or dep.get(j, False)), leaf, {}, ind + 1, pre)
-                e(f'const T {pre}tri = {self._iv_result(t, f, pre)};', ind + 1)
+                e(f'{pre}tri = {self._iv_result(t, f, pre)};', ind + 1)
                 e(f'{guard}tiles[(size_t){k} * n_tiles + {index}] = {pre}tri;', ind + 1)
                 e(f'unresolved = unresolved || {pre}tri == {literal("2", T)};', ind + 1)
                 e('}', ind)
@@ -630,10 +632,17 @@ class Emitter:
             # launch order of the main kernel: blocks with an unresolved tile from the front, the others from the back
             e('int any_unresolved = (!dead && unresolved) ? 1 : 0;')
             e('for (int off = 1; off < TEGB_TILE_SUB; off <<= 1) any_unresolved |= __shfl_xor_sync(0xffffffffu, any_unresolved, off);')
+            # the block's slot in the launch order, and its entry: (tile row << 16) | tile column
+            e('int pos = 0;')
             e('if (active && sub == 0) {')
-            e('if (any_unresolved) order[atomicAdd(&counters[0], 1)] = t;', 2)
-            e('else order[n_tx * n_ty - 1 - atomicAdd(&counters[1], 1)] = t;', 2)
+            e('pos = any_unresolved ? atomicAdd(&counters[0], 1) : n_tx * n_ty - 1 - atomicAdd(&counters[1], 1);', 2)
+            e('order[pos] = (int)(((unsigned int)ty << 16) | (unsigned int)tx);', 2)
             e('}')
+            e('pos = __shfl_sync(0xffffffffu, pos, (int)((threadIdx.x & 31u) & ~(unsigned int)(TEGB_TILE_SUB - 1)));')
+            # the same tri-states once more, in LAUNCH order: a block of the main kernel reads its order entry and its
+            # tiles' states with independent loads (tiles without a pixel read as resolved-false)
+            for k in range(len(roots)):
+                e(f'if (active) tiles_ord[(size_t){k} * n_tiles + (size_t)pos * TEGB_TILE_SUB + sub] = dead ? {zero} : k{k}_tri;')
         self.in_main = saved_main
         return self.lines
 
@@ -900,9 +909,21 @@ class Emitter:
         self.emit('{', ind)
         guard = ' && '.join(self.guard_ctx)
         self.emit(f'unsigned int coop_m{k} = __ballot_sync(0xffffffffu, {guard});', ind + 1)
+        # Short loops leave most of the warp idle when one owner is served at a time (N = 16: half of the lanes), so a
+        # pass serves G owners at once: the warp splits into G groups of W lanes (W = N rounded up to a power of two),
+        # group j takes the j-th pending owner, lane % W is the sample.  Every group folds its own N terms in sample
+        # order: the same left fold, bit for bit.
+        W = 32
+        if N <= 16:
+            W = 1
+            while W < N:
+                W *= 2
+        G = min(32 // W, self.coop_groups)
+        if G == 1:
+            W = 32
         # Many pending lanes: the ordinary per-lane loop (all of them busy at once) is cheaper than serving
-        # them one by one.  Few (the usual case along a discontinuity): serve each with the whole warp.
-        self.emit(f'if (__popc(coop_m{k}) > {self.coop_max_lanes}) {{', ind + 1)
+        # them pass by pass.  Few (the usual case along a discontinuity): serve them with the whole warp.
+        self.emit(f'if (__popc(coop_m{k}) > {self.coop_max_lanes * G}) {{', ind + 1)
         self.emit(f'if ({guard}) {{', ind + 2)
         saved_div, saved_k = self.divergent, self.loop_counter
         self.divergent += 1
@@ -910,8 +931,20 @@ class Emitter:
         self.divergent = saved_div
         self.emit('}', ind + 2)
         self.emit(f'}} else while (coop_m{k}) {{', ind + 1)
-        self.emit(f'const int coop_src{k} = __ffs(coop_m{k}) - 1;', ind + 2)
-        self.emit(f'coop_m{k} &= coop_m{k} - 1;', ind + 2)
+        if G == 1:
+            self.emit(f'const int coop_src{k} = __ffs(coop_m{k}) - 1;', ind + 2)
+            self.emit(f'coop_m{k} &= coop_m{k} - 1;', ind + 2)
+        else:
+            for j in range(G):
+                self.emit(f'const int coop_src{k}_{j} = coop_m{k} ? __ffs(coop_m{k}) - 1 : -1;', ind + 2)
+                self.emit(f'coop_m{k} &= coop_m{k} - 1;', ind + 2)         # (0 & anything stays 0)
+            pick = f'coop_src{k}_{G - 1}'
+            for j in reversed(range(G - 1)):
+                pick = f'(coop_grp{k} == {j} ? coop_src{k}_{j} : {pick})'
+            self.emit(f'const int coop_grp{k} = (int)((threadIdx.x & 31u) / {W}u);', ind + 2)
+            self.emit(f'const int coop_own{k} = {pick};', ind + 2)
+            self.emit(f'const bool coop_has{k} = coop_own{k} >= 0;                  // this group has an owner to serve', ind + 2)
+            self.emit(f'const int coop_src{k} = coop_has{k} ? coop_own{k} : coop_src{k}_0;', ind + 2)
         old_map = dict(self.coop_map)
         for i in inputs:
             n = self.nodes[i]
@@ -923,16 +956,25 @@ class Emitter:
                 self.emit(f'const T {name} = __shfl_sync(0xffffffffu, {cur}, coop_src{k});', ind + 2)
         for i in inputs:
             self.coop_map[i] = f'c{k}_{i}'
-        self._coop_loop_body(st, known, ind + 2, dry=False, k=k)
+        self._coop_loop_body(st, known, ind + 2, dry=False, k=k, width=W, groups=G)
         self.coop_map = old_map
         for q in st.quads:
-            self.emit(f'if ((int)(threadIdx.x & 31u) == coop_src{k}) v{q} = acc{k}_{q};', ind + 2)
+            if G == 1:
+                self.emit(f'if ((int)(threadIdx.x & 31u) == coop_src{k}) v{q} = acc{k}_{q};', ind + 2)
+            else:
+                for j in range(G):
+                    self.emit(f'{{ const T r_ = __shfl_sync(0xffffffffu, acc{k}_{q}, {j * W}); '
+                              f'if ((int)(threadIdx.x & 31u) == coop_src{k}_{j}) v{q} = r_; }}', ind + 2)
         self.emit('}', ind + 1)
         self.emit('}', ind)
 
-    def _coop_loop_body(self, st: LoopGroup, known: Dict[int, bool], ind: int, dry: bool, k: int):
-        """One pending loop, executed by the whole warp for the owner lane's (broadcast) inputs."""
+    def _coop_loop_body(self, st: LoopGroup, known: Dict[int, bool], ind: int, dry: bool, k: int, width: int = 32,
+                        groups: int = 1):
+        """One pending loop per group of ``width`` lanes, executed for the owner lane's (broadcast) inputs."""
         N = self.N
+        lane = '(threadIdx.x & 31u)' if width == 32 else f'((threadIdx.x & 31u) % {width}u)'
+        first = '0' if width == 32 else f'((threadIdx.x & 31u) & ~{width - 1}u)'
+        has = f'coop_has{k} && ' if groups > 1 else ''
         T = self.ctype
         zero = literal('0', T)
         self._define(st.bvar)
@@ -940,8 +982,8 @@ class Emitter:
         self.emit(f'const T step{k} = ((T)({self.ref(st.hi, known)} - lo{k})) / (T){N};', ind)
         for q in st.quads:
             self.emit(f'T acc{k}_{q} = {zero};', ind)
-        self.emit(f'for (unsigned int base{k} = 0; base{k} < {N}u; base{k} += 32u) {{', ind)
-        self.emit(f'const unsigned int s{k} = base{k} + (threadIdx.x & 31u);', ind + 1)
+        self.emit(f'for (unsigned int base{k} = 0; base{k} < {N}u; base{k} += {width}u) {{', ind)
+        self.emit(f'const unsigned int s{k} = base{k} + {lane};', ind + 1)
         self.emit(f'const T x{st.bvar} = lo{k} + step{k} * ((T)s{k} + {literal("0.5", T)});', ind + 1)
         saved_div = self.divergent
         self.divergent += 1                     # nothing inside the per-sample body may use warp collectives
@@ -953,18 +995,18 @@ class Emitter:
             if pf is not None and pf[0]:
                 conds, val = pf
                 term = f'step{k}' if val is None else f'{val} * step{k}'
-                cond = ' && '.join([f's{k} < {N}u'] + [f'({self.ref(c, st.body.known)})' for c in conds])
+                cond = ' && '.join([f'{has}s{k} < {N}u'] + [f'({self.ref(c, st.body.known)})' for c in conds])
                 self.emit(f'const T t{k}_{q} = ({cond}) ? {term} : {zero};', ind + 1)
                 fix.append(q)
             else:
                 body = self.ref(self.nodes[q].args[2], st.body.known)
-                self.emit(f'const T t{k}_{q} = (s{k} < {N}u) ? {body} * step{k} : {zero};', ind + 1)
+                self.emit(f'const T t{k}_{q} = ({has}s{k} < {N}u) ? {body} * step{k} : {zero};', ind + 1)
         # left fold in sample order, computed identically by every lane (adding the +0 of a missing /
         # skipped sample never changes the accumulator)
-        self.emit(f'const unsigned int cnt{k} = ({N}u - base{k}) < 32u ? ({N}u - base{k}) : 32u;', ind + 1)
+        self.emit(f'const unsigned int cnt{k} = ({N}u - base{k}) < {width}u ? ({N}u - base{k}) : {width}u;', ind + 1)
         self.emit(f'for (unsigned int l{k} = 0; l{k} < cnt{k}; ++l{k}) {{', ind + 1)
         for q in st.quads:
-            self.emit(f'acc{k}_{q} = acc{k}_{q} + __shfl_sync(0xffffffffu, t{k}_{q}, l{k});', ind + 2)
+            self.emit(f'acc{k}_{q} = acc{k}_{q} + __shfl_sync(0xffffffffu, t{k}_{q}, {first} + l{k});', ind + 2)
         self.emit('}', ind + 1)
         self.emit('}', ind)
         for q in fix:
@@ -1293,7 +1335,9 @@ class Emitter:
                                  'const int group_begin', 'const T* __restrict__ Utab', 'const int tile_rows'] +
                                 (['const T* __restrict__ tiles'] if tile else []) +
                                 [f'const T* __restrict__ pix{a}' for a in pix] + outs_decl)
-            src.append(f'extern "C" __global__ void __launch_bounds__({bs}) {name}_main({mparams}) {{')
+            gmb = (0 if self.min_blocks is None else self.min_blocks)
+            glb = f'{bs}, {gmb}' if gmb else f'{bs}'
+            src.append(f'extern "C" __global__ void __launch_bounds__({glb}) {name}_main({mparams}) {{')
             src.append('    // block (bx, by, bz): group group_begin + bz, tile (bx, by) of its window: B columns x tile_rows rows')
             src.append('    const int g = group_begin + blockIdx.z;')
             src.append('    const int w_r0 = max(win[4 * g + 0], row0), w_r1 = min(win[4 * g + 1], row1);')
@@ -1319,13 +1363,13 @@ class Emitter:
             # every lane of a warp runs coop bodies (dead lanes on a clamped pixel, results dropped)
             src.append('    const int nyc = live ? ny : w_c0 + (int)(blockIdx.x * blockDim.x);')
             src.append('    const T ye_lo = ye[nyc], ye_hi = ye[nyc + 1];')
-            loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye_lo', grid[3]: 'ye_hi'}
-            for a in pix:
-                loads[a] = f'pix{a}[ic]'
+            src.append('    const int rows_here = min(tile_rows, w_r1 - nx0);')
+            loads = {grid[0]: 'x_lo', grid[1]: 'x_hi', grid[2]: 'ye_lo', grid[3]: 'ye_hi'}
             if tile:
                 src.append('    const size_t n_tiles = (size_t)gridDim.x * TEGB_TILE_SUB * gridDim.y * gridDim.z;')
-                src.append('    const size_t tile_id = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * (gridDim.x * TEGB_TILE_SUB) + '
-                           'blockIdx.x * TEGB_TILE_SUB + threadIdx.x / TEGB_TILE_COLS;')
+                src.append('    const size_t tile_base = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * (gridDim.x * TEGB_TILE_SUB) + '
+                           'blockIdx.x * TEGB_TILE_SUB;')
+                src.append('    const size_t tile_id = tile_base + threadIdx.x / TEGB_TILE_COLS;')
                 for k, a in enumerate(tile):
                     src.append(f'    const T tile{k} = tiles[{k} * n_tiles + tile_id];')
                     loads[a] = f'tile{k}'
@@ -1333,30 +1377,55 @@ class Emitter:
                 src.append(f'    T rr[{K}];')
                 src.append(f'    for (int k = 0; k < {K}; k++) rr[k] = {zero};')
 
-            def g_row_loop(fn: str, with_live: bool, ind: str):
-                call = ', '.join(['sU'] + (['live'] if with_live else []) + [loads[a] for a in varying] + ['res'])
+            def g_row_loop(fn: str, with_live: bool, ind: str, r_begin: str = '0', r_step: str = '1', batch: int = 4):
+                """Rows of the tile in batches of ``batch``: every global read of the batch (the upstream-gradient
+                pixels, the old image values of accumulating launches) is issued before the first use, so one memory
+                latency is paid per batch instead of per row."""
                 src.append(f'{ind}#pragma unroll 1')
-                src.append(f'{ind}for (int r = 0; r < tile_rows; ++r) {{')
-                src.append(f'{ind}    const int nx = nx0 + r;')
-                src.append(f'{ind}    if (nx >= w_r1) break;')
-                src.append(f'{ind}    const long long i = (long long)(nx - row0) * res_y + ny;')
-                src.append(f'{ind}    const long long ic = (long long)(nx - row0) * res_y + nyc;')
-                src.append(f'{ind}    (void)ic;')
-                src.append(f'{ind}    T res[{K}];')
-                src.append(f'{ind}    for (int k = 0; k < {K}; k++) res[k] = {zero};')
+                src.append(f'{ind}for (int r0 = {r_begin}; r0 < rows_here; r0 += {batch} * {r_step}) {{')
+                for a in pix:
+                    src.append(f'{ind}    T p{a}_[{batch}];')
+                if accumulate and not reduce_outputs:
+                    src.append(f'{ind}    T old_[{batch}][{K}];')
+                src.append(f'{ind}    #pragma unroll')
+                src.append(f'{ind}    for (int u = 0; u < {batch}; u++) {{')
+                src.append(f'{ind}        const int r = r0 + u * {r_step};')
+                src.append(f'{ind}        const bool on = live && r < rows_here;')
+                src.append(f'{ind}        const long long ic = (long long)(nx0 + (r < rows_here ? r : {r_begin}) - row0) * res_y + nyc;')
+                for a in pix:
+                    src.append(f'{ind}        p{a}_[u] = pix{a}[ic];')
+                if accumulate and not reduce_outputs:
+                    for k in range(K):
+                        src.append(f'{ind}        old_[u][{k}] = on ? out{k}[ic] : {zero};')
+                src.append(f'{ind}        (void)on; (void)ic;')
+                src.append(f'{ind}    }}')
+                src.append(f'{ind}    #pragma unroll')
+                src.append(f'{ind}    for (int u = 0; u < {batch}; u++) {{')
+                src.append(f'{ind}        const int r = r0 + u * {r_step};')
+                src.append(f'{ind}        if (r >= rows_here) break;                          // warp-uniform')
+                src.append(f'{ind}        const int nx = nx0 + r;')
+                src.append(f'{ind}        const T x_lo = xe[nx], x_hi = xe[nx + 1];')
+                src.append(f'{ind}        const long long i = (long long)(nx - row0) * res_y + ny;')
+                src.append(f'{ind}        T res[{K}];')
+                src.append(f'{ind}        for (int k = 0; k < {K}; k++) res[k] = {zero};')
+                lu = dict(loads)
+                for a in pix:
+                    lu[a] = f'p{a}_[u]'
+                call = ', '.join(['sU'] + (['live'] if with_live else []) + [lu[a] for a in varying] + ['res'])
                 if with_live:
-                    src.append(f'{ind}    {fn}({call});')
+                    src.append(f'{ind}        {fn}({call});')
                 else:
-                    src.append(f'{ind}    if (live) {fn}({call});')
+                    src.append(f'{ind}        if (live) {fn}({call});')
                 if reduce_outputs:
                     for k in range(K):
-                        src.append(f'{ind}    if (live) rr[{k}] = rr[{k}] + res[{k}];')
+                        src.append(f'{ind}        if (live) rr[{k}] = rr[{k}] + res[{k}];')
                 elif accumulate:
                     for k in range(K):
-                        src.append(f'{ind}    if (live) out{k}[i] = out{k}[i] + res[{k}];')
+                        src.append(f'{ind}        if (live) out{k}[i] = old_[u][{k}] + res[{k}];')
                 else:
                     for k in range(K):
-                        src.append(f'{ind}    if (live) out{k}[i] = res[{k}];')
+                        src.append(f'{ind}        if (live) out{k}[i] = res[{k}];')
+                src.append(f'{ind}    }}')
                 src.append(f'{ind}}}')
 
             if tile_bodies:
@@ -1374,11 +1443,29 @@ class Emitter:
                         g_row_loop(f'{name}_tile_{label}', b_coop, '        ')
                     src.append('    }')
                     first = False
-                src.append('    else {')
-                g_row_loop(f'{name}_instance', coop, '        ')
+                # Unresolved tiles of this block: the per-instance program, shared by ALL warps of the block (warp w
+                # takes rows w, w + W, ... of each unresolved tile): one warp walking its tile alone would keep the
+                # other warps of the block waiting at the block sum / the end of the block.
+                mine_u = ' || '.join(f'tile{k} == {literal("2", T)}' for k in range(len(tile)))
+                src.append(f'    if (__syncthreads_or({mine_u})) {{')
+                src.append('        const int warp_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;')
+                src.append('        for (int sub = 0; sub < TEGB_TILE_SUB; ++sub) {')
+                conds_u = ' || '.join(f'tiles[{k} * n_tiles + tile_base + sub] == {literal("2", T)}' for k in range(len(tile)))
+                src.append(f'            if (!({conds_u})) continue;                 // block-uniform')
+                src.append('            for (int cw = 0; cw < TEGB_TILE_COLS / 32; ++cw) {')
+                src.append(f'                const int ny = w_c0 + (int)(blockIdx.x * {bs}) + sub * TEGB_TILE_COLS + cw * 32 + lane_;')
+                src.append('                const bool live = ny < w_c1;')
+                src.append(f'                const int nyc = live ? ny : w_c0 + (int)(blockIdx.x * {bs});')
+                src.append('                const T ye_lo = ye[nyc], ye_hi = ye[nyc + 1];')
+                for k in range(len(tile)):
+                    src.append(f'                const T tile{k} = {literal("2", T)};')
+                    src.append(f'                (void)tile{k};')
+                g_row_loop(f'{name}_instance', coop, '                ', 'warp_', f'{bs // 32}', batch=1)
+                src.append('            }')
+                src.append('        }')
                 src.append('    }')
             else:
-                g_row_loop(f'{name}_instance', coop, '    ')
+                g_row_loop(f'{name}_instance', coop, '    ', batch=1)
             if reduce_outputs:
                 src.append(f'    tegb_block_sum_store<T, {K}, {bs}>(rr, gp, tiles_n, tile_i);')
             src.append('}')
@@ -1394,7 +1481,8 @@ class Emitter:
                 if tile:
                     tparams = ', '.join([f'const T a{a}' for a in scal] +
                                         ['const T* __restrict__ ranges', 'const int res_y', 'const int n_tx', 'const int n_ty', 'const int n_txs',
-                                         'T* __restrict__ tiles', 'int* __restrict__ order', 'int* __restrict__ counters'])
+                                         'T* __restrict__ tiles', 'T* __restrict__ tiles_ord', 'int* __restrict__ order',
+                                         'int* __restrict__ counters'])
                     src.append(f'extern "C" __global__ void {name}_tiles({tparams}) {{')
                     src.append('    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;    // one thread per tile')
                     src.append('    const int t_ = gtid / TEGB_TILE_SUB, sub = gtid % TEGB_TILE_SUB;')
@@ -1420,8 +1508,9 @@ class Emitter:
                 if tile:
                     # blocks take the tiles in the order the classification listed them: unresolved (expensive) tiles
                     # first, so that they all start in the first wave instead of trailing the launch
-                    src.append('    const int tile_lin = order[blockIdx.y * gridDim.x + blockIdx.x];')
-                    src.append('    const int tby = tile_lin / (int)gridDim.x, tbx = tile_lin - tby * (int)gridDim.x;')
+                    src.append('    const unsigned int slot = blockIdx.y * gridDim.x + blockIdx.x;')
+                    src.append('    const unsigned int ord = (unsigned int)order[slot];')
+                    src.append('    const int tby = (int)(ord >> 16), tbx = (int)(ord & 0xffffu);')
                 else:
                     src.append('    const int tby = blockIdx.y, tbx = blockIdx.x;')
                 src.append('    const int ny = tbx * blockDim.x + threadIdx.x;')
@@ -1431,31 +1520,33 @@ class Emitter:
                     src.append('    const int nyc = live ? ny : 0;')
                 src.append(f'    const T ye_lo = ye[{ycol}], ye_hi = ye[{ycol} + 1];' if coop else
                            '    const T ye_lo = live ? ye[ny] : ye[0], ye_hi = live ? ye[ny + 1] : ye[1];')
-                loads = {grid[0]: 'xe[nx]', grid[1]: 'xe[nx + 1]', grid[2]: 'ye_lo', grid[3]: 'ye_hi'}
+                loads = {grid[0]: 'x_lo', grid[1]: 'x_hi', grid[2]: 'ye_lo', grid[3]: 'ye_hi'}
                 if tile:
                     src.append('    const int n_txs = gridDim.x * TEGB_TILE_SUB;')
                     src.append('    const size_t n_tiles = (size_t)n_txs * gridDim.y;')
-                    src.append('    const size_t tile_id = (size_t)tby * n_txs + tbx * TEGB_TILE_SUB + threadIdx.x / TEGB_TILE_COLS;')
+                    src.append('    const size_t tile_base = (size_t)slot * TEGB_TILE_SUB;          // states are stored in launch order')
+                    src.append('    const size_t tile_id = tile_base + threadIdx.x / TEGB_TILE_COLS;')
                     for k, a in enumerate(tile):
                         src.append(f'    const T tile{k} = tiles[{k} * n_tiles + tile_id];')
                         loads[a] = f'tile{k}'
+                # rows of this block: local tile row tby is tile row tby * row_stride + row_phase of the row range
+                # (interleaved sharding: rank r renders tile rows r, r + world, ...); the local image is compact
+                src.append('    const int rel0 = (tby * row_stride + row_phase) * tile_rows;')
+                src.append('    const int rows_here = min(tile_rows, n_rows - rel0);')
+                src.append('    const int nx0 = row0 + rel0;')
+                src.append('    const long long i0 = (long long)(tby * tile_rows) * res_y + ny;')
                 if nr:
                     src.append(f'    T rr[{nr}];')
                     src.append(f'    for (int k = 0; k < {nr}; k++) rr[k] = {zero};')
 
-                def row_loop(fn: str, with_live: bool, ind: str, r_begin: str = '0', r_end: str = 'tile_rows',
-                             r_step: str = '1'):
+                def row_loop(fn: str, with_live: bool, ind: str, r_begin: str = '0', r_step: str = '1', unroll: int = 1):
                     # (Monte Carlo: the instance index of a pixel is its index in the whole image, whatever the band)
                     call = ', '.join((['live'] if with_live else []) + [loads[a] for a in varying] +
-                                     inst('(long long)nx * res_y + ny') + ['res'])
-                    src.append(f'{ind}#pragma unroll 1')
-                    src.append(f'{ind}for (int r = {r_begin}; r < {r_end}; r += {r_step}) {{')
-                    # local tile row tby is tile row tby * row_stride + row_phase of the row range (interleaved
-                    # sharding: rank r renders tile rows r, r + world, ...); the local image is compact
-                    src.append(f'{ind}    const int rel = (tby * row_stride + row_phase) * tile_rows + r;')
-                    src.append(f'{ind}    if (rel >= n_rows) break;')
-                    src.append(f'{ind}    const int nx = row0 + rel;')
-                    src.append(f'{ind}    const long long i = (long long)(tby * tile_rows + r) * res_y + ny;')
+                                     inst('(long long)(nx0 + r) * res_y + ny') + ['res'])
+                    src.append(f'{ind}#pragma unroll {unroll}')
+                    src.append(f'{ind}for (int r = {r_begin}; r < rows_here; r += {r_step}) {{')
+                    src.append(f'{ind}    const T x_lo = xe[nx0 + r], x_hi = xe[nx0 + r + 1];')
+                    src.append(f'{ind}    const long long i = i0 + (long long)r * res_y;')
                     src.append(f'{ind}    T res[{K}];')
                     if nr:
                         src.append(f'{ind}    for (int k = 0; k < {K}; k++) res[k] = {zero};')
@@ -1471,6 +1562,11 @@ class Emitter:
                     src.append(f'{ind}}}')
 
                 if tile_bodies:
+                    per = 4 if T == 'float' else 2                  # elements of a 16-byte vector
+                    V = 'float4' if T == 'float' else 'double2'
+                    if ns_out:
+                        aligned = ' && '.join([f'(((size_t)out{k}) & 15) == 0' for k in range(ns_out)] + [f'(res_y % {per}) == 0'])
+                        src.append(f'    const bool vec_ok = {aligned};                 // uniform')
                     # the tile's conditions are the same for every thread of the block: a uniform branch picks the body
                     first = True
                     for label, match, b_coop, consts in tile_bodies:
@@ -1483,12 +1579,22 @@ class Emitter:
                                                            for c in consts[ns_out:])
                         if consts is not None and (nr == 0 or zeros):
                             # every output of this body is a constant: fill the tile's rows (summed outputs that are
-                            # +0 leave the partial sums as they are)
+                            # +0 leave the partial sums as they are).  A warp owns 32 columns x rows_here rows: with
+                            # 16-byte stores every instruction covers {per} rows of 128 / 256 bytes each.
                             if ns_out:
-                                src.append('        const int rel0 = (tby * row_stride + row_phase) * tile_rows;')
-                                src.append('        const int rows_here = min(tile_rows, n_rows - rel0);')
-                                src.append('        const long long i0 = (long long)(tby * tile_rows) * res_y + ny;')
-                                src.append('        if (live) {')
+                                src.append('        if (vec_ok) {')
+                                src.append('            const int lane_ = threadIdx.x & 31;')
+                                src.append(f'            const int vcol = (ny - lane_) + (lane_ % {32 // per}) * {per};')
+                                src.append(f'            if (vcol < res_y) {{')
+                                src.append(f'                const long long v0 = (long long)(tby * tile_rows) * res_y + vcol;')
+                                src.append('                #pragma unroll 4')
+                                src.append(f'                for (int r = lane_ / {32 // per}; r < rows_here; r += {per}) {{')
+                                for k in range(ns_out):
+                                    vals = ', '.join([consts[k]] * per)
+                                    src.append(f'                    *reinterpret_cast<{V}*>(out{k} + v0 + (long long)r * res_y) = make_{V}({vals});')
+                                src.append('                }')
+                                src.append('            }')
+                                src.append('        } else if (live) {')
                                 src.append('            #pragma unroll 4')
                                 src.append('            for (int r = 0; r < rows_here; ++r) {')
                                 for k in range(ns_out):
@@ -1496,7 +1602,9 @@ class Emitter:
                                 src.append('            }')
                                 src.append('        }')
                         else:
-                            row_loop(f'{name}_tile_{label}', b_coop, '        ')
+                            # bodies without a sample loop left (every condition fixed) are a short dependent chain per
+                            # pixel: several rows in flight hide it
+                            row_loop(f'{name}_tile_{label}', b_coop, '        ', unroll=1 if b_coop else 4)
                         src.append('    }')
                         first = False
                     # Unresolved tiles of this block: the per-instance program, shared by ALL warps of the block (warp w
@@ -1505,7 +1613,6 @@ class Emitter:
                     mine_u = ' || '.join(f'tile{k} == {literal("2", T)}' for k in range(len(tile)))
                     src.append(f'    if (__syncthreads_or({mine_u})) {{')
                     src.append('        const int warp_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;')
-                    src.append('        const size_t tile_base = (size_t)tby * n_txs + tbx * TEGB_TILE_SUB;')
                     src.append('        for (int sub = 0; sub < TEGB_TILE_SUB; ++sub) {')
                     conds_u = ' || '.join(f'tiles[{k} * n_tiles + tile_base + sub] == {literal("2", T)}' for k in range(len(tile)))
                     src.append(f'            if (!({conds_u})) continue;                 // block-uniform')
@@ -1514,10 +1621,11 @@ class Emitter:
                     src.append('                const bool live = ny < res_y;')
                     src.append('                const int nyc = live ? ny : 0;')
                     src.append('                const T ye_lo = ye[nyc], ye_hi = ye[nyc + 1];')
+                    src.append('                const long long i0 = (long long)(tby * tile_rows) * res_y + ny;')
                     for k in range(len(tile)):
                         src.append(f'                const T tile{k} = {literal("2", T)};')
                     src.append(f'                (void)nyc; (void)ye_lo; (void)ye_hi;')
-                    row_loop(f'{name}_instance', coop, '                ', 'warp_', 'tile_rows', f'{bs // 32}')
+                    row_loop(f'{name}_instance', coop, '                ', 'warp_', f'{bs // 32}')
                     src.append('            }')
                     src.append('        }')
                     src.append('    }')

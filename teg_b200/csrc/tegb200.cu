@@ -274,6 +274,7 @@ struct tegb_program {
     bool ev_valid = false;
     CUstream ev_stream = nullptr;
     int n_groups_total = 0;           // grouped programs with a peer: rows of the all-reduced [groups][outputs] result
+    const int *group_map = nullptr;   // device [n_groups_total]: this rank's index of every global group, or -1 (NULL: identity)
     CUmodule mod = nullptr;
     CUfunction f_uniform = nullptr, f_main = nullptr, f_tiles = nullptr;
     CUdeviceptr u_const = 0;      // __constant__ table inside the module
@@ -297,6 +298,7 @@ struct tegb_program {
     // tri-states of the tile conditions (render programs with n_tile_conds > 0)
     void *d_tiles = nullptr;
     size_t tiles_bytes = 0;
+    void *tiles_ord_ptr = nullptr;    // the launch-ordered copy inside d_tiles (plain tiled renders)
     // per tile row / tile column: [min, max] of the box edges and sample abscissae (valid for ranges_grid)
     int *d_order = nullptr;       // [n_tiles] tile indices in launch order, then 2 counters
     size_t order_count = 0;
@@ -843,15 +845,18 @@ static int ensure_ranges(tegb_program *p, const tegb_grid *g, int n_tx, int n_ty
 // mailboxes attached (tegb_program_set_peer_groups) `out` is the whole [n_groups_total][n_outputs] result: every
 // column is exchanged, the columns of groups this launch did not cover contribute zero.
 template <typename T>
-__global__ void __launch_bounds__(RED_THREADS) colsum_groups_peer(const T *partials, long long n_tiles, int col_begin,
-                                                                  int col_count, T *out, PeerView view,
-                                                                  unsigned long long seq) {
+__global__ void __launch_bounds__(RED_THREADS) colsum_groups_peer(const T *partials, long long n_tiles, int group_begin,
+                                                                  int group_count, int K, const int *__restrict__ local_of,
+                                                                  T *out, PeerView view, unsigned long long seq) {
     __shared__ T smem[32];
-    const int c = blockIdx.x;
-    const int lc = c - col_begin;
+    const int c = blockIdx.x;               // column of the all-reduced result: (global group, component)
+    const int g = c / K, k = c - g * K;
+    const int lg = local_of ? local_of[g] : g;       // this rank's index of the group (-1: not launched here)
     T acc = 0;
-    if (lc >= 0 && lc < col_count)          // block-uniform
-        for (long long i = threadIdx.x; i < n_tiles; i += RED_THREADS) acc = acc + partials[(long long)lc * n_tiles + i];
+    if (lg >= group_begin && lg < group_begin + group_count) {          // block-uniform
+        const T *col = partials + ((long long)(lg - group_begin) * K + k) * n_tiles;
+        for (long long i = threadIdx.x; i < n_tiles; i += RED_THREADS) acc = acc + col[i];
+    }
     T s = block_sum_fixed(acc, smem);
     if (threadIdx.x < 32) {
         const T total = peer_exchange_sum<T>(view, c, s, seq);
@@ -868,11 +873,11 @@ static int finish_group_partials(tegb_program *p, unsigned long long tiles, int 
         if (peer_failed(p->peer)) return TEGB_ERR_PEER;
         const unsigned long long seq = ++p->peer->seq;
         if (p->d.elem_size == 4)
-            colsum_groups_peer<float><<<total, RED_THREADS, 0, st>>>((const float *)p->d_partials, (long long)tiles, group_begin * K,
-                                                                     group_count * K, (float *)out, p->peer->view, seq);
+            colsum_groups_peer<float><<<total, RED_THREADS, 0, st>>>((const float *)p->d_partials, (long long)tiles, group_begin,
+                                                                     group_count, K, p->group_map, (float *)out, p->peer->view, seq);
         else
-            colsum_groups_peer<double><<<total, RED_THREADS, 0, st>>>((const double *)p->d_partials, (long long)tiles, group_begin * K,
-                                                                      group_count * K, (double *)out, p->peer->view, seq);
+            colsum_groups_peer<double><<<total, RED_THREADS, 0, st>>>((const double *)p->d_partials, (long long)tiles, group_begin,
+                                                                      group_count, K, p->group_map, (double *)out, p->peer->view, seq);
         g_launches++;
         RT_CHECK(cudaGetLastError());
         return TEGB_OK;
@@ -901,7 +906,7 @@ extern "C" int tegb_render_groups_launch(tegb_program *p, const void *const *gro
     if (g->res_x < 1 || g->res_y < 1 || g->row_begin < 0 || g->row_end > g->res_x || g->row_begin > g->row_end)
         return fail(TEGB_ERR_INVALID, "bad grid");
     const bool peer_groups = p->d.reduce_outputs && p->peer && p->n_groups_total > 0;
-    if (peer_groups && (group_begin + group_count > p->n_groups_total))
+    if (peer_groups && !p->group_map && (group_begin + group_count > p->n_groups_total))
         return fail(TEGB_ERR_INVALID, "group range exceeds the total declared with tegb_program_set_peer_groups");
     if ((group_count == 0 || g->row_end == g->row_begin) && !peer_groups) return TEGB_OK;
     if (group_count > 65535 || max_rows > 65535 * 16) return fail(TEGB_ERR_INVALID, "too many groups or rows in one launch");
@@ -1065,6 +1070,7 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
     const int n_tr = (n_rows + tile_rows - 1) / tile_rows;
     const unsigned gy = (unsigned)((n_tr - tile_phase + tile_stride - 1) / tile_stride);
     if (gy > 65535u) return fail(TEGB_ERR_INVALID, "more than 65535 tile rows in one render launch");
+    if (gx > 65535u) return fail(TEGB_ERR_INVALID, "more than 65535 tile columns in one render launch");
     args.push_back(&n_rows);
     args.push_back(&tile_rows);
     args.push_back(&tile_stride);
@@ -1074,13 +1080,17 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
         // a block of the main kernel spans block_size / tile_cols of them)
         int n_tx = (int)gx, n_ty = (int)gy;
         int n_txs = n_tx * (p->d.block_size / p->d.tile_cols);
-        const size_t need = (size_t)p->d.n_tile_conds * n_txs * n_ty * p->d.elem_size;
+        // two copies of the tri-states: by tile (diagnostics, tegb_program_tile_table) and in launch order (what the main
+        // kernel reads: its order entry and its states are then independent loads)
+        const size_t one_table = (size_t)p->d.n_tile_conds * n_txs * n_ty * p->d.elem_size;
+        const size_t need = 2 * one_table;
         if (need > p->tiles_bytes) {
             RT_CHECK(cudaStreamSynchronize((cudaStream_t)st));      // an earlier launch may still read the old table
             if (p->d_tiles) { cudaFree(p->d_tiles); p->d_tiles = nullptr; p->tiles_bytes = 0; }
             RT_CHECK(cudaMalloc(&p->d_tiles, need));
             p->tiles_bytes = need;
         }
+        void *d_tiles_ord = (char *)p->d_tiles + one_table;
         const int ns = p->d.n_scalar_args;
         std::vector<float> sf(ns > 0 ? ns : 1);
         std::vector<double> sd(ns > 0 ? ns : 1);
@@ -1106,12 +1116,14 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
         targs.push_back(&n_ty);
         targs.push_back(&n_txs);
         targs.push_back(&p->d_tiles);
+        targs.push_back(&d_tiles_ord);
         targs.push_back(&p->d_order);
         targs.push_back(&d_counters);
         const unsigned tb = 128, tg = (unsigned)(((size_t)n_txs * n_ty + tb - 1) / tb);     // a thread per tile
         CU_CHECK(drv::LaunchKernel(p->f_tiles, tg, 1, 1, tb, 1, 1, 0, st, targs.data(), nullptr));
         g_launches++;
-        args.push_back(&p->d_tiles);
+        p->tiles_ord_ptr = d_tiles_ord;
+        args.push_back(&p->tiles_ord_ptr);
         args.push_back(&p->d_order);
     }
     const int n_store = p->d.n_outputs - p->d.reduce_outputs;
@@ -1132,7 +1144,7 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
 
 extern "C" int tegb_program_tile_table(tegb_program *p, void *host_out, size_t nbytes, void *stream) {
     if (!p || !host_out) return fail(TEGB_ERR_INVALID, "tegb_program_tile_table: null argument");
-    if (!p->d_tiles || nbytes > p->tiles_bytes)
+    if (!p->d_tiles || nbytes > p->tiles_bytes / (p->d.grouped ? 1 : 2))
         return fail(TEGB_ERR_INVALID, "no tile table of that size (render first; n_tile_conds x tiles x elem_size bytes)");
     std::lock_guard<std::recursive_mutex> lock(p->mu);
     RT_CHECK(cudaSetDevice(p->device));
@@ -1293,13 +1305,16 @@ extern "C" int tegb_program_set_peer(tegb_program *prog, tegb_peer *peer) {
     std::lock_guard<std::recursive_mutex> lock(prog->mu);
     prog->peer = peer;
     prog->n_groups_total = 0;
+    prog->group_map = nullptr;
     return TEGB_OK;
 }
 
 /* grouped reduce_outputs programs: tegb_render_groups_launch then delivers the all-reduced [n_groups_total][n_outputs]
  * sums to out_ptrs[0] (ALL rows, whatever group range the launch covered; groups it did not cover contribute zero).
+ * local_of (device int32 [n_groups_total], or NULL for the identity): this rank's group index of every GLOBAL group, -1
+ * for groups it does not hold -- a rank may keep only the groups whose windows reach into its rows.
  * Every rank must make the same sequence of such launches, also ranks with nothing to render. */
-extern "C" int tegb_program_set_peer_groups(tegb_program *prog, tegb_peer *peer, int n_groups_total) {
+extern "C" int tegb_program_set_peer_groups(tegb_program *prog, tegb_peer *peer, int n_groups_total, const int32_t *local_of) {
     if (!prog || (peer && n_groups_total < 1)) return fail(TEGB_ERR_INVALID, "tegb_program_set_peer_groups: bad argument");
     if (!prog->d.grouped || !prog->d.reduce_outputs) return fail(TEGB_ERR_INVALID, "not a grouped reduce program");
     if (peer && (long long)n_groups_total * prog->d.n_outputs > peer->view.maxv)
@@ -1307,6 +1322,7 @@ extern "C" int tegb_program_set_peer_groups(tegb_program *prog, tegb_peer *peer,
     std::lock_guard<std::recursive_mutex> lock(prog->mu);
     prog->peer = peer;
     prog->n_groups_total = peer ? n_groups_total : 0;
+    prog->group_map = peer ? (const int *)local_of : nullptr;
     return TEGB_OK;
 }
 

@@ -87,12 +87,18 @@ class PeerGroup:
         from . import runtime
         runtime.check(self._L.tegb_program_set_peer(program.handle, self.handle))
 
-    def attach_groups(self, program, n_groups_total: int) -> None:
+    def attach_groups(self, program, n_groups_total: int, local_of=None) -> None:
         """Grouped reduce programs (``CUDA_EvalMode.grouped_program(..., reduce=True)[1]``): their launches then
         deliver the all-reduced ``[n_groups_total, k]`` sums -- every row, whatever group range a rank launched (the
         groups it did not cover contribute zero).  ``max_values`` of this PeerGroup must be >= n_groups_total * k."""
+        import ctypes
         from . import runtime
-        runtime.check(self._L.tegb_program_set_peer_groups(program.handle, self.handle, int(n_groups_total)))
+        if local_of is not None:
+            # int32 CUDA tensor [n_groups_total]: this rank's group index of every global group, -1 where it holds none
+            assert local_of.is_cuda and local_of.is_contiguous() and local_of.numel() == n_groups_total
+            self._maps = getattr(self, '_maps', []) + [local_of]          # keep the device array alive
+        ptr = ctypes.c_void_p(local_of.data_ptr()) if local_of is not None else None
+        runtime.check(self._L.tegb_program_set_peer_groups(program.handle, self.handle, int(n_groups_total), ptr))
 
     def detach(self, program) -> None:
         from . import runtime

@@ -33,7 +33,8 @@ PARAMS = ('px0', 'py0', 'px1', 'py1', 'px2', 'py2', 'col')
 
 class MultiTriangleRasterizer:
     def __init__(self, primal: Program, grad: Program, res: int, bands: int = 1, rank: int = 0,
-                 num_samples: int = 16, device: int = 0, float_width: str = 'float', cull: bool = True):
+                 num_samples: int = 16, device: int = 0, float_width: str = 'float', cull: bool = True,
+                 min_blocks=(None, None), rows: Optional[Tuple[int, int]] = None):
         import torch
         self.torch = torch
         self.res = int(res)
@@ -42,14 +43,22 @@ class MultiTriangleRasterizer:
         self.device = device
         self.dev = torch.device('cuda', device)
         self.tdt = torch.float32 if float_width == 'float' else torch.float64
+        # min_blocks = (value kernel, gradient kernel): resident blocks per SM the grouped kernels are compiled for
+        # (__launch_bounds__; None = the compiler's choice)
         self.m_primal = CUDA_EvalMode(primal, num_samples=num_samples, device=device, float_width=float_width,
-                                      cull=cull)
-        self.m_grad = CUDA_EvalMode(grad, num_samples=num_samples, device=device, float_width=float_width, cull=cull)
+                                      cull=cull, min_blocks=min_blocks[0])
+        self.m_grad = CUDA_EvalMode(grad, num_samples=num_samples, device=device, float_width=float_width, cull=cull,
+                                    min_blocks=min_blocks[1])
         self.p_lab = {base_name(lab): lab for lab in primal.args}
         self.g_lab = {base_name(lab): lab for lab in grad.args}
         self.bounds = ((0.0, float(bands)), (0.0, 1.0))
         self.grid_res = (self.res * self.bands, self.res)
-        self.rows = (self.res * self.rank, self.res * (self.rank + 1))
+        # rows: the pixel rows this rank owns.  Default: band `rank` of `bands` (weak scaling: one res x res band per
+        # rank).  Any other split of the (res * bands) rows works too, e.g. a slice of ONE band's rows (strong scaling):
+        # windows are clipped to the rows, groups whose windows miss them cost an empty block each.
+        self.rows = (self.res * self.rank, self.res * (self.rank + 1)) if rows is None else (int(rows[0]), int(rows[1]))
+        assert 0 <= self.rows[0] <= self.rows[1] <= self.res * self.bands
+        self.n_rows = self.rows[1] - self.rows[0]
         self.K = 0
         self.peers = None
 
@@ -60,40 +69,68 @@ class MultiTriangleRasterizer:
         number of times."""
         assert self.K > 0, 'set_scene first'
         _, prog = self.m_grad.grouped_program([self.g_lab[b] for b in BOX], [self.g_lab['dL']], reduce=True)
-        peers.attach_groups(prog, self.K)
+        peers.attach_groups(prog, self.K, self.local_of)
         self.peers = peers
 
     def set_scene(self, verts, col, windows, classes: Sequence[Tuple[int, int]], max_rows: int, max_cols: int,
                   active: Optional[Tuple[int, int]] = None):
-        """verts [K, 6], col [K] (host or device), windows int32 [K, 4], classes: disjoint-window group ranges.
-        active: the contiguous group range whose windows can touch this rank's band (default: all groups);
-        groups outside it are never launched here and get zero gradient rows."""
+        """verts [K, 6], col [K] (host or device), windows int32 [K, 4] (host), classes: group ranges with pairwise
+        disjoint windows (the forward pass adds one class per launch, in this order).
+        Only the groups whose windows reach into this rank's rows are kept on the device (``self.ids``: their global
+        indices, class by class, so every class is a contiguous LOCAL range): a rank never launches blocks for triangles
+        it cannot see.  ``active`` (a global group range) is accepted for compatibility; the windows decide."""
         torch = self.torch
-        verts = torch.as_tensor(np.asarray(verts) if not torch.is_tensor(verts) else verts)
-        col = torch.as_tensor(np.asarray(col) if not torch.is_tensor(col) else col)
-        verts = verts.to(self.dev, self.tdt)
+        verts = torch.as_tensor(np.asarray(verts) if not torch.is_tensor(verts) else verts).to(self.dev, self.tdt)
+        col = torch.as_tensor(np.asarray(col) if not torch.is_tensor(col) else col).to(self.dev, self.tdt)
+        w = np.asarray(windows.cpu() if torch.is_tensor(windows) else windows).astype(np.int64)
         self.K = int(verts.shape[0])
-        # structure of arrays: one contiguous [K] tensor per parameter
-        self.params: Dict[str, object] = {nm: verts[:, i].contiguous() for i, nm in enumerate(PARAMS[:6])}
-        self.params['col'] = col.to(self.dev, self.tdt).contiguous()
-        self.windows = torch.as_tensor(np.asarray(windows) if not torch.is_tensor(windows) else windows)
-        self.windows = self.windows.to(self.dev, torch.int32).contiguous()
-        self.active = (0, self.K) if active is None else (int(active[0]), int(active[1]))
-        self.classes = [(max(a, self.active[0]), min(b, self.active[1])) for a, b in classes
-                        if max(a, self.active[0]) < min(b, self.active[1])]
-        self.max_rows, self.max_cols = int(max_rows), int(max_cols)
+        r0, r1 = self.rows
+        hit = (w[:, 0] < r1) & (w[:, 1] > r0) & (w[:, 2] < w[:, 3])
+        ids, local_classes = [], []
+        for a, b in classes:
+            mine = [k for k in range(a, b) if hit[k]]
+            if mine:
+                local_classes.append((len(ids), len(ids) + len(mine)))
+                ids.extend(mine)
+        self.K_local = len(ids)
+        self.identity = ids == list(range(self.K))        # every group is held, in the global order
+        self.ids = torch.as_tensor(np.asarray(ids, dtype=np.int64), device=self.dev)
+        local_of = np.full(self.K, -1, dtype=np.int32)
+        local_of[np.asarray(ids, dtype=np.int64)] = np.arange(self.K_local, dtype=np.int32)
+        self.local_of = torch.as_tensor(local_of, device=self.dev)
+        self.classes = local_classes
+        # structure of arrays: one contiguous [K_local] tensor per parameter
+        self.params: Dict[str, object] = {nm: verts[self.ids, i].contiguous() for i, nm in enumerate(PARAMS[:6])}
+        self.params['col'] = col[self.ids].contiguous()
+        wl = w[np.asarray(ids, dtype=np.int64)] if ids else np.zeros((0, 4), dtype=np.int64)
+        if not ids:
+            # nothing reaches into this rank's rows: placeholders of one element keep every pointer valid; the launches
+            # cover zero groups (the rank still takes part in the fused all-reduce)
+            self.params = {nm: torch.zeros(1, dtype=self.tdt, device=self.dev) for nm in PARAMS}
+        self.windows = torch.as_tensor((wl if ids else np.zeros((1, 4), dtype=np.int64)).astype(np.int32),
+                                       device=self.dev).contiguous()
+        if self.K_local:
+            self.max_rows = int(min(max_rows, (np.minimum(wl[:, 1], r1) - np.maximum(wl[:, 0], r0)).max()))
+            self.max_cols = int(min(max_cols, (wl[:, 3] - wl[:, 2]).max()))
+        else:
+            self.max_rows, self.max_cols = 1, 1
+        self.g_local = torch.zeros((max(self.K_local, 1), 7), dtype=self.tdt, device=self.dev)
 
     def update_params(self, verts, col):
-        """New parameter values for the same windows (an optimisation step that stays inside them)."""
+        """New parameter values ([K, 6] / [K] device tensors, global order) for the same windows (an optimisation step
+        that stays inside them)."""
+        if self.K_local == 0:
+            return
+        v = verts.index_select(0, self.ids)
         for i, nm in enumerate(PARAMS[:6]):
-            self.params[nm].copy_(verts[:, i])
-        self.params['col'].copy_(col)
+            self.params[nm].copy_(v[:, i])
+        self.params['col'].copy_(col.index_select(0, self.ids))
 
     def forward(self, out=None, stream: int = 0):
         """image band [rows, res]: sum over triangles of the per-pixel value integral."""
         torch = self.torch
         if out is None:
-            out = torch.empty((1, self.res, self.res), dtype=self.tdt, device=self.dev)
+            out = torch.empty((1, self.n_rows, self.res), dtype=self.tdt, device=self.dev)
         out.zero_()
         box = [self.p_lab[b] for b in BOX]
         gb = {self.p_lab[nm]: self.params[nm] for nm in PARAMS}
@@ -111,18 +148,23 @@ class MultiTriangleRasterizer:
             out = torch.empty((self.K, 7), dtype=self.tdt, device=self.dev)
         box = [self.g_lab[b] for b in BOX]
         gb = {self.g_lab[nm]: self.params[nm] for nm in PARAMS}
-        a0, a1 = self.active
         if self.peers is not None:
-            # all K rows are written by the fused exchange (groups outside the active range contribute zero)
+            # all K rows are written by the fused exchange (groups this rank does not hold contribute zero)
             self.m_grad.render_groups(box, self.grid_res, self.bounds, gb, self.windows, self.max_rows, self.max_cols,
                                       pixel_bindings={self.g_lab['dL']: dL}, rows=self.rows, out=out, reduce=True,
-                                      group_range=(a0, a1), stream=stream)
+                                      group_range=(0, self.K_local), stream=stream)
             return out
-        if (a0, a1) != (0, self.K):
-            out.zero_()
-        self.m_grad.render_groups(box, self.grid_res, self.bounds, gb, self.windows, self.max_rows, self.max_cols,
-                                  pixel_bindings={self.g_lab['dL']: dL}, rows=self.rows, out=out[a0:a1], reduce=True,
-                                  group_range=(a0, a1), stream=stream)
+        if self.identity:
+            self.m_grad.render_groups(box, self.grid_res, self.bounds, gb, self.windows, self.max_rows, self.max_cols,
+                                      pixel_bindings={self.g_lab['dL']: dL}, rows=self.rows, out=out, reduce=True,
+                                      group_range=(0, self.K), stream=stream)
+            return out
+        out.zero_()
+        if self.K_local:
+            self.m_grad.render_groups(box, self.grid_res, self.bounds, gb, self.windows, self.max_rows, self.max_cols,
+                                      pixel_bindings={self.g_lab['dL']: dL}, rows=self.rows, out=self.g_local,
+                                      reduce=True, group_range=(0, self.K_local), stream=stream)
+            out.index_copy_(0, self.ids, self.g_local[:self.K_local])
         return out
 
     def capture(self, fn):

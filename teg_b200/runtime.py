@@ -91,7 +91,7 @@ def lib():
     L.tegb_peer_destroy.argtypes = [vp]
     L.tegb_peer_destroy.restype = None
     L.tegb_program_set_peer.argtypes = [vp, vp]
-    L.tegb_program_set_peer_groups.argtypes = [vp, vp, i32]
+    L.tegb_program_set_peer_groups.argtypes = [vp, vp, i32, vp]
     L.tegb_launch_count.restype = i64
     L.tegb_reduce_workspace_bytes.argtypes = [i32, i64, i32]
     L.tegb_reduce_workspace_bytes.restype = ctypes.c_size_t
@@ -158,6 +158,17 @@ class Module:
                 f.write(blob)
             os.replace(tmp, path)
             self.cubin_path = path
+
+    @classmethod
+    def from_cubin(cls, blob: bytes) -> "Module":
+        """A module from a ready cubin (e.g. one compiled ahead of time by nvcc)."""
+        self = cls.__new__(cls)
+        self._L = lib()
+        self.handle = ctypes.c_void_p()
+        buf = ctypes.create_string_buffer(blob, len(blob))
+        check(self._L.tegb_module_from_cubin(ctypes.cast(buf, ctypes.c_void_p), len(blob), ctypes.byref(self.handle)))
+        self.from_cache, self.cubin_path = False, None
+        return self
 
     def cubin(self) -> bytes:
         ptr = ctypes.c_void_p()

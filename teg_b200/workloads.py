@@ -109,10 +109,10 @@ def multi_triangle_scene(bands: int = 1, per_band_grid: int = 16, seed: int = 2,
     Domain: x in [0, bands] (one unit square per band / GPU), y in [0, 1]; pixel grid (res * bands) x res.
     Band b's triangles: centres on a jittered per_band_grid^2 grid of its unit square, circumradius
     U(0.03, 0.06) * 16 / per_band_grid, random rotation, counter-clockwise, colour U(0, 1),
-    ``default_rng(seed + b)``.  Triangles are ordered by (band, class) with class = ((global grid row) % 3,
-    j % 3): every (band, class) pair is a contiguous range whose pixel windows are pairwise disjoint -- the
-    forward pass adds one such range per launch into the image without atomics, in a fixed order, and a rank
-    only launches the ranges of its own and the two neighbouring bands (``band_ranges``).
+    ``default_rng(seed + b)``.  Triangles are ordered by (class, band) with class = ((global grid row) % 3,
+    j % 3): every class is a contiguous range whose pixel windows are pairwise disjoint -- the forward pass adds one
+    class per launch into the image without atomics, in class order; a rank keeps only the triangles whose windows
+    reach into its rows (raster.MultiTriangleRasterizer.set_scene).
 
     Returns dict(verts [K, 6] float64 (px0, py0, px1, py1, px2, py2), col [K], windows [K, 4] int32
     (row_begin, row_end, col_begin, col_end), classes [(begin, end)] group ranges, max_rows, max_cols)."""
@@ -134,12 +134,12 @@ def multi_triangle_scene(bands: int = 1, per_band_grid: int = 16, seed: int = 2,
                 py = cy + rad[i, j] * np.sin(ang)
                 verts.append([px[0], py[0], px[1], py[1], px[2], py[2]])
                 cols.append(col[i, j])
-                keys.append((b, ((b * g + i) % 3) * 3 + (j % 3), i, j))
+                keys.append((((b * g + i) % 3) * 3 + (j % 3), b, i, j))
     order = sorted(range(len(keys)), key=lambda k: keys[k])
     verts = np.array(verts)[order]
     cols = np.array(cols)[order]
-    cls = np.array([keys[k][1] for k in order])
-    band = np.array([keys[k][0] for k in order])
+    cls = np.array([keys[k][0] for k in order])
+    band = np.array([keys[k][1] for k in order])
     # values as the kernels see them (fp32-representable), so host-side windows are consistent
     verts = verts.astype(np.float32).astype(np.float64)
     cols = cols.astype(np.float32).astype(np.float64)
@@ -150,15 +150,15 @@ def multi_triangle_scene(bands: int = 1, per_band_grid: int = 16, seed: int = 2,
     c0 = np.clip(np.floor(ys.min(axis=1) * res).astype(np.int64) - 1, 0, res)
     c1 = np.clip(np.ceil(ys.max(axis=1) * res).astype(np.int64) + 1, 0, res)
     windows = np.stack([r0, r1, c0, c1], axis=1).astype(np.int32)
-    # groups are ordered by (band, class): every (band, class) pair is one contiguous, window-disjoint range
-    classes, band_ranges = [], []
-    for b in range(bands):
-        ib = np.nonzero(band == b)[0]
-        band_ranges.append((int(ib[0]), int(ib[-1]) + 1))
-        for c in range(9):
-            idx = np.nonzero((band == b) & (cls == c))[0]
-            if idx.size:
-                classes.append((int(idx[0]), int(idx[-1]) + 1))
+    # groups are ordered by (class, band): every class is ONE contiguous, window-disjoint range over all bands (the class
+    # of a triangle comes from its GLOBAL grid row, so the 3-row spacing also holds across band boundaries): nine
+    # accumulating launches whatever the number of bands
+    classes = []
+    for c in range(9):
+        idx = np.nonzero(cls == c)[0]
+        if idx.size:
+            classes.append((int(idx[0]), int(idx[-1]) + 1))
+    band_ranges = [(0, len(order))] * bands           # (kept for callers that pass an `active` range: the windows decide)
     return {'verts': verts, 'col': cols, 'windows': windows, 'classes': classes, 'band_ranges': band_ranges,
             'max_rows': int((r1 - r0).max()), 'max_cols': int((c1 - c0).max())}
 

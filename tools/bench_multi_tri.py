@@ -33,6 +33,8 @@ def main():
     ap.add_argument('--cull', type=int, default=1)
     ap.add_argument('--graph', type=int, default=1, help='1: replay the step as one CUDA graph (parameters live in '
                     'device arrays, so the graph stays valid while they change)')
+    ap.add_argument('--min-blocks', default='', help='experiment: "a,b" = __launch_bounds__ resident blocks per SM of '
+                    'the grouped value / gradient kernels (0 = the compiler\'s choice)')
     args = ap.parse_args()
 
     import torch
@@ -57,7 +59,9 @@ def main():
     grad = Program.load(os.path.join(pdir, 'tri_color_grad.tegp'))
     scene = multi_triangle_scene(bands=world, res=res)
     K = scene['verts'].shape[0]
-    r = MultiTriangleRasterizer(primal, grad, res, bands=world, rank=rank, device=local, cull=bool(args.cull))
+    mb = tuple((int(x) or None) for x in args.min_blocks.split(',')) if args.min_blocks else (None, None)
+    r = MultiTriangleRasterizer(primal, grad, res, bands=world, rank=rank, device=local, cull=bool(args.cull),
+                                min_blocks=mb)
     br = scene['band_ranges']
     active = (br[max(rank - 1, 0)][0], br[min(rank + 1, world - 1)][1])      # own band and its neighbours
     r.set_scene(scene['verts'], scene['col'], scene['windows'], scene['classes'], scene['max_rows'],
