@@ -352,7 +352,8 @@ class TriRaster:
         self.tdt = torch.float32 if args.dtype == 'f32' else torch.float64
         self.esz = 4 if args.dtype == 'f32' else 8
         xopts = dict(nvrtc_opts=f'--maxrregcount={args.maxreg}' if args.maxreg else '', tile_rows=args.tile_rows,
-                     block_size=args.block, min_blocks=None if args.min_blocks < 0 else args.min_blocks)
+                     block_size=args.block, min_blocks=None if args.min_blocks < 0 else args.min_blocks,
+                     coop_groups=args.coop_groups)
         self.m_primal = CUDA_EvalMode(self.primal, num_samples=NUM_SAMPLES, device=ctx.local, float_width=self.fw,
                                       cull=bool(args.cull), **xopts)
         self.m_grad = CUDA_EvalMode(self.grad, num_samples=NUM_SAMPLES, device=ctx.local, float_width=self.fw,
@@ -809,6 +810,7 @@ def main() -> int:
     ap.add_argument('--min-blocks', type=int, default=-1, help='experiment: __launch_bounds__(block, N) for render kernels')
     ap.add_argument('--block', type=int, default=128, help='experiment: threads per block of the generated kernels')
     ap.add_argument('--tile-rows', type=int, default=16, help='pixel rows per render block / classification tile')
+    ap.add_argument('--coop-groups', type=int, default=4, help='experiment: owners served per cooperative pass, at most')
     ap.add_argument('--allreduce', default='peer', choices=['peer', 'nccl'], help='N > 1: gradient all-reduce fused '
                     'into the column-sum kernel over NVLink peer memory (default), or a separate NCCL all-reduce')
     ap.add_argument('--shard', default='interleave', choices=['interleave', 'band'],

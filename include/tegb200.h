@@ -184,6 +184,16 @@ int tegb_render_groups_launch(tegb_program *p, const void *const *group_ptrs, in
                               const tegb_grid *grid, const int32_t *windows, int max_rows, int max_cols,
                               const void *const *pixel_ptrs, void *const *out_ptrs, void *stream);
 
+/* The per-group prologue of a grouped render (uniform rows + tile classification for the groups' CURRENT parameters)
+ * as a call of its own: prepare a group range once, then launch any number of sub-ranges of it with
+ * tegb_render_groups_launch_prepared (same grid, windows pointer and window bounds) -- e.g. the window-disjoint classes
+ * of a scene, one accumulating launch each.  The parameters must not change between the prepare and the launches. */
+int tegb_render_groups_prepare(tegb_program *p, const void *const *group_ptrs, int group_begin, int group_count,
+                               const tegb_grid *grid, const int32_t *windows, int max_rows, int max_cols, void *stream);
+int tegb_render_groups_launch_prepared(tegb_program *p, const void *const *group_ptrs, int group_begin, int group_count,
+                                       const tegb_grid *grid, const int32_t *windows, int max_rows, int max_cols,
+                                       const void *const *pixel_ptrs, void *const *out_ptrs, void *stream);
+
 /* kernels launched by this library since load (for accounting) */
 int64_t tegb_launch_count(void);
 

@@ -581,33 +581,29 @@ class Emitter:
                 e('}', ind)
 
         if walk:
-            # grouped launches (tiles are relative to each group's window): one warp per tile walks the tile's rows
-            # [r0, r1) and columns [c0, c1) itself -- exact ranges of the box edges and the midpoint abscissae
+            # grouped launches (tiles are relative to each group's window): one THREAD per tile walks the tile's rows
+            # [r0, r1) and columns [c0, c1) itself -- exact ranges of the box edges and the midpoint abscissae, no
+            # reasoning about rounding -- and evaluates the cones once (a warp per tile spent 32 lanes on one answer)
             e(f'T g_pz = {zero};')
             for tab, first, last, lo_n, hi_n, bvs in (('xe', 'r0', 'r1', 'xl', 'xu', bx), ('ye', 'c0', 'c1', 'yl', 'yu', by)):
                 e(f'T g_{lo_n}_lo = {tab}[{first}], g_{lo_n}_hi = {tab}[{first}], g_{hi_n}_lo = {tab}[{first} + 1], '
                   f'g_{hi_n}_hi = {tab}[{first} + 1];')
                 e(f'T g_s{lo_n}_lo = {tab}[{first}], g_s{lo_n}_hi = {tab}[{first}];')
-                e(f'for (int q = {first} + lane; q < {last}; q += 32) {{')
-                e(f'const T lb = {tab}[q], ub = {tab}[q + 1];', 2)
+                e(f'{{ T lb = {tab}[{first}];')
+                e(f'for (int q = {first}; q < {last}; ++q) {{')
+                e(f'const T ub = {tab}[q + 1];', 2)
                 e(f'g_{lo_n}_lo = {fmin}(g_{lo_n}_lo, lb); g_{lo_n}_hi = {fmax}(g_{lo_n}_hi, lb);', 2)
                 e(f'g_{hi_n}_lo = {fmin}(g_{hi_n}_lo, ub); g_{hi_n}_hi = {fmax}(g_{hi_n}_hi, ub);', 2)
                 e(f'const T st = ((T)(ub - lb)) / (T){N};', 2)
                 e(f'const T sa = lb + st * ((T)0u + {half}), sb = lb + st * ((T){N - 1}u + {half});', 2)
                 e(f'g_s{lo_n}_lo = {fmin}(g_s{lo_n}_lo, {fmin}(sa, sb)); g_s{lo_n}_hi = {fmax}(g_s{lo_n}_hi, {fmax}(sa, sb));', 2)
                 e('g_pz = g_pz + lb; g_pz = g_pz + ub; g_pz = g_pz + (ub - lb); g_pz = g_pz + sa; g_pz = g_pz + sb;', 2)
-                e('}')
-                e('for (int off = 16; off > 0; off >>= 1) {')
-                for v in (f'g_{lo_n}_lo', f'g_{hi_n}_lo', f'g_s{lo_n}_lo'):
-                    e(f'{v} = {fmin}({v}, __shfl_xor_sync(0xffffffffu, {v}, off));', 2)
-                for v in (f'g_{lo_n}_hi', f'g_{hi_n}_hi', f'g_s{lo_n}_hi'):
-                    e(f'{v} = {fmax}({v}, __shfl_xor_sync(0xffffffffu, {v}, off));', 2)
-                e('}')
+                e('lb = ub;', 2)
+                e('} }')
                 for j in bvs:
                     e(f'const T g_b{j}_lo = g_s{lo_n}_lo, g_b{j}_hi = g_s{lo_n}_hi;')
-            e('for (int off = 16; off > 0; off >>= 1) g_pz = g_pz + __shfl_xor_sync(0xffffffffu, g_pz, off);')
             points()
-            cones(1, 't', 'if (lane == 0) ')
+            cones(1, 't', '')
             e('(void)unresolved;')
         else:
             # [min, max] of the box edges and of the sample abscissae over a tile row / tile column come from the
@@ -1003,8 +999,13 @@ class Emitter:
                 self.emit(f'const T t{k}_{q} = ({has}s{k} < {N}u) ? {body} * step{k} : {zero};', ind + 1)
         # left fold in sample order, computed identically by every lane (adding the +0 of a missing /
         # skipped sample never changes the accumulator)
-        self.emit(f'const unsigned int cnt{k} = ({N}u - base{k}) < {width}u ? ({N}u - base{k}) : {width}u;', ind + 1)
-        self.emit(f'for (unsigned int l{k} = 0; l{k} < cnt{k}; ++l{k}) {{', ind + 1)
+        if N <= width:
+            # one pass covers the loop: the fold has a compile-time length (unrolled: independent shuffles, one add chain)
+            self.emit(f'#pragma unroll', ind + 1)
+            self.emit(f'for (unsigned int l{k} = 0; l{k} < {N}u; ++l{k}) {{', ind + 1)
+        else:
+            self.emit(f'const unsigned int cnt{k} = ({N}u - base{k}) < {width}u ? ({N}u - base{k}) : {width}u;', ind + 1)
+            self.emit(f'for (unsigned int l{k} = 0; l{k} < cnt{k}; ++l{k}) {{', ind + 1)
         for q in st.quads:
             self.emit(f'acc{k}_{q} = acc{k}_{q} + __shfl_sync(0xffffffffu, t{k}_{q}, {first} + l{k});', ind + 2)
         self.emit('}', ind + 1)
@@ -1308,10 +1309,9 @@ class Emitter:
                                     ['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
                                      'const int row0', 'const int row1', 'const int* __restrict__ win',
                                      'const int group_begin', 'const int group_count', 'const int tile_rows',
-                                     'const int n_tx', 'const int n_ty', 'T* __restrict__ tiles'])
+                                     'const int n_tx', 'const int n_ty', 'const int tab_groups', 'T* __restrict__ tiles'])
                 src.append(f'extern "C" __global__ void {name}_tiles({tparams}) {{')
-                src.append('    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;')
-                src.append('    const int lane = threadIdx.x & 31;')
+                src.append('    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one thread per tile')
                 src.append('    const int per_group = n_tx * n_ty;')
                 src.append('    if (w >= (long long)group_count * per_group) return;')
                 src.append('    const int j = (int)(w / per_group), tt = (int)(w - (long long)j * per_group);')
@@ -1321,9 +1321,14 @@ class Emitter:
                 src.append('    const int w_c0 = win[4 * g + 2], w_c1 = min(win[4 * g + 3], res_y);')
                 src.append('    const int r0 = w_r0 + ty * tile_rows, r1 = min(r0 + tile_rows, w_r1);')
                 src.append('    const int c0 = w_c0 + tx * TEGB_TILE_COLS, c1 = min(c0 + TEGB_TILE_COLS, w_c1);')
-                src.append('    if (r0 >= r1 || c0 >= c1) return;              // no pixel: the main kernel never reads this tile')
-                src.append('    const size_t n_tiles = (size_t)group_count * per_group;')
-                src.append('    const size_t t = (size_t)w;')
+                src.append('    // the table is indexed by ABSOLUTE group number: one classification pass may serve several launches')
+                src.append('    const size_t n_tiles = (size_t)tab_groups * per_group;')
+                src.append('    const size_t t = (size_t)g * per_group + tt;')
+                src.append('    if (r0 >= r1 || c0 >= c1) {                    // no pixel: resolved-false, nobody walks it')
+                for k in range(len(tile)):
+                    src.append(f'        tiles[(size_t){k} * n_tiles + t] = {zero};')
+                src.append('        return;')
+                src.append('    }')
                 for a2 in scal:
                     src.append(f'    const T a{a2} = g{a2}[g];')
                     src.append(f'    (void)a{a2};')
@@ -1333,7 +1338,7 @@ class Emitter:
             mparams = ', '.join(['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
                                  'const int row0', 'const int row1', 'const int* __restrict__ win',
                                  'const int group_begin', 'const T* __restrict__ Utab', 'const int tile_rows'] +
-                                (['const T* __restrict__ tiles'] if tile else []) +
+                                (['const T* __restrict__ tiles', 'const int tab_groups'] if tile else []) +
                                 [f'const T* __restrict__ pix{a}' for a in pix] + outs_decl)
             gmb = (0 if self.min_blocks is None else self.min_blocks)
             glb = f'{bs}, {gmb}' if gmb else f'{bs}'
@@ -1366,9 +1371,9 @@ class Emitter:
             src.append('    const int rows_here = min(tile_rows, w_r1 - nx0);')
             loads = {grid[0]: 'x_lo', grid[1]: 'x_hi', grid[2]: 'ye_lo', grid[3]: 'ye_hi'}
             if tile:
-                src.append('    const size_t n_tiles = (size_t)gridDim.x * TEGB_TILE_SUB * gridDim.y * gridDim.z;')
-                src.append('    const size_t tile_base = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * (gridDim.x * TEGB_TILE_SUB) + '
-                           'blockIdx.x * TEGB_TILE_SUB;')
+                src.append('    const size_t n_tiles = (size_t)gridDim.x * TEGB_TILE_SUB * gridDim.y * tab_groups;')
+                src.append('    const size_t tile_base = ((size_t)g * gridDim.y + blockIdx.y) * (gridDim.x * TEGB_TILE_SUB) + '
+                           'blockIdx.x * TEGB_TILE_SUB;         // (absolute group number)')
                 src.append('    const size_t tile_id = tile_base + threadIdx.x / TEGB_TILE_COLS;')
                 for k, a in enumerate(tile):
                     src.append(f'    const T tile{k} = tiles[{k} * n_tiles + tile_id];')

@@ -274,6 +274,11 @@ struct tegb_program {
     bool ev_valid = false;
     CUstream ev_stream = nullptr;
     int n_groups_total = 0;           // grouped programs with a peer: rows of the all-reduced [groups][outputs] result
+    // grouped programs: what the last per-group prologue (uniform rows + tile classification) covered
+    bool prep_valid = false;
+    int prep_begin = 0, prep_count = 0, prep_max_rows = 0, prep_max_cols = 0;
+    tegb_grid prep_grid{};
+    const int32_t *prep_windows = nullptr;
     const int *group_map = nullptr;   // device [n_groups_total]: this rank's index of every global group, or -1 (NULL: identity)
     CUmodule mod = nullptr;
     CUfunction f_uniform = nullptr, f_main = nullptr, f_tiles = nullptr;
@@ -893,10 +898,95 @@ static int finish_group_partials(tegb_program *p, unsigned long long tiles, int 
     return TEGB_OK;
 }
 
-extern "C" int tegb_render_groups_launch(tegb_program *p, const void *const *group_ptrs, int group_begin,
-                                         int group_count, const tegb_grid *g, const int32_t *windows,
-                                         int max_rows, int max_cols, const void *const *pixel_ptrs,
-                                         void *const *out_ptrs, void *stream) {
+// launch geometry of a grouped render: blocks of block_size columns x tile_rows rows over the largest window
+struct GroupGeom { unsigned gx, gy; int tile_rows, n_tx, n_ty; };
+
+static GroupGeom group_geom(const tegb_program *p, const tegb_grid *g, int max_rows, int max_cols) {
+    GroupGeom q;
+    const unsigned bs = (unsigned)p->d.block_size;
+    q.gx = (unsigned)((max_cols + bs - 1) / bs);
+    const int band_rows = g->row_end - g->row_begin;
+    q.tile_rows = p->d.tile_rows > 0 ? p->d.tile_rows : 1;
+    const int win_rows = max_rows < band_rows ? max_rows : band_rows;
+    q.gy = (unsigned)((win_rows + q.tile_rows - 1) / q.tile_rows);
+    q.n_tx = (int)q.gx * (p->d.tile_cols > 0 ? p->d.block_size / p->d.tile_cols : 1);
+    q.n_ty = (int)q.gy;
+    return q;
+}
+
+// Per-group prologue of a grouped render: the uniform rows and (tile-culled programs) the tri-states of every (group,
+// window tile), for the groups' CURRENT parameters.  Tables are indexed by absolute group number, so one prologue
+// over all groups can serve several launches over sub-ranges (tegb_render_groups_prepare).
+static int groups_prologue(tegb_program *p, const void *const *group_ptrs, int group_begin, int group_count,
+                           const tegb_grid *g, const int32_t *windows, int max_rows, int max_cols, CUstream st) {
+    int rc = ensure_edges(p, g, st);
+    if (rc) return rc;
+    const GroupGeom q = group_geom(p, g, max_rows, max_cols);
+    const int tab_groups = group_begin + group_count;
+    const int nu = p->d.n_uniform > 0 ? p->d.n_uniform : 1;
+    const size_t need = (size_t)tab_groups * nu * p->d.elem_size;
+    if (need > p->utab_bytes) {
+        RT_CHECK(cudaStreamSynchronize((cudaStream_t)st));
+        if (p->d_utab) { cudaFree(p->d_utab); p->d_utab = nullptr; p->utab_bytes = 0; }
+        RT_CHECK(cudaMalloc(&p->d_utab, need));
+        p->utab_bytes = need;
+    }
+    {
+        std::vector<const void *> gp(p->d.n_scalar_args > 0 ? p->d.n_scalar_args : 1);
+        std::vector<void *> args;
+        for (int i = 0; i < p->d.n_scalar_args; i++) { gp[i] = group_ptrs[i]; args.push_back(&gp[i]); }
+        args.push_back(&group_begin);
+        args.push_back(&group_count);
+        args.push_back(&p->d_utab);
+        CU_CHECK(drv::LaunchKernel(p->f_uniform, (unsigned)((group_count + 127) / 128), 1, 1, 128, 1, 1, 0, st,
+                                   args.data(), nullptr));
+        g_launches++;
+    }
+    if (p->d.n_tile_conds > 0) {
+        // classify every (group, window tile): one thread per tile
+        int n_tx = q.n_tx, n_ty = q.n_ty, tile_rows = q.tile_rows, tabg = tab_groups;
+        int res_y = g->res_y, row0 = g->row_begin, row1 = g->row_end;
+        const size_t need_t = (size_t)p->d.n_tile_conds * tab_groups * n_tx * n_ty * p->d.elem_size;
+        if (need_t > p->tiles_bytes) {
+            RT_CHECK(cudaStreamSynchronize((cudaStream_t)st));
+            if (p->d_tiles) { cudaFree(p->d_tiles); p->d_tiles = nullptr; p->tiles_bytes = 0; }
+            RT_CHECK(cudaMalloc(&p->d_tiles, need_t));
+            p->tiles_bytes = need_t;
+        }
+        std::vector<const void *> gp2(p->d.n_scalar_args > 0 ? p->d.n_scalar_args : 1);
+        std::vector<void *> targs;
+        for (int i = 0; i < p->d.n_scalar_args; i++) { gp2[i] = group_ptrs[i]; targs.push_back(&gp2[i]); }
+        targs.push_back(&p->d_xe);
+        targs.push_back(&p->d_ye);
+        targs.push_back(&res_y);
+        targs.push_back(&row0);
+        targs.push_back(&row1);
+        targs.push_back((void *)&windows);
+        targs.push_back(&group_begin);
+        targs.push_back(&group_count);
+        targs.push_back(&tile_rows);
+        targs.push_back(&n_tx);
+        targs.push_back(&n_ty);
+        targs.push_back(&tabg);
+        targs.push_back(&p->d_tiles);
+        const unsigned long long threads = (unsigned long long)group_count * n_tx * n_ty;
+        const unsigned tb = 128, tg = (unsigned)((threads + tb - 1) / tb);
+        CU_CHECK(drv::LaunchKernel(p->f_tiles, tg, 1, 1, tb, 1, 1, 0, st, targs.data(), nullptr));
+        g_launches++;
+    }
+    p->prep_valid = true;
+    p->prep_begin = group_begin;
+    p->prep_count = group_count;
+    p->prep_grid = *g;
+    p->prep_windows = windows;
+    p->prep_max_rows = max_rows;
+    p->prep_max_cols = max_cols;
+    return TEGB_OK;
+}
+
+static int groups_launch_impl(tegb_program *p, const void *const *group_ptrs, int group_begin, int group_count,
+                              const tegb_grid *g, const int32_t *windows, int max_rows, int max_cols,
+                              const void *const *pixel_ptrs, void *const *out_ptrs, void *stream, bool prepared) {
     if (!p || !g || !windows || !out_ptrs) return fail(TEGB_ERR_INVALID, "tegb_render_groups_launch: bad argument");
     if (!p->d.grouped || p->d.n_grid_args != 4) return fail(TEGB_ERR_INVALID, "not a grouped render program");
     if (p->d.n_scalar_args > 0 && !group_ptrs) return fail(TEGB_ERR_INVALID, "group_ptrs is NULL");
@@ -921,71 +1011,27 @@ extern "C" int tegb_render_groups_launch(tegb_program *p, const void *const *gro
         if (rc) return rc;
         return end_launch(p, st);
     }
-    rc = ensure_edges(p, g, st);
-    if (rc) return rc;
-    const int nu = p->d.n_uniform > 0 ? p->d.n_uniform : 1;
-    const size_t need = (size_t)(group_begin + group_count) * nu * p->d.elem_size;
-    if (need > p->utab_bytes) {
-        RT_CHECK(cudaStreamSynchronize((cudaStream_t)st));
-        if (p->d_utab) { cudaFree(p->d_utab); p->d_utab = nullptr; p->utab_bytes = 0; }
-        RT_CHECK(cudaMalloc(&p->d_utab, need));
-        p->utab_bytes = need;
+    if (prepared) {
+        const tegb_grid &c = p->prep_grid;
+        const bool same = p->prep_valid && group_begin >= p->prep_begin &&
+                          group_begin + group_count <= p->prep_begin + p->prep_count && p->prep_windows == windows &&
+                          p->prep_max_rows == max_rows && p->prep_max_cols == max_cols && c.x_lo == g->x_lo &&
+                          c.x_hi == g->x_hi && c.y_lo == g->y_lo && c.y_hi == g->y_hi && c.res_x == g->res_x &&
+                          c.res_y == g->res_y && c.row_begin == g->row_begin && c.row_end == g->row_end;
+        if (!same) return fail(TEGB_ERR_INVALID, "tegb_render_groups_launch_prepared: no matching tegb_render_groups_prepare "
+                                                 "(same grid, windows and window bounds, covering this group range)");
+    } else {
+        rc = groups_prologue(p, group_ptrs, group_begin, group_count, g, windows, max_rows, max_cols, st);
+        if (rc) return rc;
     }
-    // per-group uniform rows
-    {
-        std::vector<const void *> gp(p->d.n_scalar_args > 0 ? p->d.n_scalar_args : 1);
-        std::vector<void *> args;
-        for (int i = 0; i < p->d.n_scalar_args; i++) { gp[i] = group_ptrs[i]; args.push_back(&gp[i]); }
-        args.push_back(&group_begin);
-        args.push_back(&group_count);
-        args.push_back(&p->d_utab);
-        CU_CHECK(drv::LaunchKernel(p->f_uniform, (unsigned)((group_count + 127) / 128), 1, 1, 128, 1, 1, 0, st,
-                                   args.data(), nullptr));
-        g_launches++;
-    }
+    const GroupGeom q = group_geom(p, g, max_rows, max_cols);
     const unsigned bs = (unsigned)p->d.block_size;
-    const unsigned gx = (unsigned)((max_cols + bs - 1) / bs);
-    int band_rows = g->row_end - g->row_begin;
-    // one block per window tile: block_size columns x tile_rows rows
-    int tile_rows = p->d.tile_rows > 0 ? p->d.tile_rows : 1;
-    const int win_rows = max_rows < band_rows ? max_rows : band_rows;
-    const unsigned gy = (unsigned)((win_rows + tile_rows - 1) / tile_rows);
-    const unsigned gz = (unsigned)group_count;
+    const unsigned gx = q.gx, gy = q.gy, gz = (unsigned)group_count;
     std::vector<const void *> pix(p->d.n_pixel_args > 0 ? p->d.n_pixel_args : 1);
     std::vector<void *> outs(p->d.n_outputs);
     std::vector<void *> args;
-    int res_y = g->res_y, row0 = g->row_begin, row1 = g->row_end;
-    if (p->d.n_tile_conds > 0) {
-        // classify every (group, window tile) for the groups' current parameters
-        int n_tx = (int)gx * (p->d.block_size / p->d.tile_cols), n_ty = (int)gy;      // tiles per window row
-        const size_t need_t = (size_t)p->d.n_tile_conds * gz * n_tx * n_ty * p->d.elem_size;
-        if (need_t > p->tiles_bytes) {
-            RT_CHECK(cudaStreamSynchronize((cudaStream_t)st));
-            if (p->d_tiles) { cudaFree(p->d_tiles); p->d_tiles = nullptr; p->tiles_bytes = 0; }
-            RT_CHECK(cudaMalloc(&p->d_tiles, need_t));
-            p->tiles_bytes = need_t;
-        }
-        // (tiles without a pixel are neither written by the classification nor read by the main kernel)
-        std::vector<const void *> gp2(p->d.n_scalar_args > 0 ? p->d.n_scalar_args : 1);
-        std::vector<void *> targs;
-        for (int i = 0; i < p->d.n_scalar_args; i++) { gp2[i] = group_ptrs[i]; targs.push_back(&gp2[i]); }
-        targs.push_back(&p->d_xe);
-        targs.push_back(&p->d_ye);
-        targs.push_back(&res_y);
-        targs.push_back(&row0);
-        targs.push_back(&row1);
-        targs.push_back((void *)&windows);
-        targs.push_back(&group_begin);
-        targs.push_back(&group_count);
-        targs.push_back(&tile_rows);
-        targs.push_back(&n_tx);
-        targs.push_back(&n_ty);
-        targs.push_back(&p->d_tiles);
-        const unsigned long long warps = (unsigned long long)gz * n_tx * n_ty;
-        const unsigned tb = 128, tg = (unsigned)((warps * 32 + tb - 1) / tb);
-        CU_CHECK(drv::LaunchKernel(p->f_tiles, tg, 1, 1, tb, 1, 1, 0, st, targs.data(), nullptr));
-        g_launches++;
-    }
+    int res_y = g->res_y, row0 = g->row_begin, row1 = g->row_end, tile_rows = q.tile_rows;
+    int tab_groups = p->prep_begin + p->prep_count;
     args.push_back(&p->d_xe);
     args.push_back(&p->d_ye);
     args.push_back(&res_y);
@@ -995,7 +1041,7 @@ extern "C" int tegb_render_groups_launch(tegb_program *p, const void *const *gro
     args.push_back(&group_begin);
     args.push_back(&p->d_utab);
     args.push_back(&tile_rows);
-    if (p->d.n_tile_conds > 0) args.push_back(&p->d_tiles);
+    if (p->d.n_tile_conds > 0) { args.push_back(&p->d_tiles); args.push_back(&tab_groups); }
     for (int i = 0; i < p->d.n_pixel_args; i++) { pix[i] = pixel_ptrs[i]; args.push_back(&pix[i]); }
     const unsigned long long tiles = (unsigned long long)gx * gy;
     if (p->d.reduce_outputs) {
@@ -1012,6 +1058,42 @@ extern "C" int tegb_render_groups_launch(tegb_program *p, const void *const *gro
         if (rc) return rc;
     }
     return end_launch(p, st);
+}
+
+extern "C" int tegb_render_groups_launch(tegb_program *p, const void *const *group_ptrs, int group_begin,
+                                         int group_count, const tegb_grid *g, const int32_t *windows,
+                                         int max_rows, int max_cols, const void *const *pixel_ptrs,
+                                         void *const *out_ptrs, void *stream) {
+    return groups_launch_impl(p, group_ptrs, group_begin, group_count, g, windows, max_rows, max_cols, pixel_ptrs,
+                              out_ptrs, stream, false);
+}
+
+extern "C" int tegb_render_groups_prepare(tegb_program *p, const void *const *group_ptrs, int group_begin,
+                                          int group_count, const tegb_grid *g, const int32_t *windows, int max_rows,
+                                          int max_cols, void *stream) {
+    if (!p || !g || !windows) return fail(TEGB_ERR_INVALID, "tegb_render_groups_prepare: bad argument");
+    if (!p->d.grouped || p->d.n_grid_args != 4) return fail(TEGB_ERR_INVALID, "not a grouped render program");
+    if (p->d.n_scalar_args > 0 && !group_ptrs) return fail(TEGB_ERR_INVALID, "group_ptrs is NULL");
+    if (group_begin < 0 || group_count < 1 || group_count > 65535 || max_rows < 1 || max_cols < 1)
+        return fail(TEGB_ERR_INVALID, "bad group range or window bounds");
+    if (g->res_x < 1 || g->res_y < 1 || g->row_begin < 0 || g->row_end > g->res_x || g->row_begin >= g->row_end)
+        return fail(TEGB_ERR_INVALID, "bad grid");
+    std::lock_guard<std::recursive_mutex> lock(p->mu);
+    RT_CHECK(cudaSetDevice(p->device));
+    CUstream st = (CUstream)stream;
+    int rc = begin_launch(p, st);
+    if (rc) return rc;
+    rc = groups_prologue(p, group_ptrs, group_begin, group_count, g, windows, max_rows, max_cols, st);
+    if (rc) return rc;
+    return end_launch(p, st);
+}
+
+extern "C" int tegb_render_groups_launch_prepared(tegb_program *p, const void *const *group_ptrs, int group_begin,
+                                                  int group_count, const tegb_grid *g, const int32_t *windows,
+                                                  int max_rows, int max_cols, const void *const *pixel_ptrs,
+                                                  void *const *out_ptrs, void *stream) {
+    return groups_launch_impl(p, group_ptrs, group_begin, group_count, g, windows, max_rows, max_cols, pixel_ptrs,
+                              out_ptrs, stream, true);
 }
 
 extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars, const tegb_grid *g, int tile_stride,

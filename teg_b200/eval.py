@@ -318,7 +318,7 @@ class CUDA_EvalMode(EvalMode):
     def render_groups(self, box_vars, res: Tuple[int, int], bounds, group_bindings, windows, max_rows: int,
                       max_cols: int, pixel_bindings=None, rows: Optional[Tuple[int, int]] = None, out=None,
                       reduce: bool = False, accumulate: bool = False, group_range: Optional[Tuple[int, int]] = None,
-                      stream: int = 0):
+                      stream: int = 0, prepared: bool = False, prepare_only: bool = False):
         """One launch over many *groups* (e.g. triangles), each with its own parameter values and its own
         window of pixels of the tests/plot.py grid.
 
@@ -328,7 +328,10 @@ class CUDA_EvalMode(EvalMode):
         pixel_bindings: {Var | label: image tensor [rows, res_y]} read per pixel (an upstream dL).
         rows: the band of grid rows this device owns (multi-GPU sharding).
         Output: ``out`` images [k, rows, res_y] (assigned, or added to with ``accumulate`` -- the windows of
-        one launch must then be disjoint), or with ``reduce`` a tensor [G_range, k] of per-group sums."""
+        one launch must then be disjoint), or with ``reduce`` a tensor [G_range, k] of per-group sums.
+        prepare_only: run only the per-group prologue (uniform rows + tile classification for the groups' current
+        parameters) for ``group_range``; later calls with ``prepared=True`` over sub-ranges then skip it (the same
+        windows tensor, window bounds and rows; the parameters must not change in between)."""
         import torch
         pos = {lab: i for i, (lab, _) in enumerate(self.arglist)}
         pix = {(k if isinstance(k, str) else label_of(k)): v for k, v in (pixel_bindings or {}).items()}
@@ -357,15 +360,20 @@ class CUDA_EvalMode(EvalMode):
             assert img.is_cuda and img.dtype == tdt and img.is_contiguous() and img.numel() == (r1 - r0) * res[1]
             pptrs.append(img.data_ptr())
         assert windows.is_cuda and windows.dtype == torch.int32 and windows.is_contiguous() and windows.shape[1] == 4
+        grid = runtime.Grid(float(bounds[0][0]), float(bounds[0][1]), float(bounds[1][0]), float(bounds[1][1]),
+                            int(res[0]), int(res[1]), int(r0), int(r1))
+        self._keepalive = keep
+        if prepare_only:
+            if g1 > g0 and r1 > r0:
+                prog.prepare_groups(gptrs, g0, g1 - g0, grid, windows.data_ptr(), int(max_rows), int(max_cols),
+                                    stream=stream)
+            return None
         if out is None:
             out = (torch.empty((g1 - g0, ks.n_outputs), dtype=tdt, device=dev) if reduce
                    else torch.zeros((ks.n_outputs, r1 - r0, res[1]), dtype=tdt, device=dev))
         optrs = [out.data_ptr()] if reduce else [out[k].data_ptr() for k in range(ks.n_outputs)]
-        grid = runtime.Grid(float(bounds[0][0]), float(bounds[0][1]), float(bounds[1][0]), float(bounds[1][1]),
-                            int(res[0]), int(res[1]), int(r0), int(r1))
         prog.render_groups(gptrs, g0, g1 - g0, grid, windows.data_ptr(), int(max_rows), int(max_cols), pptrs,
-                           optrs, stream=stream)
-        self._keepalive = keep
+                           optrs, stream=stream, prepared=prepared)
         return out
 
     def prepare(self, bindings={}, reduce: bool = False):

@@ -34,7 +34,7 @@ PARAMS = ('px0', 'py0', 'px1', 'py1', 'px2', 'py2', 'col')
 class MultiTriangleRasterizer:
     def __init__(self, primal: Program, grad: Program, res: int, bands: int = 1, rank: int = 0,
                  num_samples: int = 16, device: int = 0, float_width: str = 'float', cull: bool = True,
-                 min_blocks=(None, None), rows: Optional[Tuple[int, int]] = None):
+                 min_blocks=(4, 4), rows: Optional[Tuple[int, int]] = None, tile_rows=(16, 32), **codegen_opts):
         import torch
         self.torch = torch
         self.res = int(res)
@@ -43,12 +43,15 @@ class MultiTriangleRasterizer:
         self.device = device
         self.dev = torch.device('cuda', device)
         self.tdt = torch.float32 if float_width == 'float' else torch.float64
+        # tile_rows = (value kernel, gradient kernel): pixel rows per block / classification tile (measured on config 5:
+        # 16 / 32 rows; the gradient kernel pays its per-block sum once per twice as many pixels)
+        tr = (tile_rows, tile_rows) if isinstance(tile_rows, int) else tuple(tile_rows)
         # min_blocks = (value kernel, gradient kernel): resident blocks per SM the grouped kernels are compiled for
         # (__launch_bounds__; None = the compiler's choice)
         self.m_primal = CUDA_EvalMode(primal, num_samples=num_samples, device=device, float_width=float_width,
-                                      cull=cull, min_blocks=min_blocks[0])
+                                      cull=cull, min_blocks=min_blocks[0], tile_rows=tr[0], **codegen_opts)
         self.m_grad = CUDA_EvalMode(grad, num_samples=num_samples, device=device, float_width=float_width, cull=cull,
-                                    min_blocks=min_blocks[1])
+                                    min_blocks=min_blocks[1], tile_rows=tr[1], **codegen_opts)
         self.p_lab = {base_name(lab): lab for lab in primal.args}
         self.g_lab = {base_name(lab): lab for lab in grad.args}
         self.bounds = ((0.0, float(bands)), (0.0, 1.0))
@@ -134,10 +137,15 @@ class MultiTriangleRasterizer:
         out.zero_()
         box = [self.p_lab[b] for b in BOX]
         gb = {self.p_lab[nm]: self.params[nm] for nm in PARAMS}
+        if len(self.classes) > 1:
+            # uniform rows + tile classification of ALL held triangles once, then one accumulating launch per class
+            self.m_primal.render_groups(box, self.grid_res, self.bounds, gb, self.windows, self.max_rows,
+                                        self.max_cols, rows=self.rows, accumulate=True,
+                                        group_range=(0, self.K_local), stream=stream, prepare_only=True)
         for g0, g1 in self.classes:
             self.m_primal.render_groups(box, self.grid_res, self.bounds, gb, self.windows, self.max_rows,
                                         self.max_cols, rows=self.rows, out=out, accumulate=True,
-                                        group_range=(g0, g1), stream=stream)
+                                        group_range=(g0, g1), stream=stream, prepared=len(self.classes) > 1)
         return out
 
     def backward(self, dL, out=None, stream: int = 0):

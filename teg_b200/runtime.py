@@ -37,7 +37,8 @@ SYMBOLS = [
     'tegb_last_error', 'tegb_version', 'tegb_runtime_header_hash', 'tegb_nvrtc_version', 'tegb_device_count', 'tegb_compile', 'tegb_module_from_cubin',
     'tegb_module_cubin', 'tegb_module_log', 'tegb_module_destroy', 'tegb_program_create',
     'tegb_program_destroy', 'tegb_program_launch', 'tegb_program_eval_host', 'tegb_render_launch',
-    'tegb_render_launch_strided', 'tegb_render_groups_launch', 'tegb_program_tile_table', 'tegb_peer_create', 'tegb_peer_connect',
+    'tegb_render_launch_strided', 'tegb_render_groups_launch', 'tegb_render_groups_prepare',
+    'tegb_render_groups_launch_prepared', 'tegb_program_tile_table', 'tegb_peer_create', 'tegb_peer_connect',
     'tegb_peer_allreduce_sum', 'tegb_peer_error', 'tegb_peer_destroy', 'tegb_program_set_peer',
     'tegb_program_set_peer_groups',
     'tegb_launch_count', 'tegb_reduce_workspace_bytes', 'tegb_reduce_sum', 'tegb_nccl_unique_id',
@@ -81,6 +82,8 @@ def lib():
                                      ctypes.POINTER(vp), vp]
     L.tegb_render_groups_launch.argtypes = [vp, ctypes.POINTER(vp), i32, i32, ctypes.POINTER(Grid), vp, i32, i32,
                                             ctypes.POINTER(vp), ctypes.POINTER(vp), vp]
+    L.tegb_render_groups_launch_prepared.argtypes = L.tegb_render_groups_launch.argtypes
+    L.tegb_render_groups_prepare.argtypes = [vp, ctypes.POINTER(vp), i32, i32, ctypes.POINTER(Grid), vp, i32, i32, vp]
     L.tegb_program_tile_table.argtypes = [vp, vp, ctypes.c_size_t, vp]
     L.tegb_render_launch_strided.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(Grid), i32, i32,
                                              ctypes.POINTER(vp), vp]
@@ -249,11 +252,17 @@ class Program:
 
     def render_groups(self, group_ptrs: Sequence[int], group_begin: int, group_count: int, grid: Grid,
                       windows_ptr: int, max_rows: int, max_cols: int, pixel_ptrs: Sequence[int],
-                      out_ptrs: Sequence[int], stream: int = 0) -> None:
-        check(self._L.tegb_render_groups_launch(self.handle, _ptr_array(group_ptrs), group_begin, group_count,
-                                                ctypes.byref(grid), ctypes.c_void_p(windows_ptr), max_rows,
-                                                max_cols, _ptr_array(pixel_ptrs), _ptr_array(out_ptrs),
-                                                ctypes.c_void_p(stream)))
+                      out_ptrs: Sequence[int], stream: int = 0, prepared: bool = False) -> None:
+        fn = self._L.tegb_render_groups_launch_prepared if prepared else self._L.tegb_render_groups_launch
+        check(fn(self.handle, _ptr_array(group_ptrs), group_begin, group_count, ctypes.byref(grid),
+                 ctypes.c_void_p(windows_ptr), max_rows, max_cols, _ptr_array(pixel_ptrs), _ptr_array(out_ptrs),
+                 ctypes.c_void_p(stream)))
+
+    def prepare_groups(self, group_ptrs: Sequence[int], group_begin: int, group_count: int, grid: Grid,
+                       windows_ptr: int, max_rows: int, max_cols: int, stream: int = 0) -> None:
+        check(self._L.tegb_render_groups_prepare(self.handle, _ptr_array(group_ptrs), group_begin, group_count,
+                                                 ctypes.byref(grid), ctypes.c_void_p(windows_ptr), max_rows, max_cols,
+                                                 ctypes.c_void_p(stream)))
 
     def __del__(self):
         try:

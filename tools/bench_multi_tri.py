@@ -35,6 +35,8 @@ def main():
                     'device arrays, so the graph stays valid while they change)')
     ap.add_argument('--min-blocks', default='', help='experiment: "a,b" = __launch_bounds__ resident blocks per SM of '
                     'the grouped value / gradient kernels (0 = the compiler\'s choice)')
+    ap.add_argument('--tile-rows', default='16,32', help='pixel rows per tile of the value / gradient kernels')
+    ap.add_argument('--coop-groups', type=int, default=4)
     args = ap.parse_args()
 
     import torch
@@ -61,7 +63,7 @@ def main():
     K = scene['verts'].shape[0]
     mb = tuple((int(x) or None) for x in args.min_blocks.split(',')) if args.min_blocks else (None, None)
     r = MultiTriangleRasterizer(primal, grad, res, bands=world, rank=rank, device=local, cull=bool(args.cull),
-                                min_blocks=mb)
+                                min_blocks=mb, tile_rows=tuple(int(x) for x in args.tile_rows.split(',')), coop_groups=args.coop_groups)
     br = scene['band_ranges']
     active = (br[max(rank - 1, 0)][0], br[min(rank + 1, world - 1)][1])      # own band and its neighbours
     r.set_scene(scene['verts'], scene['col'], scene['windows'], scene['classes'], scene['max_rows'],
