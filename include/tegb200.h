@@ -211,6 +211,10 @@ int tegb_nccl_comm_destroy(void *comm);
 int tegb_allreduce_sum(void *buf, int64_t count, int elem_size, void *comm, void *stream);
 
 /* --- measurement -------------------------------------------------------------------------- */
+/* CUDA events around the MAIN kernel of every launch of this handle (not its prologue / classification / column
+ * sums): tegb_program_main_kernel_ms waits for the last launch and returns that kernel's duration.  For rooflines. */
+int tegb_program_enable_timing(tegb_program *p, int on);
+int tegb_program_main_kernel_ms(tegb_program *p, double *ms);
 /* dependent-chain FMA micro-benchmark: achieved TFLOP/s (2 flops per FMA) on `device` */
 int tegb_fma_peak(int elem_size, int device, double *tflops, double *sm_clock_mhz);
 

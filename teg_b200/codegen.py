@@ -639,6 +639,10 @@ class Emitter:
             # tiles' states with independent loads (tiles without a pixel read as resolved-false)
             for k in range(len(roots)):
                 e(f'if (active) tiles_ord[(size_t){k} * n_tiles + (size_t)pos * TEGB_TILE_SUB + sub] = dead ? {zero} : k{k}_tri;')
+            # unresolved tiles of image programs are not walked by the block that owns them: their rows go on a queue
+            # that dedicated blocks of the main kernel serve (ulist: the tiles, in any order)
+            e('const bool mine_unresolved = active && !dead && unresolved;')
+            e('if (mine_unresolved) ulist[atomicAdd(&counters[2], 1)] = (int)(((unsigned int)ty << 16) | (unsigned int)txs);')
         self.in_main = saved_main
         return self.lines
 
@@ -1487,7 +1491,7 @@ class Emitter:
                     tparams = ', '.join([f'const T a{a}' for a in scal] +
                                         ['const T* __restrict__ ranges', 'const int res_y', 'const int n_tx', 'const int n_ty', 'const int n_txs',
                                          'T* __restrict__ tiles', 'T* __restrict__ tiles_ord', 'int* __restrict__ order',
-                                         'int* __restrict__ counters'])
+                                         'int* __restrict__ counters', 'int* __restrict__ ulist'])
                     src.append(f'extern "C" __global__ void {name}_tiles({tparams}) {{')
                     src.append('    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;    // one thread per tile')
                     src.append('    const int t_ = gtid / TEGB_TILE_SUB, sub = gtid % TEGB_TILE_SUB;')
@@ -1505,15 +1509,21 @@ class Emitter:
                 mparams = ', '.join(['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
                                      'const int row0', 'const int n_rows', 'const int tile_rows', 'const int row_stride',
                                      'const int row_phase'] +
-                                    (['const T* __restrict__ tiles', 'const int* __restrict__ order'] if tile else []) +
-                                    outs_decl)
+                                    (['const T* __restrict__ tiles', 'const int* __restrict__ order',
+                                      'const int* __restrict__ ulist', 'int* queue', 'const int n_tx', 'const int n_ty',
+                                      'const int n_workers'] if tile else []) +
+                                    outs_decl +
+                                    [])
                 mb = (8 if tile and bs == 128 else 0) if self.min_blocks is None else self.min_blocks
                 lb = f'{bs}, {mb}' if mb else f'{bs}'
                 src.append(f'extern "C" __global__ void __launch_bounds__({lb}) {name}_main({mparams}) {{')
                 if tile:
-                    # blocks take the tiles in the order the classification listed them: unresolved (expensive) tiles
-                    # first, so that they all start in the first wave instead of trailing the launch
-                    src.append('    const unsigned int slot = blockIdx.y * gridDim.x + blockIdx.x;')
+                    # 1-D grid: n_workers blocks that serve the queue of unresolved rows (below), then one block per
+                    # n_tx x n_ty tile block, taken in the order the classification listed them
+                    src.append('    const int n_txs = n_tx * TEGB_TILE_SUB;')
+                    src.append('    const size_t n_tiles = (size_t)n_txs * n_ty;')
+                    QUEUE_MARK = len(src)
+                    src.append('    const unsigned int slot = blockIdx.x - (unsigned int)n_workers;')
                     src.append('    const unsigned int ord = (unsigned int)order[slot];')
                     src.append('    const int tby = (int)(ord >> 16), tbx = (int)(ord & 0xffffu);')
                 else:
@@ -1527,8 +1537,6 @@ class Emitter:
                            '    const T ye_lo = live ? ye[ny] : ye[0], ye_hi = live ? ye[ny + 1] : ye[1];')
                 loads = {grid[0]: 'x_lo', grid[1]: 'x_hi', grid[2]: 'ye_lo', grid[3]: 'ye_hi'}
                 if tile:
-                    src.append('    const int n_txs = gridDim.x * TEGB_TILE_SUB;')
-                    src.append('    const size_t n_tiles = (size_t)n_txs * gridDim.y;')
                     src.append('    const size_t tile_base = (size_t)slot * TEGB_TILE_SUB;          // states are stored in launch order')
                     src.append('    const size_t tile_id = tile_base + threadIdx.x / TEGB_TILE_COLS;')
                     for k, a in enumerate(tile):
@@ -1567,6 +1575,57 @@ class Emitter:
                     src.append(f'{ind}}}')
 
                 if tile_bodies:
+                    # Rows of unresolved tiles.  One row of an unresolved tile (per-pixel interval test, then cooperative
+                    # sample loops for the pixels an edge really crosses) is a long dependent chain; a block walking 16
+                    # such rows sets the kernel's duration (19 unresolved tiles of 32768 cost 9 us).
+                    # Image programs: the first n_workers blocks of the grid serve a queue of (unresolved tile, row) items,
+                    # one row per warp at a time; surplus workers leave at once; pixels are written in place, so results
+                    # do not depend on who serves an item.  Programs with summed outputs keep the walk inside the owning
+                    # block (all its warps share its unresolved tiles, below): their partial sums stay tied to the block.
+                    if nr == 0:
+                        q = []
+                        q.append('    if (blockIdx.x < (unsigned int)n_workers) {')
+                        q.append('        const int lane_ = threadIdx.x & 31;')
+                        q.append('        const int q_nu = queue[2];                          // unresolved tiles (classification kernel)')
+                        q.append('        const int q_items = q_nu * tile_rows;')
+                        q.append(f'        if ((long long)blockIdx.x * {bs // 32} >= q_items) return;          // more workers than rows')
+                        q.append('        for (;;) {')
+                        q.append('            int it = 0;')
+                        q.append('            if (lane_ == 0) it = atomicAdd(&queue[3], 1);')
+                        q.append('            it = __shfl_sync(0xffffffffu, it, 0);')
+                        q.append('            if (it >= q_items) break;')
+                        q.append('            const int q_r = it / q_nu, q_u = it - q_r * q_nu;      // neighbouring items: different tiles')
+                        q.append('            const unsigned int q_e = (unsigned int)ulist[q_u];')
+                        q.append('            const int q_ty = (int)(q_e >> 16), q_txs = (int)(q_e & 0xffffu);')
+                        q.append('            const int q_rel0 = (q_ty * row_stride + row_phase) * tile_rows;')
+                        q.append('            if (q_r >= min(tile_rows, n_rows - q_rel0)) continue;          // (the last tile row may be short)')
+                        q.append('            const int q_nx = row0 + q_rel0 + q_r;')
+                        q.append('            const T x_lo = xe[q_nx], x_hi = xe[q_nx + 1];')
+                        q.append('            for (int cw = 0; cw < TEGB_TILE_COLS / 32; ++cw) {')
+                        q.append('                const int ny = q_txs * TEGB_TILE_COLS + cw * 32 + lane_;')
+                        q.append('                const bool live = ny < res_y;')
+                        q.append('                const int nyc = live ? ny : 0;')
+                        q.append('                const T ye_lo = ye[nyc], ye_hi = ye[nyc + 1];')
+                        q.append('                const long long i = (long long)(q_ty * tile_rows + q_r) * res_y + ny;')
+                        qloads = dict(loads)
+                        for k, a in enumerate(tile):
+                            q.append(f'                const T tile{k} = {literal("2", T)};')
+                            q.append(f'                (void)tile{k};')
+                            qloads[a] = f'tile{k}'
+                        q.append(f'                T res[{K}];')
+                        qcall = ', '.join((['live'] if coop else []) + [qloads[a] for a in varying] +
+                                          inst('(long long)q_nx * res_y + ny') + ['res'])
+                        if coop:
+                            q.append(f'                {name}_instance({qcall});')
+                        else:
+                            q.append(f'                if (live) {name}_instance({qcall});')
+                        for k in range(ns_out):
+                            q.append(f'                if (live) out{k}[i] = res[{k}];')
+                        q.append('            }')
+                        q.append('        }')
+                        q.append('        return;')
+                        q.append('    }')
+                        src[QUEUE_MARK:QUEUE_MARK] = q
                     per = 4 if T == 'float' else 2                  # elements of a 16-byte vector
                     V = 'float4' if T == 'float' else 'double2'
                     if ns_out:
@@ -1612,34 +1671,37 @@ class Emitter:
                             row_loop(f'{name}_tile_{label}', b_coop, '        ', unroll=1 if b_coop else 4)
                         src.append('    }')
                         first = False
-                    # Unresolved tiles of this block: the per-instance program, shared by ALL warps of the block (warp w
-                    # takes rows w, w + W, ... of each unresolved tile) -- the few expensive tiles would otherwise
-                    # each be walked by a single warp while the rest of its block waits.
-                    mine_u = ' || '.join(f'tile{k} == {literal("2", T)}' for k in range(len(tile)))
-                    src.append(f'    if (__syncthreads_or({mine_u})) {{')
-                    src.append('        const int warp_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;')
-                    src.append('        for (int sub = 0; sub < TEGB_TILE_SUB; ++sub) {')
-                    conds_u = ' || '.join(f'tiles[{k} * n_tiles + tile_base + sub] == {literal("2", T)}' for k in range(len(tile)))
-                    src.append(f'            if (!({conds_u})) continue;                 // block-uniform')
-                    src.append('            for (int cw = 0; cw < TEGB_TILE_COLS / 32; ++cw) {')
-                    src.append(f'                const int ny = tbx * {bs} + sub * TEGB_TILE_COLS + cw * 32 + lane_;')
-                    src.append('                const bool live = ny < res_y;')
-                    src.append('                const int nyc = live ? ny : 0;')
-                    src.append('                const T ye_lo = ye[nyc], ye_hi = ye[nyc + 1];')
-                    src.append('                const long long i0 = (long long)(tby * tile_rows) * res_y + ny;')
-                    for k in range(len(tile)):
-                        src.append(f'                const T tile{k} = {literal("2", T)};')
-                    src.append(f'                (void)nyc; (void)ye_lo; (void)ye_hi;')
-                    row_loop(f'{name}_instance', coop, '                ', 'warp_', f'{bs // 32}')
-                    src.append('            }')
-                    src.append('        }')
-                    src.append('    }')
+                    if nr:
+                        # unresolved tiles of this block, shared by ALL its warps (warp w takes rows w, w + W, ... of each)
+                        mine_u = ' || '.join(f'tile{k} == {literal("2", T)}' for k in range(len(tile)))
+                        src.append(f'    if (__syncthreads_or({mine_u})) {{')
+                        src.append('        const int warp_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;')
+                        src.append('        for (int sub = 0; sub < TEGB_TILE_SUB; ++sub) {')
+                        conds_u = ' || '.join(f'tiles[{k} * n_tiles + tile_base + sub] == {literal("2", T)}' for k in range(len(tile)))
+                        src.append(f'            if (!({conds_u})) continue;                 // block-uniform')
+                        src.append('            for (int cw = 0; cw < TEGB_TILE_COLS / 32; ++cw) {')
+                        src.append(f'                const int ny = tbx * {bs} + sub * TEGB_TILE_COLS + cw * 32 + lane_;')
+                        src.append('                const bool live = ny < res_y;')
+                        src.append('                const int nyc = live ? ny : 0;')
+                        src.append('                const T ye_lo = ye[nyc], ye_hi = ye[nyc + 1];')
+                        src.append('                const long long i0 = (long long)(tby * tile_rows) * res_y + ny;')
+                        for k in range(len(tile)):
+                            src.append(f'                const T tile{k} = {literal("2", T)};')
+                        src.append(f'                (void)nyc; (void)ye_lo; (void)ye_hi; (void)i0;')
+                        row_loop(f'{name}_instance', coop, '                ', 'warp_', f'{bs // 32}')
+                        src.append('            }')
+                        src.append('        }')
+                        src.append('    }')
                 else:
                     row_loop(f'{name}_instance', coop, '    ')
                 if nr:
                     # the partial of a tile lives at the tile's own index: the sums do not depend on the block order
-                    src.append(f'    tegb_block_sum_store<T, {nr}, {bs}>(rr, partials, (unsigned long long)gridDim.x * gridDim.y, '
-                               '(unsigned long long)tby * gridDim.x + tbx);')
+                    if tile:
+                        src.append(f'    tegb_block_sum_store<T, {nr}, {bs}>(rr, partials, (unsigned long long)n_tx * n_ty, '
+                                   '(unsigned long long)tby * n_tx + tbx);')
+                    else:
+                        src.append(f'    tegb_block_sum_store<T, {nr}, {bs}>(rr, partials, (unsigned long long)gridDim.x * gridDim.y, '
+                                   '(unsigned long long)tby * gridDim.x + tbx);')
                 src.append('}')
                 src.append('#endif')
                 text = '\n'.join(src) + '\n'

@@ -273,6 +273,10 @@ struct tegb_program {
     cudaEvent_t ev_last = nullptr;    // recorded after the last launch sequence of this handle
     bool ev_valid = false;
     CUstream ev_stream = nullptr;
+    // measurement: CUDA events around the MAIN kernel of the last launch (tegb_program_enable_timing)
+    bool timing = false;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    bool timing_valid = false;
     int n_groups_total = 0;           // grouped programs with a peer: rows of the all-reduced [groups][outputs] result
     // grouped programs: what the last per-group prologue (uniform rows + tile classification) covered
     bool prep_valid = false;
@@ -304,6 +308,8 @@ struct tegb_program {
     void *d_tiles = nullptr;
     size_t tiles_bytes = 0;
     void *tiles_ord_ptr = nullptr;    // the launch-ordered copy inside d_tiles (plain tiled renders)
+    int *q_ulist = nullptr, *q_counters = nullptr;     // unresolved-row queue of the last plain tiled launch
+    int q_n_tx = 0, q_n_ty = 0, q_workers = 0;
     // per tile row / tile column: [min, max] of the box edges and sample abscissae (valid for ranges_grid)
     int *d_order = nullptr;       // [n_tiles] tile indices in launch order, then 2 counters
     size_t order_count = 0;
@@ -387,10 +393,45 @@ static int end_launch(tegb_program *p, CUstream st) {
     return TEGB_OK;
 }
 
+// measurement hooks around the main kernel of a launch (no-ops unless enabled; never inside a stream capture)
+static void time_begin(tegb_program *p, CUstream st) {
+    if (p->timing) { cudaEventRecord(p->ev_t0, (cudaStream_t)st); p->timing_valid = false; }
+}
+static void time_end(tegb_program *p, CUstream st) {
+    if (p->timing) { cudaEventRecord(p->ev_t1, (cudaStream_t)st); p->timing_valid = true; }
+}
+
+extern "C" int tegb_program_enable_timing(tegb_program *p, int on) {
+    if (!p) return fail(TEGB_ERR_INVALID, "tegb_program_enable_timing: null program");
+    std::lock_guard<std::recursive_mutex> lock(p->mu);
+    RT_CHECK(cudaSetDevice(p->device));
+    if (on && !p->ev_t0) {
+        RT_CHECK(cudaEventCreate(&p->ev_t0));
+        RT_CHECK(cudaEventCreate(&p->ev_t1));
+    }
+    p->timing = on != 0;
+    p->timing_valid = false;
+    return TEGB_OK;
+}
+
+extern "C" int tegb_program_main_kernel_ms(tegb_program *p, double *ms) {
+    if (!p || !ms) return fail(TEGB_ERR_INVALID, "tegb_program_main_kernel_ms: null argument");
+    std::lock_guard<std::recursive_mutex> lock(p->mu);
+    if (!p->timing || !p->timing_valid) return fail(TEGB_ERR_INVALID, "no timed launch (tegb_program_enable_timing, then launch)");
+    RT_CHECK(cudaSetDevice(p->device));
+    RT_CHECK(cudaEventSynchronize(p->ev_t1));
+    float f = 0;
+    RT_CHECK(cudaEventElapsedTime(&f, p->ev_t0, p->ev_t1));
+    *ms = f;
+    return TEGB_OK;
+}
+
 extern "C" void tegb_program_destroy(tegb_program *p) {
     if (!p) return;
     cudaSetDevice(p->device);
     if (p->ev_last) cudaEventDestroy(p->ev_last);
+    if (p->ev_t0) cudaEventDestroy(p->ev_t0);
+    if (p->ev_t1) cudaEventDestroy(p->ev_t1);
     for (void *q : p->d_in) if (q) cudaFree(q);
     for (void *q : p->d_out) if (q) cudaFree(q);
     if (p->u_stage) cudaFree(p->u_stage);
@@ -685,7 +726,9 @@ extern "C" int tegb_program_launch(tegb_program *p, const double *scalars, const
     }
     long long nn = n;
     args.push_back(&nn);
+    time_begin(p, st);
     CU_CHECK(drv::LaunchKernel(p->f_main, (unsigned)blocks, 1, 1, bs, 1, 1, 0, st, args.data(), nullptr));
+    time_end(p, st);
     g_launches++;
     if (p->d.reduce_outputs) {
         rc = finish_partials(p, (unsigned long long)blocks, out_ptrs[n_store], (cudaStream_t)st);
@@ -771,6 +814,20 @@ static int ensure_edges(tegb_program *p, const tegb_grid *g, CUstream st) {
     p->grid_valid = true;
     p->ranges_valid = false;
     return TEGB_OK;
+}
+
+// Blocks of a tiled render launch that serve the queue of unresolved rows (they come first in the grid, so they start in the
+// first wave): TEGB200_QUEUE_WORKERS per SM (default 2 of the 8 resident 128-thread blocks; the rest of the wave renders;
+// measured on the 4096^2 triangle: 2 -> 28.5 us, 4 -> 30.7 us, 6 -> 32.7 us for classification + value kernel).
+static int queue_workers(int device) {
+    static int per_sm = -1;
+    if (per_sm < 0) {
+        per_sm = 2;
+        if (const char *e = getenv("TEGB200_QUEUE_WORKERS")) per_sm = atoi(e) > 0 ? atoi(e) : 1;
+    }
+    int sms = 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { cudaGetLastError(); sms = 148; }
+    return sms * per_sm;
 }
 
 // Tile classification support (generated <name>_tiles kernels read this table): for every tile row (x axis, entries
@@ -1051,7 +1108,9 @@ static int groups_launch_impl(tegb_program *p, const void *const *group_ptrs, in
     } else {
         for (int k = 0; k < p->d.n_outputs; k++) { outs[k] = out_ptrs[k]; args.push_back(&outs[k]); }
     }
+    time_begin(p, st);
     CU_CHECK(drv::LaunchKernel(p->f_main, gx, gy, gz, bs, 1, 1, 0, st, args.data(), nullptr));
+    time_end(p, st);
     g_launches++;
     if (p->d.reduce_outputs) {
         rc = finish_group_partials(p, tiles, group_begin, (int)gz, out_ptrs[0], (cudaStream_t)st);
@@ -1184,14 +1243,19 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
         rc = ensure_ranges(p, g, n_txs, n_ty, tile_stride, tile_phase, (cudaStream_t)st);
         if (rc) return rc;
         const size_t n_tiles = (size_t)n_tx * n_ty;
-        if (n_tiles > p->order_count) {
+        const size_t n_sub = (size_t)n_txs * n_ty;                   // tiles of tile_cols columns (what is classified)
+        if (n_txs > 65535) return fail(TEGB_ERR_INVALID, "more than 65535 tiles per image row in one render launch");
+        if (n_sub > p->order_count) {
             RT_CHECK(cudaStreamSynchronize((cudaStream_t)st));
             if (p->d_order) { cudaFree(p->d_order); p->d_order = nullptr; p->order_count = 0; }
-            RT_CHECK(cudaMalloc((void **)&p->d_order, (n_tiles + 2) * sizeof(int)));
-            p->order_count = n_tiles;
+            // launch order [blocks] | 4 counters | unresolved-tile list [tiles]
+            RT_CHECK(cudaMalloc((void **)&p->d_order, (2 * n_sub + 4) * sizeof(int)));
+            p->order_count = n_sub;
         }
         int *d_counters = p->d_order + p->order_count;
-        RT_CHECK(cudaMemsetAsync(d_counters, 0, 2 * sizeof(int), (cudaStream_t)st));
+        int *d_ulist = d_counters + 4;
+        // counters: blocks filed from the front / from the back of the launch order, unresolved tiles, queue cursor
+        RT_CHECK(cudaMemsetAsync(d_counters, 0, 4 * sizeof(int), (cudaStream_t)st));
         targs.push_back(&p->d_ranges);
         targs.push_back(&res_y);
         targs.push_back(&n_tx);
@@ -1201,12 +1265,25 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
         targs.push_back(&d_tiles_ord);
         targs.push_back(&p->d_order);
         targs.push_back(&d_counters);
+        targs.push_back(&d_ulist);
         const unsigned tb = 128, tg = (unsigned)(((size_t)n_txs * n_ty + tb - 1) / tb);     // a thread per tile
         CU_CHECK(drv::LaunchKernel(p->f_tiles, tg, 1, 1, tb, 1, 1, 0, st, targs.data(), nullptr));
         g_launches++;
         p->tiles_ord_ptr = d_tiles_ord;
+        p->q_ulist = d_ulist;
+        p->q_counters = d_counters;
         args.push_back(&p->tiles_ord_ptr);
         args.push_back(&p->d_order);
+        args.push_back(&p->q_ulist);
+        args.push_back(&p->q_counters);
+        p->q_n_tx = n_tx;
+        p->q_n_ty = n_ty;
+        // image programs: dedicated blocks serve the queue of unresolved rows; programs with summed outputs walk their
+        // unresolved tiles inside the owning block (their partial sums stay tied to the block)
+        p->q_workers = p->d.reduce_outputs ? 0 : queue_workers(p->device);
+        args.push_back(&p->q_n_tx);
+        args.push_back(&p->q_n_ty);
+        args.push_back(&p->q_workers);
     }
     const int n_store = p->d.n_outputs - p->d.reduce_outputs;
     for (int k = 0; k < n_store; k++) { outs[k] = out_ptrs[k]; args.push_back(&outs[k]); }
@@ -1215,7 +1292,12 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
         if (rc) return rc;
         args.push_back(&p->d_partials);
     }
-    CU_CHECK(drv::LaunchKernel(p->f_main, gx, gy, 1, bs, 1, 1, 0, st, args.data(), nullptr));
+    time_begin(p, st);
+    if (p->d.n_tile_conds > 0)      // 1-D grid: the queue workers first, then one block per tile block
+        CU_CHECK(drv::LaunchKernel(p->f_main, (unsigned)p->q_workers + gx * gy, 1, 1, bs, 1, 1, 0, st, args.data(), nullptr));
+    else
+        CU_CHECK(drv::LaunchKernel(p->f_main, gx, gy, 1, bs, 1, 1, 0, st, args.data(), nullptr));
+    time_end(p, st);
     g_launches++;
     if (p->d.reduce_outputs) {
         rc = finish_partials(p, (unsigned long long)gx * gy, out_ptrs[n_store], (cudaStream_t)st);

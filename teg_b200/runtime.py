@@ -41,7 +41,7 @@ SYMBOLS = [
     'tegb_render_groups_launch_prepared', 'tegb_program_tile_table', 'tegb_peer_create', 'tegb_peer_connect',
     'tegb_peer_allreduce_sum', 'tegb_peer_error', 'tegb_peer_destroy', 'tegb_program_set_peer',
     'tegb_program_set_peer_groups',
-    'tegb_launch_count', 'tegb_reduce_workspace_bytes', 'tegb_reduce_sum', 'tegb_nccl_unique_id',
+    'tegb_launch_count', 'tegb_program_enable_timing', 'tegb_program_main_kernel_ms', 'tegb_reduce_workspace_bytes', 'tegb_reduce_sum', 'tegb_nccl_unique_id',
     'tegb_nccl_comm_create', 'tegb_nccl_comm_destroy', 'tegb_allreduce_sum', 'tegb_fma_peak',
 ]
 
@@ -95,6 +95,8 @@ def lib():
     L.tegb_peer_destroy.restype = None
     L.tegb_program_set_peer.argtypes = [vp, vp]
     L.tegb_program_set_peer_groups.argtypes = [vp, vp, i32, vp]
+    L.tegb_program_enable_timing.argtypes = [vp, i32]
+    L.tegb_program_main_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     L.tegb_launch_count.restype = i64
     L.tegb_reduce_workspace_bytes.argtypes = [i32, i64, i32]
     L.tegb_reduce_workspace_bytes.restype = ctypes.c_size_t
@@ -263,6 +265,16 @@ class Program:
         check(self._L.tegb_render_groups_prepare(self.handle, _ptr_array(group_ptrs), group_begin, group_count,
                                                  ctypes.byref(grid), ctypes.c_void_p(windows_ptr), max_rows, max_cols,
                                                  ctypes.c_void_p(stream)))
+
+    def enable_timing(self, on: bool = True) -> None:
+        """CUDA events around the main kernel of every launch of this handle (measurement)."""
+        check(self._L.tegb_program_enable_timing(self.handle, int(bool(on))))
+
+    def main_kernel_ms(self) -> float:
+        """Duration of the main kernel of the last launch (waits for it)."""
+        ms = ctypes.c_double()
+        check(self._L.tegb_program_main_kernel_ms(self.handle, ctypes.byref(ms)))
+        return ms.value
 
     def __del__(self):
         try:

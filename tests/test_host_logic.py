@@ -97,7 +97,7 @@ def test_nvrtc_compiles_generated_kernels_for_sm100a(scene, tmp_path, monkeypatc
     assert again.from_cache and again.cubin() == mod.cubin()
     if scene.startswith('tri'):
         ksr = generate(sch, 'float', 16, grid_args=[0, 1, 2, 3])
-        assert 'xe[nx + 1]' in ksr.source
+        assert 'xe[nx0 + r + 1]' in ksr.source
         runtime.Module(ksr.source)
 
 
