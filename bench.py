@@ -384,10 +384,34 @@ class TriRaster:
             except RuntimeError as e:
                 self.peers, self.peer_note = None, f'peer mailboxes unavailable ({e}): NCCL all-reduce instead'
         self.ev = {'primal': [], 'grad': []}
+        self.graph = None
 
-    def step(self, record: bool, buf: int = 0):
+    def capture(self):
+        """The step as ONE CUDA graph (both streams, classification, kernels, column sums, the fused peer exchange --
+        its sequence number lives on the device, so every replay is a new exchange).  A step is ~10 small launches plus
+        stream bookkeeping: issued one by one from Python they cost more host time than the GPU needs to run them."""
+        torch, ctx = self.ctx.torch, self.ctx
+        if ctx.world > 1 and self.peers is None:
+            return None                     # the NCCL fallback is not captured
+        cap = torch.cuda.Stream(ctx.dev)
+        cap.wait_stream(ctx.stream)
+        with torch.cuda.stream(cap):
+            self.step(False, 0, cap)
+        ctx.stream.wait_stream(cap)
+        ctx.sync_all()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=cap):
+            self.step(False, 0, torch.cuda.current_stream(ctx.dev))
+        self.graph = g
+        return g
+
+    def step(self, record: bool, buf: int = 0, stream=None):
+        if self.graph is not None and not record and buf == 0 and stream is None:
+            self.graph.replay()             # one submission: both pipelines, the fused peer exchange included
+            return
         ctx, torch = self.ctx, self.ctx.torch
-        stream, side = ctx.stream, self.side
+        stream = ctx.stream if stream is None else stream
+        side = self.side
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
         fork, join = self.forks[buf], self.joins[buf]
         fork.record(stream)
@@ -443,13 +467,34 @@ class TriRaster:
         out['ok'] = bool(all(v for k, v in out.items() if k.endswith('_ok') or k == 'same_bits_on_every_rank'))
         return out
 
-    def measure(self, steps: int, warmup: int):
+    def measure(self, steps: int, warmup: int, use_graph: bool = True):
+        """phases: a few steps launch by launch with events around each pipeline; then the timed steps -- replays of the
+        captured graph (use_graph) or launch-by-launch steps."""
+        from teg_b200 import runtime
         ctx = self.ctx
-        ms, launches = ctx.timed_steps(lambda rec: self.step(rec), steps, warmup)
-        n_total = ctx.sum_over_ranks(float(self.n_local))
+        for _ in range(max(warmup, 3)):
+            self.step(False)
+        ctx.sync_all()
+        for k in range(5):
+            ctx.flush.fill_(k)
+            self.step(True)
+        ctx.sync_all()
         phase = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in self.ev.items() if v}
+        l0 = runtime.launch_count()
+        self.step(True)
+        per_step = runtime.launch_count() - l0
+        ctx.sync_all()
+        if use_graph:
+            self.capture()
+        ms, launches = ctx.timed_steps(lambda rec: self.step(False), steps, max(warmup, 3))
+        if self.graph is not None:
+            launches = per_step * steps            # a replay runs the step's kernels without passing the launch counter
+        n_total = ctx.sum_over_ranks(float(self.n_local))
         return {'ms_per_step': ms, 'value': n_total / (ms * 1e-3), 'unit': 'integral evals/s', 'gpu_launches': int(launches),
-                'phase_ms': phase, 'instances_all_ranks': int(n_total)}
+                'phase_ms': phase, 'instances_all_ranks': int(n_total), 'cuda_graph': self.graph is not None,
+                'phase_note': 'phases timed launch by launch before the timed region (the two pipelines run concurrently '
+                              'on two streams: their times overlap)' + ('; the timed steps replay one CUDA graph'
+                                                                         if self.graph is not None else '')}
 
     def close(self):
         if self.peers is not None:
@@ -804,6 +849,7 @@ def main() -> int:
     ap.add_argument('--cpu-seconds', type=float, default=2.5, help='target duration of one reference-arm step')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--graph', type=int, default=1, help='1: the timed steps replay ONE captured CUDA graph of the step')
     ap.add_argument('--no-extras', action='store_true', help='headline only: no "workloads" records (profiling runs)')
     ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'], help='working precision of the programs')
     ap.add_argument('--maxreg', type=int, default=0, help='experiment: --maxrregcount for the generated kernels')
@@ -841,7 +887,7 @@ def main() -> int:
         ctx.sync_all()
         if rank == 0:
             sampler.start()
-        hm = head.measure(args.steps, 0)
+        hm = head.measure(args.steps, args.warmup, use_graph=bool(args.graph))
         # the timed region lasts only milliseconds: keep the same steps running (untimed) for ~1.2 s so that nvidia-smi
         # (100 ms period) sees the clocks and throttle reasons under this very load.  The number of extra steps is
         # derived from the all-reduced time, i.e. it is the same on every rank (the steps contain a collective).
@@ -863,7 +909,7 @@ def main() -> int:
         ctx.sync_all()
         if rank == 0:
             sampler.start()
-        hm = head.measure(args.steps, args.warmup)
+        hm = head.measure(args.steps, args.warmup, bool(args.graph))
         n_hold = int(min(5000, max(20, 1200.0 / max(hm['ms_per_step'], 1e-3))))
         for k in range(n_hold):
             head.step(False)
@@ -942,7 +988,7 @@ def main() -> int:
         if tri is not None:
             try:
                 mt = MultiTri(ctx, 'weak')
-                rec = mt.measure(k_x, 3)
+                rec = mt.measure(k_x, 3, bool(args.graph))
                 rec['check'] = mt.check()
                 rec['scaling'] = 'weak'
                 rec['allreduce'] = 'fused into the per-triangle column sums over NVLink peer memory' if mt.peers is not None \
@@ -960,7 +1006,7 @@ def main() -> int:
                                    ('multi_tri_4096_strong', lambda: MultiTri(ctx, 'strong'))):
                     try:
                         w = ctor()
-                        rec = w.measure(k_x, 3)
+                        rec = w.measure(k_x, 3, bool(args.graph))
                         rec['check'] = w.check()
                         rec['scaling'] = 'strong'
                         rec['res_total'] = [res, res]
@@ -1171,8 +1217,7 @@ def main() -> int:
                         'parallelism': f'rows sharded over {world} GPU(s) ({args.shard if world > 1 else "all"}), one '
                                        f'all-reduce of the gradient per step ({allreduce_txt})'},
         'allreduce_note': (tri.peer_note if tri is not None else head.peer_note), 'phase_ms': hm['phase_ms'],
-        'phase_note': 'the value and the gradient pipelines run concurrently on two streams: their phase times overlap '
-                      'and each is longer than the same pipeline alone' if tri is not None else hm.get('phase_note'),
+        'phase_note': hm.get('phase_note'), 'cuda_graph': hm.get('cuda_graph'),
         'roofline': roofline, 'roofline_dense': roofline_dense, 'cpu_baseline': cpu, 'e2e': e2e, 'e2e_grad_only': e2e_grad,
         'gpu_launches': int(hm['gpu_launches']), 'clocks': clocks, 'check': check, 'workloads': workloads,
     }

@@ -509,7 +509,29 @@ struct PeerView {
     int rank, world, maxv;
     volatile int *err;                  // (pinned host memory, mapped) set when a peer did not answer within the time-out
     unsigned long long timeout_ns;      // 0: wait for ever
+    // The sequence number of the exchange lives on the DEVICE (not in a launch argument): every block of an exchanging
+    // kernel reads seq = *d_seq + 1, the last block to finish publishes it.  Stream order makes the next launch see it,
+    // so a captured CUDA graph that contains an exchange can be replayed (each replay is a new exchange).
+    unsigned long long *d_seq;
+    unsigned int *d_done;
 };
+
+__device__ __forceinline__ unsigned long long peer_seq_begin(const PeerView &v) {
+    return *(volatile unsigned long long *)v.d_seq + 1ull;
+}
+
+// called by every block of the exchanging kernel when it is done (all threads)
+__device__ __forceinline__ void peer_seq_end(const PeerView &v, unsigned long long seq) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(v.d_done, 1u) == gridDim.x - 1u) {
+            *(volatile unsigned int *)v.d_done = 0u;
+            __threadfence();
+            *(volatile unsigned long long *)v.d_seq = seq;
+        }
+    }
+}
 
 __device__ __forceinline__ unsigned long long tegb_globaltimer_ns() {
     unsigned long long t;
@@ -560,8 +582,9 @@ __device__ __forceinline__ T peer_exchange_sum(const PeerView &v, int col, T val
 // column sums fused with the peer all-reduce: out[c] = sum over ranks (in rank order) of this rank's column sum
 template <typename T>
 __global__ void __launch_bounds__(RED_THREADS) colsum_stage2_peer(const T *partials, long long n_blocks, T *out,
-                                                                  PeerView view, unsigned long long seq) {
+                                                                  PeerView view) {
     __shared__ T smem[32];
+    const unsigned long long seq = peer_seq_begin(view);
     const int c = blockIdx.x;
     T acc = 0;
     for (long long i = threadIdx.x; i < n_blocks; i += RED_THREADS) acc = acc + partials[(long long)c * n_blocks + i];
@@ -570,15 +593,19 @@ __global__ void __launch_bounds__(RED_THREADS) colsum_stage2_peer(const T *parti
         const T total = peer_exchange_sum<T>(view, c, s, seq);
         if (threadIdx.x == 0) out[c] = total;
     }
+    peer_seq_end(view, seq);
 }
 
-// stand-alone form: in-place all-reduce of a device vector (count <= maxv), one warp per element
+// stand-alone form: in-place all-reduce of a device vector (count <= maxv), one warp per element (grid = count blocks)
 template <typename T>
-__global__ void peer_allreduce_kernel(T *buf, int count, PeerView view, unsigned long long seq) {
+__global__ void peer_allreduce_kernel(T *buf, int count, PeerView view) {
+    const unsigned long long seq = peer_seq_begin(view);
     const int c = blockIdx.x;
-    if (c >= count) return;
-    const T total = peer_exchange_sum<T>(view, c, buf[c], seq);
-    if (threadIdx.x == 0) buf[c] = total;
+    if (c < count) {
+        const T total = peer_exchange_sum<T>(view, c, buf[c], seq);
+        if (threadIdx.x == 0) buf[c] = total;
+    }
+    peer_seq_end(view, seq);
 }
 
 struct tegb_peer {
@@ -587,7 +614,6 @@ struct tegb_peer {
     void *d_box = nullptr;
     size_t box_bytes = 0;
     std::vector<void *> opened;
-    std::atomic<unsigned long long> seq{0};
     int *h_err = nullptr;               // pinned + mapped: kernels raise it, the host reads it without synchronising
 };
 
@@ -656,14 +682,13 @@ static void sum_columns(const T *partials, int n_cols, unsigned long long n_bloc
 template <typename T>
 static void sum_columns_peer(const T *partials, int n_cols, unsigned long long n_blocks, T *out, T *slices, cudaStream_t st,
                              tegb_peer *peer) {
-    const unsigned long long seq = ++peer->seq;
     if (n_blocks >= 16384 && slices) {
         const long long chunk = (long long)((n_blocks + RED_SLICES - 1) / RED_SLICES);
         colsum_slices<T><<<dim3(RED_SLICES, n_cols), RED_THREADS, 0, st>>>(partials, (long long)n_blocks, chunk, slices);
-        colsum_stage2_peer<T><<<n_cols, RED_THREADS, 0, st>>>(slices, (long long)RED_SLICES, out, peer->view, seq);
+        colsum_stage2_peer<T><<<n_cols, RED_THREADS, 0, st>>>(slices, (long long)RED_SLICES, out, peer->view);
         g_launches += 2;
     } else {
-        colsum_stage2_peer<T><<<n_cols, RED_THREADS, 0, st>>>(partials, (long long)n_blocks, out, peer->view, seq);
+        colsum_stage2_peer<T><<<n_cols, RED_THREADS, 0, st>>>(partials, (long long)n_blocks, out, peer->view);
         g_launches++;
     }
 }
@@ -909,8 +934,9 @@ static int ensure_ranges(tegb_program *p, const tegb_grid *g, int n_tx, int n_ty
 template <typename T>
 __global__ void __launch_bounds__(RED_THREADS) colsum_groups_peer(const T *partials, long long n_tiles, int group_begin,
                                                                   int group_count, int K, const int *__restrict__ local_of,
-                                                                  T *out, PeerView view, unsigned long long seq) {
+                                                                  T *out, PeerView view) {
     __shared__ T smem[32];
+    const unsigned long long seq = peer_seq_begin(view);
     const int c = blockIdx.x;               // column of the all-reduced result: (global group, component)
     const int g = c / K, k = c - g * K;
     const int lg = local_of ? local_of[g] : g;       // this rank's index of the group (-1: not launched here)
@@ -924,6 +950,7 @@ __global__ void __launch_bounds__(RED_THREADS) colsum_groups_peer(const T *parti
         const T total = peer_exchange_sum<T>(view, c, s, seq);
         if (threadIdx.x == 0) out[c] = total;
     }
+    peer_seq_end(view, seq);
 }
 
 static int finish_group_partials(tegb_program *p, unsigned long long tiles, int group_begin, int group_count, void *out,
@@ -933,13 +960,12 @@ static int finish_group_partials(tegb_program *p, unsigned long long tiles, int 
         const int total = p->n_groups_total * K;
         if (total > p->peer->view.maxv) return fail(TEGB_ERR_INVALID, "peer mailbox smaller than the [groups][outputs] gradient");
         if (peer_failed(p->peer)) return TEGB_ERR_PEER;
-        const unsigned long long seq = ++p->peer->seq;
         if (p->d.elem_size == 4)
             colsum_groups_peer<float><<<total, RED_THREADS, 0, st>>>((const float *)p->d_partials, (long long)tiles, group_begin,
-                                                                     group_count, K, p->group_map, (float *)out, p->peer->view, seq);
+                                                                     group_count, K, p->group_map, (float *)out, p->peer->view);
         else
             colsum_groups_peer<double><<<total, RED_THREADS, 0, st>>>((const double *)p->d_partials, (long long)tiles, group_begin,
-                                                                      group_count, K, p->group_map, (double *)out, p->peer->view, seq);
+                                                                      group_count, K, p->group_map, (double *)out, p->peer->view);
         g_launches++;
         RT_CHECK(cudaGetLastError());
         return TEGB_OK;
@@ -1382,10 +1408,14 @@ extern "C" int tegb_peer_create(int rank, int world, int max_values, int device,
     tegb_peer *p = new tegb_peer();
     p->device = device;
     p->view.rank = rank; p->view.world = world; p->view.maxv = max_values;
-    p->box_bytes = sizeof(PeerSlot) * 2 * (size_t)world * max_values;
+    // mailbox slots, then this rank's sequence number and its block counter
+    const size_t slots_bytes = sizeof(PeerSlot) * 2 * (size_t)world * max_values;
+    p->box_bytes = slots_bytes + 64;
     if (cudaMalloc(&p->d_box, p->box_bytes) != cudaSuccess) { delete p; return fail(TEGB_ERR_CUDA, "cudaMalloc(mailbox) failed"); }
     cudaMemset(p->d_box, 0, p->box_bytes);
     cudaDeviceSynchronize();
+    p->view.d_seq = (unsigned long long *)((char *)p->d_box + slots_bytes);
+    p->view.d_done = (unsigned int *)((char *)p->d_box + slots_bytes + 16);
     if (cudaHostAlloc((void **)&p->h_err, sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
         cudaFree(p->d_box); delete p;
         return fail(TEGB_ERR_CUDA, "cudaHostAlloc(peer error flag) failed");
@@ -1435,10 +1465,9 @@ extern "C" int tegb_peer_allreduce_sum(tegb_peer *p, void *buf, int count, int e
     if (count == 0) return TEGB_OK;
     if (peer_failed(p)) return TEGB_ERR_PEER;
     RT_CHECK(cudaSetDevice(p->device));
-    const unsigned long long seq = ++p->seq;
     const int tb = 32, tg = count;
-    if (elem_size == 4) peer_allreduce_kernel<float><<<tg, tb, 0, (cudaStream_t)stream>>>((float *)buf, count, p->view, seq);
-    else peer_allreduce_kernel<double><<<tg, tb, 0, (cudaStream_t)stream>>>((double *)buf, count, p->view, seq);
+    if (elem_size == 4) peer_allreduce_kernel<float><<<tg, tb, 0, (cudaStream_t)stream>>>((float *)buf, count, p->view);
+    else peer_allreduce_kernel<double><<<tg, tb, 0, (cudaStream_t)stream>>>((double *)buf, count, p->view);
     RT_CHECK(cudaGetLastError());
     g_launches++;
     return TEGB_OK;

@@ -31,6 +31,28 @@ BOX = ('x_lb', 'x_ub', 'y_lb', 'y_ub')
 PARAMS = ('px0', 'py0', 'px1', 'py1', 'px2', 'py2', 'col')
 
 
+def select_groups(windows, classes: Sequence[Tuple[int, int]], rows: Tuple[int, int]):
+    """The groups a rank holds: those whose pixel windows reach into its rows [rows[0], rows[1]).
+
+    windows: int array [K, 4] = (row_begin, row_end, col_begin, col_end); classes: ranges of global group indices with
+    pairwise disjoint windows.  Returns (ids, local_classes, local_of): the held groups' global indices class by class
+    (so every class is a contiguous LOCAL range, possibly empty and then dropped), and the inverse map [K] (-1 = not
+    held) the fused all-reduce uses to find a global group's local column."""
+    w = np.asarray(windows).astype(np.int64)
+    r0, r1 = int(rows[0]), int(rows[1])
+    hit = (w[:, 0] < r1) & (w[:, 1] > r0) & (w[:, 2] < w[:, 3]) & (w[:, 0] < w[:, 1])
+    ids, local_classes = [], []
+    for a, b in classes:
+        mine = [k for k in range(a, b) if hit[k]]
+        if mine:
+            local_classes.append((len(ids), len(ids) + len(mine)))
+            ids.extend(mine)
+    local_of = np.full(len(w), -1, dtype=np.int32)
+    if ids:
+        local_of[np.asarray(ids, dtype=np.int64)] = np.arange(len(ids), dtype=np.int32)
+    return ids, local_classes, local_of
+
+
 class MultiTriangleRasterizer:
     def __init__(self, primal: Program, grad: Program, res: int, bands: int = 1, rank: int = 0,
                  num_samples: int = 16, device: int = 0, float_width: str = 'float', cull: bool = True,
@@ -88,18 +110,10 @@ class MultiTriangleRasterizer:
         w = np.asarray(windows.cpu() if torch.is_tensor(windows) else windows).astype(np.int64)
         self.K = int(verts.shape[0])
         r0, r1 = self.rows
-        hit = (w[:, 0] < r1) & (w[:, 1] > r0) & (w[:, 2] < w[:, 3])
-        ids, local_classes = [], []
-        for a, b in classes:
-            mine = [k for k in range(a, b) if hit[k]]
-            if mine:
-                local_classes.append((len(ids), len(ids) + len(mine)))
-                ids.extend(mine)
+        ids, local_classes, local_of = select_groups(w, classes, self.rows)
         self.K_local = len(ids)
         self.identity = ids == list(range(self.K))        # every group is held, in the global order
         self.ids = torch.as_tensor(np.asarray(ids, dtype=np.int64), device=self.dev)
-        local_of = np.full(self.K, -1, dtype=np.int32)
-        local_of[np.asarray(ids, dtype=np.int64)] = np.arange(self.K_local, dtype=np.int32)
         self.local_of = torch.as_tensor(local_of, device=self.dev)
         self.classes = local_classes
         # structure of arrays: one contiguous [K_local] tensor per parameter

@@ -65,12 +65,40 @@ def _worker(rank, world, port, out_dir):
         dist.all_reduce(w64)
     torch.cuda.synchronize()
     peers.check()
+    # an exchange inside a captured CUDA graph: every replay is a NEW exchange (the sequence number lives on the device),
+    # so replays with changing inputs return the current sums, not a stale mailbox
+    gbuf = torch.zeros(8, dtype=torch.float32, device=f'cuda:{rank}')
+    gsrc = torch.zeros(8, dtype=torch.float32, device=f'cuda:{rank}')
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        gbuf.copy_(gsrc)
+        peers.allreduce_(gbuf, side.cuda_stream)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        gbuf.copy_(gsrc)
+        peers.allreduce_(gbuf, torch.cuda.current_stream().cuda_stream)
+    graph_ok = True
+    for it in range(6):
+        gsrc.copy_(torch.arange(8, dtype=torch.float32, device=f'cuda:{rank}') * (it + 1) + rank)
+        want_g = gsrc.clone()
+        if world > 1:
+            dist.all_reduce(want_g)
+        if rank == it % world:
+            torch.cuda._sleep(20_000_000)                        # ranks out of step
+        graph.replay()
+        torch.cuda.synchronize()
+        graph_ok = graph_ok and bool(torch.equal(gbuf, want_g))
+    peers.check()
     peers.detach(pr.prog)
     again = pr.run(stream).clone()
     torch.cuda.synchronize()
     np.save(os.path.join(out_dir, f'peer_{rank}.npy'), outs[0].cpu().numpy())
     np.save(os.path.join(out_dir, f'ref_{rank}.npy'), ref.cpu().numpy())
-    ok = (torch.equal(again, local) and torch.equal(v32, w32) and torch.allclose(v64, w64, rtol=1e-15, atol=0))
+    ok = (graph_ok and torch.equal(again, local) and torch.equal(v32, w32) and
+          torch.allclose(v64, w64, rtol=1e-15, atol=0))
     np.save(os.path.join(out_dir, f'ok_{rank}.npy'), np.array([int(ok)]))
     peers.close()
     dist.destroy_process_group()

@@ -468,3 +468,38 @@ def test_adding_zero_to_a_negative_zero_is_not_folded_away():
     assert d2.nodes[d2.outputs[0]].op == 'mul'
     d3 = build_dag(from_teg(t + Const(0), [t], name='t0'))
     assert d3.nodes[d3.outputs[0]].op == 'add'
+
+
+def test_multi_triangle_scene_classes_and_group_selection():
+    """Config 5 host logic: nine window-disjoint classes whatever the number of bands (the class comes from the GLOBAL
+    grid row), and a rank keeps exactly the triangles whose windows reach into its rows, class by class."""
+    from teg_b200.raster import select_groups
+    from teg_b200.workloads import multi_triangle_scene, windows_disjoint
+    for bands in (1, 2, 3):
+        sc = multi_triangle_scene(bands=bands, res=512)
+        K = sc['verts'].shape[0]
+        assert K == 256 * bands and len(sc['classes']) == 9
+        assert sc['classes'][0][0] == 0 and sc['classes'][-1][1] == K
+        assert all(a1 == b0 for (_, a1), (b0, _) in zip(sc['classes'], sc['classes'][1:]))
+        assert all(windows_disjoint(sc['windows'][a:b]) for a, b in sc['classes'])
+        w = sc['windows']
+        seen = np.zeros(K, dtype=int)
+        for rank in range(bands):
+            rows = (512 * rank, 512 * (rank + 1))
+            ids, local_classes, local_of = select_groups(w, sc['classes'], rows)
+            assert sorted(ids) == [k for k in range(K) if w[k][0] < rows[1] and w[k][1] > rows[0]]
+            assert all(local_of[g] == j for j, g in enumerate(ids)) and (local_of >= 0).sum() == len(ids)
+            # local classes are contiguous, cover the held groups, and keep the class order
+            assert local_classes[0][0] == 0 and local_classes[-1][1] == len(ids)
+            cls_of = {g: c for c, (a, b) in enumerate(sc['classes']) for g in range(a, b)}
+            order = [cls_of[g] for g in ids]
+            assert order == sorted(order)
+            seen[ids] += 1
+        assert seen.min() >= 1                                   # every triangle is held by some rank
+        assert bands == 1 or seen.max() == 2                     # windows across a band boundary: held by both
+    # strong scaling: one band split into row slices
+    sc = multi_triangle_scene(bands=1, res=512)
+    held = [set(select_groups(sc['windows'], sc['classes'], (128 * r, 128 * (r + 1)))[0]) for r in range(4)]
+    assert set().union(*held) == set(range(256)) and all(len(h) < 256 for h in held)
+    ids, lc, lo = select_groups(sc['windows'], sc['classes'], (0, 0))
+    assert ids == [] and lc == [] and (lo == -1).all()
