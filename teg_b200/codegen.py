@@ -1582,6 +1582,64 @@ class Emitter:
                     # one row per warp at a time; surplus workers leave at once; pixels are written in place, so results
                     # do not depend on who serves an item.  Programs with summed outputs keep the walk inside the owning
                     # block (all its warps share its unresolved tiles, below): their partial sums stay tied to the block.
+                    per_tile_sums = bool(nr) and self.tile_cols == 32
+                    if per_tile_sums:
+                        # Programs with summed outputs: one partial sum per TILE (slot = the tile's index), so the sums
+                        # do not depend on who computes a tile either.  Resolved tiles: their own warp (warp-level
+                        # fixed-order sum, no block barrier).  Unresolved tiles: a queue of tiles served by the worker
+                        # blocks, all warps of a worker share the rows of its tile and the block adds up in a fixed order.
+                        q = []
+                        q.append('    if (blockIdx.x < (unsigned int)n_workers) {')
+                        q.append('        __shared__ int q_next;')
+                        q.append('        const int warp_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;')
+                        q.append('        const int q_nu = queue[2];                          // unresolved tiles (classification kernel)')
+                        q.append('        if ((int)blockIdx.x >= q_nu) return;                  // more workers than tiles')
+                        q.append('        for (;;) {')
+                        q.append('            __syncthreads();')
+                        q.append('            if (threadIdx.x == 0) q_next = atomicAdd(&queue[3], 1);')
+                        q.append('            __syncthreads();')
+                        q.append('            const int q_u = q_next;')
+                        q.append('            if (q_u >= q_nu) break;                            // block-uniform')
+                        q.append('            const unsigned int q_e = (unsigned int)ulist[q_u];')
+                        q.append('            const int q_ty = (int)(q_e >> 16), q_txs = (int)(q_e & 0xffffu);')
+                        q.append('            const int q_rel0 = (q_ty * row_stride + row_phase) * tile_rows;')
+                        q.append('            const int q_rows = min(tile_rows, n_rows - q_rel0);')
+                        q.append(f'            T q_rr[{nr}];')
+                        q.append(f'            for (int k = 0; k < {nr}; k++) q_rr[k] = {zero};')
+                        q.append('            const int ny = q_txs * 32 + lane_;')
+                        q.append('            const bool live = ny < res_y;')
+                        q.append('            const int nyc = live ? ny : 0;')
+                        q.append('            const T ye_lo = ye[nyc], ye_hi = ye[nyc + 1];')
+                        qloads = dict(loads)
+                        for k, a in enumerate(tile):
+                            q.append(f'            const T tile{k} = {literal("2", T)};')
+                            q.append(f'            (void)tile{k};')
+                            qloads[a] = f'tile{k}'
+                        q.append('            #pragma unroll 1')
+                        q.append(f'            for (int q_r = warp_; q_r < q_rows; q_r += {bs // 32}) {{')
+                        q.append('                const int q_nx = row0 + q_rel0 + q_r;')
+                        q.append('                const T x_lo = xe[q_nx], x_hi = xe[q_nx + 1];')
+                        q.append('                const long long i = (long long)(q_ty * tile_rows + q_r) * res_y + ny;')
+                        q.append('                (void)i;')
+                        q.append(f'                T res[{K}];')
+                        q.append(f'                for (int k = 0; k < {K}; k++) res[k] = {zero};')
+                        qcall = ', '.join((['live'] if coop else []) + [qloads[a] for a in varying] +
+                                          inst('(long long)q_nx * res_y + ny') + ['res'])
+                        if coop:
+                            q.append(f'                {name}_instance({qcall});')
+                        else:
+                            q.append(f'                if (live) {name}_instance({qcall});')
+                        for k in range(ns_out):
+                            q.append(f'                if (live) out{k}[i] = res[{k}];')
+                        for j in range(nr):
+                            q.append(f'                if (live) q_rr[{j}] = q_rr[{j}] + res[{ns_out + j}];')
+                        q.append('            }')
+                        q.append(f'            tegb_block_sum_store<T, {nr}, {bs}>(q_rr, partials, (unsigned long long)n_tiles, '
+                                 '(unsigned long long)q_ty * n_txs + q_txs);')
+                        q.append('        }')
+                        q.append('        return;')
+                        q.append('    }')
+                        src[QUEUE_MARK:QUEUE_MARK] = q
                     if nr == 0:
                         q = []
                         q.append('    if (blockIdx.x < (unsigned int)n_workers) {')
@@ -1671,7 +1729,7 @@ class Emitter:
                             row_loop(f'{name}_tile_{label}', b_coop, '        ', unroll=1 if b_coop else 4)
                         src.append('    }')
                         first = False
-                    if nr:
+                    if nr and not per_tile_sums:
                         # unresolved tiles of this block, shared by ALL its warps (warp w takes rows w, w + W, ... of each)
                         mine_u = ' || '.join(f'tile{k} == {literal("2", T)}' for k in range(len(tile)))
                         src.append(f'    if (__syncthreads_or({mine_u})) {{')
@@ -1696,7 +1754,13 @@ class Emitter:
                     row_loop(f'{name}_instance', coop, '    ')
                 if nr:
                     # the partial of a tile lives at the tile's own index: the sums do not depend on the block order
-                    if tile:
+                    if tile and self.tile_cols == 32:
+                        # one partial per tile; unresolved tiles are summed by the worker that served them
+                        unres = ' || '.join(f'tile{k} == {literal("2", T)}' for k in range(len(tile)))
+                        src.append(f'    if (!({unres}))                              // warp-uniform')
+                        src.append(f'        tegb_warp_sum_store<T, {nr}>(rr, partials + ((unsigned long long)tby * n_txs + tbx * TEGB_TILE_SUB '
+                                   '+ (threadIdx.x >> 5)), (unsigned long long)n_tiles);')
+                    elif tile:
                         src.append(f'    tegb_block_sum_store<T, {nr}, {bs}>(rr, partials, (unsigned long long)n_tx * n_ty, '
                                    '(unsigned long long)tby * n_tx + tbx);')
                     else:

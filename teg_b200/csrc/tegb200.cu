@@ -1306,15 +1306,21 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
         p->q_n_ty = n_ty;
         // image programs: dedicated blocks serve the queue of unresolved rows; programs with summed outputs walk their
         // unresolved tiles inside the owning block (their partial sums stay tied to the block)
-        p->q_workers = p->d.reduce_outputs ? 0 : queue_workers(p->device);
+        // (programs with summed outputs and 32-column tiles: a queue of whole tiles, one partial sum per tile; wider
+        // tiles keep the walk inside the owning block)
+        p->q_workers = (p->d.reduce_outputs && p->d.tile_cols != 32) ? 0
+                       : queue_workers(p->device) * (p->d.reduce_outputs ? 2 : 1);
         args.push_back(&p->q_n_tx);
         args.push_back(&p->q_n_ty);
         args.push_back(&p->q_workers);
     }
     const int n_store = p->d.n_outputs - p->d.reduce_outputs;
     for (int k = 0; k < n_store; k++) { outs[k] = out_ptrs[k]; args.push_back(&outs[k]); }
+    // partial sums: one per block, or one per tile for tiled programs with 32-column tiles
+    const unsigned long long n_partials = (p->d.n_tile_conds > 0 && p->d.tile_cols == 32)
+                                              ? (unsigned long long)gx * (bs / 32) * gy : (unsigned long long)gx * gy;
     if (p->d.reduce_outputs) {
-        rc = ensure_partials(p, (unsigned long long)gx * gy);
+        rc = ensure_partials(p, n_partials);
         if (rc) return rc;
         args.push_back(&p->d_partials);
     }
@@ -1326,7 +1332,7 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
     time_end(p, st);
     g_launches++;
     if (p->d.reduce_outputs) {
-        rc = finish_partials(p, (unsigned long long)gx * gy, out_ptrs[n_store], (cudaStream_t)st);
+        rc = finish_partials(p, n_partials, out_ptrs[n_store], (cudaStream_t)st);
         if (rc) return rc;
     }
     return end_launch(p, st);

@@ -62,6 +62,27 @@ static __device__ __forceinline__ void tegb_block_sum_store(const T (&v)[K], T* 
     tegb_block_sum_store<T, K, BLOCK>(v, partials, nblk, blk);
 }
 
+/* Fixed-order sum of K per-thread values over the 32 lanes of a warp (shuffle tree); lane 0 stores component k at
+ * dst[k * stride].  Tiled render programs keep one partial sum per tile (a warp's 32 columns x the tile's rows): the
+ * tile, not the block that happened to compute it, identifies the slot.  Warps whose lanes are all exactly zero skip
+ * the shuffles (adding zeros cannot change a sum).  Reached by all 32 lanes. */
+template <typename T, int K>
+static __device__ __forceinline__ void tegb_warp_sum_store(const T (&v)[K], T* __restrict__ dst, const unsigned long long stride) {
+    bool nz = false;
+#pragma unroll
+    for (int k = 0; k < K; k++) nz = nz || (v[k] != (T)0);
+    const bool any = __any_sync(0xffffffffu, nz);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        T s = v[k];
+        if (any) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s = s + __shfl_down_sync(0xffffffffu, s, off);
+        }
+        if ((threadIdx.x & 31u) == 0) dst[(unsigned long long)k * stride] = s;
+    }
+}
+
 /* Teams: TEAM consecutive threads (a power of two) cooperate on one instance by splitting its OUTERMOST sample loop.
  * The reference folds the outer terms left to right (rectangular_rule.template.c:4-9), and so does the team: the
  * loop advances in chunks of TEAM * U consecutive samples, member r evaluates the U samples chunk + r * U + u (its

@@ -3,7 +3,7 @@ cd "$GRAFT_REPO_ROOT" || exit 1
 O=gpurun_out
 N=8
 P=29530
-for v in "" "--allreduce nccl" "--shard band" "--scaling strong"; do
+for v in "" "--graph 0" "--allreduce nccl" "--shard band" "--scaling strong"; do
 P=$((P+1))
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P bench.py --gpus $N --steps 40 --warmup 5 --no-cpu --no-e2e --no-extras $v > $O/tmp_n8.json 2>$O/tmp_n8.err
 python - "$v" <<'PY'
