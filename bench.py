@@ -979,6 +979,38 @@ def main() -> int:
                     'what': 'same step; the image stays on the device, only the all-reduced gradient vector is copied to '
                             'pinned host memory every step'}
 
+    if not args.no_e2e and tri is None:
+        # multi_tri headline end to end: the step through MultiTriangleRasterizer.forward / backward (grouped C-ABI
+        # launches), the triangle parameters go to the device and the image band + the [K, 7] gradient come back to
+        # pinned host memory, every step
+        mt = head
+        h_img = torch.empty((mt.img.shape[1], res), dtype=torch.float32).pin_memory()
+        h_g = torch.empty((mt.K, 7), dtype=torch.float32).pin_memory()
+        h_par = torch.as_tensor(np.concatenate([mt.scene['verts'], mt.scene['col'][:, None]], axis=1),
+                                dtype=torch.float32).pin_memory()
+        d_par = torch.empty((mt.K, 7), dtype=torch.float32, device=dev)
+
+        def mt_e2e(k_steps):
+            for _ in range(k_steps):
+                d_par.copy_(h_par, non_blocking=True)
+                mt.r.update_params(d_par[:, :6], d_par[:, 6].contiguous())
+                mt.step(False)
+                h_img.copy_(mt.img[0], non_blocking=True)
+                h_g.copy_(mt.g, non_blocking=True)
+            torch.cuda.synchronize(dev)
+        mt_e2e(2)
+        ctx.sync_all()
+        k_e2e = max(4, min(args.steps, 10))
+        t0 = time.perf_counter()
+        mt_e2e(k_e2e)
+        ctx.sync_all()
+        dt = ctx.max_over_ranks(time.perf_counter() - t0)
+        e2e = {'value': hm['pairs_all_ranks'] * k_e2e / dt, 'unit': 'integral evals/s', 'h2d_bytes_per_step': int(h_par.numel() * 4),
+               'd2h_bytes_per_step': int(h_img.numel() * 4 + h_g.numel() * 4), 'steps': k_e2e, 'ms_per_step': dt / k_e2e * 1e3,
+               'api': 'MultiTriangleRasterizer.update_params / forward / backward (tegb_render_groups_* C-ABI calls, one CUDA '
+                      'graph replay per step); parameters copied in, image band + [K, 7] gradient copied to pinned host '
+                      'memory every step'}
+
     # ----------------------------------------------------------------------------------- other workloads
     workloads = {}
     if not args.no_extras:
