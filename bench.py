@@ -504,8 +504,9 @@ class TriRaster:
 
 # ------------------------------------------------------------------------------------- multi_tri_4096
 class MultiTri:
-    """BASELINE.json configs[4]: forward (9 window-disjoint classes added into the image) + dL (elementwise) + backward
-    (one grouped launch, per-triangle sums reduced in-kernel, all-reduced over the peer mailboxes when N > 1).
+    """BASELINE.json configs[4]: forward (9 window-disjoint classes added into the image) + backward with the upstream
+    gradient dL = image - target (one grouped launch, per-triangle sums reduced in-kernel, all-reduced over the peer
+    mailboxes when N > 1).
     An *evaluation* = one (pixel, triangle) pair inside a triangle's window: its value integral and its reverse
     derivative.  weak: one unit square / band of 4096 rows / 256 triangles per GPU.  strong: ONE band split by rows."""
 
@@ -550,16 +551,17 @@ class MultiTri:
             from teg_b200.parallel import PeerGroup
             try:
                 self.peers = PeerGroup(ctx.local, max_values=7 * self.K)
-                self.r.set_peers(self.peers)
+                self.r.set_peers(self.peers, diff=True)
             except RuntimeError as e:
                 self.peers, self.peer_note = None, f'peer mailboxes unavailable ({e}): NCCL all-reduce instead'
         self.ev = {'forward': [], 'backward': []}
         self.graph = None
 
     def body(self, sp):
+        # the upstream gradient dL = image - target of the L2 loss is formed inside the backward kernel (a pixel argument
+        # bound to a pair of images): the same subtraction, no dL image written and read back
         self.r.forward(out=self.img, stream=sp)
-        self.ctx.torch.sub(self.img[0], self.target, out=self.dL)
-        self.r.backward(self.dL, out=self.g, stream=sp)
+        self.r.backward((self.img[0], self.target), out=self.g, stream=sp)
 
     def step_launches(self, record: bool):
         ctx, torch = self.ctx, self.ctx.torch
@@ -570,10 +572,8 @@ class MultiTri:
         self.r.forward(out=self.img, stream=stream.cuda_stream)
         if record:
             e[1].record(stream)
-        torch.sub(self.img[0], self.target, out=self.dL)
-        if record:
             e[2].record(stream)
-        self.r.backward(self.dL, out=self.g, stream=stream.cuda_stream)
+        self.r.backward((self.img[0], self.target), out=self.g, stream=stream.cuda_stream)
         if record:
             e[3].record(stream)
         if ctx.world > 1 and self.peers is None:
@@ -625,24 +625,29 @@ class MultiTri:
         out = {'sum_image_all_ranks': ctx.sum_over_ranks(float(self.img.double().sum().item())),
                'grad_l1': float(self.g.double().abs().sum().item()), 'grad_l2': float(self.g.double().norm().item()),
                'finite': bool(torch.isfinite(self.g).all().item() and torch.isfinite(self.img).all().item())}
-        if ctx.world > 1 and self.peers is not None:
-            r = self.r
-            saved, r.peers = r.peers, None
-            _, prog = r.m_grad.grouped_program([r.g_lab[b] for b in ('x_lb', 'x_ub', 'y_lb', 'y_ub')], [r.g_lab['dL']], reduce=True)
-            self.peers.detach(prog)
-            loc = r.backward(self.dL)
+        # dL as an explicit image through the other compiled variant (no peers attached): the same bits as the in-kernel
+        # difference at N = 1; for N > 1 its local sums, all-reduced by NCCL, against the fused peer exchange
+        torch.sub(self.img[0], self.target, out=self.dL)
+        r = self.r
+        saved, r.peers = r.peers, None
+        loc = r.backward(self.dL)
+        r.peers = saved
+        if ctx.world > 1:
             ctx.dist.all_reduce(loc)
-            torch.cuda.synchronize(ctx.dev)
-            self.peers.attach_groups(prog, self.K)
-            r.peers = saved
-            ref, got = loc.double(), self.g.double()
-            scale = float(ref.abs().max().item())
-            out['peer_vs_nccl_max_abs'] = float((ref - got).abs().max().item())
+        torch.cuda.synchronize(ctx.dev)
+        ref, got = loc.double(), self.g.double()
+        scale = float(ref.abs().max().item())
+        out['explicit_dL_vs_in_kernel_difference_max_abs'] = float((ref - got).abs().max().item())
+        if ctx.world == 1:
+            out['explicit_dL_equals_in_kernel_difference'] = bool(torch.equal(loc, self.g))
+        elif self.peers is not None:
+            out['peer_vs_nccl_max_abs'] = out['explicit_dL_vs_in_kernel_difference_max_abs']
             out['peer_vs_nccl_ok'] = bool(out['peer_vs_nccl_max_abs'] <= 2e-6 * max(scale, 1e-30))
             same = [torch.empty_like(self.g) for _ in range(ctx.world)]
             ctx.dist.all_gather(same, self.g)
             out['same_bits_on_every_rank'] = bool(all(torch.equal(s, same[0]) for s in same))
-        out['ok'] = bool(out['finite'] and out.get('peer_vs_nccl_ok', True) and out.get('same_bits_on_every_rank', True))
+        out['ok'] = bool(out['finite'] and out.get('peer_vs_nccl_ok', True) and out.get('same_bits_on_every_rank', True)
+                         and out.get('explicit_dL_equals_in_kernel_difference', True))
         return out
 
     def close(self):

@@ -83,6 +83,7 @@ class KernelSource:
     team: int                       # threads cooperating on one instance (1 = thread per instance)
     grouped: bool = False           # grouped render launch: per-group scalar arguments + pixel windows
     pixel_args: List[int] = None    # arguments read from pixel-indexed images (grouped launches)
+    pixel_diff: List[int] = None    # the subset of pixel_args bound to a DIFFERENCE of two images (a - b, formed on load)
     accumulate: bool = False        # outputs are added into images
     vec: int = 1                    # instances per thread (16-byte vector loads/stores), streaming programs
     tile_conds: int = 0             # tile conditions classified by <name>_tiles before a render launch (cull.tile_cull)
@@ -1180,7 +1181,8 @@ class Emitter:
         return self.lines
 
     def generate(self, grid_args: Sequence[int] = (), reduce_outputs: bool = False, grouped: bool = False,
-                 pixel_args: Sequence[int] = (), accumulate: bool = False, vec: int = 1) -> KernelSource:
+                 pixel_args: Sequence[int] = (), accumulate: bool = False, vec: int = 1,
+                 pixel_diff: Sequence[int] = ()) -> KernelSource:
         """grid_args: argument indices of (x_lb, x_ub, y_lb, y_ub) when they are generated from the pixel
         index (render programs, tests/plot.py:8-29) instead of being streamed from per-instance arrays.
         reduce_outputs: instead of one output stream per component, every block sums its instances'
@@ -1189,7 +1191,9 @@ class Emitter:
         grouped (render programs only): the launch covers G *groups* (e.g. triangles), each with its own
         values of the scalar arguments and its own window of pixels; launch-invariant values become one
         table row per group (global memory, staged through shared memory per block) instead of the
-        constant bank.  pixel_args: arguments read from images indexed by pixel (an upstream dL).
+        constant bank.  pixel_args: arguments read from images indexed by pixel (an upstream dL); those listed in
+        pixel_diff are bound to TWO images and read as ``a[p] - b[p]`` (one IEEE subtraction, what an elementwise
+        ``a - b`` kernel would have stored): the upstream gradient ``image - target`` of an L2 loss is never written.
         accumulate: outputs are added into images (groups of one launch must not overlap).
         vec: instances per thread for streaming (loop-free) programs: 16-byte vector loads/stores of ``vec``
         consecutive instances put 4x the bytes in flight per thread, which is what an HBM-bound kernel
@@ -1207,6 +1211,7 @@ class Emitter:
         scal = list(sch.scalar_args)
         grid = list(grid_args)
         pix = list(pixel_args)
+        pdiff = [a for a in pix if a in set(pixel_diff)]
         assert all(g in sch.array_args for g in grid + pix), 'grid / pixel arguments must be scheduled as per-instance'
         assert not grid or len(grid) == 4, 'a render program takes exactly x_lb, x_ub, y_lb, y_ub on the grid'
         assert not grouped or grid, 'grouped launches are render launches'
@@ -1343,7 +1348,9 @@ class Emitter:
                                  'const int row0', 'const int row1', 'const int* __restrict__ win',
                                  'const int group_begin', 'const T* __restrict__ Utab', 'const int tile_rows'] +
                                 (['const T* __restrict__ tiles', 'const int tab_groups'] if tile else []) +
-                                [f'const T* __restrict__ pix{a}' for a in pix] + outs_decl)
+                                [p_ for a in pix for p_ in ([f'const T* __restrict__ pix{a}'] +
+                                                            ([f'const T* __restrict__ pixb{a}'] if a in pdiff else []))] +
+                                outs_decl)
             gmb = (0 if self.min_blocks is None else self.min_blocks)
             glb = f'{bs}, {gmb}' if gmb else f'{bs}'
             src.append(f'extern "C" __global__ void __launch_bounds__({glb}) {name}_main({mparams}) {{')
@@ -1402,7 +1409,7 @@ class Emitter:
                 src.append(f'{ind}        const bool on = live && r < rows_here;')
                 src.append(f'{ind}        const long long ic = (long long)(nx0 + (r < rows_here ? r : {r_begin}) - row0) * res_y + nyc;')
                 for a in pix:
-                    src.append(f'{ind}        p{a}_[u] = pix{a}[ic];')
+                    src.append(f'{ind}        p{a}_[u] = pix{a}[ic]' + (f' - pixb{a}[ic];' if a in pdiff else ';'))
                 if accumulate and not reduce_outputs:
                     for k in range(K):
                         src.append(f'{ind}        old_[u][{k}] = on ? out{k}[ic] : {zero};')
@@ -1865,7 +1872,7 @@ class Emitter:
                             uniform_kernel=f'{name}_uniform', main_kernel=f'{name}_main',
                             n_uniform=nu, scalar_args=scal, array_args=arrs, grid_args=grid,
                             n_outputs=K, block_size=bs, reduce_outputs=nr, team=team,
-                            grouped=bool(grouped), pixel_args=pix, accumulate=bool(accumulate),
+                            grouped=bool(grouped), pixel_args=pix, pixel_diff=pdiff, accumulate=bool(accumulate),
                             tile_conds=len(tile), tile_rows=self.tile_rows if (tile or grouped) else 0, tile_cols=self.tile_cols,
                             tile_kernel=f'{name}_tiles' if tile else '',
                             tile_bodies=[(lb, mt) for lb, mt, _, _ in tile_bodies],
@@ -1874,11 +1881,12 @@ class Emitter:
 
 def generate(sch: Schedule, ctype: str = 'float', num_samples: int = 50, name: Optional[str] = None,
              grid_args: Sequence[int] = (), reduce_outputs: bool = False, grouped: bool = False,
-             pixel_args: Sequence[int] = (), accumulate: bool = False, vec: int = 1, **opts) -> KernelSource:
+             pixel_args: Sequence[int] = (), accumulate: bool = False, vec: int = 1,
+             pixel_diff: Sequence[int] = (), **opts) -> KernelSource:
     name = name or _c_ident(sch.dag.name)
     return Emitter(sch, ctype, num_samples, name, **opts).generate(
         grid_args=grid_args, reduce_outputs=reduce_outputs, grouped=grouped, pixel_args=pixel_args,
-        accumulate=accumulate, vec=vec)
+        accumulate=accumulate, vec=vec, pixel_diff=pixel_diff)
 
 
 def _c_ident(s: str) -> str:

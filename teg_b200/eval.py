@@ -182,19 +182,20 @@ class CUDA_EvalMode(EvalMode):
 
     def compiled(self, array_args: Sequence[int], grid_args: Sequence[int] = (), reduce: bool = False,
                  team: int = 1, grouped: bool = False, pixel_args: Sequence[int] = (), accumulate: bool = False,
-                 vec: int = 1, private: bool = False):
+                 vec: int = 1, private: bool = False, pixel_diff: Sequence[int] = ()):
         """(KernelSource, runtime.Program) of one variant, compiled once per mode.  private: a NEW handle on the same
         module (own uniform table and scratch buffers) for callers that keep it to themselves."""
         reduce = self._n_reduce(reduce)
         key = (tuple(sorted(array_args)), tuple(grid_args), reduce, int(team), bool(grouped),
-               tuple(pixel_args), bool(accumulate), int(vec))
+               tuple(pixel_args), bool(accumulate), int(vec), tuple(sorted(pixel_diff)))
         hit = self._variants.get(key)
         if hit is None:
             if grouped:
                 sch = self.schedule(list(grid_args) + list(pixel_args), grid_args, tiled=self.tiles)
                 ks = generate(sch, self.float_width, self.num_samples, grid_args=list(grid_args),
                               reduce_outputs=reduce, grouped=True, pixel_args=list(pixel_args),
-                              accumulate=accumulate, block_size=self.block_size, **self.codegen_opts)
+                              accumulate=accumulate, block_size=self.block_size, pixel_diff=list(pixel_diff),
+                              **self.codegen_opts)
             else:
                 ks = self.kernel_source(array_args, grid_args, reduce, team, vec)
             mod = runtime.Module(ks.source, opts=self.nvrtc_opts, use_cache=self.use_cache)
@@ -306,14 +307,16 @@ class CUDA_EvalMode(EvalMode):
                     n, stream=stream)
         return out if self.out_is_tuple and ks.n_outputs > 1 else out[0]
 
-    def grouped_program(self, box_vars, pixel_vars=(), reduce: bool = False, accumulate: bool = False):
+    def grouped_program(self, box_vars, pixel_vars=(), reduce: bool = False, accumulate: bool = False,
+                        pixel_diff=()):
         """(KernelSource, runtime.Program) of the grouped render variant ``render_groups`` launches for these box /
         per-pixel arguments (e.g. to attach peer mailboxes to it: ``PeerGroup.attach_groups``)."""
         pos = {lab: i for i, (lab, _) in enumerate(self.arglist)}
         grid_args = [pos[v if isinstance(v, str) else label_of(v)] for v in box_vars]
         pixel_args = sorted(pos[v if isinstance(v, str) else label_of(v)] for v in pixel_vars)
+        diff = sorted(pos[v if isinstance(v, str) else label_of(v)] for v in pixel_diff)
         return self.compiled(grid_args, grid_args, reduce=reduce, grouped=True, pixel_args=pixel_args,
-                             accumulate=accumulate)
+                             accumulate=accumulate, pixel_diff=diff)
 
     def render_groups(self, box_vars, res: Tuple[int, int], bounds, group_bindings, windows, max_rows: int,
                       max_cols: int, pixel_bindings=None, rows: Optional[Tuple[int, int]] = None, out=None,
@@ -325,7 +328,8 @@ class CUDA_EvalMode(EvalMode):
         group_bindings: {Var | label: torch CUDA tensor [G]} for every non-box, non-pixel argument.
         windows: int32 CUDA tensor [G, 4] = (row_begin, row_end, col_begin, col_end) per group, in pixels.
         max_rows / max_cols: upper bounds on the window sizes (launch geometry).
-        pixel_bindings: {Var | label: image tensor [rows, res_y]} read per pixel (an upstream dL).
+        pixel_bindings: {Var | label: image tensor [rows, res_y]} read per pixel (an upstream dL); a pair of images
+        ``(a, b)`` binds the argument to ``a - b`` (formed on load: the difference image is never written).
         rows: the band of grid rows this device owns (multi-GPU sharding).
         Output: ``out`` images [k, rows, res_y] (assigned, or added to with ``accumulate`` -- the windows of
         one launch must then be disjoint), or with ``reduce`` a tensor [G_range, k] of per-group sums.
@@ -336,7 +340,9 @@ class CUDA_EvalMode(EvalMode):
         pos = {lab: i for i, (lab, _) in enumerate(self.arglist)}
         pix = {(k if isinstance(k, str) else label_of(k)): v for k, v in (pixel_bindings or {}).items()}
         grp = {(k if isinstance(k, str) else label_of(k)): v for k, v in (group_bindings or {}).items()}
-        ks, prog = self.grouped_program(box_vars, list(pix), reduce=reduce, accumulate=accumulate)
+        # a pixel binding may be a pair (a, b) of images: the argument is then a[p] - b[p], formed on load
+        ks, prog = self.grouped_program(box_vars, list(pix), reduce=reduce, accumulate=accumulate,
+                                        pixel_diff=[lab for lab, v in pix.items() if isinstance(v, (tuple, list))])
         tdt = torch.float32 if self.float_width == 'float' else torch.float64
         dev = torch.device('cuda', self.device)
         G = int(windows.shape[0])
@@ -356,9 +362,11 @@ class CUDA_EvalMode(EvalMode):
         r0, r1 = (0, res[0]) if rows is None else rows
         pptrs = []
         for a in ks.pixel_args:
-            img = pix[self.arglist[a][0]]
-            assert img.is_cuda and img.dtype == tdt and img.is_contiguous() and img.numel() == (r1 - r0) * res[1]
-            pptrs.append(img.data_ptr())
+            bound = pix[self.arglist[a][0]]
+            for img in (bound if isinstance(bound, (tuple, list)) else (bound,)):
+                assert img.is_cuda and img.dtype == tdt and img.is_contiguous() and img.numel() == (r1 - r0) * res[1]
+                pptrs.append(img.data_ptr())
+                keep.append(img)
         assert windows.is_cuda and windows.dtype == torch.int32 and windows.is_contiguous() and windows.shape[1] == 4
         grid = runtime.Grid(float(bounds[0][0]), float(bounds[0][1]), float(bounds[1][0]), float(bounds[1][1]),
                             int(res[0]), int(res[1]), int(r0), int(r1))

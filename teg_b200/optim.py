@@ -67,7 +67,7 @@ class AdamFit:
         self.scale = float(rasterizer.grid_res[0] * rasterizer.grid_res[1]) / float(rasterizer.bands)
         self.peers = peers
         if peers is not None:
-            rasterizer.set_peers(peers)
+            rasterizer.set_peers(peers, diff=True)
         self._w = torch.empty((self.K, 7), dtype=tdt, device=dev)
         self._push_params()
         self.graph = None
@@ -85,7 +85,8 @@ class AdamFit:
         loss = 0.5 * self.scale * (self.dL.double() ** 2).sum()
         self._slot.copy_(self.it.reshape(1))
         self.losses.index_copy_(0, self._slot, loss.reshape(1))
-        self.r.backward(self.dL, out=self.g, stream=sp)
+        # (the kernel forms image - target itself from the two images; dL above only feeds the loss)
+        self.r.backward((self.img[0], self.target), out=self.g, stream=sp)
         if self.peers is None and torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1:
             torch.distributed.all_reduce(self.g)

@@ -87,13 +87,15 @@ class MultiTriangleRasterizer:
         self.K = 0
         self.peers = None
 
-    def set_peers(self, peers) -> None:
+    def set_peers(self, peers, diff: bool = False) -> None:
         """peers: a ``parallel.PeerGroup`` with max_values >= 7 K.  ``backward`` then returns the gradient summed over
         all ranks: the last per-triangle column-sum kernel exchanges the [K, 7] sums over NVLink peer memory itself
         (no separate collective).  Call after ``set_scene`` on every rank; every rank must call ``backward`` the same
         number of times."""
         assert self.K > 0, 'set_scene first'
-        _, prog = self.m_grad.grouped_program([self.g_lab[b] for b in BOX], [self.g_lab['dL']], reduce=True)
+        # (one compiled variant per way dL is bound: attach both the image form and the (image, target) form on demand)
+        _, prog = self.m_grad.grouped_program([self.g_lab[b] for b in BOX], [self.g_lab['dL']], reduce=True,
+                                              pixel_diff=[self.g_lab['dL']] if diff else [])
         peers.attach_groups(prog, self.K, self.local_of)
         self.peers = peers
 
@@ -164,7 +166,8 @@ class MultiTriangleRasterizer:
 
     def backward(self, dL, out=None, stream: int = 0):
         """grad [K, 7]: d(sum_p dL(p) * image(p)) / d(px0, py0, px1, py1, px2, py2, col) of every triangle,
-        summed over this rank's band (all-reduce it across ranks)."""
+        summed over this rank's band (all-reduce it across ranks).  dL: the upstream gradient image of this rank's
+        rows, or a pair ``(image, target)`` for dL = image - target formed inside the kernel."""
         torch = self.torch
         if out is None:
             out = torch.empty((self.K, 7), dtype=self.tdt, device=self.dev)

@@ -223,7 +223,8 @@ class Program:
                            len(ks.scalar_args), len(ks.array_args), len(getattr(ks, 'grid_args', ())),
                            ks.n_outputs, ks.block_size, int(getattr(ks, 'reduce_outputs', False)),
                            int(getattr(ks, 'team', 1)), int(getattr(ks, 'vec', 1)), int(getattr(ks, 'grouped', False)),
-                           len(getattr(ks, 'pixel_args', None) or ()), int(getattr(ks, 'accumulate', False)),
+                           len(getattr(ks, 'pixel_args', None) or ()) + len(getattr(ks, 'pixel_diff', None) or ()),
+                           int(getattr(ks, 'accumulate', False)),
                            int(getattr(ks, 'tile_conds', 0)), int(getattr(ks, 'tile_rows', 0)),
                            int(getattr(ks, 'tile_cols', 0) or 32), int(ks.num_samples), self._names[3])
         self.handle = ctypes.c_void_p()

@@ -129,3 +129,19 @@ def test_bench_reference_arm_prints_one_json_line_without_a_gpu():
     r1 = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
                          '--warmup', '1', '--cpu-rows', '4'], capture_output=True, text=True, env=dict(env, RANK='1'))
     assert r1.returncode == 0 and r1.stdout.strip() == ''
+
+
+def test_bench_reference_arm_of_the_multi_triangle_workload():
+    """`--workload multi_tri_4096 --impl reference`: config 5 on the host cores, the same config dict as the CUDA arm."""
+    import json
+    import bench
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                        '--warmup', '0', '--workload', 'multi_tri_4096', '--res', '1024'], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][-1])
+    assert d['impl'] == 'reference' and d['value'] > 0 and d['scaling'] == 'weak'
+    assert d['config'] == bench.headline_config('multi_tri_4096', 1024, 'weak')
+    assert d['config']['programs'] == ['tri_color_primal', 'tri_color_grad']
+    # the two arms of the headline workload describe it with the same dict too (the driver compares them)
+    assert bench.headline_config('tri_raster_4096', 4096, 'weak')['workload'] == 'tri_raster_4096'

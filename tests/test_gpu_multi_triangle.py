@@ -215,3 +215,21 @@ def test_config5_at_baseline_size_against_the_oracle(cuda_device, bands):
     for k in ks:
         assert np.all(np.abs(got_g[k] - want_g[k]) <= 2e-6 * want_gabs[k] + 1e-12), (k, got_g[k], want_g[k])
     assert max(np.abs(want_g[k]).max() for k in ks) > 1e-3
+
+
+def test_upstream_gradient_as_a_difference_of_two_images(cuda_device):
+    """``backward((image, target))`` forms dL = image - target inside the kernel (one IEEE subtraction on load): the same
+    bits as ``backward(image - target)`` with the difference written out by an elementwise kernel first."""
+    import torch
+    from teg_b200.raster import MultiTriangleRasterizer
+    res = 192
+    scene = multi_triangle_scene(bands=1, per_band_grid=4, res=res)
+    r = MultiTriangleRasterizer(load_program('tri_color_primal'), load_program('tri_color_grad'), res)
+    r.set_scene(scene['verts'], scene['col'], scene['windows'], scene['classes'], scene['max_rows'], scene['max_cols'])
+    img = r.forward()
+    target = torch.rand((res, res), device='cuda')
+    dL = (img[0] - target).contiguous()
+    a = r.backward(dL).clone()
+    b = r.backward((img[0], target)).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and float(a.abs().sum()) > 0
