@@ -33,7 +33,7 @@ def main():
     ap.add_argument('--cull', type=int, default=1)
     ap.add_argument('--graph', type=int, default=1, help='1: replay the step as one CUDA graph (parameters live in '
                     'device arrays, so the graph stays valid while they change)')
-    ap.add_argument('--min-blocks', default='', help='experiment: "a,b" = __launch_bounds__ resident blocks per SM of '
+    ap.add_argument('--min-blocks', default='4,4', help='experiment: "a,b" = __launch_bounds__ resident blocks per SM of '
                     'the grouped value / gradient kernels (0 = the compiler\'s choice)')
     ap.add_argument('--tile-rows', default='16,32', help='pixel rows per tile of the value / gradient kernels')
     ap.add_argument('--coop-groups', type=int, default=4)
