@@ -325,7 +325,7 @@ class TriRaster:
     when N > 1.  The two programs are independent: the gradient pipeline (classification, kernel, column sums,
     all-reduce) runs on a second stream next to the value pipeline, joined at the end."""
 
-    def __init__(self, ctx: Ctx, scaling: str, allreduce: str = 'peer'):
+    def __init__(self, ctx: Ctx, scaling: str, allreduce: str = 'peer', fused: bool = False):
         from teg_b200 import CUDA_EvalMode
         from teg_b200.eval import interleaved_rows
         from teg_b200.tegp import Program
@@ -366,10 +366,22 @@ class TriRaster:
         self.imgs = [torch.empty((1, self.n_local_rows, res), dtype=self.tdt, device=dev) for _ in range(2)]
         self.gsums = [torch.zeros(6, dtype=self.tdt, device=dev) for _ in range(2)]
         grid = (self.res_x_total, res)
-        self.pr_grad = [self.m_grad.prepare_render(self.box, grid, self.bounds, self.gparams, rows=self.rows,
-                                                   out=self.gsums[b], reduce=True, interleave=self.inter) for b in range(2)]
-        self.pr_primal = [self.m_primal.prepare_render(self.box, grid, self.bounds, self.params, rows=self.rows,
-                                                       out=self.imgs[b], interleave=self.inter) for b in range(2)]
+        self.fused = bool(fused)
+        if self.fused:
+            # value and reverse derivative as ONE program (tegp.bundle): one classification, one main kernel that writes
+            # the image and the per-tile gradient partials, one column sum
+            self.m_fused = CUDA_EvalMode([self.primal, self.grad], num_samples=NUM_SAMPLES, device=ctx.local,
+                                         float_width=self.fw, cull=bool(args.cull), **xopts)
+            self.pr_fused = [self.m_fused.prepare_render(self.box, grid, self.bounds, self.gparams, rows=self.rows,
+                                                         out=(self.imgs[b], self.gsums[b]), reduce=6,
+                                                         interleave=self.inter) for b in range(2)]
+            self.pr_grad = self.pr_fused
+            self.pr_primal = self.pr_fused
+        else:
+            self.pr_grad = [self.m_grad.prepare_render(self.box, grid, self.bounds, self.gparams, rows=self.rows,
+                                                       out=self.gsums[b], reduce=True, interleave=self.inter) for b in range(2)]
+            self.pr_primal = [self.m_primal.prepare_render(self.box, grid, self.bounds, self.params, rows=self.rows,
+                                                           out=self.imgs[b], interleave=self.inter) for b in range(2)]
         # the gradient pipeline is the longer one (and ends in the all-reduce): its blocks get priority
         self.side = torch.cuda.Stream(dev, priority=-1)
         self.forks = [torch.cuda.Event() for _ in range(2)]
@@ -380,7 +392,7 @@ class TriRaster:
             try:
                 self.peers = PeerGroup(ctx.local, max_values=16)       # raises on every rank or on none
                 for pr in self.pr_grad:
-                    self.peers.attach(pr.prog)      # the last column-sum kernel of the gradient does the exchange itself
+                    self.peers.attach(pr.prog)          # (fused: the bundle's handle)      # the last column-sum kernel of the gradient does the exchange itself
             except RuntimeError as e:
                 self.peers, self.peer_note = None, f'peer mailboxes unavailable ({e}): NCCL all-reduce instead'
         self.ev = {'primal': [], 'grad': []}
@@ -412,6 +424,18 @@ class TriRaster:
         ctx, torch = self.ctx, self.ctx.torch
         stream = ctx.stream if stream is None else stream
         side = self.side
+        if self.fused:
+            a, b = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if record else (None, None)
+            if record:
+                a.record(stream)
+            self.pr_fused[buf].run(stream.cuda_stream)
+            if ctx.world > 1 and self.peers is None:
+                ctx.dist.all_reduce(self.gsums[buf])
+            if record:
+                b.record(stream)
+                self.ev['primal'].append((a, b))
+                self.ev['grad'].append((a, b))
+            return
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
         fork, join = self.forks[buf], self.joins[buf]
         fork.record(stream)
@@ -854,6 +878,7 @@ def main() -> int:
     ap.add_argument('--cpu-seconds', type=float, default=2.5, help='target duration of one reference-arm step')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--fused', type=int, default=0, help='1: value and reverse derivative as ONE program bundle (one kernel)')
     ap.add_argument('--graph', type=int, default=1, help='1: the timed steps replay ONE captured CUDA graph of the step')
     ap.add_argument('--no-extras', action='store_true', help='headline only: no "workloads" records (profiling runs)')
     ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'], help='working precision of the programs')
@@ -886,7 +911,7 @@ def main() -> int:
 
     # ------------------------------------------------------------------ headline
     if args.workload == 'tri_raster_4096':
-        head = TriRaster(ctx, args.scaling, args.allreduce)
+        head = TriRaster(ctx, args.scaling, args.allreduce, fused=bool(args.fused))
         for _ in range(args.warmup):
             head.step(False)
         ctx.sync_all()

@@ -424,7 +424,7 @@ class CUDA_EvalMode(EvalMode):
                        rows: Optional[Tuple[int, int]] = None, out=None, reduce: bool = False,
                        interleave: Tuple[int, int] = (1, 0)) -> "PreparedRender":
         """``render`` bound once (arguments resolved, output allocated): the returned object's ``run(stream)`` costs
-        one C call.  Same arguments and output conventions as ``render`` (bundles with 0 < reduce < k excluded)."""
+        one C call.  Same arguments and output conventions as ``render`` (bundles: ``out`` = (images, sums))."""
         import torch
         labels = [v if isinstance(v, str) else label_of(v) for v in box_vars]
         pos = {lab: i for i, (lab, _) in enumerate(self.arglist)}
@@ -432,17 +432,29 @@ class CUDA_EvalMode(EvalMode):
         # a prepared render owns its handle (its own uniform table and scratch): several of them -- also of the same
         # program with different scalars, on different streams or threads -- run concurrently
         ks, prog = self.compiled(grid_args, grid_args, reduce=reduce, private=True)
-        assert ks.reduce_outputs in (0, ks.n_outputs), 'prepare_render: all outputs are images, or all are sums'
         scalars = self._resolve_scalars(bindings, ks.scalar_args)
         r0, r1 = (0, res[0]) if rows is None else rows
         tdt = torch.float32 if self.float_width == 'float' else torch.float64
         dev = torch.device('cuda', self.device)
         n_local = len(interleaved_rows(r1 - r0, ks.tile_rows, *interleave)) if tuple(interleave) != (1, 0) else r1 - r0
-        if out is None:
-            out = (torch.empty(ks.n_outputs, dtype=tdt, device=dev) if ks.reduce_outputs
-                   else torch.empty((ks.n_outputs, n_local, res[1]), dtype=tdt, device=dev))
-        assert ks.reduce_outputs or (out.shape[1] == n_local and out.is_contiguous()), 'output image has the wrong rows'
-        ptrs = [out.data_ptr()] if ks.reduce_outputs else [out[k].data_ptr() for k in range(ks.n_outputs)]
+        nr = ks.reduce_outputs
+        n_store = ks.n_outputs - nr
+        if 0 < nr < ks.n_outputs:
+            # bundle (value + derivative in ONE kernel): the leading outputs are images, the trailing ones sums
+            imgs, sums = out if out is not None else (None, None)
+            if imgs is None:
+                imgs = torch.empty((n_store, n_local, res[1]), dtype=tdt, device=dev)
+            if sums is None:
+                sums = torch.empty(nr, dtype=tdt, device=dev)
+            assert imgs.shape[1] == n_local and imgs.is_contiguous(), 'output image has the wrong rows'
+            out = (imgs, sums)
+            ptrs = [imgs[k].data_ptr() for k in range(n_store)] + [sums.data_ptr()]
+        else:
+            if out is None:
+                out = (torch.empty(ks.n_outputs, dtype=tdt, device=dev) if nr
+                       else torch.empty((ks.n_outputs, n_local, res[1]), dtype=tdt, device=dev))
+            assert nr or (out.shape[1] == n_local and out.is_contiguous()), 'output image has the wrong rows'
+            ptrs = [out.data_ptr()] if nr else [out[k].data_ptr() for k in range(ks.n_outputs)]
         grid = runtime.Grid(float(bounds[0][0]), float(bounds[0][1]), float(bounds[1][0]), float(bounds[1][1]),
                             int(res[0]), int(res[1]), int(r0), int(r1))
         return PreparedRender(self, ks, prog, scalars, grid, out, ptrs, interleave)

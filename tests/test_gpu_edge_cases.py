@@ -122,6 +122,16 @@ def test_full_size_properties_4096(cuda_device):
         vals = scene_values('tri_primal', res=(res, res), rows=(r, r + 1))
         a = np.asarray(mp.eval(dict(zip(primal.args, bind(primal.args, vals)))))
         assert np.array_equal(a, img[r].cpu().numpy())
+    # (5b) ... and against the ORACLE itself, value image and per-pixel gradient images: 24 rows spread over the image
+    #      (interior, exterior and edge tiles; the rows of unresolved tiles come from the worker queue of the kernel)
+    rows = [int(r) for r in np.linspace(600, 3700, 24)]
+    vals = [scene_values('tri_primal', res=(res, res), rows=(r, r + 1)) for r in rows]
+    cat = {k: (np.concatenate([v[k] for v in vals]) if np.ndim(vals[0][k]) else vals[0][k]) for k in vals[0]}
+    want = _oracle('tri_primal', bind(primal.args, cat), 16).reshape(len(rows), res)
+    assert np.array_equal(img[rows].cpu().numpy(), want)
+    want_g = _oracle('tri_grad', bind(grad.args, cat), 16).reshape(6, len(rows), res)
+    assert np.array_equal(g_img[:, rows].cpu().numpy(), want_g)
+    assert np.count_nonzero(want_g) > 100 and 0 < np.count_nonzero(want) < want.size
     # (6) sharding: two bands rendered separately tile the full image
     top = mp.render(primal.args[:4], (res, res), ((0, 1), (0, 1)), params, rows=(0, 1500))[0]
     bot = mp.render(primal.args[:4], (res, res), ((0, 1), (0, 1)), params, rows=(1500, res))[0]
