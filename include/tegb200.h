@@ -194,6 +194,17 @@ int tegb_render_groups_launch_prepared(tegb_program *p, const void *const *group
                                        const tegb_grid *grid, const int32_t *windows, int max_rows, int max_cols,
                                        const void *const *pixel_ptrs, void *const *out_ptrs, void *stream);
 
+/* Groups with OVERLAPPING windows in one launch (accumulating image programs; the reference adds the triangles of a
+ * scene one expression at a time, tests/plot.py:8-29 per triangle).  The launch covers the band in blocks of block_size
+ * columns x tile_rows rows; block (bx, by) -- bin by * ceil(res_y / block_size) + bx -- walks the groups
+ * bin_groups[bin_begin[bin] .. bin_begin[bin + 1]) (device int32 arrays, built by the caller from the windows: every group
+ * whose window reaches into the block, ASCENDING), so every pixel is owned by one thread for the whole launch and adds
+ * its contributions in ascending group order: the result of launching the groups one after the other, in one launch and
+ * without the read-modify-write passes.  Runs its own prologue (groups [0, group_count)). */
+int tegb_render_groups_gather(tegb_program *p, const void *const *group_ptrs, int group_count, const tegb_grid *grid,
+                              const int32_t *windows, int max_rows, int max_cols, const int32_t *bin_begin,
+                              const int32_t *bin_groups, const void *const *pixel_ptrs, void *const *out_ptrs, void *stream);
+
 /* kernels launched by this library since load (for accounting) */
 int64_t tegb_launch_count(void);
 

@@ -90,6 +90,7 @@ class KernelSource:
     tile_rows: int = 0              # pixel rows per tile
     tile_cols: int = 0              # pixel columns per tile (whole warps; divides block_size)
     tile_kernel: str = ''
+    gather_kernel: str = ''         # grouped accumulating programs: <name>_gather, one block per IMAGE block walking its bin of groups
     takes_instance_index: bool = False     # instance functions take the instance index (monte_carlo_uniform)
     tile_bodies: List = None        # [(label, {condition: admitted states})]: bodies <name>_tile_<label> for resolved tiles
     stats: Dict[str, float] = None
@@ -1318,7 +1319,8 @@ class Emitter:
                                     ['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
                                      'const int row0', 'const int row1', 'const int* __restrict__ win',
                                      'const int group_begin', 'const int group_count', 'const int tile_rows',
-                                     'const int n_tx', 'const int n_ty', 'const int tab_groups', 'T* __restrict__ tiles'])
+                                     'const int n_tx', 'const int n_ty', 'const int tab_groups', 'const int aligned',
+                                     'T* __restrict__ tiles'])
                 src.append(f'extern "C" __global__ void {name}_tiles({tparams}) {{')
                 src.append('    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one thread per tile')
                 src.append('    const int per_group = n_tx * n_ty;')
@@ -1328,8 +1330,12 @@ class Emitter:
                 src.append('    const int g = group_begin + j;')
                 src.append('    const int w_r0 = max(win[4 * g + 0], row0), w_r1 = min(win[4 * g + 1], row1);')
                 src.append('    const int w_c0 = win[4 * g + 2], w_c1 = min(win[4 * g + 3], res_y);')
-                src.append('    const int r0 = w_r0 + ty * tile_rows, r1 = min(r0 + tile_rows, w_r1);')
-                src.append('    const int c0 = w_c0 + tx * TEGB_TILE_COLS, c1 = min(c0 + TEGB_TILE_COLS, w_c1);')
+                src.append('    // aligned (gather launches): tiles of the absolute grid -- rows from row0 in steps of tile_rows, columns in')
+                src.append('    // steps of TEGB_TILE_COLS -- numbered from the first one the window reaches into; else tiles of the window')
+                src.append('    const int o_r0 = aligned ? row0 + ((w_r0 - row0) / tile_rows) * tile_rows : w_r0;')
+                src.append('    const int o_c0 = aligned ? (w_c0 / TEGB_TILE_COLS) * TEGB_TILE_COLS : w_c0;')
+                src.append('    const int r0 = max(o_r0 + ty * tile_rows, w_r0), r1 = min(o_r0 + (ty + 1) * tile_rows, w_r1);')
+                src.append('    const int c0 = max(o_c0 + tx * TEGB_TILE_COLS, w_c0), c1 = min(o_c0 + (tx + 1) * TEGB_TILE_COLS, w_c1);')
                 src.append('    // the table is indexed by ABSOLUTE group number: one classification pass may serve several launches')
                 src.append('    const size_t n_tiles = (size_t)tab_groups * per_group;')
                 src.append('    const size_t t = (size_t)g * per_group + tt;')
@@ -1344,147 +1350,219 @@ class Emitter:
                 src += self.tiles_body(grid, walk=True)
                 src.append('}')
                 src.append('')
-            mparams = ', '.join(['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
-                                 'const int row0', 'const int row1', 'const int* __restrict__ win',
-                                 'const int group_begin', 'const T* __restrict__ Utab', 'const int tile_rows'] +
-                                (['const T* __restrict__ tiles', 'const int tab_groups'] if tile else []) +
-                                [p_ for a in pix for p_ in ([f'const T* __restrict__ pix{a}'] +
-                                                            ([f'const T* __restrict__ pixb{a}'] if a in pdiff else []))] +
-                                outs_decl)
-            gmb = (0 if self.min_blocks is None else self.min_blocks)
-            glb = f'{bs}, {gmb}' if gmb else f'{bs}'
-            src.append(f'extern "C" __global__ void __launch_bounds__({glb}) {name}_main({mparams}) {{')
-            src.append('    // block (bx, by, bz): group group_begin + bz, tile (bx, by) of its window: B columns x tile_rows rows')
-            src.append('    const int g = group_begin + blockIdx.z;')
-            src.append('    const int w_r0 = max(win[4 * g + 0], row0), w_r1 = min(win[4 * g + 1], row1);')
-            src.append('    const int w_c0 = win[4 * g + 2], w_c1 = win[4 * g + 3];')
-            src.append('    const int nx0 = w_r0 + blockIdx.y * tile_rows;')
-            src.append('    const int ny = w_c0 + blockIdx.x * blockDim.x + threadIdx.x;')
-            src.append('    const bool block_live = nx0 < w_r1 && (w_c0 + (int)(blockIdx.x * blockDim.x)) < w_c1;')
-            if reduce_outputs:
-                src.append('    const unsigned long long tiles_n = (unsigned long long)gridDim.x * gridDim.y;')
-                src.append('    const unsigned long long tile_i = (unsigned long long)blockIdx.y * gridDim.x + blockIdx.x;')
-                src.append(f'    T* gp = partials + (unsigned long long)blockIdx.z * {K} * tiles_n;')
-                src.append('    if (!block_live) {')
-                src.append(f'        if (threadIdx.x < {K}) gp[threadIdx.x * tiles_n + tile_i] = {zero};')
-                src.append('        return;')
-                src.append('    }')
-            else:
-                src.append('    if (!block_live) return;')
-            src.append('    __shared__ T sU[TEGB_NUM_UNIFORM];')
-            src.append('    for (int j = threadIdx.x; j < TEGB_NUM_UNIFORM; j += blockDim.x) '
-                       'sU[j] = Utab[(size_t)g * TEGB_NUM_UNIFORM + j];')
-            src.append('    __syncthreads();')
-            src.append('    const bool live = ny < w_c1;')
-            # every lane of a warp runs coop bodies (dead lanes on a clamped pixel, results dropped)
-            src.append('    const int nyc = live ? ny : w_c0 + (int)(blockIdx.x * blockDim.x);')
-            src.append('    const T ye_lo = ye[nyc], ye_hi = ye[nyc + 1];')
-            src.append('    const int rows_here = min(tile_rows, w_r1 - nx0);')
-            loads = {grid[0]: 'x_lo', grid[1]: 'x_hi', grid[2]: 'ye_lo', grid[3]: 'ye_hi'}
-            if tile:
-                src.append('    const size_t n_tiles = (size_t)gridDim.x * TEGB_TILE_SUB * gridDim.y * tab_groups;')
-                src.append('    const size_t tile_base = ((size_t)g * gridDim.y + blockIdx.y) * (gridDim.x * TEGB_TILE_SUB) + '
-                           'blockIdx.x * TEGB_TILE_SUB;         // (absolute group number)')
-                src.append('    const size_t tile_id = tile_base + threadIdx.x / TEGB_TILE_COLS;')
-                for k, a in enumerate(tile):
-                    src.append(f'    const T tile{k} = tiles[{k} * n_tiles + tile_id];')
-                    loads[a] = f'tile{k}'
-            if reduce_outputs:
-                src.append(f'    T rr[{K}];')
-                src.append(f'    for (int k = 0; k < {K}; k++) rr[k] = {zero};')
-
-            def g_row_loop(fn: str, with_live: bool, ind: str, r_begin: str = '0', r_step: str = '1', batch: int = 4):
-                """Rows of the tile in batches of ``batch``: every global read of the batch (the upstream-gradient
-                pixels, the old image values of accumulating launches) is issued before the first use, so one memory
-                latency is paid per batch instead of per row."""
-                src.append(f'{ind}#pragma unroll 1')
-                src.append(f'{ind}for (int r0 = {r_begin}; r0 < rows_here; r0 += {batch} * {r_step}) {{')
-                for a in pix:
-                    src.append(f'{ind}    T p{a}_[{batch}];')
-                if accumulate and not reduce_outputs:
-                    src.append(f'{ind}    T old_[{batch}][{K}];')
-                src.append(f'{ind}    #pragma unroll')
-                src.append(f'{ind}    for (int u = 0; u < {batch}; u++) {{')
-                src.append(f'{ind}        const int r = r0 + u * {r_step};')
-                src.append(f'{ind}        const bool on = live && r < rows_here;')
-                src.append(f'{ind}        const long long ic = (long long)(nx0 + (r < rows_here ? r : {r_begin}) - row0) * res_y + nyc;')
-                for a in pix:
-                    src.append(f'{ind}        p{a}_[u] = pix{a}[ic]' + (f' - pixb{a}[ic];' if a in pdiff else ';'))
-                if accumulate and not reduce_outputs:
-                    for k in range(K):
-                        src.append(f'{ind}        old_[u][{k}] = on ? out{k}[ic] : {zero};')
-                src.append(f'{ind}        (void)on; (void)ic;')
-                src.append(f'{ind}    }}')
-                src.append(f'{ind}    #pragma unroll')
-                src.append(f'{ind}    for (int u = 0; u < {batch}; u++) {{')
-                src.append(f'{ind}        const int r = r0 + u * {r_step};')
-                src.append(f'{ind}        if (r >= rows_here) break;                          // warp-uniform')
-                src.append(f'{ind}        const int nx = nx0 + r;')
-                src.append(f'{ind}        const T x_lo = xe[nx], x_hi = xe[nx + 1];')
-                src.append(f'{ind}        const long long i = (long long)(nx - row0) * res_y + ny;')
-                src.append(f'{ind}        T res[{K}];')
-                src.append(f'{ind}        for (int k = 0; k < {K}; k++) res[k] = {zero};')
-                lu = dict(loads)
-                for a in pix:
-                    lu[a] = f'p{a}_[u]'
-                call = ', '.join(['sU'] + (['live'] if with_live else []) + [lu[a] for a in varying] + ['res'])
-                if with_live:
-                    src.append(f'{ind}        {fn}({call});')
+            def emit_grouped_main(gather: bool):
+                """``<name>_main``: block (bx, by, bz) = tile (bx, by) of the window of group ``group_begin + bz``.
+                ``<name>_gather`` (accumulating image programs): block (bx, by) = block (bx, by) of the IMAGE; it walks
+                the groups whose windows reach into it, in the order of its bin (ascending group number), so every
+                pixel has one owner for the whole launch: overlapping windows need no launch of their own, and a pixel
+                sums its contributions in group order.  Tiles are then those of the absolute grid (classification with
+                ``aligned`` = 1): rows from row0 in steps of tile_rows, columns in steps of TEGB_TILE_COLS."""
+                I = '        ' if gather else '    '
+                mparams = ', '.join(['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
+                                     'const int row0', 'const int row1', 'const int* __restrict__ win'] +
+                                    (['const int* __restrict__ bin_begin', 'const int* __restrict__ bin_groups']
+                                     if gather else ['const int group_begin']) +
+                                    ['const T* __restrict__ Utab', 'const int tile_rows'] +
+                                    (['const T* __restrict__ tiles', 'const int tab_groups'] if tile else []) +
+                                    (['const int n_tx', 'const int n_ty'] if tile and gather else []) +
+                                    [p_ for a in pix for p_ in ([f'const T* __restrict__ pix{a}'] +
+                                                                ([f'const T* __restrict__ pixb{a}'] if a in pdiff else []))] +
+                                    outs_decl)
+                gmb = (0 if self.min_blocks is None else self.min_blocks)
+                glb = f'{bs}, {gmb}' if gmb else f'{bs}'
+                kname = f'{name}_gather' if gather else f'{name}_main'
+                src.append(f'extern "C" __global__ void __launch_bounds__({glb}) {kname}({mparams}) {{')
+                src.append('    __shared__ T sU[TEGB_NUM_UNIFORM];')
+                if gather:
+                    src.append('    // block (bx, by) of the image: B columns x tile_rows rows; its bin lists the groups to walk')
+                    src.append('    const int nx0 = row0 + blockIdx.y * tile_rows;')
+                    src.append('    const int col0 = (int)(blockIdx.x * blockDim.x);')
+                    src.append('    const int ny = col0 + threadIdx.x;')
+                    src.append('    const int bin = blockIdx.y * gridDim.x + blockIdx.x;')
+                    src.append('    for (int e_ = bin_begin[bin]; e_ < bin_begin[bin + 1]; ++e_) {')
+                    src.append('        const int g = bin_groups[e_];')
+                    src.append('        const int w_r0 = max(win[4 * g + 0], row0), w_r1 = min(win[4 * g + 1], row1);')
+                    src.append('        const int w_c0 = win[4 * g + 2], w_c1 = min(win[4 * g + 3], res_y);')
+                    src.append('        if (nx0 + tile_rows <= w_r0 || nx0 >= w_r1 || col0 + (int)blockDim.x <= w_c0 || col0 >= w_c1) '
+                               'continue;     // (block-uniform)')
+                    src.append('        __syncthreads();                    // everybody is done with the previous group')
+                    src.append('        for (int j = threadIdx.x; j < TEGB_NUM_UNIFORM; j += blockDim.x) '
+                               'sU[j] = Utab[(size_t)g * TEGB_NUM_UNIFORM + j];')
+                    src.append('        __syncthreads();')
+                    # rows of this block inside the window: r_first <= r < rows_here (relative to nx0)
+                    src.append('        const int r_first = max(w_r0 - nx0, 0);')
+                    src.append('        const int rows_here = min(tile_rows, w_r1 - nx0);')
+                    src.append('        const bool live = ny >= w_c0 && ny < w_c1;')
+                    src.append('        const int nyc = live ? ny : w_c0;')
                 else:
-                    src.append(f'{ind}        if (live) {fn}({call});')
-                if reduce_outputs:
-                    for k in range(K):
-                        src.append(f'{ind}        if (live) rr[{k}] = rr[{k}] + res[{k}];')
-                elif accumulate:
-                    for k in range(K):
-                        src.append(f'{ind}        if (live) out{k}[i] = old_[u][{k}] + res[{k}];')
-                else:
-                    for k in range(K):
-                        src.append(f'{ind}        if (live) out{k}[i] = res[{k}];')
-                src.append(f'{ind}    }}')
-                src.append(f'{ind}}}')
-
-            if tile_bodies:
-                first = True
-                for label, match, b_coop, consts in tile_bodies:
-                    terms = []
-                    for k2 in sorted(match):
-                        alts = ' || '.join(f'tile{k2} == {literal(str(v), T)}' for v in match[k2])
-                        terms.append(f'({alts})')
-                    src.append(f'    {"if" if first else "else if"} ({" && ".join(terms)}) {{')
-                    zeros = consts is not None and all(float(c.rstrip('f')) == 0.0 and not c.startswith('-') for c in consts)
-                    if zeros and (reduce_outputs or accumulate):
-                        src.append('        // every output is +0 over this tile: nothing to add')
+                    src.append('    // block (bx, by, bz): group group_begin + bz, tile (bx, by) of its window: B columns x tile_rows rows')
+                    src.append('    const int g = group_begin + blockIdx.z;')
+                    src.append('    const int w_r0 = max(win[4 * g + 0], row0), w_r1 = min(win[4 * g + 1], row1);')
+                    src.append('    const int w_c0 = win[4 * g + 2], w_c1 = win[4 * g + 3];')
+                    src.append('    const int nx0 = w_r0 + blockIdx.y * tile_rows;')
+                    src.append('    const int ny = w_c0 + blockIdx.x * blockDim.x + threadIdx.x;')
+                    src.append('    const bool block_live = nx0 < w_r1 && (w_c0 + (int)(blockIdx.x * blockDim.x)) < w_c1;')
+                    if reduce_outputs:
+                        src.append('    const unsigned long long tiles_n = (unsigned long long)gridDim.x * gridDim.y;')
+                        src.append('    const unsigned long long tile_i = (unsigned long long)blockIdx.y * gridDim.x + blockIdx.x;')
+                        src.append(f'    T* gp = partials + (unsigned long long)blockIdx.z * {K} * tiles_n;')
+                        src.append('    if (!block_live) {')
+                        src.append(f'        if (threadIdx.x < {K}) gp[threadIdx.x * tiles_n + tile_i] = {zero};')
+                        src.append('        return;')
+                        src.append('    }')
                     else:
-                        g_row_loop(f'{name}_tile_{label}', b_coop, '        ')
+                        src.append('    if (!block_live) return;')
+                    src.append('    for (int j = threadIdx.x; j < TEGB_NUM_UNIFORM; j += blockDim.x) '
+                               'sU[j] = Utab[(size_t)g * TEGB_NUM_UNIFORM + j];')
+                    src.append('    __syncthreads();')
+                    src.append('    const bool live = ny < w_c1;')
+                    # every lane of a warp runs coop bodies (dead lanes on a clamped pixel, results dropped)
+                    src.append('    const int nyc = live ? ny : w_c0 + (int)(blockIdx.x * blockDim.x);')
+                    src.append('    const int rows_here = min(tile_rows, w_r1 - nx0);')
+                r_first = 'r_first' if gather else '0'
+                src.append(f'{I}const T ye_lo = ye[nyc], ye_hi = ye[nyc + 1];')
+                loads = {grid[0]: 'x_lo', grid[1]: 'x_hi', grid[2]: 'ye_lo', grid[3]: 'ye_hi'}
+                if tile:
+                    if gather:
+                        # tiles of the absolute grid, numbered within the group's (aligned) window
+                        src.append('        const size_t n_tiles = (size_t)n_tx * n_ty * tab_groups;')
+                        src.append('        const int o_c0 = (w_c0 / TEGB_TILE_COLS) * TEGB_TILE_COLS;')
+                        src.append('        const int t_row = (nx0 - row0) / tile_rows - (w_r0 - row0) / tile_rows;')
+                        src.append('        // tile columns of this block, relative to the window (negative / past the end: outside)')
+                        src.append('        const int t_col0 = (col0 - o_c0) / TEGB_TILE_COLS;          // (both multiples of TEGB_TILE_COLS)')
+                        src.append('        const size_t tile_row_base = ((size_t)g * n_ty + t_row) * n_tx;')
+                        src.append('        const int t_col = t_col0 + (int)(threadIdx.x / TEGB_TILE_COLS);')
+                        src.append('        const bool in_win = t_col >= 0 && o_c0 + t_col * TEGB_TILE_COLS < w_c1;      // warp-uniform')
+                        for k, a in enumerate(tile):
+                            src.append(f'        const T tile{k} = in_win ? tiles[{k} * n_tiles + tile_row_base + t_col] : {zero};')
+                            loads[a] = f'tile{k}'
+                    else:
+                        src.append('    const size_t n_tiles = (size_t)gridDim.x * TEGB_TILE_SUB * gridDim.y * tab_groups;')
+                        src.append('    const size_t tile_base = ((size_t)g * gridDim.y + blockIdx.y) * (gridDim.x * TEGB_TILE_SUB) + '
+                                   'blockIdx.x * TEGB_TILE_SUB;         // (absolute group number)')
+                        src.append('    const size_t tile_id = tile_base + threadIdx.x / TEGB_TILE_COLS;')
+                        for k, a in enumerate(tile):
+                            src.append(f'    const T tile{k} = tiles[{k} * n_tiles + tile_id];')
+                            loads[a] = f'tile{k}'
+                if reduce_outputs:
+                    src.append(f'    T rr[{K}];')
+                    src.append(f'    for (int k = 0; k < {K}; k++) rr[k] = {zero};')
+
+                def g_row_loop(fn: str, with_live: bool, ind: str, r_begin: str = '0', r_step: str = '1', batch: int = 4):
+                    """Rows of the tile in batches of ``batch``: every global read of the batch (the upstream-gradient
+                    pixels, the old image values of accumulating launches) is issued before the first use, so one memory
+                    latency is paid per batch instead of per row."""
+                    if gather:
+                        r_begin = f'r_first + {r_begin}' if r_begin != '0' else 'r_first'
+                    src.append(f'{ind}#pragma unroll 1')
+                    src.append(f'{ind}for (int r0 = {r_begin}; r0 < rows_here; r0 += {batch} * {r_step}) {{')
+                    for a in pix:
+                        src.append(f'{ind}    T p{a}_[{batch}];')
+                    if accumulate and not reduce_outputs:
+                        src.append(f'{ind}    T old_[{batch}][{K}];')
+                    src.append(f'{ind}    #pragma unroll')
+                    src.append(f'{ind}    for (int u = 0; u < {batch}; u++) {{')
+                    src.append(f'{ind}        const int r = r0 + u * {r_step};')
+                    src.append(f'{ind}        const bool on = live && r < rows_here;')
+                    src.append(f'{ind}        const long long ic = (long long)(nx0 + (r < rows_here ? r : {r_first}) - row0) * res_y + nyc;')
+                    for a in pix:
+                        src.append(f'{ind}        p{a}_[u] = pix{a}[ic]' + (f' - pixb{a}[ic];' if a in pdiff else ';'))
+                    if accumulate and not reduce_outputs:
+                        for k in range(K):
+                            src.append(f'{ind}        old_[u][{k}] = on ? out{k}[ic] : {zero};')
+                    src.append(f'{ind}        (void)on; (void)ic;')
+                    src.append(f'{ind}    }}')
+                    src.append(f'{ind}    #pragma unroll')
+                    src.append(f'{ind}    for (int u = 0; u < {batch}; u++) {{')
+                    src.append(f'{ind}        const int r = r0 + u * {r_step};')
+                    src.append(f'{ind}        if (r >= rows_here) break;                          // warp-uniform')
+                    src.append(f'{ind}        const int nx = nx0 + r;')
+                    src.append(f'{ind}        const T x_lo = xe[nx], x_hi = xe[nx + 1];')
+                    src.append(f'{ind}        const long long i = (long long)(nx - row0) * res_y + ny;')
+                    src.append(f'{ind}        T res[{K}];')
+                    src.append(f'{ind}        for (int k = 0; k < {K}; k++) res[k] = {zero};')
+                    lu = dict(loads)
+                    for a in pix:
+                        lu[a] = f'p{a}_[u]'
+                    call = ', '.join(['sU'] + (['live'] if with_live else []) + [lu[a] for a in varying] + ['res'])
+                    if with_live:
+                        src.append(f'{ind}        {fn}({call});')
+                    else:
+                        src.append(f'{ind}        if (live) {fn}({call});')
+                    if reduce_outputs:
+                        for k in range(K):
+                            src.append(f'{ind}        if (live) rr[{k}] = rr[{k}] + res[{k}];')
+                    elif accumulate:
+                        for k in range(K):
+                            src.append(f'{ind}        if (live) out{k}[i] = old_[u][{k}] + res[{k}];')
+                    else:
+                        for k in range(K):
+                            src.append(f'{ind}        if (live) out{k}[i] = res[{k}];')
+                    src.append(f'{ind}    }}')
+                    src.append(f'{ind}}}')
+
+                if tile_bodies:
+                    first = True
+                    for label, match, b_coop, consts in tile_bodies:
+                        terms = ['in_win'] if gather else []
+                        for k2 in sorted(match):
+                            alts = ' || '.join(f'tile{k2} == {literal(str(v), T)}' for v in match[k2])
+                            terms.append(f'({alts})')
+                        src.append(f'{I}{"if" if first else "else if"} ({" && ".join(terms)}) {{')
+                        zeros = consts is not None and all(float(c.rstrip('f')) == 0.0 and not c.startswith('-') for c in consts)
+                        if zeros and (reduce_outputs or accumulate):
+                            src.append(f'{I}    // every output is +0 over this tile: nothing to add')
+                        else:
+                            g_row_loop(f'{name}_tile_{label}', b_coop, I + '    ')
+                        src.append(f'{I}}}')
+                        first = False
+                    # Unresolved tiles of this block: the per-instance program, shared by ALL warps of the block (warp w
+                    # takes rows w, w + W, ... of each unresolved tile): one warp walking its tile alone would keep the
+                    # other warps of the block waiting at the block sum / the end of the block.
+                    mine_u = ' || '.join(f'tile{k} == {literal("2", T)}' for k in range(len(tile)))
+                    src.append(f'{I}if (__syncthreads_or({mine_u})) {{')
+                    src.append(f'{I}    const int warp_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;')
+                    src.append(f'{I}    for (int sub = 0; sub < TEGB_TILE_SUB; ++sub) {{')
+                    if gather:
+                        src.append(f'{I}        const int s_col = t_col0 + sub;')
+                        src.append(f'{I}        if (s_col < 0 || o_c0 + s_col * TEGB_TILE_COLS >= w_c1) continue;      // outside the window')
+                        conds_u = ' || '.join(f'tiles[{k} * n_tiles + tile_row_base + s_col] == {literal("2", T)}'
+                                              for k in range(len(tile)))
+                    else:
+                        conds_u = ' || '.join(f'tiles[{k} * n_tiles + tile_base + sub] == {literal("2", T)}'
+                                              for k in range(len(tile)))
+                    src.append(f'{I}        if (!({conds_u})) continue;                 // block-uniform')
+                    src.append(f'{I}        for (int cw = 0; cw < TEGB_TILE_COLS / 32; ++cw) {{')
+                    if gather:
+                        src.append(f'{I}            const int ny = col0 + sub * TEGB_TILE_COLS + cw * 32 + lane_;')
+                        src.append(f'{I}            const bool live = ny >= w_c0 && ny < w_c1;')
+                        src.append(f'{I}            const int nyc = live ? ny : w_c0;')
+                    else:
+                        src.append(f'{I}            const int ny = w_c0 + (int)(blockIdx.x * {bs}) + sub * TEGB_TILE_COLS + cw * 32 + lane_;')
+                        src.append(f'{I}            const bool live = ny < w_c1;')
+                        src.append(f'{I}            const int nyc = live ? ny : w_c0 + (int)(blockIdx.x * {bs});')
+                    src.append(f'{I}            const T ye_lo = ye[nyc], ye_hi = ye[nyc + 1];')
+                    for k in range(len(tile)):
+                        src.append(f'{I}            const T tile{k} = {literal("2", T)};')
+                        src.append(f'{I}            (void)tile{k};')
+                    g_row_loop(f'{name}_instance', coop, I + '            ', 'warp_', f'{bs // 32}', batch=1)
+                    src.append(f'{I}        }}')
+                    src.append(f'{I}    }}')
+                    src.append(f'{I}}}')
+                else:
+                    g_row_loop(f'{name}_instance', coop, I, batch=1)
+                if gather:
                     src.append('    }')
-                    first = False
-                # Unresolved tiles of this block: the per-instance program, shared by ALL warps of the block (warp w
-                # takes rows w, w + W, ... of each unresolved tile): one warp walking its tile alone would keep the
-                # other warps of the block waiting at the block sum / the end of the block.
-                mine_u = ' || '.join(f'tile{k} == {literal("2", T)}' for k in range(len(tile)))
-                src.append(f'    if (__syncthreads_or({mine_u})) {{')
-                src.append('        const int warp_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;')
-                src.append('        for (int sub = 0; sub < TEGB_TILE_SUB; ++sub) {')
-                conds_u = ' || '.join(f'tiles[{k} * n_tiles + tile_base + sub] == {literal("2", T)}' for k in range(len(tile)))
-                src.append(f'            if (!({conds_u})) continue;                 // block-uniform')
-                src.append('            for (int cw = 0; cw < TEGB_TILE_COLS / 32; ++cw) {')
-                src.append(f'                const int ny = w_c0 + (int)(blockIdx.x * {bs}) + sub * TEGB_TILE_COLS + cw * 32 + lane_;')
-                src.append('                const bool live = ny < w_c1;')
-                src.append(f'                const int nyc = live ? ny : w_c0 + (int)(blockIdx.x * {bs});')
-                src.append('                const T ye_lo = ye[nyc], ye_hi = ye[nyc + 1];')
-                for k in range(len(tile)):
-                    src.append(f'                const T tile{k} = {literal("2", T)};')
-                    src.append(f'                (void)tile{k};')
-                g_row_loop(f'{name}_instance', coop, '                ', 'warp_', f'{bs // 32}', batch=1)
-                src.append('            }')
-                src.append('        }')
-                src.append('    }')
-            else:
-                g_row_loop(f'{name}_instance', coop, '    ', batch=1)
-            if reduce_outputs:
-                src.append(f'    tegb_block_sum_store<T, {K}, {bs}>(rr, gp, tiles_n, tile_i);')
-            src.append('}')
+                if reduce_outputs:
+                    src.append(f'    tegb_block_sum_store<T, {K}, {bs}>(rr, gp, tiles_n, tile_i);')
+                src.append('}')
+
+            emit_grouped_main(False)
+            self.has_gather = bool(accumulate and not reduce_outputs)
+            if self.has_gather:
+                # (an image block walks SEVERAL groups: rows outside a group's window are skipped by r_first / rows_here)
+                src.append('')
+                emit_grouped_main(True)
         else:
             src.append(f'extern "C" __global__ void {name}_uniform({ubody_params}) {{')
             src.append(f'    if (blockIdx.x == 0 && threadIdx.x == 0) {name}_uniform_body('
@@ -1875,6 +1953,7 @@ class Emitter:
                             grouped=bool(grouped), pixel_args=pix, pixel_diff=pdiff, accumulate=bool(accumulate),
                             tile_conds=len(tile), tile_rows=self.tile_rows if (tile or grouped) else 0, tile_cols=self.tile_cols,
                             tile_kernel=f'{name}_tiles' if tile else '',
+                            gather_kernel=f'{name}_gather' if (grouped and getattr(self, 'has_gather', False)) else '',
                             tile_bodies=[(lb, mt) for lb, mt, _, _ in tile_bodies],
                             stats={'uses_coop': self.uses_coop, 'loops': self.loop_counter})
 

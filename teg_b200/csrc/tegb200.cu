@@ -285,7 +285,7 @@ struct tegb_program {
     const int32_t *prep_windows = nullptr;
     const int *group_map = nullptr;   // device [n_groups_total]: this rank's index of every global group, or -1 (NULL: identity)
     CUmodule mod = nullptr;
-    CUfunction f_uniform = nullptr, f_main = nullptr, f_tiles = nullptr;
+    CUfunction f_uniform = nullptr, f_main = nullptr, f_tiles = nullptr, f_gather = nullptr;
     CUdeviceptr u_const = 0;      // __constant__ table inside the module
     size_t u_const_bytes = 0;
     void *u_stage = nullptr;      // device buffer the uniform kernel writes
@@ -358,6 +358,16 @@ extern "C" int tegb_program_create(tegb_module *m, const tegb_program_desc *desc
             return bail(fail(TEGB_ERR_INVALID, "tile conditions need a render program, tile_rows >= 1 and a tile kernel"));
         r = drv::ModuleGetFunction(&p->f_tiles, p->mod, desc->tile_kernel);
         if (r != CUDA_SUCCESS) return bail(fail(TEGB_ERR_CUDA, "kernel %s: %s", desc->tile_kernel, drv::errstr(r)));
+    }
+    if (desc->grouped && desc->accumulate && !desc->reduce_outputs) {
+        // accumulating grouped image programs also carry <name>_gather (same module, name derived from <name>_main);
+        // modules generated without one simply cannot take tegb_render_groups_gather
+        std::string nm(desc->main_kernel);
+        const std::string suffix("_main");
+        if (nm.size() > suffix.size() && nm.compare(nm.size() - suffix.size(), suffix.size(), suffix) == 0) {
+            nm.replace(nm.size() - suffix.size(), suffix.size(), "_gather");
+            if (drv::ModuleGetFunction(&p->f_gather, p->mod, nm.c_str()) != CUDA_SUCCESS) p->f_gather = nullptr;
+        }
     }
     size_t want = (size_t)(desc->n_uniform > 0 ? desc->n_uniform : 1) * desc->elem_size;
     if (!desc->grouped) {
@@ -989,7 +999,7 @@ static int finish_group_partials(tegb_program *p, unsigned long long tiles, int 
 // launch geometry of a grouped render: blocks of block_size columns x tile_rows rows over the largest window
 struct GroupGeom { unsigned gx, gy; int tile_rows, n_tx, n_ty; };
 
-static GroupGeom group_geom(const tegb_program *p, const tegb_grid *g, int max_rows, int max_cols) {
+static GroupGeom group_geom(const tegb_program *p, const tegb_grid *g, int max_rows, int max_cols, bool aligned = false) {
     GroupGeom q;
     const unsigned bs = (unsigned)p->d.block_size;
     q.gx = (unsigned)((max_cols + bs - 1) / bs);
@@ -999,6 +1009,15 @@ static GroupGeom group_geom(const tegb_program *p, const tegb_grid *g, int max_r
     q.gy = (unsigned)((win_rows + q.tile_rows - 1) / q.tile_rows);
     q.n_tx = (int)q.gx * (p->d.tile_cols > 0 ? p->d.block_size / p->d.tile_cols : 1);
     q.n_ty = (int)q.gy;
+    if (aligned) {
+        // gather launches: the tiles of a window are those of the ABSOLUTE grid it reaches into (a window that starts
+        // inside a tile spans one more); the launch itself covers the image (blocks of block_size columns x tile_rows rows)
+        const int tc = p->d.tile_cols > 0 ? p->d.tile_cols : p->d.block_size;
+        q.n_tx = (max_cols + tc - 1) / tc + 1;
+        q.n_ty = (win_rows + q.tile_rows - 1) / q.tile_rows + 1;
+        q.gx = (unsigned)((g->res_y + bs - 1) / bs);
+        q.gy = (unsigned)((band_rows + q.tile_rows - 1) / q.tile_rows);
+    }
     return q;
 }
 
@@ -1006,10 +1025,11 @@ static GroupGeom group_geom(const tegb_program *p, const tegb_grid *g, int max_r
 // window tile), for the groups' CURRENT parameters.  Tables are indexed by absolute group number, so one prologue
 // over all groups can serve several launches over sub-ranges (tegb_render_groups_prepare).
 static int groups_prologue(tegb_program *p, const void *const *group_ptrs, int group_begin, int group_count,
-                           const tegb_grid *g, const int32_t *windows, int max_rows, int max_cols, CUstream st) {
+                           const tegb_grid *g, const int32_t *windows, int max_rows, int max_cols, CUstream st,
+                           bool aligned_tiles = false) {
     int rc = ensure_edges(p, g, st);
     if (rc) return rc;
-    const GroupGeom q = group_geom(p, g, max_rows, max_cols);
+    const GroupGeom q = group_geom(p, g, max_rows, max_cols, aligned_tiles);
     const int tab_groups = group_begin + group_count;
     const int nu = p->d.n_uniform > 0 ? p->d.n_uniform : 1;
     const size_t need = (size_t)tab_groups * nu * p->d.elem_size;
@@ -1056,13 +1076,15 @@ static int groups_prologue(tegb_program *p, const void *const *group_ptrs, int g
         targs.push_back(&n_tx);
         targs.push_back(&n_ty);
         targs.push_back(&tabg);
+        int aligned = aligned_tiles ? 1 : 0;
+        targs.push_back(&aligned);
         targs.push_back(&p->d_tiles);
         const unsigned long long threads = (unsigned long long)group_count * n_tx * n_ty;
         const unsigned tb = 128, tg = (unsigned)((threads + tb - 1) / tb);
         CU_CHECK(drv::LaunchKernel(p->f_tiles, tg, 1, 1, tb, 1, 1, 0, st, targs.data(), nullptr));
         g_launches++;
     }
-    p->prep_valid = true;
+    p->prep_valid = !aligned_tiles;              // (a gather launch classifies for itself, every time)
     p->prep_begin = group_begin;
     p->prep_count = group_count;
     p->prep_grid = *g;
@@ -1156,6 +1178,61 @@ extern "C" int tegb_render_groups_launch(tegb_program *p, const void *const *gro
                                          void *const *out_ptrs, void *stream) {
     return groups_launch_impl(p, group_ptrs, group_begin, group_count, g, windows, max_rows, max_cols, pixel_ptrs,
                               out_ptrs, stream, false);
+}
+
+// One launch over the IMAGE for groups with overlapping windows (accumulating image programs): block (bx, by) of the
+// image walks the groups of its bin in order, so every pixel adds its contributions in ascending group order.
+extern "C" int tegb_render_groups_gather(tegb_program *p, const void *const *group_ptrs, int group_count,
+                                         const tegb_grid *g, const int32_t *windows, int max_rows, int max_cols,
+                                         const int32_t *bin_begin, const int32_t *bin_groups,
+                                         const void *const *pixel_ptrs, void *const *out_ptrs, void *stream) {
+    if (!p || !g || !windows || !out_ptrs || !bin_begin || !bin_groups)
+        return fail(TEGB_ERR_INVALID, "tegb_render_groups_gather: bad argument");
+    if (!p->d.grouped || p->d.n_grid_args != 4) return fail(TEGB_ERR_INVALID, "not a grouped render program");
+    if (!p->f_gather) return fail(TEGB_ERR_INVALID, "not an accumulating grouped image program (no <name>_gather kernel)");
+    if (p->d.n_scalar_args > 0 && !group_ptrs) return fail(TEGB_ERR_INVALID, "group_ptrs is NULL");
+    if (p->d.n_pixel_args > 0 && !pixel_ptrs) return fail(TEGB_ERR_INVALID, "pixel_ptrs is NULL");
+    if (group_count < 0 || max_rows < 1 || max_cols < 1) return fail(TEGB_ERR_INVALID, "bad group count or window bounds");
+    if (g->res_x < 1 || g->res_y < 1 || g->row_begin < 0 || g->row_end > g->res_x || g->row_begin > g->row_end)
+        return fail(TEGB_ERR_INVALID, "bad grid");
+    if (group_count == 0 || g->row_end == g->row_begin) return TEGB_OK;
+    std::lock_guard<std::recursive_mutex> lock(p->mu);
+    RT_CHECK(cudaSetDevice(p->device));
+    CUstream st = (CUstream)stream;
+    int rc = begin_launch(p, st);
+    if (rc) return rc;
+    rc = groups_prologue(p, group_ptrs, 0, group_count, g, windows, max_rows, max_cols, st, true);
+    if (rc) return rc;
+    const GroupGeom q = group_geom(p, g, max_rows, max_cols, true);
+    if (q.gy > 65535u) return fail(TEGB_ERR_INVALID, "too many tile rows in one launch");
+    std::vector<const void *> pix(p->d.n_pixel_args > 0 ? p->d.n_pixel_args : 1);
+    std::vector<void *> outs(p->d.n_outputs);
+    std::vector<void *> args;
+    int res_y = g->res_y, row0 = g->row_begin, row1 = g->row_end, tile_rows = q.tile_rows;
+    int tab_groups = group_count, n_tx = q.n_tx, n_ty = q.n_ty;
+    args.push_back(&p->d_xe);
+    args.push_back(&p->d_ye);
+    args.push_back(&res_y);
+    args.push_back(&row0);
+    args.push_back(&row1);
+    args.push_back((void *)&windows);
+    args.push_back((void *)&bin_begin);
+    args.push_back((void *)&bin_groups);
+    args.push_back(&p->d_utab);
+    args.push_back(&tile_rows);
+    if (p->d.n_tile_conds > 0) {
+        args.push_back(&p->d_tiles);
+        args.push_back(&tab_groups);
+        args.push_back(&n_tx);
+        args.push_back(&n_ty);
+    }
+    for (int i = 0; i < p->d.n_pixel_args; i++) { pix[i] = pixel_ptrs[i]; args.push_back(&pix[i]); }
+    for (int k = 0; k < p->d.n_outputs; k++) { outs[k] = out_ptrs[k]; args.push_back(&outs[k]); }
+    time_begin(p, st);
+    CU_CHECK(drv::LaunchKernel(p->f_gather, q.gx, q.gy, 1, (unsigned)p->d.block_size, 1, 1, 0, st, args.data(), nullptr));
+    time_end(p, st);
+    g_launches++;
+    return end_launch(p, st);
 }
 
 extern "C" int tegb_render_groups_prepare(tegb_program *p, const void *const *group_ptrs, int group_begin,

@@ -321,7 +321,7 @@ class CUDA_EvalMode(EvalMode):
     def render_groups(self, box_vars, res: Tuple[int, int], bounds, group_bindings, windows, max_rows: int,
                       max_cols: int, pixel_bindings=None, rows: Optional[Tuple[int, int]] = None, out=None,
                       reduce: bool = False, accumulate: bool = False, group_range: Optional[Tuple[int, int]] = None,
-                      stream: int = 0, prepared: bool = False, prepare_only: bool = False):
+                      stream: int = 0, prepared: bool = False, prepare_only: bool = False, gather=None):
         """One launch over many *groups* (e.g. triangles), each with its own parameter values and its own
         window of pixels of the tests/plot.py grid.
 
@@ -335,7 +335,10 @@ class CUDA_EvalMode(EvalMode):
         one launch must then be disjoint), or with ``reduce`` a tensor [G_range, k] of per-group sums.
         prepare_only: run only the per-group prologue (uniform rows + tile classification for the groups' current
         parameters) for ``group_range``; later calls with ``prepared=True`` over sub-ranges then skip it (the same
-        windows tensor, window bounds and rows; the parameters must not change in between)."""
+        windows tensor, window bounds and rows; the parameters must not change in between).
+        gather: ``(bin_begin, bin_groups)`` int32 CUDA tensors (``group_bins``): ALL groups in one launch over the image,
+        every block walking the groups of its bin in ascending order -- for accumulating image programs whose windows
+        overlap; the result is that of launching the groups one after the other."""
         import torch
         pos = {lab: i for i, (lab, _) in enumerate(self.arglist)}
         pix = {(k if isinstance(k, str) else label_of(k)): v for k, v in (pixel_bindings or {}).items()}
@@ -380,6 +383,17 @@ class CUDA_EvalMode(EvalMode):
             out = (torch.empty((g1 - g0, ks.n_outputs), dtype=tdt, device=dev) if reduce
                    else torch.zeros((ks.n_outputs, r1 - r0, res[1]), dtype=tdt, device=dev))
         optrs = [out.data_ptr()] if reduce else [out[k].data_ptr() for k in range(ks.n_outputs)]
+        if gather is not None:
+            assert accumulate and not reduce and ks.gather_kernel and (g0, g1) == (0, G), \
+                'gather launches: accumulating image programs, all groups at once'
+            bb, bg = gather
+            n_bins = -(-int(res[1]) // ks.block_size) * -(-(r1 - r0) // max(ks.tile_rows, 1))
+            assert bb.is_cuda and bb.dtype == torch.int32 and bb.is_contiguous() and bb.numel() == n_bins + 1
+            assert bg.is_cuda and bg.dtype == torch.int32 and bg.is_contiguous()
+            self._keepalive = keep + [bb, bg]
+            prog.render_groups_gather(gptrs, G, grid, windows.data_ptr(), int(max_rows), int(max_cols), bb.data_ptr(),
+                                      bg.data_ptr(), pptrs, optrs, stream=stream)
+            return out
         prog.render_groups(gptrs, g0, g1 - g0, grid, windows.data_ptr(), int(max_rows), int(max_cols), pptrs,
                            optrs, stream=stream, prepared=prepared)
         return out

@@ -53,10 +53,40 @@ def select_groups(windows, classes: Sequence[Tuple[int, int]], rows: Tuple[int, 
     return ids, local_classes, local_of
 
 
+def group_bins(windows, rows: Tuple[int, int], res_y: int, block_cols: int, tile_rows: int):
+    """Bins of a gather launch (``tegb_render_groups_gather``): the band ``rows`` in blocks of ``block_cols`` columns x
+    ``tile_rows`` rows (row-major: bin = block_row * ceil(res_y / block_cols) + block_col); every block lists, ASCENDING,
+    the groups whose windows reach into it.  Returns (bin_begin int32 [n_bins + 1], bin_groups int32 [n_entries])
+    (``bin_groups`` has one padding element when empty, so that it always has an address)."""
+    w = np.asarray(windows).astype(np.int64).reshape(-1, 4)
+    r0, r1 = int(rows[0]), int(rows[1])
+    nbx = -(-int(res_y) // block_cols)
+    nby = -(-(r1 - r0) // tile_rows)
+    bins, grps = [], []
+    for k in range(len(w)):
+        a, b = max(int(w[k, 0]), r0), min(int(w[k, 1]), r1)
+        c, d = max(int(w[k, 2]), 0), min(int(w[k, 3]), int(res_y))
+        if a >= b or c >= d:
+            continue
+        by = np.arange((a - r0) // tile_rows, (b - 1 - r0) // tile_rows + 1, dtype=np.int64)
+        bx = np.arange(c // block_cols, (d - 1) // block_cols + 1, dtype=np.int64)
+        ids = (by[:, None] * nbx + bx[None, :]).ravel()
+        bins.append(ids)
+        grps.append(np.full(ids.shape, k, dtype=np.int64))
+    begin = np.zeros(nbx * nby + 1, dtype=np.int32)
+    if not bins:
+        return begin, np.zeros(1, dtype=np.int32)
+    bins, grps = np.concatenate(bins), np.concatenate(grps)
+    order = np.lexsort((grps, bins))                    # by bin, then ascending group
+    begin[1:] = np.cumsum(np.bincount(bins, minlength=nbx * nby))
+    return begin, grps[order].astype(np.int32)
+
+
 class MultiTriangleRasterizer:
     def __init__(self, primal: Program, grad: Program, res: int, bands: int = 1, rank: int = 0,
                  num_samples: int = 16, device: int = 0, float_width: str = 'float', cull: bool = True,
-                 min_blocks=(4, 4), rows: Optional[Tuple[int, int]] = None, tile_rows=(16, 32), **codegen_opts):
+                 min_blocks=(4, 4), rows: Optional[Tuple[int, int]] = None, tile_rows=(16, 32), gather: bool = True,
+                 **codegen_opts):
         import torch
         self.torch = torch
         self.res = int(res)
@@ -86,6 +116,10 @@ class MultiTriangleRasterizer:
         self.n_rows = self.rows[1] - self.rows[0]
         self.K = 0
         self.peers = None
+        # forward pass: ONE launch over the image, every block walking the triangles of its bin (False: one accumulating
+        # launch per class of window-disjoint triangles; the same image bit for bit)
+        self.gather = bool(gather)
+        self.tile_rows = tr
 
     def set_peers(self, peers, diff: bool = False) -> None:
         """peers: a ``parallel.PeerGroup`` with max_values >= 7 K.  ``backward`` then returns the gradient summed over
@@ -134,6 +168,10 @@ class MultiTriangleRasterizer:
         else:
             self.max_rows, self.max_cols = 1, 1
         self.g_local = torch.zeros((max(self.K_local, 1), 7), dtype=self.tdt, device=self.dev)
+        self.bins = None
+        if self.gather and self.K_local:
+            bb, bg = group_bins(wl, self.rows, self.res, self.m_primal.block_size, self.tile_rows[0])
+            self.bins = (torch.as_tensor(bb, device=self.dev), torch.as_tensor(bg, device=self.dev))
 
     def update_params(self, verts, col):
         """New parameter values ([K, 6] / [K] device tensors, global order) for the same windows (an optimisation step
@@ -153,6 +191,11 @@ class MultiTriangleRasterizer:
         out.zero_()
         box = [self.p_lab[b] for b in BOX]
         gb = {self.p_lab[nm]: self.params[nm] for nm in PARAMS}
+        if self.bins is not None:
+            self.m_primal.render_groups(box, self.grid_res, self.bounds, gb, self.windows, self.max_rows,
+                                        self.max_cols, rows=self.rows, out=out, accumulate=True, stream=stream,
+                                        gather=self.bins)
+            return out
         if len(self.classes) > 1:
             # uniform rows + tile classification of ALL held triangles once, then one accumulating launch per class
             self.m_primal.render_groups(box, self.grid_res, self.bounds, gb, self.windows, self.max_rows,

@@ -38,7 +38,7 @@ SYMBOLS = [
     'tegb_module_cubin', 'tegb_module_log', 'tegb_module_destroy', 'tegb_program_create',
     'tegb_program_destroy', 'tegb_program_launch', 'tegb_program_eval_host', 'tegb_render_launch',
     'tegb_render_launch_strided', 'tegb_render_groups_launch', 'tegb_render_groups_prepare',
-    'tegb_render_groups_launch_prepared', 'tegb_program_tile_table', 'tegb_peer_create', 'tegb_peer_connect',
+    'tegb_render_groups_launch_prepared', 'tegb_render_groups_gather', 'tegb_program_tile_table', 'tegb_peer_create', 'tegb_peer_connect',
     'tegb_peer_allreduce_sum', 'tegb_peer_error', 'tegb_peer_destroy', 'tegb_program_set_peer',
     'tegb_program_set_peer_groups',
     'tegb_launch_count', 'tegb_program_enable_timing', 'tegb_program_main_kernel_ms', 'tegb_reduce_workspace_bytes', 'tegb_reduce_sum', 'tegb_nccl_unique_id',
@@ -84,6 +84,8 @@ def lib():
                                             ctypes.POINTER(vp), ctypes.POINTER(vp), vp]
     L.tegb_render_groups_launch_prepared.argtypes = L.tegb_render_groups_launch.argtypes
     L.tegb_render_groups_prepare.argtypes = [vp, ctypes.POINTER(vp), i32, i32, ctypes.POINTER(Grid), vp, i32, i32, vp]
+    L.tegb_render_groups_gather.argtypes = [vp, ctypes.POINTER(vp), i32, ctypes.POINTER(Grid), vp, i32, i32, vp, vp,
+                                            ctypes.POINTER(vp), ctypes.POINTER(vp), vp]
     L.tegb_program_tile_table.argtypes = [vp, vp, ctypes.c_size_t, vp]
     L.tegb_render_launch_strided.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(Grid), i32, i32,
                                              ctypes.POINTER(vp), vp]
@@ -260,6 +262,14 @@ class Program:
         check(fn(self.handle, _ptr_array(group_ptrs), group_begin, group_count, ctypes.byref(grid),
                  ctypes.c_void_p(windows_ptr), max_rows, max_cols, _ptr_array(pixel_ptrs), _ptr_array(out_ptrs),
                  ctypes.c_void_p(stream)))
+
+    def render_groups_gather(self, group_ptrs: Sequence[int], group_count: int, grid: Grid, windows_ptr: int,
+                             max_rows: int, max_cols: int, bin_begin_ptr: int, bin_groups_ptr: int,
+                             pixel_ptrs: Sequence[int], out_ptrs: Sequence[int], stream: int = 0) -> None:
+        check(self._L.tegb_render_groups_gather(self.handle, _ptr_array(group_ptrs), group_count, ctypes.byref(grid),
+                                                ctypes.c_void_p(windows_ptr), max_rows, max_cols,
+                                                ctypes.c_void_p(bin_begin_ptr), ctypes.c_void_p(bin_groups_ptr),
+                                                _ptr_array(pixel_ptrs), _ptr_array(out_ptrs), ctypes.c_void_p(stream)))
 
     def prepare_groups(self, group_ptrs: Sequence[int], group_begin: int, group_count: int, grid: Grid,
                        windows_ptr: int, max_rows: int, max_cols: int, stream: int = 0) -> None:

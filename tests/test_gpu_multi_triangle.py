@@ -233,3 +233,75 @@ def test_upstream_gradient_as_a_difference_of_two_images(cuda_device):
     b = r.backward((img[0], target)).clone()
     torch.cuda.synchronize()
     assert torch.equal(a, b) and float(a.abs().sum()) > 0
+
+
+@pytest.mark.parametrize('rows', [None, (40, 171)])
+def test_gather_launch_equals_the_launches_per_class(cuda_device, rows):
+    """tegb_render_groups_gather (one launch over the image, every block walking the triangles of its bin in ascending
+    order) against one accumulating launch per class of window-disjoint triangles: the same image, bit for bit -- for
+    windows that start anywhere (not on tile boundaries) and a band of rows that starts and ends anywhere."""
+    import torch
+    from teg_b200.raster import MultiTriangleRasterizer
+    res = 192
+    scene = multi_triangle_scene(bands=1, per_band_grid=5, res=res)
+    w = scene['windows']
+    assert np.any(w[:, 0] % 16 != 0) and np.any(w[:, 2] % 32 != 0), 'the scene should have unaligned windows'
+    imgs = {}
+    for gather in (True, False):
+        r = MultiTriangleRasterizer(load_program('tri_color_primal'), load_program('tri_color_grad'), res, rows=rows,
+                                    gather=gather)
+        r.set_scene(scene['verts'], scene['col'], scene['windows'], scene['classes'], scene['max_rows'],
+                    scene['max_cols'])
+        assert (r.bins is not None) == gather
+        imgs[gather] = r.forward()[0].cpu().numpy()
+    assert np.count_nonzero(imgs[False]) > 1000
+    assert np.array_equal(imgs[True].view(np.uint32), imgs[False].view(np.uint32)), \
+        f'{np.count_nonzero(imgs[True] != imgs[False])} pixels differ'
+
+
+def test_gather_launch_with_heavily_overlapping_windows_against_the_oracle(cuda_device):
+    """Twelve triangles whose windows all overlap (no class structure at all; some windows cut their triangle): the
+    gather launch adds every pixel's contributions in ascending triangle order, like the oracle's loop."""
+    import torch
+    from oracle import Oracle
+    import teg_b200
+    from teg_b200.raster import BOX, PARAMS, group_bins
+    from teg_b200.workloads import base_name
+    res = 160
+    rng = np.random.default_rng(11)
+    K = 12
+    verts = rng.uniform(0.15, 0.85, size=(K, 6))
+    col = rng.uniform(0.2, 1.0, size=K)
+    win = np.zeros((K, 4), dtype=np.int32)
+    for k in range(K):
+        win[k] = (max(int(verts[k, 0::2].min() * res) - 2, 0), min(int(verts[k, 0::2].max() * res) + 3, res),
+                  max(int(verts[k, 1::2].min() * res) - 2, 0), min(int(verts[k, 1::2].max() * res) + 3, res))
+    win[3, 1] = (win[3, 0] + win[3, 1]) // 2            # a window that cuts its triangle
+    win[7, 2] = (win[7, 2] + win[7, 3]) // 2
+    prog = load_program('tri_color_primal')
+    mode = teg_b200.CUDA_EvalMode(prog, num_samples=16, tile_rows=16)
+    lab = {base_name(l): l for l in prog.args}
+    dev = torch.device('cuda', 0)
+    gb = {lab[nm]: torch.as_tensor(np.ascontiguousarray(verts[:, i]), dtype=torch.float32, device=dev)
+          for i, nm in enumerate(PARAMS[:6])}
+    gb[lab['col']] = torch.as_tensor(col, dtype=torch.float32, device=dev)
+    bb, bg = group_bins(win, (0, res), res, mode.block_size, 16)
+    out = torch.zeros((1, res, res), dtype=torch.float32, device=dev)
+    mode.render_groups([lab[b] for b in BOX], (res, res), ((0, 1), (0, 1)), gb,
+                       torch.as_tensor(win, device=dev), int((win[:, 1] - win[:, 0]).max()),
+                       int((win[:, 3] - win[:, 2]).max()), out=out, accumulate=True,
+                       gather=(torch.as_tensor(bb, device=dev), torch.as_tensor(bg, device=dev)))
+    got = out[0].cpu().numpy()
+    orc = Oracle(program_text('tri_color_primal'))
+    want = np.zeros((res, res), dtype=np.float32)
+    xs = np.linspace(0.0, 1.0, res + 1)
+    v32 = verts.astype(np.float32).astype(np.float64)
+    c32 = col.astype(np.float32).astype(np.float64)
+    for k in range(K):
+        r0, r1, c0, c1 = win[k]
+        nx = np.repeat(np.arange(r0, r1), c1 - c0)
+        ny = np.tile(np.arange(c0, c1), r1 - r0)
+        v = orc.eval([xs[nx], xs[nx + 1], xs[ny], xs[ny + 1]] + list(v32[k]) + [c32[k]], 16, np.float32, threads=8)[0]
+        want[nx, ny] = want[nx, ny] + v
+    assert np.count_nonzero(want) > 2000
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f'{np.count_nonzero(got != want)} pixels differ'

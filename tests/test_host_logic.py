@@ -503,3 +503,28 @@ def test_multi_triangle_scene_classes_and_group_selection():
     assert set().union(*held) == set(range(256)) and all(len(h) < 256 for h in held)
     ids, lc, lo = select_groups(sc['windows'], sc['classes'], (0, 0))
     assert ids == [] and lc == [] and (lo == -1).all()
+
+
+def test_group_bins_list_every_overlapping_group_in_ascending_order():
+    """raster.group_bins (the bins of tegb_render_groups_gather) against a brute-force overlap test per block."""
+    from teg_b200.raster import group_bins
+    rng = np.random.default_rng(3)
+    res_y, rows, bc, tr = 300, (37, 251), 128, 16
+    w = np.zeros((40, 4), dtype=np.int32)
+    w[:, 0] = rng.integers(0, 280, 40)
+    w[:, 1] = w[:, 0] + rng.integers(0, 90, 40)          # (some windows are empty, some leave the band)
+    w[:, 2] = rng.integers(0, 290, 40)
+    w[:, 3] = np.minimum(w[:, 2] + rng.integers(0, 200, 40), 320)
+    begin, groups = group_bins(w, rows, res_y, bc, tr)
+    nbx, nby = -(-res_y // bc), -(-(rows[1] - rows[0]) // tr)
+    assert begin.dtype == np.int32 and groups.dtype == np.int32 and len(begin) == nbx * nby + 1
+    assert begin[0] == 0 and begin[-1] == len(groups)
+    for by in range(nby):
+        for bx in range(nbx):
+            a, b = rows[0] + by * tr, min(rows[0] + (by + 1) * tr, rows[1])
+            c, d = bx * bc, min((bx + 1) * bc, res_y)
+            want = [k for k in range(40) if max(w[k, 0], a) < min(w[k, 1], b) and max(w[k, 2], c) < min(w[k, 3], d)]
+            got = list(groups[begin[by * nbx + bx]:begin[by * nbx + bx + 1]])
+            assert got == want, (by, bx)
+    e_begin, e_groups = group_bins(np.zeros((0, 4), dtype=np.int32), rows, res_y, bc, tr)
+    assert not e_begin.any() and len(e_groups) == 1

@@ -37,6 +37,8 @@ def main():
                     'the grouped value / gradient kernels (0 = the compiler\'s choice)')
     ap.add_argument('--tile-rows', default='16,32', help='pixel rows per tile of the value / gradient kernels')
     ap.add_argument('--coop-groups', type=int, default=4)
+    ap.add_argument('--gather', type=int, default=1, help='1: forward as ONE launch over the image (every block walks the '
+                    'triangles of its bin); 0: one accumulating launch per class of window-disjoint triangles')
     args = ap.parse_args()
 
     import torch
@@ -63,7 +65,7 @@ def main():
     K = scene['verts'].shape[0]
     mb = tuple((int(x) or None) for x in args.min_blocks.split(',')) if args.min_blocks else (None, None)
     r = MultiTriangleRasterizer(primal, grad, res, bands=world, rank=rank, device=local, cull=bool(args.cull),
-                                min_blocks=mb, tile_rows=tuple(int(x) for x in args.tile_rows.split(',')), coop_groups=args.coop_groups)
+                                min_blocks=mb, tile_rows=tuple(int(x) for x in args.tile_rows.split(',')), coop_groups=args.coop_groups, gather=bool(args.gather))
     br = scene['band_ranges']
     active = (br[max(rank - 1, 0)][0], br[min(rank + 1, world - 1)][1])      # own band and its neighbours
     r.set_scene(scene['verts'], scene['col'], scene['windows'], scene['classes'], scene['max_rows'],
