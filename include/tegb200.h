@@ -200,10 +200,12 @@ int tegb_render_groups_launch_prepared(tegb_program *p, const void *const *group
  * bin_groups[bin_begin[bin] .. bin_begin[bin + 1]) (device int32 arrays, built by the caller from the windows: every group
  * whose window reaches into the block, ASCENDING), so every pixel is owned by one thread for the whole launch and adds
  * its contributions in ascending group order: the result of launching the groups one after the other, in one launch and
- * without the read-modify-write passes.  Runs its own prologue (groups [0, group_count)). */
+ * without the read-modify-write passes.  clear != 0: the images are zeroed by the launch itself (every block clears its
+ * pixels before it adds to them) instead of being added to.  Runs its own prologue (groups [0, group_count)). */
 int tegb_render_groups_gather(tegb_program *p, const void *const *group_ptrs, int group_count, const tegb_grid *grid,
                               const int32_t *windows, int max_rows, int max_cols, const int32_t *bin_begin,
-                              const int32_t *bin_groups, const void *const *pixel_ptrs, void *const *out_ptrs, void *stream);
+                              const int32_t *bin_groups, int clear, const void *const *pixel_ptrs, void *const *out_ptrs,
+                              void *stream);
 
 /* kernels launched by this library since load (for accounting) */
 int64_t tegb_launch_count(void);

@@ -1360,7 +1360,7 @@ class Emitter:
                 I = '        ' if gather else '    '
                 mparams = ', '.join(['const T* __restrict__ xe', 'const T* __restrict__ ye', 'const int res_y',
                                      'const int row0', 'const int row1', 'const int* __restrict__ win'] +
-                                    (['const int* __restrict__ bin_begin', 'const int* __restrict__ bin_groups']
+                                    (['const int* __restrict__ bin_begin', 'const int* __restrict__ bin_groups', 'const int clear']
                                      if gather else ['const int group_begin']) +
                                     ['const T* __restrict__ Utab', 'const int tile_rows'] +
                                     (['const T* __restrict__ tiles', 'const int tab_groups'] if tile else []) +
@@ -1379,6 +1379,13 @@ class Emitter:
                     src.append('    const int col0 = (int)(blockIdx.x * blockDim.x);')
                     src.append('    const int ny = col0 + threadIdx.x;')
                     src.append('    const int bin = blockIdx.y * gridDim.x + blockIdx.x;')
+                    src.append('    if (clear && ny < res_y) {              // the launch starts from a zero image: no fill pass before it')
+                    src.append('        const int rows_blk = min(tile_rows, row1 - nx0);')
+                    src.append('        for (int r = 0; r < rows_blk; ++r) {')
+                    for k in range(K):
+                        src.append(f'            out{k}[(long long)(nx0 + r - row0) * res_y + ny] = {zero};')
+                    src.append('        }')
+                    src.append('    }')
                     src.append('    for (int e_ = bin_begin[bin]; e_ < bin_begin[bin + 1]; ++e_) {')
                     src.append('        const int g = bin_groups[e_];')
                     src.append('        const int w_r0 = max(win[4 * g + 0], row0), w_r1 = min(win[4 * g + 1], row1);')

@@ -1184,7 +1184,7 @@ extern "C" int tegb_render_groups_launch(tegb_program *p, const void *const *gro
 // image walks the groups of its bin in order, so every pixel adds its contributions in ascending group order.
 extern "C" int tegb_render_groups_gather(tegb_program *p, const void *const *group_ptrs, int group_count,
                                          const tegb_grid *g, const int32_t *windows, int max_rows, int max_cols,
-                                         const int32_t *bin_begin, const int32_t *bin_groups,
+                                         const int32_t *bin_begin, const int32_t *bin_groups, int clear,
                                          const void *const *pixel_ptrs, void *const *out_ptrs, void *stream) {
     if (!p || !g || !windows || !out_ptrs || !bin_begin || !bin_groups)
         return fail(TEGB_ERR_INVALID, "tegb_render_groups_gather: bad argument");
@@ -1195,12 +1195,17 @@ extern "C" int tegb_render_groups_gather(tegb_program *p, const void *const *gro
     if (group_count < 0 || max_rows < 1 || max_cols < 1) return fail(TEGB_ERR_INVALID, "bad group count or window bounds");
     if (g->res_x < 1 || g->res_y < 1 || g->row_begin < 0 || g->row_end > g->res_x || g->row_begin > g->row_end)
         return fail(TEGB_ERR_INVALID, "bad grid");
-    if (group_count == 0 || g->row_end == g->row_begin) return TEGB_OK;
+    if (g->row_end == g->row_begin || (group_count == 0 && !clear)) return TEGB_OK;
     std::lock_guard<std::recursive_mutex> lock(p->mu);
     RT_CHECK(cudaSetDevice(p->device));
     CUstream st = (CUstream)stream;
     int rc = begin_launch(p, st);
     if (rc) return rc;
+    if (group_count == 0) {                          // nothing to add: the cleared image
+        const size_t bytes = (size_t)(g->row_end - g->row_begin) * g->res_y * p->d.elem_size;
+        for (int k = 0; k < p->d.n_outputs; k++) RT_CHECK(cudaMemsetAsync(out_ptrs[k], 0, bytes, (cudaStream_t)st));
+        return end_launch(p, st);
+    }
     rc = groups_prologue(p, group_ptrs, 0, group_count, g, windows, max_rows, max_cols, st, true);
     if (rc) return rc;
     const GroupGeom q = group_geom(p, g, max_rows, max_cols, true);
@@ -1218,6 +1223,7 @@ extern "C" int tegb_render_groups_gather(tegb_program *p, const void *const *gro
     args.push_back((void *)&windows);
     args.push_back((void *)&bin_begin);
     args.push_back((void *)&bin_groups);
+    args.push_back(&clear);
     args.push_back(&p->d_utab);
     args.push_back(&tile_rows);
     if (p->d.n_tile_conds > 0) {

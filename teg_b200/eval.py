@@ -321,7 +321,8 @@ class CUDA_EvalMode(EvalMode):
     def render_groups(self, box_vars, res: Tuple[int, int], bounds, group_bindings, windows, max_rows: int,
                       max_cols: int, pixel_bindings=None, rows: Optional[Tuple[int, int]] = None, out=None,
                       reduce: bool = False, accumulate: bool = False, group_range: Optional[Tuple[int, int]] = None,
-                      stream: int = 0, prepared: bool = False, prepare_only: bool = False, gather=None):
+                      stream: int = 0, prepared: bool = False, prepare_only: bool = False, gather=None,
+                      clear: bool = False):
         """One launch over many *groups* (e.g. triangles), each with its own parameter values and its own
         window of pixels of the tests/plot.py grid.
 
@@ -338,7 +339,8 @@ class CUDA_EvalMode(EvalMode):
         windows tensor, window bounds and rows; the parameters must not change in between).
         gather: ``(bin_begin, bin_groups)`` int32 CUDA tensors (``group_bins``): ALL groups in one launch over the image,
         every block walking the groups of its bin in ascending order -- for accumulating image programs whose windows
-        overlap; the result is that of launching the groups one after the other."""
+        overlap; the result is that of launching the groups one after the other.  ``clear``: the gather launch zeroes
+        ``out`` itself (every block clears its pixels first) instead of adding to what it holds."""
         import torch
         pos = {lab: i for i, (lab, _) in enumerate(self.arglist)}
         pix = {(k if isinstance(k, str) else label_of(k)): v for k, v in (pixel_bindings or {}).items()}
@@ -392,7 +394,7 @@ class CUDA_EvalMode(EvalMode):
             assert bg.is_cuda and bg.dtype == torch.int32 and bg.is_contiguous()
             self._keepalive = keep + [bb, bg]
             prog.render_groups_gather(gptrs, G, grid, windows.data_ptr(), int(max_rows), int(max_cols), bb.data_ptr(),
-                                      bg.data_ptr(), pptrs, optrs, stream=stream)
+                                      bg.data_ptr(), pptrs, optrs, stream=stream, clear=clear)
             return out
         prog.render_groups(gptrs, g0, g1 - g0, grid, windows.data_ptr(), int(max_rows), int(max_cols), pptrs,
                            optrs, stream=stream, prepared=prepared)

@@ -85,7 +85,7 @@ def group_bins(windows, rows: Tuple[int, int], res_y: int, block_cols: int, tile
 class MultiTriangleRasterizer:
     def __init__(self, primal: Program, grad: Program, res: int, bands: int = 1, rank: int = 0,
                  num_samples: int = 16, device: int = 0, float_width: str = 'float', cull: bool = True,
-                 min_blocks=(4, 4), rows: Optional[Tuple[int, int]] = None, tile_rows=(16, 32), gather: bool = True,
+                 min_blocks=(4, 4), rows: Optional[Tuple[int, int]] = None, tile_rows=(32, 32), gather: bool = True,
                  **codegen_opts):
         import torch
         self.torch = torch
@@ -96,7 +96,8 @@ class MultiTriangleRasterizer:
         self.dev = torch.device('cuda', device)
         self.tdt = torch.float32 if float_width == 'float' else torch.float64
         # tile_rows = (value kernel, gradient kernel): pixel rows per block / classification tile (measured on config 5:
-        # 16 / 32 rows; the gradient kernel pays its per-block sum once per twice as many pixels)
+        # 32 / 32 rows with the gather forward, 16 / 32 with one launch per class; the gradient kernel pays its
+        # per-block sum once per twice as many pixels)
         tr = (tile_rows, tile_rows) if isinstance(tile_rows, int) else tuple(tile_rows)
         # min_blocks = (value kernel, gradient kernel): resident blocks per SM the grouped kernels are compiled for
         # (__launch_bounds__; None = the compiler's choice)
@@ -188,14 +189,15 @@ class MultiTriangleRasterizer:
         torch = self.torch
         if out is None:
             out = torch.empty((1, self.n_rows, self.res), dtype=self.tdt, device=self.dev)
-        out.zero_()
         box = [self.p_lab[b] for b in BOX]
         gb = {self.p_lab[nm]: self.params[nm] for nm in PARAMS}
         if self.bins is not None:
+            # (no fill pass: every block of the gather launch clears its pixels before it adds to them)
             self.m_primal.render_groups(box, self.grid_res, self.bounds, gb, self.windows, self.max_rows,
                                         self.max_cols, rows=self.rows, out=out, accumulate=True, stream=stream,
-                                        gather=self.bins)
+                                        gather=self.bins, clear=True)
             return out
+        out.zero_()
         if len(self.classes) > 1:
             # uniform rows + tile classification of ALL held triangles once, then one accumulating launch per class
             self.m_primal.render_groups(box, self.grid_res, self.bounds, gb, self.windows, self.max_rows,

@@ -84,7 +84,7 @@ def lib():
                                             ctypes.POINTER(vp), ctypes.POINTER(vp), vp]
     L.tegb_render_groups_launch_prepared.argtypes = L.tegb_render_groups_launch.argtypes
     L.tegb_render_groups_prepare.argtypes = [vp, ctypes.POINTER(vp), i32, i32, ctypes.POINTER(Grid), vp, i32, i32, vp]
-    L.tegb_render_groups_gather.argtypes = [vp, ctypes.POINTER(vp), i32, ctypes.POINTER(Grid), vp, i32, i32, vp, vp,
+    L.tegb_render_groups_gather.argtypes = [vp, ctypes.POINTER(vp), i32, ctypes.POINTER(Grid), vp, i32, i32, vp, vp, i32,
                                             ctypes.POINTER(vp), ctypes.POINTER(vp), vp]
     L.tegb_program_tile_table.argtypes = [vp, vp, ctypes.c_size_t, vp]
     L.tegb_render_launch_strided.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(Grid), i32, i32,
@@ -265,10 +265,12 @@ class Program:
 
     def render_groups_gather(self, group_ptrs: Sequence[int], group_count: int, grid: Grid, windows_ptr: int,
                              max_rows: int, max_cols: int, bin_begin_ptr: int, bin_groups_ptr: int,
-                             pixel_ptrs: Sequence[int], out_ptrs: Sequence[int], stream: int = 0) -> None:
+                             pixel_ptrs: Sequence[int], out_ptrs: Sequence[int], stream: int = 0,
+                             clear: bool = False) -> None:
         check(self._L.tegb_render_groups_gather(self.handle, _ptr_array(group_ptrs), group_count, ctypes.byref(grid),
                                                 ctypes.c_void_p(windows_ptr), max_rows, max_cols,
                                                 ctypes.c_void_p(bin_begin_ptr), ctypes.c_void_p(bin_groups_ptr),
+                                                int(bool(clear)),
                                                 _ptr_array(pixel_ptrs), _ptr_array(out_ptrs), ctypes.c_void_p(stream)))
 
     def prepare_groups(self, group_ptrs: Sequence[int], group_begin: int, group_count: int, grid: Grid,

@@ -253,7 +253,8 @@ def test_gather_launch_equals_the_launches_per_class(cuda_device, rows):
         r.set_scene(scene['verts'], scene['col'], scene['windows'], scene['classes'], scene['max_rows'],
                     scene['max_cols'])
         assert (r.bins is not None) == gather
-        imgs[gather] = r.forward()[0].cpu().numpy()
+        out = torch.full((1, r.n_rows, res), float('nan'), dtype=torch.float32, device='cuda')     # (forward clears it)
+        imgs[gather] = r.forward(out=out)[0].cpu().numpy()
     assert np.count_nonzero(imgs[False]) > 1000
     assert np.array_equal(imgs[True].view(np.uint32), imgs[False].view(np.uint32)), \
         f'{np.count_nonzero(imgs[True] != imgs[False])} pixels differ'

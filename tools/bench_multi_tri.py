@@ -35,7 +35,7 @@ def main():
                     'device arrays, so the graph stays valid while they change)')
     ap.add_argument('--min-blocks', default='4,4', help='experiment: "a,b" = __launch_bounds__ resident blocks per SM of '
                     'the grouped value / gradient kernels (0 = the compiler\'s choice)')
-    ap.add_argument('--tile-rows', default='16,32', help='pixel rows per tile of the value / gradient kernels')
+    ap.add_argument('--tile-rows', default='32,32', help='pixel rows per tile of the value / gradient kernels')
     ap.add_argument('--coop-groups', type=int, default=4)
     ap.add_argument('--gather', type=int, default=1, help='1: forward as ONE launch over the image (every block walks the '
                     'triangles of its bin); 0: one accumulating launch per class of window-disjoint triangles')

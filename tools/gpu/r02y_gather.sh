@@ -4,7 +4,7 @@ cd "$GRAFT_REPO_ROOT" || exit 1
 O=gpurun_out
 timeout 900 python -m pytest tests/test_gpu_multi_triangle.py tests/test_gpu_fit.py -m gpu -x -q > $O/r02y_pytest.log 2>&1; echo "pytest rc=$?" >> $O/r02y_pytest.log
 : > $O/r02y_sweep.txt
-for v in "--gather 1" "--gather 0" "--gather 1 --tile-rows 32,32" "--gather 1 --tile-rows 8,32" "--gather 1 --min-blocks 5,4"; do
+for v in "--gather 1" "--gather 0" "--gather 1 --tile-rows 32,32"; do
   timeout 600 python tools/bench_multi_tri.py --steps 10 --no-cpu --graph 1 $v > $O/tmp.json 2>$O/tmp.err
   python - "$v" <<'PY' >> $O/r02y_sweep.txt
 import json,sys
