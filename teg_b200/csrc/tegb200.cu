@@ -301,6 +301,7 @@ struct tegb_program {
     CUstream last_stream = nullptr;
     // per-block partial sums of reduce_outputs programs
     void *d_partials = nullptr;
+    unsigned int *d_red_done = nullptr;     // per-column counters of the one-launch column sum (zero between launches)
     size_t partials_bytes = 0;
     // set by tegb_program_set_peer: the sums of reduce_outputs launches are all-reduced over the peer mailboxes
     struct tegb_peer *peer = nullptr;
@@ -446,6 +447,7 @@ extern "C" void tegb_program_destroy(tegb_program *p) {
     for (void *q : p->d_out) if (q) cudaFree(q);
     if (p->u_stage) cudaFree(p->u_stage);
     if (p->d_partials) cudaFree(p->d_partials);
+    if (p->d_red_done) cudaFree(p->d_red_done);
     if (p->d_utab) cudaFree(p->d_utab);
     if (p->d_tiles) cudaFree(p->d_tiles);
     if (p->d_ranges) cudaFree(p->d_ranges);
@@ -531,11 +533,12 @@ __device__ __forceinline__ unsigned long long peer_seq_begin(const PeerView &v) 
 }
 
 // called by every block of the exchanging kernel when it is done (all threads)
-__device__ __forceinline__ void peer_seq_end(const PeerView &v, unsigned long long seq) {
+__device__ __forceinline__ void peer_seq_end(const PeerView &v, unsigned long long seq, unsigned int n_blocks = 0u) {
+    if (n_blocks == 0u) n_blocks = gridDim.x;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(v.d_done, 1u) == gridDim.x - 1u) {
+        if (atomicAdd(v.d_done, 1u) == n_blocks - 1u) {
             *(volatile unsigned int *)v.d_done = 0u;
             __threadfence();
             *(volatile unsigned long long *)v.d_seq = seq;
@@ -676,9 +679,58 @@ __global__ void __launch_bounds__(RED_THREADS) colsum_slices(const T *partials, 
     if (threadIdx.x == 0) slices[(long long)c * gridDim.x + blockIdx.x] = s;
 }
 
+// Both stages in ONE launch: the block that finishes a column's last slice (a counter per column, reset by that block:
+// replay-safe) adds the slice sums -- the same additions in the same order as colsum_stage2 over the slices, whoever
+// that block is -- and, with peers, runs the exchange.  One launch and one launch gap less on the critical path of
+// every gradient.
+template <typename T, bool PEER>
+__global__ void __launch_bounds__(RED_THREADS) colsum_slices_finish(const T *partials, long long n_blocks, long long chunk,
+                                                                    T *slices, unsigned int *done, T *out, PeerView view) {
+    __shared__ T smem[32];
+    __shared__ int last_;
+    unsigned long long seq = 0;
+    if (PEER) seq = peer_seq_begin(view);
+    const int c = blockIdx.y;
+    const long long lo = (long long)blockIdx.x * chunk;
+    long long hi = lo + chunk;
+    if (hi > n_blocks) hi = n_blocks;
+    T acc = 0;
+    for (long long i = lo + threadIdx.x; i < hi; i += RED_THREADS) acc = acc + partials[(long long)c * n_blocks + i];
+    T s = block_sum_fixed(acc, smem);
+    if (threadIdx.x == 0) {
+        slices[(long long)c * gridDim.x + blockIdx.x] = s;
+        __threadfence();
+        last_ = atomicAdd(&done[c], 1u) == gridDim.x - 1u;
+    }
+    __syncthreads();
+    if (last_) {                                   // (block-uniform)
+        __threadfence();
+        T a2 = 0;
+        for (long long i = threadIdx.x; i < (long long)gridDim.x; i += RED_THREADS)
+            a2 = a2 + __ldcg(&slices[(long long)c * gridDim.x + i]);
+        T t = block_sum_fixed(a2, smem);
+        if (PEER) {
+            if (threadIdx.x < 32) {
+                const T total = peer_exchange_sum<T>(view, c, t, seq);
+                if (threadIdx.x == 0) out[c] = total;
+            }
+        } else if (threadIdx.x == 0) {
+            out[c] = t;
+        }
+        if (threadIdx.x == 0) done[c] = 0u;
+    }
+    if (PEER) peer_seq_end(view, seq, gridDim.x * gridDim.y);
+}
+
 template <typename T>
-static void sum_columns(const T *partials, int n_cols, unsigned long long n_blocks, T *out, T *slices, cudaStream_t st) {
-    if (n_blocks >= 16384 && slices) {
+static void sum_columns(const T *partials, int n_cols, unsigned long long n_blocks, T *out, T *slices, cudaStream_t st,
+                        unsigned int *done) {
+    if (n_blocks >= 16384 && slices && done) {
+        const long long chunk = (long long)((n_blocks + RED_SLICES - 1) / RED_SLICES);
+        colsum_slices_finish<T, false><<<dim3(RED_SLICES, n_cols), RED_THREADS, 0, st>>>(partials, (long long)n_blocks, chunk,
+                                                                                         slices, done, out, PeerView{});
+        g_launches++;
+    } else if (n_blocks >= 16384 && slices) {
         const long long chunk = (long long)((n_blocks + RED_SLICES - 1) / RED_SLICES);
         colsum_slices<T><<<dim3(RED_SLICES, n_cols), RED_THREADS, 0, st>>>(partials, (long long)n_blocks, chunk, slices);
         colsum_stage2<T><<<n_cols, RED_THREADS, 0, st>>>(slices, (long long)RED_SLICES, out);
@@ -691,8 +743,13 @@ static void sum_columns(const T *partials, int n_cols, unsigned long long n_bloc
 
 template <typename T>
 static void sum_columns_peer(const T *partials, int n_cols, unsigned long long n_blocks, T *out, T *slices, cudaStream_t st,
-                             tegb_peer *peer) {
-    if (n_blocks >= 16384 && slices) {
+                             tegb_peer *peer, unsigned int *done) {
+    if (n_blocks >= 16384 && slices && done) {
+        const long long chunk = (long long)((n_blocks + RED_SLICES - 1) / RED_SLICES);
+        colsum_slices_finish<T, true><<<dim3(RED_SLICES, n_cols), RED_THREADS, 0, st>>>(partials, (long long)n_blocks, chunk,
+                                                                                        slices, done, out, peer->view);
+        g_launches++;
+    } else if (n_blocks >= 16384 && slices) {
         const long long chunk = (long long)((n_blocks + RED_SLICES - 1) / RED_SLICES);
         colsum_slices<T><<<dim3(RED_SLICES, n_cols), RED_THREADS, 0, st>>>(partials, (long long)n_blocks, chunk, slices);
         colsum_stage2_peer<T><<<n_cols, RED_THREADS, 0, st>>>(slices, (long long)RED_SLICES, out, peer->view);
@@ -706,20 +763,25 @@ static void sum_columns_peer(const T *partials, int n_cols, unsigned long long n
 static int finish_partials(tegb_program *p, unsigned long long n_blocks, void *out, cudaStream_t st) {
     // slice sums live behind the partials (ensure_partials reserves the room)
     char *slices = (char *)p->d_partials + (size_t)p->d.reduce_outputs * n_blocks * p->d.elem_size;
+    if (!p->d_red_done) {                        // per-column "slices done" counters of the one-launch column sum
+        RT_CHECK(cudaMalloc(&p->d_red_done, (size_t)p->d.reduce_outputs * sizeof(unsigned int)));
+        RT_CHECK(cudaMemsetAsync(p->d_red_done, 0, (size_t)p->d.reduce_outputs * sizeof(unsigned int), st));
+    }
+    unsigned int *done = p->d_red_done;
     if (p->peer) {
         if (p->d.reduce_outputs > p->peer->view.maxv) return fail(TEGB_ERR_INVALID, "peer mailbox smaller than the gradient");
         if (peer_failed(p->peer)) return TEGB_ERR_PEER;
         if (p->d.elem_size == 4)
-            sum_columns_peer<float>((const float *)p->d_partials, p->d.reduce_outputs, n_blocks, (float *)out, (float *)slices, st, p->peer);
+            sum_columns_peer<float>((const float *)p->d_partials, p->d.reduce_outputs, n_blocks, (float *)out, (float *)slices, st, p->peer, done);
         else
-            sum_columns_peer<double>((const double *)p->d_partials, p->d.reduce_outputs, n_blocks, (double *)out, (double *)slices, st, p->peer);
+            sum_columns_peer<double>((const double *)p->d_partials, p->d.reduce_outputs, n_blocks, (double *)out, (double *)slices, st, p->peer, done);
         RT_CHECK(cudaGetLastError());
         return TEGB_OK;
     }
     if (p->d.elem_size == 4)
-        sum_columns<float>((const float *)p->d_partials, p->d.reduce_outputs, n_blocks, (float *)out, (float *)slices, st);
+        sum_columns<float>((const float *)p->d_partials, p->d.reduce_outputs, n_blocks, (float *)out, (float *)slices, st, done);
     else
-        sum_columns<double>((const double *)p->d_partials, p->d.reduce_outputs, n_blocks, (double *)out, (double *)slices, st);
+        sum_columns<double>((const double *)p->d_partials, p->d.reduce_outputs, n_blocks, (double *)out, (double *)slices, st, done);
     RT_CHECK(cudaGetLastError());
     return TEGB_OK;
 }
@@ -1330,6 +1392,10 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
     args.push_back(&tile_rows);
     args.push_back(&tile_stride);
     args.push_back(&tile_phase);
+    // Tiled programs whose outputs are ALL summed, one partial per 32-column tile (the generated code makes the same
+    // test): tiles without work get their zero partials from the classification kernel, and the main kernel is a fixed
+    // number of blocks walking the (few) listed tile blocks next to the workers that serve the unresolved tiles.
+    const bool sparse = p->d.n_tile_conds > 0 && p->d.reduce_outputs == p->d.n_outputs && p->d.tile_cols == 32;
     if (p->d.n_tile_conds > 0) {
         // classify the tiles for these launch-wide arguments and this band (tile_cols columns x tile_rows rows each;
         // a block of the main kernel spans block_size / tile_cols of them)
@@ -1380,6 +1446,12 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
         targs.push_back(&p->d_order);
         targs.push_back(&d_counters);
         targs.push_back(&d_ulist);
+        if (sparse) {
+            // (the classification kernel writes the zero partials of the tiles without work)
+            rc = ensure_partials(p, (unsigned long long)n_sub);
+            if (rc) return rc;
+            targs.push_back(&p->d_partials);
+        }
         const unsigned tb = 128, tg = (unsigned)(((size_t)n_txs * n_ty + tb - 1) / tb);     // a thread per tile
         CU_CHECK(drv::LaunchKernel(p->f_tiles, tg, 1, 1, tb, 1, 1, 0, st, targs.data(), nullptr));
         g_launches++;
@@ -1413,8 +1485,14 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
         args.push_back(&p->d_partials);
     }
     time_begin(p, st);
-    if (p->d.n_tile_conds > 0)      // 1-D grid: the queue workers first, then one block per tile block
-        CU_CHECK(drv::LaunchKernel(p->f_main, (unsigned)p->q_workers + gx * gy, 1, 1, bs, 1, 1, 0, st, args.data(), nullptr));
+    if (p->d.n_tile_conds > 0) {    // 1-D grid: the queue workers first, then one block per tile block (sparse: per listed one)
+        unsigned ordinary = gx * gy;
+        if (sparse) {
+            const unsigned cap = (unsigned)queue_workers(p->device) * 2u;
+            if (ordinary > cap) ordinary = cap;
+        }
+        CU_CHECK(drv::LaunchKernel(p->f_main, (unsigned)p->q_workers + ordinary, 1, 1, bs, 1, 1, 0, st, args.data(), nullptr));
+    }
     else
         CU_CHECK(drv::LaunchKernel(p->f_main, gx, gy, 1, bs, 1, 1, 0, st, args.data(), nullptr));
     time_end(p, st);
