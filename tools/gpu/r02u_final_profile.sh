@@ -9,10 +9,7 @@ $B > /dev/null 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'tri_(primal|grad)_(main|tiles)' -s 12 -c 4 -o $O/r02u_prof_tri $B > $O/r02u_ncu_tri.log 2>&1
 M="python tools/bench_multi_tri.py --steps 3 --no-cpu --graph 0"
 $M > $O/r02u_mt_plain.json 2> $O/r02u_mt_plain.err &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 40 --csv --log-file $O/r02u_launches_mt.csv $M > $O/r02u_ncu_lm.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 40 --csv --log-file $O/r02u_launches_mt.csv $M > $O/r02u_ncu_lm.log 2>&1
 $M > /dev/null 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'tri_color_(primal|grad)_(main|tiles)' -s 22 -c 12 -o $O/r02u_prof_mt $M > $O/r02u_ncu_mt.log 2>&1
-D="python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --no-extras --graph 0 --cull 0"
-$D > $O/r02u_dense_plain.json 2> $O/r02u_dense_plain.err &&
-ncu --set full --clock-control none --import-source on -k regex:'tri_primal_main' -s 4 -c 1 -o $O/r02u_prof_dense $D > $O/r02u_ncu_dense.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'tri_color_(primal|grad)_(main|tiles|gather)' -s 8 -c 8 -o $O/r02u_prof_mt $M > $O/r02u_ncu_mt.log 2>&1
 ls -la $O | grep r02u
