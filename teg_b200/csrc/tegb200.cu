@@ -310,6 +310,7 @@ struct tegb_program {
     size_t tiles_bytes = 0;
     void *tiles_ord_ptr = nullptr;    // the launch-ordered copy inside d_tiles (plain tiled renders)
     int *q_ulist = nullptr, *q_counters = nullptr;     // unresolved-row queue of the last plain tiled launch
+    bool counters_dirty = true;                        // the counters are not known to be zero (first launch / after a failure)
     int q_n_tx = 0, q_n_ty = 0, q_workers = 0;
     // per tile row / tile column: [min, max] of the box edges and sample abscissae (valid for ranges_grid)
     int *d_order = nullptr;       // [n_tiles] tile indices in launch order, then 2 counters
@@ -1431,11 +1432,16 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
             // launch order [blocks] | 4 counters | unresolved-tile list [tiles]
             RT_CHECK(cudaMalloc((void **)&p->d_order, (2 * n_sub + 4) * sizeof(int)));
             p->order_count = n_sub;
+            p->counters_dirty = true;
         }
         int *d_counters = p->d_order + p->order_count;
         int *d_ulist = d_counters + 4;
-        // counters: blocks filed from the front / from the back of the launch order, unresolved tiles, queue cursor
-        RT_CHECK(cudaMemsetAsync(d_counters, 0, 4 * sizeof(int), (cudaStream_t)st));
+        // counters: blocks filed from the front / from the back of the launch order, unresolved tiles, queue cursor.
+        // They are zeroed BEHIND the main kernel for the next launch (off the critical path of this one: a 16-byte
+        // memset node in front of the classification kernel cost ~2 us per call); only a first launch, or one after a
+        // call that failed half-way, zeroes them here.
+        if (p->counters_dirty) RT_CHECK(cudaMemsetAsync(d_counters, 0, 4 * sizeof(int), (cudaStream_t)st));
+        p->counters_dirty = true;
         targs.push_back(&p->d_ranges);
         targs.push_back(&res_y);
         targs.push_back(&n_tx);
@@ -1497,6 +1503,10 @@ extern "C" int tegb_render_launch_strided(tegb_program *p, const double *scalars
         CU_CHECK(drv::LaunchKernel(p->f_main, gx, gy, 1, bs, 1, 1, 0, st, args.data(), nullptr));
     time_end(p, st);
     g_launches++;
+    if (p->d.n_tile_conds > 0) {
+        RT_CHECK(cudaMemsetAsync(p->q_counters, 0, 4 * sizeof(int), (cudaStream_t)st));
+        p->counters_dirty = false;
+    }
     if (p->d.reduce_outputs) {
         rc = finish_partials(p, n_partials, out_ptrs[n_store], (cudaStream_t)st);
         if (rc) return rc;
