@@ -235,8 +235,8 @@ def test_upstream_gradient_as_a_difference_of_two_images(cuda_device):
     assert torch.equal(a, b) and float(a.abs().sum()) > 0
 
 
-@pytest.mark.parametrize('rows', [None, (40, 171)])
-def test_gather_launch_equals_the_launches_per_class(cuda_device, rows):
+@pytest.mark.parametrize('rows,cull', [(None, True), ((40, 171), True), ((40, 171), False)])
+def test_gather_launch_equals_the_launches_per_class(cuda_device, rows, cull):
     """tegb_render_groups_gather (one launch over the image, every block walking the triangles of its bin in ascending
     order) against one accumulating launch per class of window-disjoint triangles: the same image, bit for bit -- for
     windows that start anywhere (not on tile boundaries) and a band of rows that starts and ends anywhere."""
@@ -249,7 +249,7 @@ def test_gather_launch_equals_the_launches_per_class(cuda_device, rows):
     imgs = {}
     for gather in (True, False):
         r = MultiTriangleRasterizer(load_program('tri_color_primal'), load_program('tri_color_grad'), res, rows=rows,
-                                    gather=gather)
+                                    gather=gather, cull=cull)           # (cull=False: no tile table, the dense program)
         r.set_scene(scene['verts'], scene['col'], scene['windows'], scene['classes'], scene['max_rows'],
                     scene['max_cols'])
         assert (r.bins is not None) == gather
@@ -258,6 +258,12 @@ def test_gather_launch_equals_the_launches_per_class(cuda_device, rows):
     assert np.count_nonzero(imgs[False]) > 1000
     assert np.array_equal(imgs[True].view(np.uint32), imgs[False].view(np.uint32)), \
         f'{np.count_nonzero(imgs[True] != imgs[False])} pixels differ'
+    if not cull:
+        # (and the dense program equals the culled one: the culled image of the same scene, bit for bit)
+        r = MultiTriangleRasterizer(load_program('tri_color_primal'), load_program('tri_color_grad'), res, rows=rows)
+        r.set_scene(scene['verts'], scene['col'], scene['windows'], scene['classes'], scene['max_rows'],
+                    scene['max_cols'])
+        assert np.array_equal(r.forward()[0].cpu().numpy().view(np.uint32), imgs[True].view(np.uint32))
 
 
 def test_gather_launch_with_heavily_overlapping_windows_against_the_oracle(cuda_device):
