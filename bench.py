@@ -528,7 +528,7 @@ class TriRaster:
 
 # ------------------------------------------------------------------------------------- multi_tri_4096
 class MultiTri:
-    """BASELINE.json configs[4]: forward (9 window-disjoint classes added into the image) + backward with the upstream
+    """BASELINE.json configs[4]: forward (ONE gather launch: every image block adds the triangles of its bin) + backward with the upstream
     gradient dL = image - target (one grouped launch, per-triangle sums reduced in-kernel, all-reduced over the peer
     mailboxes when N > 1).
     An *evaluation* = one (pixel, triangle) pair inside a triangle's window: its value integral and its reverse
@@ -1196,7 +1196,7 @@ def main() -> int:
         oc = op_count(sch, NUM_SAMPLES)
         fwd_ms = hm['phase_ms']['forward']
         ach = oc.unguarded * head.pairs_local / (fwd_ms * 1e-3) / 1e12
-        roofline = {'bound': 'fp32_fma', 'kernel': 'tri_color_primal_main (grouped, 9 class launches)', 'achieved': ach,
+        roofline = {'bound': 'fp32_fma', 'kernel': 'tri_color_primal_gather (one launch over the image, every block walks the triangles of its bin)', 'achieved': ach,
                     'peak': peak_tflops, 'unit': 'TFLOP/s', 'frac': ach / peak_tflops, 'traffic': None,
                     'algorithmic_ops_per_instance': oc.unguarded, 'kernel_ms': fwd_ms,
                     'note': 'reference-program operations over the forward phase; culled kernels skip most of them'}
@@ -1206,7 +1206,7 @@ def main() -> int:
         rec = workloads['multi_tri_4096']
         fwd_ms = rec['phase_ms']['forward']
         ach = oc5.unguarded * mt_weak.pairs_local / (fwd_ms * 1e-3) / 1e12
-        rec['roofline'] = {'bound': 'fp32_fma', 'kernel': 'tri_color_primal_main (grouped, 9 class launches)',
+        rec['roofline'] = {'bound': 'fp32_fma', 'kernel': 'tri_color_primal_gather (one launch over the image, every block walks the triangles of its bin)',
                            'achieved': ach, 'peak': peak_tflops, 'unit': 'TFLOP/s', 'frac': ach / peak_tflops,
                            'traffic': None, 'algorithmic_ops_per_instance': oc5.unguarded, 'kernel_ms': fwd_ms,
                            'note': 'reference-program operations over the forward phase; culled kernels skip most of them'}

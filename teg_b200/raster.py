@@ -5,8 +5,9 @@ The reference renders by looping over pixels in Python and evaluating ONE progra
 programs (value, and reverse derivative with an upstream per-pixel ``dL``) are evaluated for every
 (pixel, triangle) pair inside each triangle's bounding window, as *grouped* launches:
 
-  forward    image[p] = sum_k value_k(p)        one launch per window-disjoint class of triangles, adding
-                                                into the image in a fixed class order (no atomics)
+  forward    image[p] = sum_k value_k(p)        ONE gather launch over the image: every block walks the triangles
+                                                of its bin in ascending order (no atomics, no fill; `gather=False`:
+                                                one accumulating launch per window-disjoint class, the same bits)
   backward   grad[k, :] = sum_p d value_k(p) . dL(p)     ONE launch over all triangles; per-triangle sums are
                                                 reduced in-kernel (fixed order) -> [K, 7]
   multi-GPU  every rank owns a band of pixel rows; windows are clipped to the band; the [K, 7] gradient is
