@@ -1,9 +1,7 @@
 #!/usr/bin/env python
-"""Small run of every kernel variant, meant to be wrapped in compute-sanitizer:
-
-    compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
-    compute-sanitizer --tool racecheck python tools/sanitize_smoke.py
-"""
+"""Small run of every kernel variant (odd grids, bands that start inside a tile, every launch path).  Where
+compute-sanitizer may be used, wrap it: ``compute-sanitizer --tool memcheck python tools/sanitize_smoke.py``; on this
+round's GPU pool the sanitizer is closed, so the parity suite (every variant against the oracle) is the bounds check."""
 import os
 import sys
 
@@ -48,12 +46,21 @@ def main():
             m.render(prog.args[:4], (300, 200), ((0, 1), (0, 1)), scal, reduce=True, interleave=(2, 1), rows=(5, 290))
             CUDA_EvalMode(prog, num_samples=ns, cull=False).render(prog.args[:4], (100, 130), ((0, 1), (0, 1)), scal)
             CUDA_EvalMode(prog, num_samples=ns, tiles=False).render(prog.args[:4], (100, 130), ((0, 1), (0, 1)), scal)
-    res = 64
-    scene = multi_triangle_scene(bands=1, per_band_grid=4, res=res)
-    r = MultiTriangleRasterizer(load('tri_color_primal'), load('tri_color_grad'), res)
-    r.set_scene(scene['verts'], scene['col'], scene['windows'], scene['classes'], scene['max_rows'], scene['max_cols'])
-    img = r.forward()
-    g = r.backward(img[0].contiguous())
+    # sparse gradient programs whose interior is NOT zero (listed tile blocks next to the queue workers)
+    prog = load('shaded_grad')
+    b = dict(zip(prog.args, bind(prog.args, scene_values('shaded_grad', res=(2, 2)))))
+    scal = {lab: float(v) for lab, v in b.items() if np.ndim(v) == 0}
+    box = [next(a for a in prog.args if a.rsplit('_', 1)[0] == nm) for nm in ('x_lb', 'x_ub', 'y_lb', 'y_ub')]
+    CUDA_EvalMode(prog, num_samples=16).render(box, (150, 333), ((0, 1), (0, 1)), scal, reduce=True, rows=(7, 149))
+    # grouped: gather forward (image blocks walk their bins; unaligned windows, a band that starts inside a tile), the
+    # launches per class, the dense programs, the backward pass with dL and with dL as a difference of two images
+    for res, rows, kw in ((64, None, {}), (192, (40, 171), {}), (192, (40, 171), {'gather': False}), (96, (5, 90), {'cull': False})):
+        scene = multi_triangle_scene(bands=1, per_band_grid=4, res=res)
+        r = MultiTriangleRasterizer(load('tri_color_primal'), load('tri_color_grad'), res, rows=rows, **kw)
+        r.set_scene(scene['verts'], scene['col'], scene['windows'], scene['classes'], scene['max_rows'], scene['max_cols'])
+        img = r.forward()
+        g = r.backward(img[0].contiguous())
+        g = g + r.backward((img[0].contiguous(), torch.zeros_like(img[0])))
     torch.cuda.synchronize()
     print('sanitize_smoke ok', float(img.sum()), float(g.abs().sum()))
 
