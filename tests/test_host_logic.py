@@ -528,3 +528,39 @@ def test_group_bins_list_every_overlapping_group_in_ascending_order():
             assert got == want, (by, bx)
     e_begin, e_groups = group_bins(np.zeros((0, 4), dtype=np.int32), rows, res_y, bc, tr)
     assert not e_begin.any() and len(e_groups) == 1
+
+
+def test_bins_of_row_bands_partition_the_pairs_of_the_whole_image():
+    """N ranks, one band of rows each (MultiTriangleRasterizer per rank: select_groups, then group_bins over the held
+    groups): every (pixel row, triangle) pair of the whole image is served by exactly one rank, and a rank's bins list its
+    LOCAL group numbers in ascending global order (class order: the order the image adds them in)."""
+    from teg_b200.raster import group_bins, select_groups
+    from teg_b200.workloads import multi_triangle_scene
+    res, bands, tr, bc = 128, 1, 16, 128
+    sc = multi_triangle_scene(bands=bands, per_band_grid=4, res=res)
+    w = np.asarray(sc['windows']).astype(np.int64)
+    K = len(w)
+    total_rows = res * bands
+    served = np.zeros((total_rows, K), dtype=np.int32)
+    for world in (1, 2, 4):
+        served[:] = 0
+        for rank in range(world):
+            rows = (total_rows * rank // world, total_rows * (rank + 1) // world)
+            ids, classes, local_of = select_groups(w, sc['classes'], rows)
+            assert ids == sorted(ids) or all(ids[a:b] == sorted(ids[a:b]) for a, b in classes)
+            begin, groups = group_bins(w[ids] if ids else np.zeros((0, 4), dtype=np.int64), rows, res, bc, tr)
+            nbx = -(-res // bc)
+            for b in range(len(begin) - 1):
+                mine = groups[begin[b]:begin[b + 1]]
+                assert list(mine) == sorted(mine)                     # ascending local = ascending (class, band) order
+                by = b // nbx
+                r_lo, r_hi = rows[0] + by * tr, min(rows[0] + (by + 1) * tr, rows[1])
+                for g in mine:
+                    k = ids[g]
+                    a, c = max(w[k, 0], r_lo), min(w[k, 1], r_hi)
+                    assert a < c                                      # the bin's groups do reach into the block
+                    served[a:c, k] += 1
+        want = np.zeros_like(served)
+        for k in range(K):
+            want[w[k, 0]:w[k, 1], k] = 1
+        assert np.array_equal(served, want), world
